@@ -1,0 +1,138 @@
+"""Seeded synthetic workloads for the parity tests and ``bench.py``.
+
+Nothing here is on the scoring path; it only manufactures inputs of the shapes
+``BASELINE.json`` names: a proteome with realistic residue frequencies, and reads that are
+either back-translated from that proteome (coding) or uniform ACGT (random), plus the
+low-complexity / ``N`` / short / mixed-case flavours the classification branches need.
+"""
+import numpy as np
+
+AMINO_ACIDS = "SLTEAVPGKDRIQNFHYMCW"
+# empirical residue frequencies of the reference's test proteome subset, in AMINO_ACIDS order
+_AA_FREQ = np.array(
+    [9.8, 9.4, 7.8, 6.8, 6.8, 6.4, 6.2, 6.0, 5.7, 5.2, 4.6, 4.6, 4.3, 3.5, 3.3, 2.5, 2.3, 2.2, 1.6, 0.9]
+)
+
+# standard genetic code, index = 16*b0 + 4*b1 + b2 with T,C,A,G = 0..3
+_CODE_TCAG = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"
+_BASES_TCAG = "TCAG"
+
+
+def _synonymous_codon_table():
+    """(codons[256, 6, 3] uint8, counts[256] int64): sense codons per amino-acid byte."""
+    codons = np.zeros((256, 6, 3), dtype=np.uint8)
+    counts = np.zeros(256, dtype=np.int64)
+    for i, aa in enumerate(_CODE_TCAG):
+        if aa == "*":
+            continue
+        trip = (_BASES_TCAG[i // 16], _BASES_TCAG[(i // 4) % 4], _BASES_TCAG[i % 4])
+        a = ord(aa)
+        codons[a, counts[a]] = [ord(c) for c in trip]
+        counts[a] += 1
+    return codons, counts
+
+
+_SYN_CODONS, _SYN_COUNTS = _synonymous_codon_table()
+_COMPLEMENT = np.arange(256, dtype=np.uint8)
+for _a, _b in zip(b"ACGT", b"TGCA"):
+    _COMPLEMENT[_a] = _b
+_ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def make_proteome(n_proteins=20000, seed=1001):
+    """Synthetic proteome: (residues uint8[total], offsets uint64[n+1]).  P20M: defaults; P100M:
+    n_proteins=187000, seed=1004."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    lengths = np.clip(np.round(rng.lognormal(6.1, 0.6, n_proteins)), 50, 5000).astype(np.int64)
+    offsets = np.zeros(n_proteins + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum(lengths)
+    p = _AA_FREQ / _AA_FREQ.sum()
+    idx = rng.choice(len(AMINO_ACIDS), size=int(offsets[-1]), p=p)
+    residues = np.frombuffer(AMINO_ACIDS.encode(), dtype=np.uint8)[idx]
+    return np.ascontiguousarray(residues), offsets
+
+
+def _coding_reads(rng, n, length, residues, prot_offsets, sub_rate):
+    """n back-translated reads of `length` nt (uint8 [n, length])."""
+    n_res = length // 3 + 2
+    n_prot = len(prot_offsets) - 1
+    plen = (prot_offsets[1:] - prot_offsets[:-1]).astype(np.int64)
+    ok = np.nonzero(plen >= n_res)[0]
+    prot = ok[rng.integers(0, len(ok), n)]
+    start = prot_offsets[prot].astype(np.int64) + (rng.random(n) * (plen[prot] - n_res + 1)).astype(np.int64)
+    aa = residues[start[:, None] + np.arange(n_res)[None, :]]          # [n, n_res]
+    pick = (rng.random(aa.shape) * _SYN_COUNTS[aa]).astype(np.int64)
+    nt = _SYN_CODONS[aa, pick].reshape(n, n_res * 3)                   # [n, 3*n_res]
+    phase = rng.integers(0, 3, n)
+    cols = phase[:, None] + np.arange(length)[None, :]
+    reads = np.take_along_axis(nt, cols, axis=1)
+    # substitutions: replace by one of the three other bases
+    sub = rng.random(reads.shape) < sub_rate
+    if sub.any():
+        code = np.zeros(256, dtype=np.uint8)
+        code[_ACGT] = np.arange(4, dtype=np.uint8)
+        shifted = (code[reads[sub]] + rng.integers(1, 4, int(sub.sum()))) % 4
+        reads[sub] = _ACGT[shifted]
+    # reverse-complement half of them
+    flip = rng.random(n) < 0.5
+    reads[flip] = _COMPLEMENT[reads[flip][:, ::-1]]
+    return reads
+
+
+def make_reads_fixed(n_reads, residues, prot_offsets, length=150, seed=2002, sub_rate=0.01, chunk=1 << 18):
+    """R150 recipe: read i is coding iff i is even, else uniform ACGT.  Returns uint8 [n_reads, length]."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = np.empty((n_reads, length), dtype=np.uint8)
+    for lo in range(0, n_reads, chunk):
+        hi = min(n_reads, lo + chunk)
+        m = hi - lo
+        block = _ACGT[rng.integers(0, 4, (m, length))]
+        even = np.nonzero((np.arange(lo, hi) % 2) == 0)[0]
+        if len(even):
+            block[even] = _coding_reads(rng, len(even), length, residues, prot_offsets, sub_rate)
+        out[lo:hi] = block
+    return out
+
+
+def make_reads_mixed(n_reads, residues, prot_offsets, ksize=7, seed=5005, min_len=50, max_len=300):
+    """cfg5 recipe: mixed lengths with every classification branch represented.
+    45 % coding, 45 % random, 4 % homopolymer-rich, 3 % triplet repeats, 2 % with 1-5 N, 1 % shorter
+    than 3k+3.  Returns (bytes uint8[total], offsets uint64[n+1])."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    kinds = rng.choice(6, size=n_reads, p=[0.45, 0.45, 0.04, 0.03, 0.02, 0.01])
+    lengths = rng.integers(min_len, max_len + 1, n_reads)
+    short = kinds == 5
+    lengths[short] = rng.integers(1, 3 * ksize + 3, int(short.sum()))
+    offsets = np.zeros(n_reads + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum(lengths)
+    buf = _ACGT[rng.integers(0, 4, int(offsets[-1]))]
+    coding_full = _coding_reads(rng, int((kinds == 0).sum()) + int((kinds == 4).sum()), max_len, residues,
+                                prot_offsets, 0.01)
+    ci = 0
+    for i in range(n_reads):
+        lo, L, kind = int(offsets[i]), int(lengths[i]), int(kinds[i])
+        if kind == 0 or kind == 4:
+            buf[lo:lo + L] = coding_full[ci, :L]
+            ci += 1
+            if kind == 4:
+                pos = rng.integers(0, L, rng.integers(1, 6))
+                buf[lo + pos] = ord("N")
+        elif kind == 2:
+            # long runs of one base with sparse interruptions: ndiff / L < 0.3
+            base = _ACGT[rng.integers(0, 4)]
+            seg = np.full(L, base, dtype=np.uint8)
+            n_breaks = int(0.1 * L)
+            if n_breaks:
+                seg[rng.integers(0, L, n_breaks)] = _ACGT[rng.integers(0, 4, n_breaks)]
+            buf[lo:lo + L] = seg
+        elif kind == 3:
+            unit = _ACGT[rng.integers(0, 4, 3)]
+            buf[lo:lo + L] = np.tile(unit, L // 3 + 1)[:L]
+    return buf, offsets
+
+
+def concat_fixed(reads2d):
+    """[n, L] matrix -> (flat bytes, offsets) in the layout the C ABI takes."""
+    n, L = reads2d.shape
+    offsets = np.arange(n + 1, dtype=np.uint64) * np.uint64(L)
+    return np.ascontiguousarray(reads2d).reshape(-1), offsets
