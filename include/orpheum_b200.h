@@ -1,0 +1,191 @@
+/*
+ * orpheum_b200.h -- C ABI of the B200-native orpheum `translate` / `index` hot path.
+ *
+ * The reference (czbiohub-sf/orpheum) is pure Python and has no FFI of its own; its per-read
+ * arithmetic lives behind two third-party native calls (sourmash `hash_murmur`, khmer
+ * `Nodegraph.add/get`).  This library replaces the whole per-read body -- everything under
+ * `Translate.score_reads_per_file` (orpheum/translate.py:367-372) and the inner loop of
+ * `make_peptide_bloom_filter` (orpheum/index.py:105-122) -- with sm_100a CUDA kernels.  Each entry
+ * point below names the reference interface it stands in for.  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - Plain C, no C++/torch types.  Every function returns 0 (ORPH_OK) or a negative orph_status;
+ *     orph_last_error() returns a thread-local message for the last failure on this thread.
+ *   - The caller owns every host array it passes in; the library owns device memory behind the
+ *     opaque handles.  Nothing returned needs freeing except handles (`*_destroy`).
+ *   - One orph_ctx per GPU per host thread.  Filters are immutable while scoring and may be shared
+ *     by several contexts on the same device.
+ *   - "host" entry points take host pointers and include the H2D/D2H copies; "_device" entry points
+ *     take device pointers (e.g. torch tensors' data_ptr()) and only enqueue work on the context's
+ *     stream -- call orph_ctx_synchronize (or synchronize the stream yourself) before reading.
+ *   - Frame order in every [6] array is 1, 2, 3, -1, -2, -3 (translate_single_seq.py:70-78,
+ *     translate.py:320).
+ */
+#ifndef ORPHEUM_B200_H
+#define ORPHEUM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORPH_ABI_VERSION 1
+#define ORPH_MAX_TABLES 16
+
+typedef enum orph_status {
+    ORPH_OK = 0,
+    ORPH_E_INVALID = -1,    /* bad argument */
+    ORPH_E_CUDA = -2,       /* CUDA runtime failure (message has the CUDA error string) */
+    ORPH_E_NOMEM = -3,      /* host or device allocation failed */
+    ORPH_E_TOO_LONG = -4,   /* a read is longer than ORPH_MAX_READ_LEN */
+    ORPH_E_EMPTY_READ = -5, /* a zero-length read: the reference raises ZeroDivisionError (translate.py:83) */
+    ORPH_E_IO = -6
+} orph_status;
+
+/* Per-frame category codes.  Text forms: constants_translate.py:27-44. */
+typedef enum orph_category {
+    ORPH_CAT_STOP_CODONS = 0,       /* "Translation frame has stop codon(s)"                 translate.py:218-226 */
+    ORPH_CAT_TOO_SHORT_PEPTIDE = 1, /* "Translation is shorter than peptide k-mer size + 1"  translate.py:227-237 */
+    ORPH_CAT_LOW_COMPLEXITY_PEPTIDE = 2, /* "Low complexity peptide in {alphabet} alphabet"  translate.py:244-259 */
+    ORPH_CAT_CODING = 3,            /* "Coding"                                              translate.py:271-284 */
+    ORPH_CAT_NON_CODING = 4,        /* "Non-coding"                                          translate.py:285-298 */
+    ORPH_CAT_LOW_COMPLEXITY_NUCLEOTIDE = 5, /* fastp-low-complexity read; the reference labels it "Read length was
+                                       shorter than 3 * peptide k-mer size" (translate.py:301-331 quirk) */
+    ORPH_CAT_INVALID = 255          /* empty read (no reference result exists) */
+} orph_category;
+
+/* One record per read, 32 bytes.  For categories 0, 1 and 5 the reference reports NaN for both
+ * jaccard and n_kmers (counts are 0 here); for category 2 jaccard is NaN but n_kmers is kept;
+ * for 3 and 4 jaccard = n_hits / n_kmers (one IEEE double division, done by the caller or by
+ * orph_jaccard()).  Replaces the 6 SingleReadScore tuples of Translate.maybe_score_single_read
+ * (translate.py:323-331, constants_translate.py:46-54). */
+typedef struct orph_read_result {
+    uint16_t n_kmers[6];  /* distinct peptide k-mers of the frame (translate.py:186,188) */
+    uint16_t n_hits[6];   /* of those, how many are in the Bloom filter (translate.py:189-191) */
+    uint8_t category[6];  /* orph_category */
+    int8_t best_frame;    /* frame (1,2,3,-1,-2,-3) with the maximum jaccard among categories 3/4, exact rational
+                             comparison, first in frame order on ties; 0 if no frame was scored (README.md:49-54) */
+    uint8_t flags;        /* ORPH_FLAG_* */
+} orph_read_result;
+
+#define ORPH_FLAG_OPEN_MASK 0x3f      /* bit f: frame f had no stop codon and was longer than k (was scored) */
+#define ORPH_FLAG_LOW_COMPLEXITY 0x40 /* fastp nucleotide complexity < 0.3 (translate.py:56-84) */
+#define ORPH_FLAG_BYTE_PATH 0x80      /* read went through the byte-exact path (non-ACGT bytes or over-long) */
+
+/* Input encodings of read batches. */
+typedef enum orph_reads_format {
+    ORPH_READS_ASCII = 0,  /* concatenated raw sequence bytes exactly as screed yields them (any byte, any case) */
+    ORPH_READS_PACKED2 = 1 /* 2 bits per base, base g of the concatenated stream at bits [2*(g%32), +2) of
+                              little-endian u64 word g/32; code = (ascii >> 1) & 3, i.e. A=0 C=1 T=2 G=3.
+                              Only upper-case ACGT reads can be represented: the caller routes other reads
+                              through an ASCII batch (orph_pack_reads reports which). */
+} orph_reads_format;
+
+#define ORPH_MAX_READ_LEN 6144u /* longest read the byte-exact path scores (over-long -> ORPH_E_TOO_LONG) */
+
+typedef struct orph_ctx orph_ctx;
+typedef struct orph_filter orph_filter;
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* `stream`: a cudaStream_t to enqueue on (e.g. torch.cuda.current_stream().cuda_stream), or NULL to
+ * let the context create its own non-blocking stream. */
+int orph_ctx_create(int device, void *stream, orph_ctx **out);
+void orph_ctx_destroy(orph_ctx *ctx);
+int orph_ctx_synchronize(orph_ctx *ctx);
+/* Returns (and clears) the sticky device-side status of work enqueued so far: ORPH_OK,
+ * ORPH_E_EMPTY_READ or ORPH_E_TOO_LONG.  Synchronizes the stream. */
+int orph_ctx_check(orph_ctx *ctx);
+/* Test hook: force the exact all-pairs de-duplication path in the scoring kernels (normally only
+ * taken on a 64-bit MurmurHash collision between two different k-mers of one frame). */
+int orph_ctx_set_force_exact_dedup(orph_ctx *ctx, int on);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t orph_ctx_launch_count(const orph_ctx *ctx);
+const char *orph_last_error(void);
+int orph_abi_version(void);
+
+/* ---- Bloom filter: khmer.Nodegraph ---------------------------------------------------------- */
+/* khmer's table sizing: the n_tables largest odd primes below `tablesize`, descending
+ * (khmer.Nodegraph(k, tablesize, n_tables), index.py:101). */
+int orph_table_sizes(uint64_t tablesize, uint32_t n_tables, uint64_t *out_sizes);
+
+/* Empty filter with explicit table sizes (bits).  khmer.Nodegraph ctor, index.py:101. */
+int orph_filter_create(orph_ctx *ctx, uint32_t ksize, uint32_t n_tables, const uint64_t *table_sizes,
+                       orph_filter **out);
+/* Filter from host tables laid out exactly as in a .nodegraph file: table i is table_sizes[i]/8+1
+ * bytes, bit b at byte b>>3, mask 1<<(b&7).  khmer load path, index.py:70-77. */
+int orph_filter_from_host(orph_ctx *ctx, uint32_t ksize, uint32_t n_tables, const uint64_t *table_sizes,
+                          const uint8_t *const *tables, orph_filter **out);
+/* Copies the tables back (same layout) and returns popcount(table 0), the OXLI header's
+ * occupied_bins field.  Either output may be NULL.  Nodegraph.save, index.py:206,218. */
+int orph_filter_to_host(const orph_filter *f, uint8_t *const *tables, uint64_t *occupied_bins_table0);
+void orph_filter_destroy(orph_filter *f);
+/* Geometry; Nodegraph.ksize() (translate.py:145, index.py:164,202).  Outputs may be NULL. */
+int orph_filter_info(const orph_filter *f, uint32_t *ksize, uint32_t *n_tables, uint64_t *table_sizes);
+/* Nodegraph.n_unique_kmers() (tests/test_index.py:54,82): number of add operations that set at least
+ * one new bit.  Order dependent in khmer, therefore only approximately reproducible under parallel
+ * insertion (the reference checks it to rtol 1e-3); the bits themselves are exact. */
+uint64_t orph_filter_n_unique_kmers(const orph_filter *f);
+/* popcount of one table (table 0 = occupied_bins). */
+int orph_filter_popcount(const orph_filter *f, uint32_t table, uint64_t *out);
+/* The single contiguous device allocation that holds all tables (table i at byte offset
+ * table_offsets[i], 256-byte aligned), for replication with ncclBroadcast / cudaMemcpyPeer by the
+ * caller's plumbing.  A filter created with the same geometry on another device has the same layout. */
+int orph_filter_device_buffer(const orph_filter *f, void **device_ptr, uint64_t *n_bytes, uint64_t *table_offsets);
+/* Single-process replication onto another context's device over NVLink (cudaMemcpyPeerAsync). */
+int orph_filter_replicate(const orph_filter *src, orph_ctx *dst_ctx, orph_filter **out);
+
+/* The inner loop of index.make_peptide_bloom_filter (index.py:107-122): for each record, skip it if it
+ * contains '*', re-encode through lut (encode_peptide), hash every k-mer (MurmurHash3_x64_128 seed 42,
+ * low 64 bits) and OR bit (hash % size_i) into every table.  residues/offsets are HOST arrays
+ * (offsets has n_records+1 entries).  n_unique_kmers_inc (optional) receives the increment. */
+int orph_filter_add_peptides(orph_filter *f, const uint8_t *residues, const uint64_t *offsets, uint64_t n_records,
+                             const uint8_t lut[256], uint64_t *n_unique_kmers_inc);
+/* Nodegraph.add(hash) for a batch of precomputed hashes (index.py:119); is_new (optional) gets 0/1. */
+int orph_filter_add_hashes(orph_filter *f, const uint64_t *hashes, uint64_t n, uint8_t *is_new);
+/* Nodegraph.get(hash) for a batch of hashes (translate.py:190); out01[i] = 0/1.  Host arrays. */
+int orph_filter_query_hashes(const orph_filter *f, const uint64_t *hashes, uint64_t n, uint8_t *out01);
+/* sourmash.minhash.hash_murmur for a batch of equal-length keys, computed on the GPU (test hook for the
+ * device hash; translate.py:187).  keys is n*len bytes. */
+int orph_hash_kmers(orph_ctx *ctx, const uint8_t *keys, uint32_t len, uint64_t n, uint64_t *out_hashes);
+
+/* ---- scoring: Translate.score_reads_per_file's per-read body -------------------------------- */
+/* Host-buffer form (the drop-in seam, translate.py:323-372).  reads/offsets/out are HOST arrays;
+ * offsets has n_reads+1 entries, in bases, offsets[0] may be non-zero.  For ORPH_READS_ASCII every read
+ * gets the reference's byte-exact semantics (N, lower case, ... included).  Includes H2D, all kernels,
+ * D2H and a stream synchronize.  Returns ORPH_E_EMPTY_READ / ORPH_E_TOO_LONG after filling every other
+ * read's record if such reads were present. */
+int orph_score_reads(orph_ctx *ctx, const orph_filter *f, const void *reads, int reads_format,
+                     const uint64_t *offsets, uint64_t n_reads, const uint8_t lut[256], double jaccard_threshold,
+                     orph_read_result *out);
+/* Device-buffer form: same contract, but reads/offsets/out are DEVICE pointers (reads 16-byte aligned)
+ * and the call only enqueues on the context's stream.  max_read_len is an upper bound on the read
+ * length in this batch (reads beyond it are still scored, through the slower byte path); pass 0 if
+ * unknown (assumes ORPH_MAX_READ_LEN).  Use orph_ctx_check() for the deferred status. */
+int orph_score_reads_device(orph_ctx *ctx, const orph_filter *f, const void *d_reads, int reads_format,
+                            const uint64_t *d_offsets, uint64_t n_reads, uint32_t max_read_len,
+                            const uint8_t lut[256], double jaccard_threshold, orph_read_result *d_out);
+/* Host helper for callers that want to ship 2-bit reads over PCIe: packs the concatenated ASCII stream
+ * [offsets[0], offsets[n_reads]) into out_packed (ceil(total/32) u64 words) and sets needs_ascii[i]=1
+ * for every read that contains a byte other than upper-case ACGT (its packed bits are unspecified).
+ * Multi-threaded on the host; n_threads <= 0 picks the hardware concurrency. */
+int orph_pack_reads(const uint8_t *reads, const uint64_t *offsets, uint64_t n_reads, uint64_t *out_packed,
+                    uint8_t *needs_ascii, int n_threads);
+/* jaccard of frame i of a record exactly as the reference computes it: n_hits / n_kmers in IEEE double
+ * for categories 3/4, NaN otherwise (translate.py:204). */
+double orph_jaccard(const orph_read_result *r, int frame_index);
+
+/* ---- measurement helpers (bench.py) ---------------------------------------------------------- */
+/* Random 32-byte-sector gather micro-benchmark over `footprint_bytes` of device memory: every thread
+ * issues `loads_per_thread` dependent-free byte loads at pseudo-random addresses.  Returns sectors/s
+ * measured with CUDA events on the context's stream.  This is the ceiling the Bloom-probe rate is
+ * graded against. */
+int orph_bench_gather_peak(orph_ctx *ctx, uint64_t footprint_bytes, uint32_t loads_per_thread, int persist_l2,
+                           double *sectors_per_second);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORPHEUM_B200_H */

@@ -1,0 +1,856 @@
+// C ABI of the B200-native orpheum translate/index hot path (see include/orpheum_b200.h).
+// Host side: handles, device memory, launch plumbing.  Kernels live in score_kernels.cuh and
+// bloom_kernels.cuh.  Built with: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "bloom_kernels.cuh"
+#include "score_kernels.cuh"
+
+using namespace orph;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fail(e__ == cudaErrorMemoryAllocation ? ORPH_E_NOMEM : ORPH_E_CUDA, "%s: %s (%s:%d)", #expr, \
+                        cudaGetErrorString(e__), __FILE__, __LINE__);                               \
+    } while (0)
+
+extern "C" const char *orph_last_error(void) { return g_err; }
+extern "C" int orph_abi_version(void) { return ORPH_ABI_VERSION; }
+
+// ------------------------------------------------------------------------------------------------
+// handles
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t need)
+    {
+        if (need <= cap) return ORPH_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = need + need / 8 + 256;
+        CUDA_TRY(cudaMalloc(&p, want));
+        cap = want;
+        return ORPH_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct orph_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    size_t l2_persist_max = 0, l2_window_max = 0;
+    const void *l2_window_base = nullptr;  // filter buffer the access-policy window currently covers
+    bool force_exact = false;
+    uint64_t launches = 0;
+    uint32_t sticky_status = 0;  // device status bits folded in by the host-buffer entry points
+    DevBuf counters;             // ScoreCounters (one per in-flight call; calls on a ctx are serialised on its stream)
+    DevBuf queue, bytes_queue;   // uint32 read indices
+    DevBuf needs_bytes;          // uint8 per read (ASCII input)
+    DevBuf packed;               // 2-bit stream built from ASCII input
+    DevBuf in_reads, in_offsets, out_results;  // staging for the host-buffer entry points
+    DevBuf misc;                 // small transfers (hash batches, ...)
+};
+
+struct orph_filter {
+    int device = 0;
+    uint32_t ksize = 0, n_tables = 0;
+    uint64_t sizes[ORPH_MAX_TABLES] = {0};
+    uint64_t offsets[ORPH_MAX_TABLES] = {0};  // byte offset of each table in buf
+    uint64_t padded[ORPH_MAX_TABLES] = {0};   // bytes reserved per table (multiple of 256)
+    uint8_t *buf = nullptr;
+    uint64_t n_bytes = 0;
+    unsigned long long *d_scalars = nullptr;  // [0] n_unique, [1] popcount scratch, [2] next record
+    uint64_t n_unique = 0;
+    orph_ctx *ctx = nullptr;  // context the filter was created on (its stream orders builds)
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+static FilterDev filter_dev(const orph_filter *f)
+{
+    FilterDev F;
+    memset(&F, 0, sizeof(F));
+    F.ksize = f->ksize;
+    F.n_tables = f->n_tables;
+    for (uint32_t i = 0; i < f->n_tables; i++) {
+        F.size[i] = f->sizes[i];
+        F.magic[i] = ~0ULL / f->sizes[i];
+        F.table[i] = f->buf + f->offsets[i];
+    }
+    return F;
+}
+
+static int grid_for(uint64_t n_items, int block, int sm_count, int waves = 8)
+{
+    uint64_t g = (n_items + block - 1) / block;
+    uint64_t cap = (uint64_t)sm_count * waves;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+extern "C" int orph_ctx_create(int device, void *stream, orph_ctx **out)
+{
+    if (!out) return fail(ORPH_E_INVALID, "orph_ctx_create: out is NULL");
+    *out = nullptr;
+    int n_dev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&n_dev));
+    if (device < 0 || device >= n_dev) return fail(ORPH_E_INVALID, "orph_ctx_create: device %d of %d", device, n_dev);
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(ORPH_E_INVALID, "orph_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    orph_ctx *ctx = new (std::nothrow) orph_ctx();
+    if (!ctx) return fail(ORPH_E_NOMEM, "orph_ctx_create: out of host memory");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    ctx->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+    ctx->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete ctx;
+            return fail(ORPH_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+        }
+        ctx->own_stream = true;
+    }
+    int rc = ctx->counters.ensure(sizeof(ScoreCounters));
+    if (rc != ORPH_OK) {
+        orph_ctx_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return ORPH_OK;
+}
+
+extern "C" void orph_ctx_destroy(orph_ctx *ctx)
+{
+    if (!ctx) return;
+    DeviceGuard guard(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (DevBuf *b : {&ctx->counters, &ctx->queue, &ctx->bytes_queue, &ctx->needs_bytes, &ctx->packed, &ctx->in_reads,
+                      &ctx->in_offsets, &ctx->out_results, &ctx->misc})
+        b->release();
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int orph_ctx_synchronize(orph_ctx *ctx)
+{
+    if (!ctx) return fail(ORPH_E_INVALID, "orph_ctx_synchronize: ctx is NULL");
+    DeviceGuard guard(ctx->device);
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return ORPH_OK;
+}
+
+static int status_to_code(uint32_t bits)
+{
+    if (bits & kStatusEmptyRead) return fail(ORPH_E_EMPTY_READ, "a read of length 0 was passed (the reference raises ZeroDivisionError, translate.py:83)");
+    if (bits & kStatusTooLong) return fail(ORPH_E_TOO_LONG, "a read is longer than the declared bound / ORPH_MAX_READ_LEN (%u)", ORPH_MAX_READ_LEN);
+    return ORPH_OK;
+}
+
+extern "C" int orph_ctx_check(orph_ctx *ctx)
+{
+    if (!ctx) return fail(ORPH_E_INVALID, "orph_ctx_check: ctx is NULL");
+    DeviceGuard guard(ctx->device);
+    ScoreCounters c;
+    CUDA_TRY(cudaMemcpyAsync(&c, ctx->counters.p, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    uint32_t bits = c.status | ctx->sticky_status;
+    ctx->sticky_status = 0;
+    CUDA_TRY(cudaMemsetAsync((uint8_t *)ctx->counters.p + offsetof(ScoreCounters, status), 0, sizeof(uint32_t), ctx->stream));
+    return status_to_code(bits);
+}
+
+extern "C" int orph_ctx_set_force_exact_dedup(orph_ctx *ctx, int on)
+{
+    if (!ctx) return fail(ORPH_E_INVALID, "ctx is NULL");
+    ctx->force_exact = on != 0;
+    return ORPH_OK;
+}
+
+extern "C" uint64_t orph_ctx_launch_count(const orph_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// filter
+// ------------------------------------------------------------------------------------------------
+static bool is_prime_u64(uint64_t n)
+{
+    if (n < 2) return false;
+    if (n < 4) return true;
+    if (!(n & 1)) return false;
+    for (uint64_t d = 3; d * d <= n; d += 2)
+        if (n % d == 0) return false;
+    return true;
+}
+
+extern "C" int orph_table_sizes(uint64_t tablesize, uint32_t n_tables, uint64_t *out_sizes)
+{
+    if (!out_sizes || n_tables == 0 || n_tables > ORPH_MAX_TABLES || tablesize < 3)
+        return fail(ORPH_E_INVALID, "orph_table_sizes: bad arguments (tablesize %llu, n_tables %u)", (unsigned long long)tablesize, n_tables);
+    uint64_t i = tablesize - 1;
+    if (!(i & 1)) i--;
+    uint32_t found = 0;
+    while (found < n_tables && i > 0) {
+        if (is_prime_u64(i)) out_sizes[found++] = i;
+        if (i < 2) break;
+        i -= 2;
+    }
+    if (found != n_tables) return fail(ORPH_E_INVALID, "orph_table_sizes: fewer than %u primes below %llu", n_tables, (unsigned long long)tablesize);
+    return ORPH_OK;
+}
+
+extern "C" void orph_filter_destroy(orph_filter *f)
+{
+    if (!f) return;
+    DeviceGuard guard(f->device);
+    if (f->ctx && f->ctx->l2_window_base == f->buf) f->ctx->l2_window_base = nullptr;
+    if (f->buf) cudaFree(f->buf);
+    if (f->d_scalars) cudaFree(f->d_scalars);
+    delete f;
+}
+
+extern "C" int orph_filter_create(orph_ctx *ctx, uint32_t ksize, uint32_t n_tables, const uint64_t *table_sizes, orph_filter **out)
+{
+    if (!ctx || !out || !table_sizes) return fail(ORPH_E_INVALID, "orph_filter_create: NULL argument");
+    *out = nullptr;
+    if (ksize == 0 || ksize > (uint32_t)kMaxKsize) return fail(ORPH_E_INVALID, "orph_filter_create: ksize %u not in 1..%d", ksize, kMaxKsize);
+    if (n_tables == 0 || n_tables > ORPH_MAX_TABLES) return fail(ORPH_E_INVALID, "orph_filter_create: n_tables %u not in 1..%d", n_tables, ORPH_MAX_TABLES);
+    DeviceGuard guard(ctx->device);
+    orph_filter *f = new (std::nothrow) orph_filter();
+    if (!f) return fail(ORPH_E_NOMEM, "out of host memory");
+    f->device = ctx->device;
+    f->ctx = ctx;
+    f->ksize = ksize;
+    f->n_tables = n_tables;
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n_tables; i++) {
+        if (table_sizes[i] < 2 || table_sizes[i] >= (1ULL << 48)) {
+            delete f;
+            return fail(ORPH_E_INVALID, "orph_filter_create: table size %llu out of range", (unsigned long long)table_sizes[i]);
+        }
+        f->sizes[i] = table_sizes[i];
+        f->offsets[i] = total;
+        f->padded[i] = (table_sizes[i] / 8 + 1 + 255) & ~255ULL;
+        total += f->padded[i];
+    }
+    f->n_bytes = total;
+    cudaError_t e = cudaMalloc((void **)&f->buf, total);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&f->d_scalars, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemsetAsync(f->buf, 0, total, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(f->d_scalars, 0, 4 * sizeof(unsigned long long), ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        int code = fail(e == cudaErrorMemoryAllocation ? ORPH_E_NOMEM : ORPH_E_CUDA, "orph_filter_create (%llu bytes): %s", (unsigned long long)total, cudaGetErrorString(e));
+        orph_filter_destroy(f);
+        return code;
+    }
+    *out = f;
+    return ORPH_OK;
+}
+
+extern "C" int orph_filter_from_host(orph_ctx *ctx, uint32_t ksize, uint32_t n_tables, const uint64_t *table_sizes,
+                                     const uint8_t *const *tables, orph_filter **out)
+{
+    if (!tables) return fail(ORPH_E_INVALID, "orph_filter_from_host: tables is NULL");
+    int rc = orph_filter_create(ctx, ksize, n_tables, table_sizes, out);
+    if (rc != ORPH_OK) return rc;
+    orph_filter *f = *out;
+    DeviceGuard guard(ctx->device);
+    for (uint32_t i = 0; i < n_tables; i++) {
+        cudaError_t e = cudaMemcpyAsync(f->buf + f->offsets[i], tables[i], f->sizes[i] / 8 + 1, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) {
+            orph_filter_destroy(f);
+            *out = nullptr;
+            return fail(ORPH_E_CUDA, "orph_filter_from_host: %s", cudaGetErrorString(e));
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return ORPH_OK;
+}
+
+extern "C" int orph_filter_popcount(const orph_filter *f, uint32_t table, uint64_t *out)
+{
+    if (!f || !out || table >= f->n_tables) return fail(ORPH_E_INVALID, "orph_filter_popcount: bad arguments");
+    DeviceGuard guard(f->device);
+    cudaStream_t s = f->ctx->stream;
+    CUDA_TRY(cudaMemsetAsync(f->d_scalars + 1, 0, sizeof(unsigned long long), s));
+    // only the bytes that exist in the file take part; the padding is zero anyway
+    const uint64_t n_words = f->padded[table] / 4;
+    popcount_kernel<<<grid_for(n_words, 256, f->ctx->sm_count), 256, 0, s>>>(reinterpret_cast<const uint32_t *>(f->buf + f->offsets[table]), n_words, f->d_scalars + 1);
+    f->ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    unsigned long long v = 0;
+    CUDA_TRY(cudaMemcpyAsync(&v, f->d_scalars + 1, sizeof(v), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    *out = v;
+    return ORPH_OK;
+}
+
+extern "C" int orph_filter_to_host(const orph_filter *f, uint8_t *const *tables, uint64_t *occupied_bins_table0)
+{
+    if (!f) return fail(ORPH_E_INVALID, "orph_filter_to_host: filter is NULL");
+    DeviceGuard guard(f->device);
+    cudaStream_t s = f->ctx->stream;
+    if (tables) {
+        for (uint32_t i = 0; i < f->n_tables; i++)
+            CUDA_TRY(cudaMemcpyAsync(tables[i], f->buf + f->offsets[i], f->sizes[i] / 8 + 1, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    if (occupied_bins_table0) return orph_filter_popcount(f, 0, occupied_bins_table0);
+    return ORPH_OK;
+}
+
+extern "C" int orph_filter_info(const orph_filter *f, uint32_t *ksize, uint32_t *n_tables, uint64_t *table_sizes)
+{
+    if (!f) return fail(ORPH_E_INVALID, "orph_filter_info: filter is NULL");
+    if (ksize) *ksize = f->ksize;
+    if (n_tables) *n_tables = f->n_tables;
+    if (table_sizes) memcpy(table_sizes, f->sizes, f->n_tables * sizeof(uint64_t));
+    return ORPH_OK;
+}
+
+extern "C" uint64_t orph_filter_n_unique_kmers(const orph_filter *f) { return f ? f->n_unique : 0; }
+
+extern "C" int orph_filter_device_buffer(const orph_filter *f, void **device_ptr, uint64_t *n_bytes, uint64_t *table_offsets)
+{
+    if (!f) return fail(ORPH_E_INVALID, "orph_filter_device_buffer: filter is NULL");
+    if (device_ptr) *device_ptr = f->buf;
+    if (n_bytes) *n_bytes = f->n_bytes;
+    if (table_offsets) memcpy(table_offsets, f->offsets, f->n_tables * sizeof(uint64_t));
+    return ORPH_OK;
+}
+
+extern "C" int orph_filter_replicate(const orph_filter *src, orph_ctx *dst_ctx, orph_filter **out)
+{
+    if (!src || !dst_ctx || !out) return fail(ORPH_E_INVALID, "orph_filter_replicate: NULL argument");
+    int rc = orph_filter_create(dst_ctx, src->ksize, src->n_tables, src->sizes, out);
+    if (rc != ORPH_OK) return rc;
+    orph_filter *dst = *out;
+    {
+        DeviceGuard g(src->device);
+        cudaStreamSynchronize(src->ctx->stream);  // the source must be fully built
+    }
+    DeviceGuard guard(dst_ctx->device);
+    if (src->device != dst_ctx->device) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, dst_ctx->device, src->device);
+        if (can) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else cudaGetLastError();
+        }
+    }
+    cudaError_t e = cudaMemcpyPeerAsync(dst->buf, dst_ctx->device, src->buf, src->device, src->n_bytes, dst_ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(dst_ctx->stream);
+    if (e != cudaSuccess) {
+        orph_filter_destroy(dst);
+        *out = nullptr;
+        return fail(ORPH_E_CUDA, "orph_filter_replicate: %s", cudaGetErrorString(e));
+    }
+    dst->n_unique = src->n_unique;
+    return ORPH_OK;
+}
+
+static int fetch_n_unique(orph_filter *f, uint64_t *inc)
+{
+    unsigned long long v = 0;
+    CUDA_TRY(cudaMemcpyAsync(&v, f->d_scalars, sizeof(v), cudaMemcpyDeviceToHost, f->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(f->ctx->stream));
+    if (inc) *inc = v - f->n_unique;
+    f->n_unique = v;
+    return ORPH_OK;
+}
+
+extern "C" int orph_filter_add_peptides(orph_filter *f, const uint8_t *residues, const uint64_t *offsets, uint64_t n_records,
+                                        const uint8_t lut[256], uint64_t *n_unique_kmers_inc)
+{
+    if (!f || !offsets || !lut || (!residues && n_records)) return fail(ORPH_E_INVALID, "orph_filter_add_peptides: NULL argument");
+    if (n_unique_kmers_inc) *n_unique_kmers_inc = 0;
+    if (n_records == 0) return ORPH_OK;
+    orph_ctx *ctx = f->ctx;
+    DeviceGuard guard(f->device);
+    cudaStream_t s = ctx->stream;
+    const uint64_t base = offsets[0], total = offsets[n_records] - base;
+    int rc;
+    if ((rc = ctx->in_reads.ensure(total + 16)) != ORPH_OK) return rc;
+    if ((rc = ctx->in_offsets.ensure((n_records + 1) * sizeof(uint64_t))) != ORPH_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(ctx->in_reads.p, residues + base, total, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(ctx->in_offsets.p, offsets, (n_records + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemsetAsync(f->d_scalars + 2, 0, sizeof(unsigned long long), s));
+    BuildParams P;
+    P.F = filter_dev(f);
+    memcpy(P.lut, lut, 256);
+    const int grid = ctx->sm_count * 8;
+    // residues pointer is shifted so that absolute offsets index it directly
+    bloom_add_peptides_kernel<<<grid, 256, 0, s>>>(P, (const uint8_t *)ctx->in_reads.p - base, (const uint64_t *)ctx->in_offsets.p, n_records, f->d_scalars + 2, f->d_scalars);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return fetch_n_unique(f, n_unique_kmers_inc);
+}
+
+extern "C" int orph_filter_add_hashes(orph_filter *f, const uint64_t *hashes, uint64_t n, uint8_t *is_new)
+{
+    if (!f || (!hashes && n)) return fail(ORPH_E_INVALID, "orph_filter_add_hashes: NULL argument");
+    if (n == 0) return ORPH_OK;
+    orph_ctx *ctx = f->ctx;
+    DeviceGuard guard(f->device);
+    cudaStream_t s = ctx->stream;
+    int rc;
+    if ((rc = ctx->misc.ensure(n * 9 + 16)) != ORPH_OK) return rc;
+    uint64_t *d_h = (uint64_t *)ctx->misc.p;
+    uint8_t *d_new = (uint8_t *)ctx->misc.p + n * 8;
+    CUDA_TRY(cudaMemcpyAsync(d_h, hashes, n * 8, cudaMemcpyHostToDevice, s));
+    bloom_add_hashes_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, s>>>(filter_dev(f), d_h, n, is_new ? d_new : nullptr, f->d_scalars);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (is_new) CUDA_TRY(cudaMemcpyAsync(is_new, d_new, n, cudaMemcpyDeviceToHost, s));
+    return fetch_n_unique(f, nullptr);
+}
+
+extern "C" int orph_filter_query_hashes(const orph_filter *f, const uint64_t *hashes, uint64_t n, uint8_t *out01)
+{
+    if (!f || ((!hashes || !out01) && n)) return fail(ORPH_E_INVALID, "orph_filter_query_hashes: NULL argument");
+    if (n == 0) return ORPH_OK;
+    orph_ctx *ctx = f->ctx;
+    DeviceGuard guard(f->device);
+    cudaStream_t s = ctx->stream;
+    int rc;
+    if ((rc = ctx->misc.ensure(n * 9 + 16)) != ORPH_OK) return rc;
+    uint64_t *d_h = (uint64_t *)ctx->misc.p;
+    uint8_t *d_o = (uint8_t *)ctx->misc.p + n * 8;
+    CUDA_TRY(cudaMemcpyAsync(d_h, hashes, n * 8, cudaMemcpyHostToDevice, s));
+    bloom_query_hashes_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, s>>>(filter_dev(f), d_h, n, d_o);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out01, d_o, n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return ORPH_OK;
+}
+
+extern "C" int orph_hash_kmers(orph_ctx *ctx, const uint8_t *keys, uint32_t len, uint64_t n, uint64_t *out_hashes)
+{
+    if (!ctx || ((!keys && len) || !out_hashes) && n) return fail(ORPH_E_INVALID, "orph_hash_kmers: NULL argument");
+    if (n == 0) return ORPH_OK;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = ctx->stream;
+    int rc;
+    const uint64_t key_bytes = (uint64_t)len * n;
+    const uint64_t key_pad = (key_bytes + 15) & ~15ULL;
+    if ((rc = ctx->misc.ensure(key_pad + n * 8 + 16)) != ORPH_OK) return rc;
+    uint8_t *d_k = (uint8_t *)ctx->misc.p;
+    uint64_t *d_o = (uint64_t *)((uint8_t *)ctx->misc.p + key_pad);
+    if (key_bytes) CUDA_TRY(cudaMemcpyAsync(d_k, keys, key_bytes, cudaMemcpyHostToDevice, s));
+    hash_kmers_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, s>>>(d_k, len, n, d_o);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out_hashes, d_o, n * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return ORPH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scoring
+// ------------------------------------------------------------------------------------------------
+static uint32_t next_pow2(uint32_t x)
+{
+    uint32_t p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+// Pin the filter's bit tables in L2 when they fit (BASELINE north_star): a persisting access-policy
+// window on the context's stream over the single contiguous filter allocation.
+static void apply_l2_window(orph_ctx *ctx, const orph_filter *f)
+{
+    if (ctx->l2_window_base == f->buf) return;
+    ctx->l2_window_base = f->buf;
+    if (ctx->l2_persist_max == 0 || ctx->l2_window_max == 0) return;
+    size_t want = std::min<size_t>(f->n_bytes, ctx->l2_persist_max);
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    attr.accessPolicyWindow.base_ptr = f->buf;
+    attr.accessPolicyWindow.num_bytes = std::min<size_t>(f->n_bytes, ctx->l2_window_max);
+    attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)attr.accessPolicyWindow.num_bytes);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+}
+
+template <int K>
+static int launch_score_frames(orph_ctx *ctx, const ScoreParams &P, const uint32_t *packed32, const uint64_t *d_offsets,
+                               uint64_t pbase0, const uint32_t *queue, ScoreCounters *counters, orph_read_result *d_out)
+{
+    const int warps = 8;
+    const uint32_t per_warp = (P.slots * 8 + P.read_words * 4 + P.pep_bytes + P.slots * 2 + 15) & ~15u;
+    const size_t smem = (size_t)per_warp * warps;
+    if (smem > (size_t)ctx->max_smem_optin) return fail(ORPH_E_INVALID, "score_frames: %zu bytes of shared memory needed", smem);
+    auto kern = score_frames_kernel<K>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    kern<<<ctx->sm_count * per_sm, warps * 32, smem, ctx->stream>>>(P, packed32, d_offsets, pbase0, queue, counters, d_out);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ORPH_OK;
+}
+
+// Core pipeline on device-resident inputs.  Exactly one of (d_ascii, d_packed_in) is the source:
+//   ASCII : pack_ascii -> prefilter -> score_frames -> score_bytes<ASCII> on flagged reads
+//   PACKED: prefilter -> score_frames -> score_bytes<PACKED> on over-long reads
+static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t *d_ascii, uint64_t abase0,
+                             const uint64_t *d_packed_in, uint64_t pbase0_in, uint64_t total_bases_ascii,
+                             const uint64_t *d_offsets, uint64_t n_reads, uint32_t max_read_len, const uint8_t lut[256],
+                             double thr, orph_read_result *d_out)
+{
+    if (n_reads >= (1ULL << 32)) return fail(ORPH_E_INVALID, "more than 2^32-1 reads in one call");
+    cudaStream_t s = ctx->stream;
+    int rc;
+    const uint32_t bound = (max_read_len == 0 || max_read_len > ORPH_MAX_READ_LEN) ? ORPH_MAX_READ_LEN : max_read_len;
+    const uint32_t fast_len = std::min(bound, kFastMaxLen);
+    if ((rc = ctx->queue.ensure(n_reads * 4)) != ORPH_OK) return rc;
+    if ((rc = ctx->bytes_queue.ensure(n_reads * 4)) != ORPH_OK) return rc;
+    ScoreCounters *counters = (ScoreCounters *)ctx->counters.p;
+    // status is sticky across calls until orph_ctx_check; everything else restarts
+    CUDA_TRY(cudaMemsetAsync(counters, 0, offsetof(ScoreCounters, status), s));
+    apply_l2_window(ctx, f);
+
+    ScoreParams P;
+    memset(&P, 0, sizeof(P));
+    P.F = filter_dev(f);
+    memcpy(P.lut, lut, 256);
+    P.jaccard_threshold = thr;
+    P.k = f->ksize;
+    P.max_len = bound;
+    P.fast_max_len = fast_len;
+    P.force_exact = ctx->force_exact ? 1u : 0u;
+
+    const uint64_t *d_packed = d_packed_in;
+    uint64_t pbase0 = pbase0_in;
+    const uint8_t *d_needs = nullptr;
+    if (d_ascii) {
+        const uint64_t n_words = (total_bases_ascii + 31) / 32;
+        if ((rc = ctx->packed.ensure((n_words + 2) * 8)) != ORPH_OK) return rc;
+        if ((rc = ctx->needs_bytes.ensure(n_reads)) != ORPH_OK) return rc;
+        CUDA_TRY(cudaMemsetAsync(ctx->needs_bytes.p, 0, n_reads, s));
+        pbase0 = abase0;
+        if (n_words) {
+            pack_ascii_kernel<<<grid_for(n_words, 256, ctx->sm_count, 16), 256, 0, s>>>(
+                d_ascii, abase0, d_offsets, n_reads, pbase0, total_bases_ascii, (uint64_t *)ctx->packed.p, (uint8_t *)ctx->needs_bytes.p);
+            ctx->launches++;
+            CUDA_TRY(cudaGetLastError());
+        }
+        d_packed = (const uint64_t *)ctx->packed.p;
+        d_needs = (const uint8_t *)ctx->needs_bytes.p;
+    }
+
+    prefilter_kernel<<<grid_for(n_reads, 256, ctx->sm_count, 16), 256, 0, s>>>(
+        d_packed, d_offsets, pbase0, n_reads, d_needs, P.k, fast_len, bound, d_out, (uint32_t *)ctx->queue.p,
+        (uint32_t *)ctx->bytes_queue.p, counters);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+
+    // fast path: open frames of clean reads
+    P.slots = std::max(64u, next_pow2(2 * std::max(1u, fast_len / 3)));
+    P.pep_bytes = (fast_len / 3 + kPepPad + 3) & ~3u;
+    P.read_words = (2 * fast_len + 62) / 32 + 2;
+    const uint32_t *packed32 = reinterpret_cast<const uint32_t *>(d_packed);
+    switch (P.k) {
+    case 7: rc = launch_score_frames<7>(ctx, P, packed32, d_offsets, pbase0, (const uint32_t *)ctx->queue.p, counters, d_out); break;
+    case 12: rc = launch_score_frames<12>(ctx, P, packed32, d_offsets, pbase0, (const uint32_t *)ctx->queue.p, counters, d_out); break;
+    case 31: rc = launch_score_frames<31>(ctx, P, packed32, d_offsets, pbase0, (const uint32_t *)ctx->queue.p, counters, d_out); break;
+    default: rc = launch_score_frames<0>(ctx, P, packed32, d_offsets, pbase0, (const uint32_t *)ctx->queue.p, counters, d_out); break;
+    }
+    if (rc != ORPH_OK) return rc;
+
+    // byte-exact path for whatever prefilter routed away (non-ACGT bytes, reads longer than the fast path)
+    if (d_ascii || bound > fast_len) {
+        ScoreParams B = P;
+        B.slots = std::max(64u, next_pow2(2 * std::max(1u, bound / 3)));
+        B.pep_bytes = (bound / 3 + kPepPad + 3) & ~3u;
+        B.read_words = 0;
+        const uint32_t per_warp = (B.slots * 8 + B.pep_bytes + B.slots * 2 + 15) & ~15u;
+        int warps = (int)std::min<size_t>(8, std::max<size_t>(1, (size_t)96 * 1024 / per_warp));
+        const size_t smem = (size_t)per_warp * warps;
+        if (d_ascii) {
+            auto kern = score_bytes_kernel<false>;
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+            kern<<<ctx->sm_count * std::max(1, per_sm), warps * 32, smem, s>>>(B, d_ascii, d_offsets, abase0, n_reads, (const uint32_t *)ctx->bytes_queue.p, counters, d_out);
+        } else {
+            auto kern = score_bytes_kernel<true>;
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+            kern<<<ctx->sm_count * std::max(1, per_sm), warps * 32, smem, s>>>(B, d_packed, d_offsets, pbase0, n_reads, (const uint32_t *)ctx->bytes_queue.p, counters, d_out);
+        }
+        ctx->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    return ORPH_OK;
+}
+
+static int check_score_args(orph_ctx *ctx, const orph_filter *f, const void *reads, int fmt, const uint64_t *offsets,
+                            uint64_t n_reads, const uint8_t *lut, double thr, const void *out)
+{
+    if (!ctx || !f || !lut) return fail(ORPH_E_INVALID, "orph_score_reads: NULL ctx / filter / lut");
+    if (n_reads && (!reads || !offsets || !out)) return fail(ORPH_E_INVALID, "orph_score_reads: NULL buffer");
+    if (fmt != ORPH_READS_ASCII && fmt != ORPH_READS_PACKED2) return fail(ORPH_E_INVALID, "orph_score_reads: unknown reads_format %d", fmt);
+    if (f->device != ctx->device) return fail(ORPH_E_INVALID, "orph_score_reads: filter lives on device %d, context on %d", f->device, ctx->device);
+    if (std::isnan(thr)) return fail(ORPH_E_INVALID, "orph_score_reads: jaccard_threshold is NaN");
+    return ORPH_OK;
+}
+
+extern "C" int orph_score_reads_device(orph_ctx *ctx, const orph_filter *f, const void *d_reads, int reads_format,
+                                       const uint64_t *d_offsets, uint64_t n_reads, uint32_t max_read_len,
+                                       const uint8_t lut[256], double jaccard_threshold, orph_read_result *d_out)
+{
+    int rc = check_score_args(ctx, f, d_reads, reads_format, d_offsets, n_reads, lut, jaccard_threshold, d_out);
+    if (rc != ORPH_OK) return rc;
+    if (n_reads == 0) return ORPH_OK;
+    if (reinterpret_cast<uintptr_t>(d_reads) & 15) return fail(ORPH_E_INVALID, "orph_score_reads_device: reads must be 16-byte aligned");
+    DeviceGuard guard(ctx->device);
+    if (reads_format == ORPH_READS_PACKED2)
+        return score_device_impl(ctx, f, nullptr, 0, (const uint64_t *)d_reads, 0, 0, d_offsets, n_reads, max_read_len, lut, jaccard_threshold, d_out);
+    // ASCII: the size of the packed scratch depends on the first and last offset, which live on the device
+    uint64_t ends[2];
+    CUDA_TRY(cudaMemcpyAsync(&ends[0], d_offsets, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(&ends[1], d_offsets + n_reads, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (ends[1] < ends[0]) return fail(ORPH_E_INVALID, "orph_score_reads_device: offsets are not monotonic");
+    // d_reads[0] is absolute base 0; pack only [ends[0], ends[1])
+    return score_device_impl(ctx, f, (const uint8_t *)d_reads + ends[0], ends[0], nullptr, 0, ends[1] - ends[0], d_offsets, n_reads,
+                             max_read_len, lut, jaccard_threshold, d_out);
+}
+
+extern "C" int orph_score_reads(orph_ctx *ctx, const orph_filter *f, const void *reads, int reads_format,
+                                const uint64_t *offsets, uint64_t n_reads, const uint8_t lut[256], double jaccard_threshold,
+                                orph_read_result *out)
+{
+    int rc = check_score_args(ctx, f, reads, reads_format, offsets, n_reads, lut, jaccard_threshold, out);
+    if (rc != ORPH_OK) return rc;
+    if (n_reads == 0) return ORPH_OK;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = ctx->stream;
+    // chunks bounded by reads and by bases so that scratch stays modest
+    const uint64_t kMaxChunkReads = 1ULL << 24;
+    const uint64_t kMaxChunkBases = 1ULL << 31;
+    uint32_t status_bits = 0;
+    uint64_t lo = 0;
+    while (lo < n_reads) {
+        uint64_t hi = std::min(n_reads, lo + kMaxChunkReads);
+        while (hi > lo + 1 && offsets[hi] - offsets[lo] > kMaxChunkBases) hi = lo + (hi - lo) / 2;
+        const uint64_t m = hi - lo;
+        uint32_t max_len = 0;
+        for (uint64_t r = lo; r < hi; r++) {
+            if (offsets[r + 1] < offsets[r]) return fail(ORPH_E_INVALID, "orph_score_reads: offsets are not monotonic at read %llu", (unsigned long long)r);
+            const uint64_t L = offsets[r + 1] - offsets[r];
+            if (L > max_len) max_len = (uint32_t)std::min<uint64_t>(L, 0xFFFFFFFFu);
+        }
+        if (max_len > ORPH_MAX_READ_LEN) max_len = ORPH_MAX_READ_LEN;  // over-long reads are reported through the status
+        if (max_len == 0) max_len = 1;
+        if ((rc = ctx->in_offsets.ensure((m + 1) * 8)) != ORPH_OK) return rc;
+        if ((rc = ctx->out_results.ensure(m * sizeof(orph_read_result))) != ORPH_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(ctx->in_offsets.p, offsets + lo, (m + 1) * 8, cudaMemcpyHostToDevice, s));
+        const uint64_t b0 = offsets[lo], b1 = offsets[hi];
+        if (reads_format == ORPH_READS_ASCII) {
+            const uint64_t nbytes = b1 - b0;
+            if ((rc = ctx->in_reads.ensure(nbytes + 64)) != ORPH_OK) return rc;
+            if (nbytes) CUDA_TRY(cudaMemcpyAsync(ctx->in_reads.p, (const uint8_t *)reads + b0, nbytes, cudaMemcpyHostToDevice, s));
+            rc = score_device_impl(ctx, f, (const uint8_t *)ctx->in_reads.p, b0, nullptr, 0, nbytes, (const uint64_t *)ctx->in_offsets.p, m,
+                                   max_len, lut, jaccard_threshold, (orph_read_result *)ctx->out_results.p);
+        } else {
+            const uint64_t w0 = b0 / 32, w1 = (b1 + 31) / 32;
+            if ((rc = ctx->in_reads.ensure((w1 - w0 + 2) * 8)) != ORPH_OK) return rc;
+            if (w1 > w0) CUDA_TRY(cudaMemcpyAsync(ctx->in_reads.p, (const uint64_t *)reads + w0, (w1 - w0) * 8, cudaMemcpyHostToDevice, s));
+            rc = score_device_impl(ctx, f, nullptr, 0, (const uint64_t *)ctx->in_reads.p, w0 * 32, 0, (const uint64_t *)ctx->in_offsets.p, m,
+                                   max_len, lut, jaccard_threshold, (orph_read_result *)ctx->out_results.p);
+        }
+        if (rc != ORPH_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(out + lo, ctx->out_results.p, m * sizeof(orph_read_result), cudaMemcpyDeviceToHost, s));
+        ScoreCounters c;
+        CUDA_TRY(cudaMemcpyAsync(&c, ctx->counters.p, sizeof(c), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        status_bits |= c.status;
+        lo = hi;
+    }
+    CUDA_TRY(cudaMemsetAsync((uint8_t *)ctx->counters.p + offsetof(ScoreCounters, status), 0, sizeof(uint32_t), s));
+    return status_to_code(status_bits);
+}
+
+extern "C" double orph_jaccard(const orph_read_result *r, int frame_index)
+{
+    if (!r || frame_index < 0 || frame_index > 5) return NAN;
+    const uint8_t c = r->category[frame_index];
+    if (c != ORPH_CAT_CODING && c != ORPH_CAT_NON_CODING) return NAN;
+    return (double)r->n_hits[frame_index] / (double)r->n_kmers[frame_index];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side 2-bit packer (for callers that ship packed reads over PCIe)
+// ------------------------------------------------------------------------------------------------
+extern "C" int orph_pack_reads(const uint8_t *reads, const uint64_t *offsets, uint64_t n_reads, uint64_t *out_packed,
+                               uint8_t *needs_ascii, int n_threads)
+{
+    if (!offsets || (n_reads && (!reads || !out_packed))) return fail(ORPH_E_INVALID, "orph_pack_reads: NULL argument");
+    if (n_reads == 0) return ORPH_OK;
+    const uint64_t b0 = offsets[0], total = offsets[n_reads] - b0;
+    const uint64_t n_words = (total + 31) / 32;
+    if (needs_ascii) memset(needs_ascii, 0, n_reads);
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    n_threads = (int)std::min<uint64_t>(n_threads, std::max<uint64_t>(1, n_words / 4096));
+    uint8_t valid[256];
+    memset(valid, 0, sizeof(valid));
+    valid['A'] = valid['C'] = valid['G'] = valid['T'] = 1;
+    auto work = [&](uint64_t w_lo, uint64_t w_hi) {
+        for (uint64_t w = w_lo; w < w_hi; w++) {
+            const uint64_t g0 = 32 * w;
+            const uint32_t count = (uint32_t)std::min<uint64_t>(32, total - g0);
+            const uint8_t *p = reads + b0 + g0;
+            uint64_t bits = 0;
+            uint32_t bad = 0;
+            for (uint32_t i = 0; i < count; i++) {
+                bits |= (uint64_t)((p[i] >> 1) & 3u) << (2 * i);
+                bad |= (uint32_t)(valid[p[i]] ^ 1u) << i;
+            }
+            out_packed[w] = bits;
+            if (bad && needs_ascii) {
+                for (uint32_t i = 0; i < count; i++) {
+                    if (!((bad >> i) & 1u)) continue;
+                    const uint64_t g = b0 + g0 + i;
+                    const uint64_t *it = std::upper_bound(offsets, offsets + n_reads + 1, g);
+                    uint64_t r = (uint64_t)(it - offsets) - 1;
+                    if (r >= n_reads) r = n_reads - 1;
+                    needs_ascii[r] = 1;
+                }
+            }
+        }
+    };
+    if (n_threads <= 1) {
+        work(0, n_words);
+    } else {
+        std::vector<std::thread> pool;
+        const uint64_t per = (n_words + n_threads - 1) / n_threads;
+        for (int t = 0; t < n_threads; t++) {
+            const uint64_t lo = std::min(n_words, per * t), hi = std::min(n_words, per * (t + 1));
+            if (lo < hi) pool.emplace_back(work, lo, hi);
+        }
+        for (auto &th : pool) th.join();
+    }
+    return ORPH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// measurement helper
+// ------------------------------------------------------------------------------------------------
+extern "C" int orph_bench_gather_peak(orph_ctx *ctx, uint64_t footprint_bytes, uint32_t loads_per_thread, int persist_l2,
+                                      double *sectors_per_second)
+{
+    if (!ctx || !sectors_per_second || footprint_bytes < 4096 || loads_per_thread < 4)
+        return fail(ORPH_E_INVALID, "orph_bench_gather_peak: bad arguments");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = ctx->stream;
+    uint8_t *buf = nullptr;
+    uint32_t *sink = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&buf, footprint_bytes));
+    CUDA_TRY(cudaMalloc((void **)&sink, 4));
+    CUDA_TRY(cudaMemsetAsync(buf, 1, footprint_bytes, s));
+    if (persist_l2 && ctx->l2_persist_max && ctx->l2_window_max) {
+        size_t want = std::min<size_t>(footprint_bytes, ctx->l2_persist_max);
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        attr.accessPolicyWindow.base_ptr = buf;
+        attr.accessPolicyWindow.num_bytes = std::min<size_t>(footprint_bytes, ctx->l2_window_max);
+        attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)attr.accessPolicyWindow.num_bytes);
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+        ctx->l2_window_base = nullptr;  // the filter window must be re-applied afterwards
+    }
+    loads_per_thread &= ~3u;
+    const int block = 256, grid = ctx->sm_count * 8;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    for (int warm = 0; warm < 2; warm++) gather_peak_kernel<<<grid, block, 0, s>>>(buf, footprint_bytes, loads_per_thread, sink);
+    const int reps = 5;
+    CUDA_TRY(cudaEventRecord(e0, s));
+    for (int i = 0; i < reps; i++) gather_peak_kernel<<<grid, block, 0, s>>>(buf, footprint_bytes, loads_per_thread, sink);
+    CUDA_TRY(cudaEventRecord(e1, s));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    ctx->launches += reps + 2;
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    *sectors_per_second = (double)grid * block * loads_per_thread * reps / (ms * 1e-3);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (persist_l2) {
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaCtxResetPersistingL2Cache();
+        cudaGetLastError();
+    }
+    cudaFree(buf);
+    cudaFree(sink);
+    return ORPH_OK;
+}

@@ -1,0 +1,539 @@
+// Scoring kernels: everything under Translate.maybe_score_single_read (orpheum/translate.py:323-331).
+//
+//   pack_ascii_kernel      ASCII -> 2-bit stream, flags reads that need the byte-exact path
+//   prefilter_kernel       one THREAD per read on the 2-bit stream: fastp complexity
+//                          (translate.py:56-84), stop codons in all six frames by bit-parallel
+//                          matching (translate.py:218), too-short test (translate.py:227); writes the
+//                          whole result record and queues reads that still have frames to score
+//   score_frames_kernel    one WARP per queued read: translates only the open frames through a
+//                          shared-memory codon table (translate_single_seq.py:21-28 fused with
+//                          encode_peptide, sequence_encodings.py:457-468), then score_frame()
+//   score_bytes_kernel     one WARP per read with the reference's byte semantics (N, lower case,
+//                          IUPAC, over-long reads); used for the reads the two kernels above skip
+//
+// score_frame(): distinct k-mers (compare_kmer_content.py:116-118) via a per-warp shared-memory
+// hash set keyed by the k-mer's MurmurHash (verified byte-wise on equality, exact all-pairs
+// fallback on a true 64-bit collision), Bloom probes with early exit (translate.py:187-191).
+#pragma once
+#include "device_common.cuh"
+
+namespace orph {
+
+constexpr int kWarp = 32;
+constexpr uint32_t kFastMaxLen = 1536;   // longest read the packed fast path handles
+constexpr uint32_t kStatusEmptyRead = 1u;
+constexpr uint32_t kStatusTooLong = 2u;
+
+struct ScoreParams {
+    FilterDev F;
+    uint8_t lut[256];          // encode_peptide as a byte table
+    double jaccard_threshold;
+    uint32_t k;                // peptide k-mer size (== F.ksize)
+    uint32_t max_len;          // declared upper bound of read length in this batch
+    uint32_t fast_max_len;     // reads longer than this skip the packed fast path
+    uint32_t slots;            // dedup table slots per warp (power of two, >= 2 * max k-mers per frame)
+    uint32_t pep_bytes;        // peptide buffer bytes per warp (multiple of 4, incl. kPepPad)
+    uint32_t read_words;       // staged read words per warp (fast path)
+    uint32_t force_exact;      // test hook: always take the exact all-pairs dedup path
+};
+
+// device counters shared by one scoring call
+struct ScoreCounters {
+    uint32_t n_queue;      // reads queued for score_frames_kernel
+    uint32_t next_queue;   // dynamic work fetch
+    uint32_t n_bytes;      // reads queued for score_bytes_kernel
+    uint32_t next_bytes;
+    uint32_t status;       // kStatus* bits (sticky within the call)
+    uint32_t pad[3];
+};
+
+// ------------------------------------------------------------------------------------------------
+// score_frame: all lanes of one warp.  enc = encoded peptide bytes in shared memory (4-byte aligned,
+// kPepPad readable bytes behind plen), plen > k.  Returns warp-uniform (n_distinct, n_hits).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool kmer_bytes_equal(const uint8_t *enc, uint32_t a, uint32_t b, uint32_t k)
+{
+    for (uint32_t i = 0; i < k; i++)
+        if (enc[a + i] != enc[b + i]) return false;
+    return true;
+}
+
+// Exact reference semantics with no hashing shortcuts for the de-duplication: k-mer j counts iff no
+// earlier position holds the same bytes.  O(n^2 k); only reached on a genuine 64-bit hash collision
+// (or through the force_exact test hook).
+__device__ __noinline__ void score_frame_exact(const uint8_t *enc, uint32_t plen, uint32_t k, const FilterDev &F,
+                                               int lane, uint32_t &n_distinct, uint32_t &n_hits)
+{
+    const uint32_t n = plen - k + 1;
+    uint32_t nd = 0, nh = 0;
+    const SmemKeyWords base{reinterpret_cast<const uint32_t *>(enc), 0, k};
+    for (uint32_t j0 = 0; j0 < n; j0 += kWarp) {
+        const uint32_t j = j0 + lane;
+        bool first = j < n;
+        for (uint32_t e = 0; first && e < j; e++)
+            if (kmer_bytes_equal(enc, e, j, k)) first = false;
+        bool hit = false;
+        if (first) {
+            SmemKeyWords kw = base;
+            kw.j = j;
+            hit = filter_contains(F, murmur3_h1(kw, k));
+        }
+        nd += __popc(__ballot_sync(0xffffffffu, first));
+        nh += __popc(__ballot_sync(0xffffffffu, hit));
+    }
+    n_distinct = nd;
+    n_hits = nh;
+}
+
+template <int K>  // K > 0: compile-time k-mer size; K == 0: runtime k
+__device__ __forceinline__ void score_frame(const uint8_t *enc, uint32_t plen, uint32_t k_rt, const FilterDev &F,
+                                            unsigned long long *keys, uint16_t *pos, uint32_t slots, int lane,
+                                            bool force_exact, uint32_t &n_distinct, uint32_t &n_hits)
+{
+    const uint32_t k = K > 0 ? (uint32_t)K : k_rt;
+    const uint32_t n = plen - k + 1;
+    // smallest power-of-two table with load <= 1/2 for this frame
+    uint32_t mask = 63;
+    while (mask + 1 < 2 * n) mask = 2 * mask + 1;
+    if (mask >= slots) mask = slots - 1;
+    for (uint32_t s = lane; s <= mask; s += kWarp) keys[s] = kEmptyKey;
+    __syncwarp();
+
+    uint32_t nd = 0, nh = 0;
+    bool need_exact = force_exact;
+    const uint32_t *encw = reinterpret_cast<const uint32_t *>(enc);
+    for (uint32_t j0 = 0; j0 < n; j0 += kWarp) {
+        const uint32_t j = j0 + lane;
+        const bool active = j < n;
+        uint64_t h = 0;
+        bool winner = false, dup = false;
+        uint32_t slot = 0;
+        if (active) {
+            h = murmur3_h1(SmemKeyWords{encw, j, k}, k);
+            if (h == kEmptyKey) need_exact = true;  // cannot be stored: take the exact path for this frame
+            slot = (uint32_t)h & mask;
+            while (true) {
+                const unsigned long long old = atomicCAS(&keys[slot], (unsigned long long)kEmptyKey, (unsigned long long)h);
+                if (old == kEmptyKey) { winner = true; break; }
+                if (old == h) { dup = true; break; }
+                slot = (slot + 1) & mask;
+            }
+        }
+        __syncwarp();
+        if (winner) pos[slot] = (uint16_t)j;
+        __syncwarp();
+        if (dup && !kmer_bytes_equal(enc, pos[slot], j, k)) need_exact = true;  // true 64-bit collision
+        const bool hit = winner && filter_contains(F, h);
+        nd += __popc(__ballot_sync(0xffffffffu, winner));
+        nh += __popc(__ballot_sync(0xffffffffu, hit));
+    }
+    if (__any_sync(0xffffffffu, need_exact)) {
+        score_frame_exact(enc, plen, k, F, lane, nd, nh);
+    }
+    n_distinct = nd;
+    n_hits = nh;
+}
+
+// category of a scored frame (translate.py:241-298): low-complexity test first, then the threshold
+__device__ __forceinline__ uint8_t scored_category(uint32_t n_distinct, uint32_t n_hits, uint32_t plen, uint32_t k,
+                                                   double thr)
+{
+    // evaluate_is_kmer_low_complexity: n_kmers <= (len - k + 1) / 2   (translate.py:98-100)
+    if ((double)n_distinct <= (double)(plen - k + 1) / 2.0) return ORPH_CAT_LOW_COMPLEXITY_PEPTIDE;
+    const double jaccard = (double)n_hits / (double)n_distinct;  // translate.py:204
+    return jaccard > thr ? ORPH_CAT_CODING : ORPH_CAT_NON_CODING;
+}
+
+struct BestFrame {
+    uint32_t hits = 0, n = 0;
+    int frame = 0;
+    // exact rational comparison hits/n > best.hits/best.n; ties keep the first frame in order
+    __device__ __forceinline__ void offer(uint32_t h, uint32_t nk, uint8_t cat, int f)
+    {
+        if (cat != ORPH_CAT_CODING && cat != ORPH_CAT_NON_CODING) return;
+        if (frame == 0 || (uint64_t)h * n > (uint64_t)hits * nk) { hits = h; n = nk; frame = f; }
+    }
+};
+
+__device__ __forceinline__ int frame_key(int f) { return f < 3 ? f + 1 : -(f - 2); }  // 0..5 -> 1,2,3,-1,-2,-3
+
+// ------------------------------------------------------------------------------------------------
+// pack_ascii_kernel: thread t packs bases [32t, 32t+32) of the concatenated ASCII stream.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t find_read(const uint64_t *offsets, uint64_t n_reads, uint64_t g)
+{
+    // largest r with offsets[r] <= g  (g is an absolute base index)
+    uint64_t lo = 0, hi = n_reads;
+    while (lo + 1 < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= g) lo = mid; else hi = mid;
+    }
+    return (uint32_t)lo;
+}
+
+// `ascii` points at the byte of absolute base index abase0; the packed stream starts at absolute base pbase0.
+__global__ void pack_ascii_kernel(const uint8_t *__restrict__ ascii, uint64_t abase0, const uint64_t *__restrict__ offsets,
+                                  uint64_t n_reads, uint64_t pbase0, uint64_t total_bases,
+                                  uint64_t *__restrict__ packed, uint8_t *__restrict__ needs_bytes)
+{
+    const uint8_t *reads = ascii + (pbase0 - abase0);  // byte of the first base to pack
+    const uint64_t n_words = (total_bases + 31) / 32;
+    for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words;
+         w += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t g0 = 32 * w;  // base index of this word's first base, relative to pbase0
+        const uint32_t count = (uint32_t)((total_bases - 32 * w) < 32 ? (total_bases - 32 * w) : 32);
+        uint64_t bits = 0;
+        uint32_t bad = 0;  // bit i: byte i is not upper-case ACGT
+        if (count == 32 && ((reinterpret_cast<uintptr_t>(reads + g0) & 15) == 0)) {
+            const uint4 *p = reinterpret_cast<const uint4 *>(reads + g0);
+            const uint4 v0 = __ldg(p), v1 = __ldg(p + 1);
+            const uint32_t x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const uint32_t c0 = (x[q] >> 1) & 0x01010101u, c1 = (x[q] >> 2) & 0x01010101u;
+                // expected byte for each 2-bit code: A 0x41, C 0x43, T 0x54, G 0x47
+                const uint32_t e = 0x41414141u + (c0 << 1) + c1 * 0x13u - (c0 & c1) * 0x0Fu;
+                uint32_t d = e ^ x[q];
+                d |= d >> 4; d |= d >> 2; d |= d >> 1; d &= 0x01010101u;                // any bit differs, per byte
+                bad |= ((d | (d >> 7) | (d >> 14) | (d >> 21)) & 0xFu) << (4 * q);
+                const uint32_t c = (x[q] >> 1) & 0x03030303u;
+                const uint32_t b8 = (c | (c >> 6) | (c >> 12) | (c >> 18)) & 0xFFu;
+                bits |= (uint64_t)b8 << (8 * q);
+            }
+        } else {
+            for (uint32_t i = 0; i < count; i++) {
+                const uint8_t b = reads[g0 + i];
+                const uint32_t c = (b >> 1) & 3u;
+                if (b != (uint8_t)"ACTG"[c]) bad |= 1u << i;
+                bits |= (uint64_t)c << (2 * i);
+            }
+        }
+        packed[w] = bits;
+        while (bad) {
+            const int i = __ffs(bad) - 1;
+            bad &= bad - 1;
+            needs_bytes[find_read(offsets, n_reads, pbase0 + g0 + i)] = 1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// prefilter_kernel
+// ------------------------------------------------------------------------------------------------
+constexpr uint64_t kLo = 0x5555555555555555ULL;
+
+// per-base predicates on a word of 32 2-bit codes (result bit at the even bit of each field)
+struct Planes {
+    uint64_t isA, isC, isT, isG;
+    __device__ __forceinline__ explicit Planes(uint64_t x)
+    {
+        const uint64_t lo = x & kLo, hi = (x >> 1) & kLo;
+        isA = ~(hi | lo) & kLo;
+        isC = ~hi & lo;
+        isT = hi & ~lo;
+        isG = hi & lo;
+    }
+};
+
+__global__ void __launch_bounds__(256)
+prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict__ offsets, uint64_t base0,
+                 uint64_t n_reads, const uint8_t *__restrict__ needs_bytes, uint32_t k, uint32_t fast_max_len,
+                 uint32_t max_len, orph_read_result *__restrict__ out, uint32_t *__restrict__ queue,
+                 uint32_t *__restrict__ bytes_queue, ScoreCounters *__restrict__ counters)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t first = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) & ~31ull;  // warp-uniform loop bound
+    for (uint64_t r0 = first; r0 < n_reads; r0 += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = r0 + lane;
+        const bool in_range = r < n_reads;
+        bool to_queue = false, to_bytes = false;
+        if (in_range) {
+            const uint64_t o0 = offsets[r], o1 = offsets[r + 1];
+            const uint64_t L = o1 - o0;
+            __align__(16) orph_read_result rec;
+#pragma unroll
+            for (int f = 0; f < 6; f++) { rec.n_kmers[f] = 0; rec.n_hits[f] = 0; rec.category[f] = ORPH_CAT_INVALID; }
+            rec.best_frame = 0;
+            rec.flags = 0;
+            if (L == 0) {
+                atomicOr(&counters->status, kStatusEmptyRead);
+            } else if (L > max_len) {
+                atomicOr(&counters->status, kStatusTooLong);
+            } else if ((needs_bytes && needs_bytes[r]) || L > fast_max_len) {
+                to_bytes = true;
+                rec.flags = ORPH_FLAG_BYTE_PATH;
+            } else {
+                const uint64_t bitpos = 2 * (o0 - base0);
+                const uint64_t w0 = bitpos >> 6;
+                const uint32_t sh = (uint32_t)(bitpos & 63);
+                const uint32_t n_chunks = (uint32_t)((L + 31) / 32);
+                const uint64_t last_word = (2 * (o1 - base0) - 1) >> 6;  // last word holding a base of this read
+                // aligned word m of the read = bases [32m, 32m+32)
+                uint64_t raw_cur = packed[w0];
+                uint64_t raw_nxt = (w0 + 1 <= last_word) ? packed[w0 + 1] : 0;
+                auto align = [&](uint64_t a, uint64_t b) { return sh ? (a >> sh) | (b << (64 - sh)) : a; };
+                uint64_t cur = align(raw_cur, raw_nxt);
+                uint32_t ndiff = 0;
+                uint64_t fwd[3] = {0, 0, 0}, rev[3] = {0, 0, 0};  // stop hits by (position mod 3)
+                for (uint32_t m = 0; m < n_chunks; m++) {
+                    // fetch aligned word m+1 (zero past the read)
+                    raw_cur = raw_nxt;
+                    raw_nxt = (w0 + m + 2 <= last_word) ? packed[w0 + m + 2] : 0;
+                    uint64_t nxt = (m + 1 < n_chunks) ? align(raw_cur, raw_nxt) : 0;
+                    const uint32_t remaining = (uint32_t)(L - 32ull * m);  // bases from this chunk's start
+                    if (remaining < 32) cur &= (1ull << (2 * remaining)) - 1;
+                    if (m + 1 < n_chunks && remaining - 32 < 32) nxt &= (1ull << (2 * (remaining - 32))) - 1;
+                    const uint64_t x1 = (cur >> 2) | (nxt << 62);
+                    const uint64_t x2 = (cur >> 4) | (nxt << 60);
+                    // positions p = 32m + t valid for a pair (p+1 < L) / a codon (p+2 < L)
+                    const uint32_t v2 = remaining > 1 ? (remaining - 1 < 32 ? remaining - 1 : 32) : 0;
+                    const uint32_t v3 = remaining > 2 ? (remaining - 2 < 32 ? remaining - 2 : 32) : 0;
+                    const uint64_t m2 = v2 >= 32 ? kLo : (((1ull << (2 * v2)) - 1) & kLo);
+                    const uint64_t m3 = v3 >= 32 ? kLo : (((1ull << (2 * v3)) - 1) & kLo);
+                    const uint64_t d = cur ^ x1;
+                    ndiff += __popcll((d | (d >> 1)) & m2);
+                    const Planes b0(cur), b1(x1), b2(x2);
+                    // forward stops TAA TAG TGA
+                    const uint64_t fs = b0.isT & ((b1.isA & (b2.isA | b2.isG)) | (b1.isG & b2.isA)) & m3;
+                    // triples whose reverse complement is a stop: TTA CTA TCA
+                    const uint64_t rs = b2.isA & ((b1.isT & (b0.isT | b0.isC)) | (b1.isC & b0.isT)) & m3;
+                    // bit 2t of the word is position 32m + t; (32m + t) mod 3 = (2m + t) mod 3
+                    constexpr uint64_t kPh0 = 0x1041041041041041ULL;  // fields t = 0, 3, 6, ...
+                    const uint32_t rot = (2 * m) % 3;
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const uint64_t ph = kPh0 << (2 * c);  // fields t with t mod 3 == c
+                        const uint32_t cls = (c + rot) % 3;      // position class of those fields
+                        fwd[cls] |= fs & ph;
+                        rev[cls] |= rs & ph;
+                    }
+                    cur = nxt;
+                }
+                // evaluate_is_fastp_low_complexity: ndiff / len < 0.3  (translate.py:75-84)
+                if ((double)ndiff / (double)L < 0.3) {
+                    rec.flags = ORPH_FLAG_LOW_COMPLEXITY;
+#pragma unroll
+                    for (int f = 0; f < 6; f++) rec.category[f] = ORPH_CAT_LOW_COMPLEXITY_NUCLEOTIDE;
+                } else {
+                    uint32_t open = 0;
+#pragma unroll
+                    for (int f = 0; f < 3; f++) {
+                        const uint32_t plen = (uint32_t)((L - f) / 3);  // L >= 1; (L - f) may wrap for L < f: guard
+                        const uint32_t plen_ok = L >= (uint64_t)f ? plen : 0;
+                        // forward frame f: codons at positions p = f (mod 3)
+                        if (fwd[f]) rec.category[f] = ORPH_CAT_STOP_CODONS;
+                        else if (plen_ok <= k) rec.category[f] = ORPH_CAT_TOO_SHORT_PEPTIDE;
+                        else open |= 1u << f;
+                        // reverse frame f: codons at forward positions p = (L - f) (mod 3)
+                        const uint32_t cls = (uint32_t)((L + 3 - f) % 3);
+                        if (rev[cls]) rec.category[3 + f] = ORPH_CAT_STOP_CODONS;
+                        else if (plen_ok <= k) rec.category[3 + f] = ORPH_CAT_TOO_SHORT_PEPTIDE;
+                        else open |= 8u << f;
+                    }
+                    rec.flags = (uint8_t)open;
+                    to_queue = open != 0;
+                }
+            }
+            // one 32-byte record per read
+            uint4 *dst = reinterpret_cast<uint4 *>(out + r);
+            const uint4 *src = reinterpret_cast<const uint4 *>(&rec);
+            dst[0] = src[0];
+            dst[1] = src[1];
+        }
+        // warp-aggregated queue pushes
+        const uint32_t mq = __ballot_sync(0xffffffffu, to_queue);
+        const uint32_t mb = __ballot_sync(0xffffffffu, to_bytes);
+        uint32_t base_q = 0, base_b = 0;
+        if (lane == 0) {
+            if (mq) base_q = atomicAdd(&counters->n_queue, __popc(mq));
+            if (mb) base_b = atomicAdd(&counters->n_bytes, __popc(mb));
+        }
+        base_q = __shfl_sync(0xffffffffu, base_q, 0);
+        base_b = __shfl_sync(0xffffffffu, base_b, 0);
+        const uint32_t below = (1u << lane) - 1;
+        if (to_queue) queue[base_q + __popc(mq & below)] = (uint32_t)r;
+        if (to_bytes) bytes_queue[base_b + __popc(mb & below)] = (uint32_t)r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// score_frames_kernel: persistent warps, dynamic fetch from the queue written by prefilter_kernel
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256)
+score_frames_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, const uint64_t *__restrict__ offsets,
+                    uint64_t base0, const uint32_t *__restrict__ queue, ScoreCounters *__restrict__ counters,
+                    orph_read_result *__restrict__ out)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ uint8_t lut_fwd[64], lut_rev[64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 64) {
+        const int t = threadIdx.x, b0 = t & 3, b1 = (t >> 2) & 3, b2 = t >> 4;
+        lut_fwd[t] = P.lut[translate_codes(b0, b1, b2)];
+        lut_rev[t] = P.lut[translate_codes(b2 ^ 2, b1 ^ 2, b0 ^ 2)];  // complement = code ^ 2, order reversed
+    }
+    __syncthreads();
+    // per-warp carve-out: [keys | read words | peptide | pos]
+    const uint32_t per_warp = P.slots * 8 + P.read_words * 4 + P.pep_bytes + P.slots * 2;
+    uint8_t *mine = smem + (size_t)warp * ((per_warp + 15) & ~15u);
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(mine);
+    uint32_t *rd = reinterpret_cast<uint32_t *>(mine + P.slots * 8);
+    uint8_t *pep = mine + P.slots * 8 + P.read_words * 4;
+    uint16_t *pos = reinterpret_cast<uint16_t *>(pep + P.pep_bytes);
+    const uint32_t k = K > 0 ? (uint32_t)K : P.k;
+
+    while (true) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(&counters->next_queue, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= counters->n_queue) break;
+        const uint32_t r = queue[item];
+        const uint64_t o0 = offsets[r];
+        const uint32_t L = (uint32_t)(offsets[r + 1] - o0);
+        const uint64_t bitpos = 2 * (o0 - base0);
+        const uint64_t w0 = bitpos >> 5;
+        const uint32_t bit0 = (uint32_t)(bitpos & 31);
+        const uint32_t n_words = (bit0 + 2 * L + 31) / 32;
+        __syncwarp();
+        for (uint32_t t = lane; t <= n_words; t += kWarp) rd[t] = t < n_words ? __ldg(packed32 + w0 + t) : 0u;
+        const uint32_t open = out[r].flags & ORPH_FLAG_OPEN_MASK;
+        __syncwarp();
+        BestFrame best;
+        for (int f = 0; f < 6; f++) {
+            if (!((open >> f) & 1u)) continue;
+            const uint32_t phase = f % 3;
+            const uint32_t plen = (L - phase) / 3;
+            // translate + re-encode this frame only
+            for (uint32_t i = lane; i < plen; i += kWarp) {
+                const uint32_t p = f < 3 ? phase + 3 * i : L - 3 - phase - 3 * i;
+                const uint32_t bit = bit0 + 2 * p;
+                const uint32_t c = __funnelshift_r(rd[bit >> 5], rd[(bit >> 5) + 1], bit & 31) & 63u;
+                pep[i] = f < 3 ? lut_fwd[c] : lut_rev[c];
+            }
+            __syncwarp();
+            uint32_t nd, nh;
+            score_frame<K>(pep, plen, k, P.F, keys, pos, P.slots, lane, P.force_exact != 0, nd, nh);
+            const uint8_t cat = scored_category(nd, nh, plen, k, P.jaccard_threshold);
+            if (lane == 0) {
+                out[r].n_kmers[f] = (uint16_t)nd;
+                out[r].n_hits[f] = (uint16_t)nh;
+                out[r].category[f] = cat;
+            }
+            best.offer(nh, nd, cat, frame_key(f));
+            __syncwarp();
+        }
+        if (lane == 0) out[r].best_frame = (int8_t)best.frame;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// score_bytes_kernel: byte-exact path, one warp per read taken from `list` (or all reads if list is null)
+// ------------------------------------------------------------------------------------------------
+template <bool PACKED_SRC>
+__device__ __forceinline__ uint8_t read_base(const void *src, uint64_t base0, uint64_t g)
+{
+    if (PACKED_SRC) {
+        const uint64_t *w = static_cast<const uint64_t *>(src);
+        const uint64_t rel = g - base0;
+        return (uint8_t)"ACTG"[(w[rel >> 5] >> (2 * (rel & 31))) & 3];
+    }
+    return static_cast<const uint8_t *>(src)[g - base0];
+}
+
+template <bool PACKED_SRC>
+__global__ void __launch_bounds__(256)
+score_bytes_kernel(const ScoreParams P, const void *__restrict__ src, const uint64_t *__restrict__ offsets,
+                   uint64_t base0, uint64_t n_reads, const uint32_t *__restrict__ list,
+                   ScoreCounters *__restrict__ counters, orph_read_result *__restrict__ out)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t per_warp = P.slots * 8 + P.pep_bytes + P.slots * 2;
+    uint8_t *mine = smem + (size_t)warp * ((per_warp + 15) & ~15u);
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(mine);
+    uint8_t *pep = mine + P.slots * 8;
+    uint16_t *pos = reinterpret_cast<uint16_t *>(pep + P.pep_bytes);
+    const uint32_t k = P.k;
+
+    while (true) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(&counters->next_bytes, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        const uint64_t limit = list ? (uint64_t)counters->n_bytes : n_reads;
+        if (item >= limit) break;
+        const uint64_t r = list ? list[item] : item;
+        const uint64_t o0 = offsets[r];
+        const uint64_t L64 = offsets[r + 1] - o0;
+        uint8_t cat[6];
+        uint32_t nk[6] = {0, 0, 0, 0, 0, 0}, nh[6] = {0, 0, 0, 0, 0, 0};
+        uint8_t flags = ORPH_FLAG_BYTE_PATH;
+        BestFrame best;
+        if (L64 == 0 || L64 > P.max_len) {
+            if (lane == 0) atomicOr(&counters->status, L64 == 0 ? kStatusEmptyRead : kStatusTooLong);
+#pragma unroll
+            for (int f = 0; f < 6; f++) cat[f] = ORPH_CAT_INVALID;
+        } else {
+            const uint32_t L = (uint32_t)L64;
+            // compute_fastp_complexity (translate.py:79-84): case-sensitive byte compare
+            uint32_t ndiff = 0;
+            for (uint32_t i = lane; i + 1 < L; i += kWarp)
+                ndiff += read_base<PACKED_SRC>(src, base0, o0 + i) != read_base<PACKED_SRC>(src, base0, o0 + i + 1);
+            ndiff = __reduce_add_sync(0xffffffffu, ndiff);
+            if ((double)ndiff / (double)L < 0.3) {
+                flags |= ORPH_FLAG_LOW_COMPLEXITY;
+#pragma unroll
+                for (int f = 0; f < 6; f++) cat[f] = ORPH_CAT_LOW_COMPLEXITY_NUCLEOTIDE;
+            } else {
+                // which frames contain a stop codon
+                uint32_t stops = 0;
+                for (uint32_t p = lane; p + 3 <= L; p += kWarp) {
+                    const uint8_t a = read_base<PACKED_SRC>(src, base0, o0 + p), b = read_base<PACKED_SRC>(src, base0, o0 + p + 1),
+                                  c = read_base<PACKED_SRC>(src, base0, o0 + p + 2);
+                    if (translate_bytes(a, b, c) == '*') stops |= 1u << (p % 3);
+                    if (translate_bytes(complement_byte(c), complement_byte(b), complement_byte(a)) == '*')
+                        stops |= 8u << ((L - p) % 3);
+                }
+                stops = __reduce_or_sync(0xffffffffu, stops);
+                uint32_t open = 0;
+                for (int f = 0; f < 6; f++) {
+                    const uint32_t phase = f % 3;
+                    const uint32_t plen = L >= phase ? (L - phase) / 3 : 0;
+                    if ((stops >> f) & 1u) { cat[f] = ORPH_CAT_STOP_CODONS; continue; }
+                    if (plen <= k) { cat[f] = ORPH_CAT_TOO_SHORT_PEPTIDE; continue; }
+                    open |= 1u << f;
+                    __syncwarp();
+                    for (uint32_t i = lane; i < plen; i += kWarp) {
+                        uint8_t aa;
+                        if (f < 3) {
+                            const uint64_t g = o0 + phase + 3 * i;
+                            aa = translate_bytes(read_base<PACKED_SRC>(src, base0, g), read_base<PACKED_SRC>(src, base0, g + 1),
+                                                 read_base<PACKED_SRC>(src, base0, g + 2));
+                        } else {
+                            const uint64_t g = o0 + (L - 3 - phase - 3 * i);  // forward position of the codon's last base
+                            aa = translate_bytes(complement_byte(read_base<PACKED_SRC>(src, base0, g + 2)),
+                                                 complement_byte(read_base<PACKED_SRC>(src, base0, g + 1)),
+                                                 complement_byte(read_base<PACKED_SRC>(src, base0, g)));
+                        }
+                        pep[i] = P.lut[aa];
+                    }
+                    __syncwarp();
+                    score_frame<0>(pep, plen, k, P.F, keys, pos, P.slots, lane, P.force_exact != 0, nk[f], nh[f]);
+                    cat[f] = scored_category(nk[f], nh[f], plen, k, P.jaccard_threshold);
+                    best.offer(nh[f], nk[f], cat[f], frame_key(f));
+                }
+                flags |= (uint8_t)open;
+            }
+        }
+        if (lane == 0) {
+            orph_read_result rec;
+#pragma unroll
+            for (int f = 0; f < 6; f++) { rec.n_kmers[f] = (uint16_t)nk[f]; rec.n_hits[f] = (uint16_t)nh[f]; rec.category[f] = cat[f]; }
+            rec.best_frame = (int8_t)best.frame;
+            rec.flags = flags;
+            out[r] = rec;
+        }
+    }
+}
+
+}  // namespace orph

@@ -1,0 +1,293 @@
+"""Thin object layer over the C ABI: a device context, the khmer-compatible Bloom filter
+(``GpuNodegraph``) and batch scoring.  Everything here calls ``liborpheum_b200.so``; nothing
+computes on the host.
+
+``GpuNodegraph`` quacks like ``khmer.Nodegraph`` for the calls the reference makes
+(``ksize / get / add / save / n_unique_kmers``, classmethod ``load``; index.py:70-77,101,119,
+202-218; translate.py:145,190,198).
+"""
+import ctypes
+import os
+import struct
+import threading
+
+import numpy as np
+
+from . import _lib
+from ._lib import READ_RESULT_DTYPE, READS_ASCII, READS_PACKED2, check, ptr
+
+_default_ctx = None
+_default_lock = threading.Lock()
+
+
+class Context:
+    """One GPU + one CUDA stream (``orph_ctx``)."""
+
+    def __init__(self, device=0, stream=None):
+        self._lib = _lib.load()
+        h = ctypes.c_void_p()
+        check(self._lib.orph_ctx_create(int(device), ctypes.c_void_p(stream) if stream else None, ctypes.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.orph_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        check(self._lib.orph_ctx_synchronize(self._h))
+
+    def check(self):
+        check(self._lib.orph_ctx_check(self._h))
+
+    def set_force_exact_dedup(self, on):
+        check(self._lib.orph_ctx_set_force_exact_dedup(self._h, int(bool(on))))
+
+    @property
+    def launch_count(self):
+        return int(self._lib.orph_ctx_launch_count(self._h))
+
+    def hash_kmers(self, kmers):
+        """hash_murmur of equal-length byte strings, on the GPU."""
+        kmers = [k.encode("latin-1") if isinstance(k, str) else bytes(k) for k in kmers]
+        n = len(kmers)
+        out = np.zeros(n, dtype=np.uint64)
+        if n == 0:
+            return out
+        length = len(kmers[0])
+        assert all(len(k) == length for k in kmers)
+        flat = np.frombuffer(b"".join(kmers), dtype=np.uint8) if length else np.zeros(1, dtype=np.uint8)
+        check(self._lib.orph_hash_kmers(self._h, ptr(flat), length, n, ptr(out)))
+        return out
+
+    def gather_peak(self, footprint_bytes, loads_per_thread=256, persist_l2=False):
+        v = ctypes.c_double()
+        check(self._lib.orph_bench_gather_peak(self._h, int(footprint_bytes), int(loads_per_thread), int(persist_l2),
+                                               ctypes.byref(v)))
+        return v.value
+
+
+def default_context():
+    global _default_ctx
+    with _default_lock:
+        if _default_ctx is None:
+            _default_ctx = Context(int(os.environ.get("LOCAL_RANK", "0")) if os.environ.get("ORPHEUM_B200_USE_LOCAL_RANK") else 0)
+        return _default_ctx
+
+
+def table_sizes(tablesize, n_tables):
+    out = np.zeros(int(n_tables), dtype=np.uint64)
+    check(_lib.load().orph_table_sizes(int(tablesize), int(n_tables), ptr(out)))
+    return [int(x) for x in out]
+
+
+class GpuNodegraph:
+    """khmer.Nodegraph on the GPU: n_tables prime-sized bit tables resident in HBM."""
+
+    def __init__(self, ksize, starting_size, n_tables, ctx=None, _sizes=None, _handle=None):
+        self._lib = _lib.load()
+        self.ctx = ctx or default_context()
+        if _handle is not None:
+            self._h = _handle
+        else:
+            sizes = np.asarray(_sizes if _sizes is not None else table_sizes(int(starting_size), int(n_tables)), dtype=np.uint64)
+            h = ctypes.c_void_p()
+            check(self._lib.orph_filter_create(self.ctx._h, int(ksize), len(sizes), ptr(sizes), ctypes.byref(h)))
+            self._h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+                self._lib.orph_filter_destroy(self._h)
+            self._h = None
+        except Exception:
+            pass
+
+    # -- khmer API -----------------------------------------------------------------------------
+    def ksize(self):
+        k = ctypes.c_uint32()
+        check(self._lib.orph_filter_info(self._h, ctypes.byref(k), None, None))
+        return int(k.value)
+
+    def n_tables(self):
+        n = ctypes.c_uint32()
+        check(self._lib.orph_filter_info(self._h, None, ctypes.byref(n), None))
+        return int(n.value)
+
+    def hashsizes(self):
+        sizes = np.zeros(_lib.MAX_TABLES, dtype=np.uint64)
+        n = ctypes.c_uint32()
+        check(self._lib.orph_filter_info(self._h, None, ctypes.byref(n), ptr(sizes)))
+        return [int(x) for x in sizes[: n.value]]
+
+    def n_unique_kmers(self):
+        return int(self._lib.orph_filter_n_unique_kmers(self._h))
+
+    def n_occupied(self, table=0):
+        v = ctypes.c_uint64()
+        check(self._lib.orph_filter_popcount(self._h, int(table), ctypes.byref(v)))
+        return int(v.value)
+
+    def add(self, hashed):
+        """Nodegraph.add(int): True if at least one bit was newly set."""
+        h = np.array([int(hashed) & 0xFFFFFFFFFFFFFFFF], dtype=np.uint64)
+        new = np.zeros(1, dtype=np.uint8)
+        check(self._lib.orph_filter_add_hashes(self._h, ptr(h), 1, ptr(new)))
+        return bool(new[0])
+
+    def add_many(self, hashes):
+        h = np.ascontiguousarray(hashes, dtype=np.uint64)
+        new = np.zeros(len(h), dtype=np.uint8)
+        check(self._lib.orph_filter_add_hashes(self._h, ptr(h), len(h), ptr(new)))
+        return new.astype(bool)
+
+    def get(self, hashed):
+        """Nodegraph.get(int) -> 0 / 1."""
+        return int(self.get_many([int(hashed) & 0xFFFFFFFFFFFFFFFF])[0])
+
+    def get_many(self, hashes):
+        h = np.ascontiguousarray(hashes, dtype=np.uint64)
+        out = np.zeros(len(h), dtype=np.uint8)
+        check(self._lib.orph_filter_query_hashes(self._h, ptr(h), len(h), ptr(out)))
+        return out
+
+    def add_peptides(self, residues, offsets, lut):
+        """The inner loop of index.make_peptide_bloom_filter for a batch of records (index.py:107-122)."""
+        residues = np.ascontiguousarray(residues, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        lut = np.ascontiguousarray(lut, dtype=np.uint8)
+        assert lut.shape == (256,)
+        inc = ctypes.c_uint64()
+        check(self._lib.orph_filter_add_peptides(self._h, ptr(residues), ptr(offsets), len(offsets) - 1, ptr(lut),
+                                                 ctypes.byref(inc)))
+        return int(inc.value)
+
+    def tables(self):
+        """Host copies of the tables, byte for byte as in the .nodegraph file."""
+        sizes = self.hashsizes()
+        tabs = [np.zeros(s // 8 + 1, dtype=np.uint8) for s in sizes]
+        arr = (ctypes.c_void_p * len(tabs))(*[t.ctypes.data for t in tabs])
+        occ = ctypes.c_uint64()
+        check(self._lib.orph_filter_to_host(self._h, arr, ctypes.byref(occ)))
+        return tabs, int(occ.value)
+
+    def save(self, path):
+        """Write an OXLI v4 nodegraph file (khmer format), byte-identical to khmer's."""
+        tabs, occupied = self.tables()
+        sizes = self.hashsizes()
+        with open(path, "wb") as f:
+            f.write(b"OXLI" + bytes([4, 2]) + struct.pack("<IBQ", self.ksize(), len(sizes), occupied))
+            for size, tab in zip(sizes, tabs):
+                f.write(struct.pack("<Q", size))
+                f.write(tab.tobytes())
+
+    @classmethod
+    def load(cls, path, ctx=None):
+        """khmer.Nodegraph.load / khmer.load_nodegraph: OSError on anything that is not a nodegraph file."""
+        with open(path, "rb") as f:
+            head = f.read(19)
+            if len(head) != 19 or head[:4] != b"OXLI" or head[4] != 4 or head[5] != 2:
+                raise OSError(f"{path} is not a khmer nodegraph (OXLI v4, type 2) file")
+            ksize, n_tables, _occupied = struct.unpack("<IBQ", head[6:])
+            if not 1 <= n_tables <= _lib.MAX_TABLES:
+                raise OSError(f"{path}: unsupported number of tables {n_tables}")
+            sizes, tabs = [], []
+            for _ in range(n_tables):
+                raw = f.read(8)
+                if len(raw) != 8:
+                    raise OSError(f"{path} is truncated")
+                (size,) = struct.unpack("<Q", raw)
+                data = np.frombuffer(f.read(size // 8 + 1), dtype=np.uint8)
+                if len(data) != size // 8 + 1:
+                    raise OSError(f"{path} is truncated")
+                sizes.append(size)
+                tabs.append(np.ascontiguousarray(data))
+        ctx = ctx or default_context()
+        lib = _lib.load()
+        sizes_a = np.asarray(sizes, dtype=np.uint64)
+        arr = (ctypes.c_void_p * n_tables)(*[t.ctypes.data for t in tabs])
+        h = ctypes.c_void_p()
+        check(lib.orph_filter_from_host(ctx._h, ksize, n_tables, ptr(sizes_a), arr, ctypes.byref(h)))
+        return cls(None, None, None, ctx=ctx, _handle=h)
+
+    # -- replication ---------------------------------------------------------------------------
+    def device_buffer(self):
+        """(device pointer, n_bytes, table byte offsets) of the one contiguous allocation."""
+        p = ctypes.c_void_p()
+        n = ctypes.c_uint64()
+        offs = np.zeros(_lib.MAX_TABLES, dtype=np.uint64)
+        check(self._lib.orph_filter_device_buffer(self._h, ctypes.byref(p), ctypes.byref(n), ptr(offs)))
+        return int(p.value), int(n.value), [int(x) for x in offs[: self.n_tables()]]
+
+    def replicate(self, dst_ctx):
+        h = ctypes.c_void_p()
+        check(self._lib.orph_filter_replicate(self._h, dst_ctx._h, ctypes.byref(h)))
+        return GpuNodegraph(None, None, None, ctx=dst_ctx, _handle=h)
+
+
+# -- scoring ---------------------------------------------------------------------------------------
+def concat_reads(sequences):
+    """list of str/bytes -> (uint8 flat, uint64 offsets[n+1])."""
+    seqs = [s.encode("latin-1") if isinstance(s, str) else bytes(s) for s in sequences]
+    offsets = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    if seqs:
+        offsets[1:] = np.cumsum([len(s) for s in seqs])
+    flat = np.frombuffer(b"".join(seqs), dtype=np.uint8) if seqs else np.zeros(0, dtype=np.uint8)
+    return np.ascontiguousarray(flat), offsets
+
+
+def pack_reads(flat, offsets, n_threads=0):
+    """Host 2-bit packer: (uint64 words, uint8 needs_ascii[n])."""
+    flat = np.ascontiguousarray(flat, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(offsets) - 1
+    total = int(offsets[-1] - offsets[0]) if n > 0 else 0
+    packed = np.zeros((total + 31) // 32 + 1, dtype=np.uint64)
+    needs = np.zeros(max(n, 1), dtype=np.uint8)
+    check(_lib.load().orph_pack_reads(ptr(flat), ptr(offsets), n, ptr(packed), ptr(needs), int(n_threads)))
+    return packed, needs[:n]
+
+
+def score_reads(graph, reads, offsets, lut, jaccard_threshold, reads_format=READS_ASCII, ctx=None):
+    """One C call for a batch held in HOST memory -> structured array of orph_read_result.
+
+    ``reads`` is the concatenated ASCII byte stream (READS_ASCII) or the 2-bit stream (READS_PACKED2)."""
+    ctx = ctx or graph.ctx
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    lut = np.ascontiguousarray(lut, dtype=np.uint8)
+    n = len(offsets) - 1
+    out = np.zeros(n, dtype=READ_RESULT_DTYPE)
+    if reads_format == READS_ASCII:
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    else:
+        reads = np.ascontiguousarray(reads, dtype=np.uint64)
+    rc = _lib.load().orph_score_reads(ctx._h, graph._h, ptr(reads) if reads.size else ptr(np.zeros(1, np.uint8)),
+                                      int(reads_format), ptr(offsets), n, ptr(lut), float(jaccard_threshold), ptr(out))
+    check(rc)
+    return out
+
+
+def score_reads_device(graph, d_reads_ptr, d_offsets_ptr, n_reads, max_read_len, lut, jaccard_threshold, d_out_ptr,
+                       reads_format=READS_PACKED2, ctx=None):
+    """Enqueue scoring of a batch already resident in HBM (raw device pointers, e.g. tensor.data_ptr())."""
+    ctx = ctx or graph.ctx
+    lut = np.ascontiguousarray(lut, dtype=np.uint8)
+    check(_lib.load().orph_score_reads_device(ctx._h, graph._h, ctypes.c_void_p(d_reads_ptr), int(reads_format),
+                                              ctypes.c_void_p(d_offsets_ptr), int(n_reads), int(max_read_len), ptr(lut),
+                                              float(jaccard_threshold), ctypes.c_void_p(d_out_ptr)))
+
+
+def jaccard_column(results):
+    """float64 [n, 6] jaccard exactly as the reference computes it (NaN where it reports NaN)."""
+    cat = results["category"]
+    scored = (cat == _lib.CAT_CODING) | (cat == _lib.CAT_NON_CODING)
+    out = np.full(cat.shape, np.nan)
+    np.divide(results["n_hits"], results["n_kmers"], out=out, where=scored)
+    return out

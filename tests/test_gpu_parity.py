@@ -1,0 +1,339 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the committed golden
+vectors.  Integer / byte work: everything is compared bit-exactly."""
+import hashlib
+import math
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from tests.conftest import SCORE_VECTORS, load_score_vector, read_fastx
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from orpheum_b200 import build, gpu as g
+
+    build.build()
+    return g
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+
+    return oracle
+
+
+@pytest.fixture(scope="module")
+def enc():
+    from orpheum_b200 import sequence_encodings
+
+    return sequence_encodings
+
+
+def fasta_arrays(path):
+    recs = read_fastx(path)
+    seqs = [s.encode() for _, s in recs]
+    offsets = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum([len(s) for s in seqs])
+    return np.frombuffer(b"".join(seqs), dtype=np.uint8), offsets
+
+
+def oracle_filter(orc, fasta, alphabet, ksize, tablesize=1e6, n_tables=4):
+    g = orc.Nodegraph(ksize, tablesize, n_tables)
+    res, offs = fasta_arrays(fasta)
+    g.add_peptides(res, offs, orc.encode_lut(alphabet))
+    return g
+
+
+def gpu_filter(gpu, enc, fasta, alphabet, ksize, tablesize=1e6, n_tables=4):
+    g = gpu.GpuNodegraph(ksize, tablesize, n_tables)
+    res, offs = fasta_arrays(fasta)
+    g.add_peptides(res, offs, enc.encode_lut(alphabet))
+    return g
+
+
+def assert_same_as_oracle(res, ora, where=""):
+    """res: READ_RESULT_DTYPE [n]; ora: oracle FRAME_SCORE_DTYPE [n, 6]."""
+    from orpheum_b200 import _lib
+
+    cat = res["category"].astype(np.int64)
+    np.testing.assert_array_equal(cat, ora["category"], err_msg=f"category {where}")
+    scored = ora["n_kmers"] >= 0
+    np.testing.assert_array_equal(res["n_kmers"][scored], ora["n_kmers"][scored], err_msg=f"n_kmers {where}")
+    np.testing.assert_array_equal(res["n_hits"][scored], ora["n_hits"][scored], err_msg=f"n_hits {where}")
+    assert (res["n_kmers"][~scored] == 0).all() and (res["n_hits"][~scored] == 0).all()
+    # best frame: exact rational argmax over coding / non-coding frames, first on ties
+    frames = np.array(_lib.FRAMES)
+    for i in range(len(res)):
+        best, bh, bn = 0, 0, 0
+        for f in range(6):
+            if ora["category"][i, f] in (3, 4):
+                h, n = int(ora["n_hits"][i, f]), int(ora["n_kmers"][i, f])
+                if best == 0 or h * bn > bh * n:
+                    best, bh, bn = int(frames[f]), h, n
+        assert int(res["best_frame"][i]) == best, (where, i)
+
+
+# ---- hash ------------------------------------------------------------------------------------------
+def test_device_murmur(gpu, orc, misc_kats):
+    ctx = gpu.default_context()
+    assert int(ctx.hash_kmers(["ACG"])[0]) == 1731421407650554201
+    for key, value in misc_kats["hash_murmur"].items():
+        assert int(ctx.hash_kmers([key])[0]) == value, key
+    rng = np.random.default_rng(1)
+    for length in list(range(0, 40)) + [47, 48, 49, 63, 64]:
+        keys = [bytes(rng.integers(0, 256, length, dtype=np.uint8)) for _ in range(50)]
+        got = ctx.hash_kmers(keys)
+        assert [int(x) for x in got] == [orc.hash_murmur(k) for k in keys], length
+
+
+# ---- filter ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("alphabet,ksize", [("protein", 7), ("dayhoff", 12)])
+def test_load_query_save_golden_nodegraph(gpu, orc, refdata, tmp_path, alphabet, ksize):
+    path = os.path.join(refdata, "index", f"Homo_sapiens.GRCh38.pep.subset.alphabet-{alphabet}_ksize-{ksize}.bloomfilter.nodegraph")
+    g = gpu.GpuNodegraph.load(path)
+    o = orc.Nodegraph.load(path)
+    assert g.ksize() == ksize and g.hashsizes() == o.hashsizes() and g.n_tables() == 4
+    assert g.n_occupied() == o.n_occupied()
+    rng = np.random.default_rng(2)
+    hashes = rng.integers(0, 2**64, 20000, dtype=np.uint64)
+    # plus hashes that are certainly present
+    lut = orc.encode_lut(alphabet)
+    recs = read_fastx(os.path.join(refdata, "index", "Homo_sapiens.GRCh38.pep.first1000lines.fa"))[:30]
+    present = []
+    for _, s in recs:
+        e = bytes(lut[np.frombuffer(s.encode(), dtype=np.uint8)])
+        present += [orc.hash_murmur(e[i:i + ksize]) for i in range(len(e) - ksize + 1)]
+    allh = np.concatenate([hashes, np.array(present, dtype=np.uint64)])
+    got = g.get_many(allh)
+    want = np.array([o.get(int(h)) for h in allh], dtype=np.uint8)
+    np.testing.assert_array_equal(got, want)
+    assert got[len(hashes):].mean() > 0.5
+    assert g.get(int(allh[-1])) == o.get(int(allh[-1]))
+    out = tmp_path / "resaved.nodegraph"
+    g.save(str(out))
+    assert out.read_bytes() == open(path, "rb").read()
+    with pytest.raises(OSError):
+        gpu.GpuNodegraph.load(os.path.join(refdata, "index", "Homo_sapiens.GRCh38.pep.first1000lines.fa"))
+
+
+@pytest.mark.parametrize("alphabet,ksize", [("protein", 7), ("dayhoff", 12)])
+def test_build_golden_nodegraph_byte_identical(gpu, enc, refdata, tmp_path, alphabet, ksize):
+    """orpheum index on the GPU reproduces the reference's golden .nodegraph files byte for byte."""
+    golden = os.path.join(refdata, "index", f"Homo_sapiens.GRCh38.pep.subset.alphabet-{alphabet}_ksize-{ksize}.bloomfilter.nodegraph")
+    g = gpu_filter(gpu, enc, os.path.join(refdata, "index", "Homo_sapiens.GRCh38.pep.subset.fa.gz"), alphabet, ksize)
+    out = tmp_path / "built.nodegraph"
+    g.save(str(out))
+    assert out.read_bytes() == open(golden, "rb").read()
+    expected = {("protein", 7): 506352, ("dayhoff", 12): 488469}[(alphabet, ksize)]
+    np.testing.assert_allclose(g.n_unique_kmers(), expected, rtol=1e-3)  # tests/test_index.py:54
+
+
+def test_build_index_kats(gpu, enc, refdata, index_kats, tmp_path):
+    fasta = os.path.join(refdata, "index", "Homo_sapiens.GRCh38.pep.first1000lines.fa")
+    for kat in index_kats:
+        g = gpu_filter(gpu, enc, fasta, kat["alphabet"], kat["ksize"], kat["tablesize"], kat["n_tables"])
+        assert [g.n_occupied(i) for i in range(kat["n_tables"])] == kat["popcounts"], kat
+        out = tmp_path / "k.nodegraph"
+        g.save(str(out))
+        assert hashlib.sha256(out.read_bytes()).hexdigest() == kat["sha256"], kat
+        np.testing.assert_allclose(g.n_unique_kmers(), kat["n_unique_kmers"], rtol=1e-3)
+
+
+def test_add_get_single_hash_and_replicate(gpu):
+    g = gpu.GpuNodegraph(7, 1e4, 4)
+    assert g.get(12345) == 0
+    assert g.add(12345) is True
+    assert g.add(12345) is False
+    assert g.get(12345) == 1 and g.n_unique_kmers() == 1
+    assert g.n_occupied() == 1
+    copy = g.replicate(gpu.Context(0))
+    assert copy.get(12345) == 1 and copy.get(54321) == 0 and copy.hashsizes() == g.hashsizes()
+    ptr, nbytes, offs = g.device_buffer()
+    assert ptr != 0 and nbytes >= sum(s // 8 + 1 for s in g.hashsizes()) and offs[0] == 0
+
+
+# ---- scoring ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("alphabet,ksize", [("protein", 7), ("dayhoff", 12)])
+def test_golden_csv_23_reads(gpu, enc, refdata, reads_n22, misc_kats, alphabet, ksize):
+    """The reference's own end-to-end golden (tests/test_translate.py:279-315), through the GPU."""
+    from orpheum_b200 import _lib
+
+    g = gpu.GpuNodegraph.load(os.path.join(
+        refdata, "index", f"Homo_sapiens.GRCh38.pep.subset.alphabet-{alphabet}_ksize-{ksize}.bloomfilter.nodegraph"))
+    true = pd.read_csv(os.path.join(
+        refdata, "translate", f"SRR306838_GSM752691_hsa_br_F_1_trimmed_subsampled_n22__alphabet-{alphabet}_ksize-{ksize}.csv"))
+    recs = read_fastx(reads_n22)
+    flat, offsets = gpu.concat_reads([s for _, s in recs])
+    res = gpu.score_reads(g, flat, offsets, enc.encode_lut(alphabet), 0.5)
+    jac = gpu.jaccard_column(res)
+    text = {0: "Translation frame has stop codon(s)", 1: "Translation is shorter than peptide k-mer size + 1",
+            2: misc_kats["low_complexity_categories"][alphabet], 3: "Coding", 4: "Non-coding",
+            5: "Read length was shorter than 3 * peptide k-mer size"}
+    rows = [(recs[i][0], jac[i, f], int(res["n_kmers"][i, f]), text[int(res["category"][i, f])], _lib.FRAMES[f])
+            for i in range(len(recs)) for f in range(6)]
+    assert len(rows) == len(true) == 138
+    for (name, j, n, cat, frame), t in zip(rows, true.itertuples()):
+        assert (name, cat, frame) == (t.read_id, t.category, t.translation_frame)
+        if math.isnan(t.n_kmers):
+            assert n == 0
+        else:
+            assert n == int(t.n_kmers)
+        if math.isnan(t.jaccard_in_peptide_db):
+            assert math.isnan(j)
+        else:
+            assert j == pytest.approx(t.jaccard_in_peptide_db, abs=1e-12)
+
+
+@pytest.mark.parametrize("force_exact", [False, True])
+@pytest.mark.parametrize("alphabet,ksize", SCORE_VECTORS)
+def test_reference_vectors(gpu, enc, orc, refdata, misc_kats, alphabet, ksize, force_exact):
+    """Rows produced by the UNMODIFIED reference (tests/golden/ref_scores_*.json): categories, n_kmers,
+    integer hit counts and jaccard, for every read incl. N / lower-case / short / low-complexity ones."""
+    vec = load_score_vector(alphabet, ksize)
+    g = gpu_filter(gpu, enc, os.path.join(refdata, vec["peptides"]), alphabet, ksize, vec["tablesize"], vec["n_tables"])
+    assert [g.n_occupied(i) for i in range(4)] == vec["filter_popcounts"]
+    flat, offsets = gpu.concat_reads([r["seq"] for r in vec["reads"]])
+    ctx = g.ctx
+    ctx.set_force_exact_dedup(force_exact)
+    try:
+        res = gpu.score_reads(g, flat, offsets, enc.encode_lut(alphabet), vec["jaccard_threshold"])
+    finally:
+        ctx.set_force_exact_dedup(False)
+    jac = gpu.jaccard_column(res)
+    text = {0: "Translation frame has stop codon(s)", 1: "Translation is shorter than peptide k-mer size + 1",
+            2: misc_kats["low_complexity_categories"][alphabet], 3: "Coding", 4: "Non-coding",
+            5: "Read length was shorter than 3 * peptide k-mer size"}
+    n_bytes_path = 0
+    for i, read in enumerate(vec["reads"]):
+        n_bytes_path += bool(res["flags"][i] & 0x80)
+        for f, (j, n, cat, frame, hits) in enumerate(read["rows"]):
+            assert text[int(res["category"][i, f])] == cat, (read["name"], frame)
+            assert int(res["n_kmers"][i, f]) == (n or 0), (read["name"], frame)
+            assert int(res["n_hits"][i, f]) == (hits or 0), (read["name"], frame)
+            if j is None:
+                assert math.isnan(jac[i, f])
+            else:
+                assert jac[i, f] == j
+    assert 0 < n_bytes_path < len(vec["reads"])  # both the packed fast path and the byte path were exercised
+
+
+def synthetic_case(gpu, enc, orc, refdata, alphabet, ksize, thr, n, mixed):
+    from orpheum_b200 import synth
+
+    fasta = os.path.join(refdata, "index", "Homo_sapiens.GRCh38.pep.subset.fa.gz")
+    res_, offs_ = fasta_arrays(fasta)
+    # proteome without the 4 records that contain '*'
+    go = oracle_filter(orc, fasta, alphabet, ksize, 1e6)
+    gg = gpu_filter(gpu, enc, fasta, alphabet, ksize, 1e6)
+    keep = [i for i in range(len(offs_) - 1) if offs_[i + 1] - offs_[i] >= 120 and 42 not in res_[int(offs_[i]):int(offs_[i + 1])]]
+    residues = np.concatenate([res_[int(offs_[i]):int(offs_[i + 1])] for i in keep])
+    poffs = np.zeros(len(keep) + 1, dtype=np.uint64)
+    poffs[1:] = np.cumsum([int(offs_[i + 1] - offs_[i]) for i in keep])
+    if mixed:
+        flat, offsets = synth.make_reads_mixed(n, residues, poffs, ksize=ksize, seed=5005)
+        nz = np.nonzero(np.diff(offsets.astype(np.int64)) > 0)[0]
+        assert len(nz) == n
+    else:
+        flat, offsets = synth.concat_fixed(synth.make_reads_fixed(n, residues, poffs, length=150, seed=2002))
+    return go, gg, flat, offsets
+
+
+@pytest.mark.parametrize("alphabet,ksize,thr", [("protein", 7, 0.5), ("dayhoff", 12, 0.5), ("hp", 31, 0.8)])
+def test_synthetic_r150_vs_oracle(gpu, enc, orc, refdata, alphabet, ksize, thr):
+    """cfg2 / cfg3 shape: 150-nt reads, half back-translated from the proteome; ASCII and packed inputs."""
+    n = 20000
+    go, gg, flat, offsets = synthetic_case(gpu, enc, orc, refdata, alphabet, ksize, thr, n, mixed=False)
+    lut = enc.encode_lut(alphabet)
+    ora, n_empty = orc.score_reads(go, flat, offsets, orc.encode_lut(alphabet), thr, n_threads=0)
+    assert n_empty == 0
+    res = gpu.score_reads(gg, flat, offsets, lut, thr)
+    assert_same_as_oracle(res, ora, f"ascii {alphabet}")
+    assert (ora["category"] == 3).sum() > n // 10
+    packed, needs = gpu.pack_reads(flat, offsets)
+    assert not needs.any()
+    res2 = gpu.score_reads(gg, packed, offsets, lut, thr, reads_format=1)
+    assert res2.tobytes() == res.tobytes()
+    assert not (res["flags"] & 0x80).any()
+
+
+@pytest.mark.parametrize("alphabet,ksize,thr", [("protein", 7, 0.5), ("dayhoff", 12, 0.5), ("hp", 31, 0.8)])
+def test_synthetic_mixed_vs_oracle(gpu, enc, orc, refdata, alphabet, ksize, thr):
+    """cfg5 shape: 50-300 nt, homopolymers, triplet repeats, N bases, too-short reads."""
+    n = 20000
+    go, gg, flat, offsets = synthetic_case(gpu, enc, orc, refdata, alphabet, ksize, thr, n, mixed=True)
+    ora, n_empty = orc.score_reads(go, flat, offsets, orc.encode_lut(alphabet), thr, n_threads=0)
+    assert n_empty == 0
+    res = gpu.score_reads(gg, flat, offsets, enc.encode_lut(alphabet), thr)
+    assert_same_as_oracle(res, ora, f"mixed {alphabet}")
+    cats = set(np.unique(ora["category"]).tolist())
+    assert {0, 1, 2, 3, 4, 5} <= cats or alphabet == "hp"
+    assert (res["flags"] & 0x80).any() and not (res["flags"] & 0x80).all()
+
+
+def test_sub_batch_offsets_and_device_api(gpu, enc, orc, refdata):
+    """offsets[0] != 0 (a view into a larger buffer) and the device-pointer entry point."""
+    import torch
+
+    go, gg, flat, offsets = synthetic_case(gpu, enc, orc, refdata, "protein", 7, 0.5, 3000, mixed=True)
+    lut = enc.encode_lut("protein")
+    ora, _ = orc.score_reads(go, flat, offsets, orc.encode_lut("protein"), 0.5)
+    lo, hi = 1001, 2500
+    res = gpu.score_reads(gg, flat, offsets[lo:hi + 1], lut, 0.5)
+    assert_same_as_oracle(res, ora[lo:hi], "sub-batch ascii")
+    # packed sub-batch on clean reads only
+    go2, gg2, flat2, offsets2 = synthetic_case(gpu, enc, orc, refdata, "protein", 7, 0.5, 3000, mixed=False)
+    ora2, _ = orc.score_reads(go2, flat2, offsets2, orc.encode_lut("protein"), 0.5)
+    packed, _ = gpu.pack_reads(flat2, offsets2)
+    res2 = gpu.score_reads(gg2, packed, offsets2[lo:hi + 1], lut, 0.5, reads_format=1)
+    assert_same_as_oracle(res2, ora2[lo:hi], "sub-batch packed")
+    # device API (torch only provides the memory)
+    dev = torch.device("cuda", 0)
+    d_packed = torch.from_numpy(packed.view(np.int64)).to(dev)
+    d_offsets = torch.from_numpy(offsets2.view(np.int64)).to(dev)
+    d_out = torch.zeros(3000 * 32, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    gpu.score_reads_device(gg2, d_packed.data_ptr(), d_offsets.data_ptr(), 3000, 150, lut, 0.5, d_out.data_ptr())
+    gg2.ctx.check()
+    from orpheum_b200._lib import READ_RESULT_DTYPE
+    res3 = d_out.cpu().numpy().view(READ_RESULT_DTYPE)
+    assert_same_as_oracle(res3, ora2, "device packed")
+    d_ascii = torch.from_numpy(flat2).to(dev)
+    d_out.zero_()
+    torch.cuda.synchronize()
+    gpu.score_reads_device(gg2, d_ascii.data_ptr(), d_offsets.data_ptr(), 3000, 0, lut, 0.5, d_out.data_ptr(), reads_format=0)
+    gg2.ctx.check()
+    assert d_out.cpu().numpy().view(READ_RESULT_DTYPE).tobytes() == res3.tobytes()
+
+
+def test_edge_cases(gpu, enc, orc, refdata):
+    fasta = os.path.join(refdata, "index", "Homo_sapiens.GRCh38.pep.first1000lines.fa")
+    gg = gpu_filter(gpu, enc, fasta, "protein", 7)
+    go = oracle_filter(orc, fasta, "protein", 7)
+    lut = enc.encode_lut("protein")
+    # no reads at all
+    assert len(gpu.score_reads(gg, np.zeros(0, np.uint8), np.zeros(1, np.uint64), lut, 0.5)) == 0
+    # an empty read: the reference raises ZeroDivisionError (translate.py:83)
+    flat, offsets = gpu.concat_reads(["ACGTACGTAGCTAGCTAGCATCGATCGATCAGCTAC", "", "ACGT"])
+    with pytest.raises(ZeroDivisionError):
+        gpu.score_reads(gg, flat, offsets, lut, 0.5)
+    # long reads: beyond the packed fast path (1536) -> byte path; beyond ORPH_MAX_READ_LEN -> ValueError
+    rng = np.random.default_rng(3)
+    long_reads = ["".join(rng.choice(list("ACGT"), size=n)) for n in (1536, 1537, 3000, 6144)]
+    # make one of them free of stop codons in frame 1 so it is actually scored
+    long_reads.append("GCTGAAAAGCTGGTT" * 200)
+    flat, offsets = gpu.concat_reads(long_reads)
+    res = gpu.score_reads(gg, flat, offsets, lut, 0.5)
+    ora, _ = orc.score_reads(go, flat, offsets, orc.encode_lut("protein"), 0.5)
+    assert_same_as_oracle(res, ora, "long")
+    flat, offsets = gpu.concat_reads(["A" * 6145])
+    with pytest.raises(ValueError):
+        gpu.score_reads(gg, flat, offsets, lut, 0.5)
+    # mismatched arguments fail loudly
+    with pytest.raises(ValueError):
+        gpu.score_reads(gg, flat, offsets, lut, float("nan"))
