@@ -46,10 +46,17 @@ struct GlobalLutKeyWords {
 
 // One warp per peptide record (dynamic fetch).  A record containing '*' is skipped as a whole
 // (index.py:108-109); records shorter than k contribute nothing (index.py:120-122).
+//
+// `seen` (optional, `seen_mask`+1 slots initialised to kEmptyKey) is a global hash set of the k-mer
+// hashes of this call: only the first occurrence of a hash goes on to the bit tables.  The bits are
+// the same either way; what it buys is khmer's n_unique_kmers (the number of adds that set a new bit),
+// which concurrent duplicate k-mers -- isoforms of one gene in neighbouring records -- would otherwise
+// over-count, because two in-flight copies can each win a different table's bit.
 __global__ void __launch_bounds__(256)
 bloom_add_peptides_kernel(const BuildParams P, const uint8_t *__restrict__ residues,
                           const uint64_t *__restrict__ offsets, uint64_t n_records,
-                          unsigned long long *__restrict__ next_record, unsigned long long *__restrict__ n_unique)
+                          unsigned long long *__restrict__ next_record, unsigned long long *__restrict__ n_unique,
+                          unsigned long long *__restrict__ seen, uint64_t seen_mask)
 {
     __shared__ uint8_t lut[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = P.lut[i];
@@ -71,7 +78,17 @@ bloom_add_peptides_kernel(const BuildParams P, const uint8_t *__restrict__ resid
         const uint64_t n = len - k + 1;
         for (uint64_t j = lane; j < n; j += 32) {
             const uint64_t h = murmur3_h1(GlobalLutKeyWords{seq + j, lut, k}, k);
-            my_new += filter_add(P.F, h) ? 1u : 0u;
+            bool first = true;
+            if (seen && h != kEmptyKey) {
+                uint64_t slot = h & seen_mask;
+                while (true) {
+                    const unsigned long long old = atomicCAS(&seen[slot], (unsigned long long)kEmptyKey, (unsigned long long)h);
+                    if (old == kEmptyKey) break;
+                    if (old == h) { first = false; break; }
+                    slot = (slot + 1) & seen_mask;
+                }
+            }
+            if (first) my_new += filter_add(P.F, h) ? 1u : 0u;
         }
     }
     my_new = __reduce_add_sync(0xffffffffu, my_new);

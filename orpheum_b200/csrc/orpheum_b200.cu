@@ -3,6 +3,7 @@
 // bloom_kernels.cuh.  Built with: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -83,6 +84,7 @@ struct orph_ctx {
     DevBuf packed;               // 2-bit stream built from ASCII input
     DevBuf in_reads, in_offsets, out_results;  // staging for the host-buffer entry points
     DevBuf misc;                 // small transfers (hash batches, ...)
+    DevBuf seen;                 // hash set of k-mer hashes seen during one index-build chunk
 };
 
 struct orph_filter {
@@ -143,7 +145,15 @@ extern "C" int orph_ctx_create(int device, void *stream, orph_ctx **out)
     if (!out) return fail(ORPH_E_INVALID, "orph_ctx_create: out is NULL");
     *out = nullptr;
     int n_dev = 0;
-    CUDA_TRY(cudaGetDeviceCount(&n_dev));
+    // the very first CUDA call of a process can fail transiently while a previous process on the same
+    // GPU is still tearing down; retry briefly before giving up
+    for (int attempt = 0;; attempt++) {
+        cudaError_t e = cudaGetDeviceCount(&n_dev);
+        if (e == cudaSuccess) break;
+        cudaGetLastError();
+        if (attempt >= 4) return fail(ORPH_E_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        std::this_thread::sleep_for(std::chrono::milliseconds(250 * (attempt + 1)));
+    }
     if (device < 0 || device >= n_dev) return fail(ORPH_E_INVALID, "orph_ctx_create: device %d of %d", device, n_dev);
     DeviceGuard guard(device);
     cudaDeviceProp prop;
@@ -183,7 +193,7 @@ extern "C" void orph_ctx_destroy(orph_ctx *ctx)
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf *b : {&ctx->counters, &ctx->queue, &ctx->bytes_queue, &ctx->needs_bytes, &ctx->packed, &ctx->in_reads,
-                      &ctx->in_offsets, &ctx->out_results, &ctx->misc})
+                      &ctx->in_offsets, &ctx->out_results, &ctx->misc, &ctx->seen})
         b->release();
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -426,22 +436,42 @@ extern "C" int orph_filter_add_peptides(orph_filter *f, const uint8_t *residues,
     orph_ctx *ctx = f->ctx;
     DeviceGuard guard(f->device);
     cudaStream_t s = ctx->stream;
-    const uint64_t base = offsets[0], total = offsets[n_records] - base;
-    int rc;
-    if ((rc = ctx->in_reads.ensure(total + 16)) != ORPH_OK) return rc;
-    if ((rc = ctx->in_offsets.ensure((n_records + 1) * sizeof(uint64_t))) != ORPH_OK) return rc;
-    CUDA_TRY(cudaMemcpyAsync(ctx->in_reads.p, residues + base, total, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(ctx->in_offsets.p, offsets, (n_records + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemsetAsync(f->d_scalars + 2, 0, sizeof(unsigned long long), s));
     BuildParams P;
     P.F = filter_dev(f);
     memcpy(P.lut, lut, 256);
-    const int grid = ctx->sm_count * 8;
-    // residues pointer is shifted so that absolute offsets index it directly
-    bloom_add_peptides_kernel<<<grid, 256, 0, s>>>(P, (const uint8_t *)ctx->in_reads.p - base, (const uint64_t *)ctx->in_offsets.p, n_records, f->d_scalars + 2, f->d_scalars);
-    ctx->launches++;
-    CUDA_TRY(cudaGetLastError());
-    return fetch_n_unique(f, n_unique_kmers_inc);
+    const uint64_t before = f->n_unique;
+    // chunks of records bounded by residues, so that the per-call hash set of seen k-mers stays <= 1 GiB
+    const uint64_t kMaxChunkResidues = 1ULL << 26;
+    uint64_t lo = 0;
+    while (lo < n_records) {
+        uint64_t hi = lo + 1;
+        while (hi < n_records && offsets[hi + 1] - offsets[lo] <= kMaxChunkResidues) hi++;
+        const uint64_t m = hi - lo;
+        if (offsets[hi] < offsets[lo]) return fail(ORPH_E_INVALID, "orph_filter_add_peptides: offsets are not monotonic");
+        const uint64_t base = offsets[lo], total = offsets[hi] - base;
+        int rc;
+        if ((rc = ctx->in_reads.ensure(total + 16)) != ORPH_OK) return rc;
+        if ((rc = ctx->in_offsets.ensure((m + 1) * sizeof(uint64_t))) != ORPH_OK) return rc;
+        uint64_t slots = 1024;
+        while (slots < 2 * total) slots <<= 1;
+        if ((rc = ctx->seen.ensure(slots * 8)) != ORPH_OK) return rc;
+        CUDA_TRY(cudaMemsetAsync(ctx->seen.p, 0xFF, slots * 8, s));
+        if (total) CUDA_TRY(cudaMemcpyAsync(ctx->in_reads.p, residues + base, total, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(ctx->in_offsets.p, offsets + lo, (m + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemsetAsync(f->d_scalars + 2, 0, sizeof(unsigned long long), s));
+        const int grid = ctx->sm_count * 8;
+        // the residues pointer is shifted so that the absolute offsets index it directly
+        bloom_add_peptides_kernel<<<grid, 256, 0, s>>>(P, (const uint8_t *)ctx->in_reads.p - base, (const uint64_t *)ctx->in_offsets.p, m,
+                                                      f->d_scalars + 2, f->d_scalars, (unsigned long long *)ctx->seen.p, slots - 1);
+        ctx->launches++;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(s));  // the staging buffers are reused by the next chunk
+        lo = hi;
+    }
+    int rc = fetch_n_unique(f, nullptr);
+    if (rc != ORPH_OK) return rc;
+    if (n_unique_kmers_inc) *n_unique_kmers_inc = f->n_unique - before;
+    return ORPH_OK;
 }
 
 extern "C" int orph_filter_add_hashes(orph_filter *f, const uint64_t *hashes, uint64_t n, uint8_t *is_new)

