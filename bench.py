@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""Headline benchmark: reads/s scored (six-frame translation + Bloom probes) on N B200s.
+
+Workload (BASELINE.json configs[1]): 10 M synthetic 150-nt reads per GPU (half of
+them back-translated from the proteome, half uniform ACGT) against a Bloom filter built from a
+human-proteome-sized synthetic proteome (20 000 proteins, ~1.07e7 residues), protein alphabet, k=7,
+tablesize 1e8 x 4 tables (50 MB).  One step = one pass of the scoring hot path over the whole batch.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N ...            # the CPU arm (oracle port, all host threads)
+
+Our arm prints one JSON line: `value` = kernel-level reads/s with inputs resident in HBM (CUDA events,
+max over ranks); `e2e` = the same metric through the host-buffer C-ABI call (pinned host ASCII reads
+in, result records out, H2D and D2H inside the timed region); `roofline` for the dominant kernel;
+`cpu_baseline` = the oracle timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "reads/sec scored (six-frame+Bloom)"
+UNIT = "reads/s"
+READ_LEN = 150
+STREAM_BYTES_PER_READ = (READ_LEN + 3) // 4 + 4 + 32  # 2-bit payload + offset + result record = 74 B
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU per step")
+    ap.add_argument("--alphabet", default="protein")
+    ap.add_argument("--ksize", type=int, default=None)
+    ap.add_argument("--tablesize", type=float, default=1e8)
+    ap.add_argument("--n-tables", type=int, default=4)
+    ap.add_argument("--proteins", type=int, default=20000)
+    ap.add_argument("--cpu-sample", type=int, default=400_000, help="reads in the bounded CPU-baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(args):
+    return (f"cfg2: {args.reads} synthetic {READ_LEN}-nt reads/GPU (50% back-translated, 1% subst.) vs "
+            f"{args.proteins}-protein synthetic proteome Bloom filter, {args.alphabet} k={args.ksize}, "
+            f"tablesize {int(args.tablesize):.0e} x {args.n_tables}")
+
+
+def default_ksize(alphabet):
+    from orpheum_b200.sequence_encodings import BEST_KSIZES
+
+    return BEST_KSIZES[alphabet]
+
+
+def default_threshold(alphabet):
+    return 0.8 if alphabet in ("hp", "hydrophobic-polar") else 0.5  # translate.py:31-37
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU while the timed region runs (NVML)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if visible:
+                ids = [v for v in visible.split(",") if v.strip() != ""]
+                try:
+                    index = int(ids[index])
+                except (ValueError, IndexError):
+                    pass
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+
+    def _run(self):
+        nv = self._nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for name, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self._nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+
+    def summary(self):
+        return {
+            "sm_mhz": float(np.median(self.samples)) if self.samples else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+        }
+
+
+def make_inputs(args, rank):
+    from orpheum_b200 import synth
+
+    residues, poffs = synth.make_proteome(n_proteins=args.proteins, seed=1001)
+    reads2d = synth.make_reads_fixed(args.reads, residues, poffs, length=READ_LEN, seed=2002 + rank)
+    flat, offsets = synth.concat_fixed(reads2d)
+    return residues, poffs, flat, offsets
+
+
+def oracle_filter(args, residues, poffs):
+    from oracle import oracle as orc
+
+    g = orc.Nodegraph(args.ksize, int(args.tablesize), args.n_tables)
+    g.add_peptides(residues, poffs, orc.encode_lut(args.alphabet))
+    return g
+
+
+def time_oracle(args, g, flat, offsets, n_sample, threads):
+    from oracle import oracle as orc
+
+    n_sample = min(n_sample, len(offsets) - 1)
+    sub_off = offsets[: n_sample + 1]
+    t0 = time.perf_counter()
+    out, _ = orc.score_reads(g, flat, sub_off, orc.encode_lut(args.alphabet), default_threshold(args.alphabet),
+                             n_threads=threads)
+    dt = time.perf_counter() - t0
+    return n_sample / dt, out
+
+
+def run_reference(args):
+    """CPU arm: the oracle port (the reference's algorithm restated in C; the reference itself is
+    single-threaded Python and cannot travel to this box) with every host thread, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+
+    residues, poffs, flat, offsets = make_inputs(argparse.Namespace(**{**vars(args), "reads": args.cpu_sample}), 0)
+    g = oracle_filter(args, residues, poffs)
+    threads = orc.max_threads()
+    for _ in range(args.warmup):
+        time_oracle(args, g, flat, offsets, args.cpu_sample // 4, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        time_oracle(args, g, flat, offsets, args.cpu_sample, threads)
+    dt = time.perf_counter() - t0
+    value = args.steps * args.cpu_sample / dt
+    sample = f"{args.cpu_sample} reads per step (prefix of the same synthetic workload), {threads} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "reads_per_step_measured": args.cpu_sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+class CudaArrayView:
+    """Expose a raw device pointer to torch (for the NCCL broadcast of the filter)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from orpheum_b200 import _lib, build, gpu, sequence_encodings as enc
+
+    build.build()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.Stream(device=dev)
+    ctx = gpu.Context(local, stream=stream.cuda_stream)
+    lut = enc.encode_lut(args.alphabet)
+    thr = default_threshold(args.alphabet)
+
+    t_gen = time.perf_counter()
+    residues, poffs, flat, offsets = make_inputs(args, rank)
+    t_gen = time.perf_counter() - t_gen
+
+    # ---- filter: built on rank 0's GPU, replicated to the other GPUs over NVLink (NCCL broadcast) ----
+    graph = gpu.GpuNodegraph(args.ksize, int(args.tablesize), args.n_tables, ctx=ctx)
+    t_build = time.perf_counter()
+    if rank == 0:
+        graph.add_peptides(residues, poffs, lut)
+    ctx.synchronize()
+    t_build = time.perf_counter() - t_build
+    if world > 1:
+        ptr, nbytes, _ = graph.device_buffer()
+        view = torch.as_tensor(CudaArrayView(ptr, nbytes), device=dev)
+        dist.broadcast(view, src=0)
+        torch.cuda.synchronize()
+    fill = graph.n_occupied(0) / graph.hashsizes()[0]
+
+    # ---- device-resident inputs (kernel-level number) ----
+    packed, needs = gpu.pack_reads(flat, offsets)
+    assert not needs.any()
+    d_packed = torch.from_numpy(packed.view(np.int64)).to(dev)
+    d_offsets = torch.from_numpy(offsets.view(np.int64)).to(dev)
+    d_out = torch.zeros(args.reads * 32, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    def step_device():
+        gpu.score_reads_device(graph, d_packed.data_ptr(), d_offsets.data_ptr(), args.reads, READ_LEN, lut, thr,
+                               d_out.data_ptr(), ctx=ctx)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step_device()
+        ctx.check()
+        barrier()
+        ctx.set_kernel_timing(True)
+        ctx.kernel_times()
+        launches0 = ctx.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clocks:
+            barrier()
+            e0.record(stream)
+            for _ in range(args.steps):
+                step_device()
+            e1.record(stream)
+            barrier()
+        ms_total = e0.elapsed_time(e1)
+        launches = ctx.launch_count - launches0
+        ktimes = ctx.kernel_times()
+        ctx.set_kernel_timing(False)
+        ctx.check()
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * args.reads / (ms_per_step * 1e-3)
+
+    # ---- parity spot check against the oracle (not timed) ----
+    res_dev = d_out.cpu().numpy().view(_lib.READ_RESULT_DTYPE)
+    parity = None
+    pmin_mean = None
+    cpu = None
+    if rank == 0:
+        from oracle import oracle as orc
+
+        g_cpu = oracle_filter(args, residues, poffs)
+        n_chk = min(args.cpu_sample, args.reads)
+        if not args.no_cpu_baseline and world == 1:
+            threads = orc.max_threads()
+            rate, ora = time_oracle(args, g_cpu, flat, offsets, n_chk, threads)
+            cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"first {n_chk} reads of the same workload, C oracle (oracle/orpheum_oracle.c), {threads} threads"}
+        else:
+            n_chk = min(50_000, args.reads)
+            _, ora = time_oracle(args, g_cpu, flat, offsets, n_chk, orc.max_threads())
+        sub = res_dev[:n_chk]
+        scored = ora["n_kmers"] >= 0
+        parity = bool((sub["category"].astype(np.int64) == ora["category"]).all()
+                      and (sub["n_kmers"][scored] == ora["n_kmers"][scored]).all()
+                      and (sub["n_hits"][scored] == ora["n_hits"][scored]).all())
+        pmin_mean = float(ora["probes_min"].sum()) / n_chk
+        pmax_mean = float(ora["probes_max"].sum()) / n_chk
+        if not parity:
+            raise SystemExit("bench: GPU results differ from the oracle on the checked prefix")
+
+    # ---- end to end through the host-buffer C ABI (pinned host ASCII in, records out) ----
+    e2e = None
+    if not args.no_e2e:
+        h_reads = torch.empty(flat.size, dtype=torch.uint8).pin_memory()
+        h_reads.numpy()[:] = flat
+        h_offsets = torch.empty(offsets.size, dtype=torch.int64).pin_memory()
+        h_offsets.numpy()[:] = offsets.view(np.int64)
+        h_out = torch.empty(args.reads * 32, dtype=torch.uint8).pin_memory()
+        lib = _lib.load()
+
+        def step_host():
+            rc = lib.orph_score_reads(ctx._h, graph._h, h_reads.data_ptr(), _lib.READS_ASCII, h_offsets.data_ptr(),
+                                      args.reads, lut.ctypes.data, thr, h_out.data_ptr())
+            _lib.check(rc)
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_host()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        same = h_out.numpy().view(_lib.READ_RESULT_DTYPE).tobytes() == res_dev.tobytes()
+        e2e = {"value": world * args.reads * args.steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(flat.nbytes + offsets.nbytes), "d2h_bytes_per_step": int(args.reads * 32),
+               "input": "pinned host ASCII reads + u64 offsets via orph_score_reads()", "ms_per_step": 1e3 * dt / args.steps,
+               "identical_to_device_path": bool(same)}
+
+    # ---- measured random-gather ceiling for this filter footprint ----
+    gather = None
+    if rank == 0:
+        _, fbytes, _ = graph.device_buffer()
+        try:
+            gather = {"footprint_bytes": fbytes, "sectors_per_s_plain": ctx.gather_peak(fbytes, 512, False),
+                      "sectors_per_s_l2_persist": ctx.gather_peak(fbytes, 512, True)}
+        except Exception as exc:  # measurement helper only
+            gather = {"error": str(exc)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak_gbs, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak_gbs, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    sf_ms, sf_n = ktimes["score_frames"]
+    sf_ms_per_launch = sf_ms / max(1, sf_n)
+    # algorithmic bytes of one score_frames launch: stream bytes of every read + 32 B per required probe
+    algo_bytes = args.reads * (STREAM_BYTES_PER_READ + 32.0 * pmin_mean)
+    achieved = algo_bytes / (sf_ms_per_launch * 1e-3) / 1e9
+    roofline = {
+        "kernel": "score_frames_kernel", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+        "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+        "ms_per_launch": sf_ms_per_launch, "share_of_step": sf_ms_per_launch / ms_per_step,
+        "algorithmic_bytes_per_read": STREAM_BYTES_PER_READ + 32.0 * pmin_mean,
+        "probes_min_per_read": pmin_mean, "probes_max_per_read": pmax_mean,
+        "probe_sectors_per_s": args.reads * pmin_mean / (sf_ms_per_launch * 1e-3),
+        "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items()},
+    }
+    if gather and "sectors_per_s_plain" in gather:
+        best = max(gather["sectors_per_s_plain"], gather["sectors_per_s_l2_persist"])
+        roofline["gather_peak_sectors_per_s"] = best
+        roofline["gather_frac"] = roofline["probe_sectors_per_s"] / best
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args), "reads_per_gpu": args.reads, "read_len": READ_LEN,
+                   "filter_fill_table0": fill, "l2_flush": "inputs (375 MB packed + 80 MB offsets + 320 MB results per step) exceed the 126 MB L2",
+                   "parallelism": f"reads sharded over {world} GPU(s), filter replicated (NCCL broadcast), no steady-state collectives"},
+        "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        "gather_peak": gather, "parity_checked_vs_oracle": parity,
+        "setup_s": {"generate_inputs": t_gen, "bloom_build_gpu": t_build},
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.ksize is None:
+        args.ksize = default_ksize(args.alphabet)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

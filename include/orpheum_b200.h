@@ -103,6 +103,13 @@ int orph_ctx_check(orph_ctx *ctx);
 int orph_ctx_set_force_exact_dedup(orph_ctx *ctx, int on);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t orph_ctx_launch_count(const orph_ctx *ctx);
+/* Per-kernel device timing (CUDA events on the context's stream around every scoring kernel), for
+ * bench.py's roofline.  Kernel ids: 0 pack_ascii, 1 prefilter, 2 score_frames, 3 score_bytes. */
+#define ORPH_N_TIMED_KERNELS 4
+int orph_ctx_set_kernel_timing(orph_ctx *ctx, int on);
+/* Adds up (and clears) the intervals recorded so far: ms[i] total milliseconds and launches[i] count of
+ * kernel i.  Synchronizes the stream. */
+int orph_ctx_kernel_times(orph_ctx *ctx, double *ms, uint64_t *launches);
 const char *orph_last_error(void);
 int orph_abi_version(void);
 

@@ -41,6 +41,8 @@ PROTOTYPES = {
     "orph_ctx_check": (ctypes.c_int, [_vp]),
     "orph_ctx_set_force_exact_dedup": (ctypes.c_int, [_vp, ctypes.c_int]),
     "orph_ctx_launch_count": (ctypes.c_uint64, [_vp]),
+    "orph_ctx_set_kernel_timing": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "orph_ctx_kernel_times": (ctypes.c_int, [_vp, _vp, _u64p]),
     "orph_last_error": (ctypes.c_char_p, []),
     "orph_abi_version": (ctypes.c_int, []),
     "orph_table_sizes": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint32, _u64p]),

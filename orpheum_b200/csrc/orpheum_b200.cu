@@ -84,6 +84,9 @@ struct orph_ctx {
     DevBuf packed;               // 2-bit stream built from ASCII input
     DevBuf in_reads, in_offsets, out_results;  // staging for the host-buffer entry points
     DevBuf misc;                 // small transfers (hash batches, ...)
+    bool timing = false;
+    struct Interval { cudaEvent_t a, b; int id; };
+    std::vector<Interval> intervals;
     DevBuf seen;                 // hash set of k-mer hashes seen during one index-build chunk
 };
 
@@ -231,6 +234,54 @@ extern "C" int orph_ctx_set_force_exact_dedup(orph_ctx *ctx, int on)
 {
     if (!ctx) return fail(ORPH_E_INVALID, "ctx is NULL");
     ctx->force_exact = on != 0;
+    return ORPH_OK;
+}
+
+// RAII helper: brackets one kernel launch with events when timing is on
+struct Timed {
+    orph_ctx *ctx;
+    cudaEvent_t a = nullptr, b = nullptr;
+    int id;
+    Timed(orph_ctx *c, int kernel_id) : ctx(c), id(kernel_id)
+    {
+        if (!ctx->timing) return;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { a = b = nullptr; cudaGetLastError(); return; }
+        cudaEventRecord(a, ctx->stream);
+    }
+    ~Timed()
+    {
+        if (!a) return;
+        cudaEventRecord(b, ctx->stream);
+        ctx->intervals.push_back({a, b, id});
+    }
+};
+
+extern "C" int orph_ctx_set_kernel_timing(orph_ctx *ctx, int on)
+{
+    if (!ctx) return fail(ORPH_E_INVALID, "ctx is NULL");
+    ctx->timing = on != 0;
+    return ORPH_OK;
+}
+
+extern "C" int orph_ctx_kernel_times(orph_ctx *ctx, double *ms, uint64_t *launches)
+{
+    if (!ctx) return fail(ORPH_E_INVALID, "ctx is NULL");
+    DeviceGuard guard(ctx->device);
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < ORPH_N_TIMED_KERNELS; i++) {
+        if (ms) ms[i] = 0;
+        if (launches) launches[i] = 0;
+    }
+    for (auto &iv : ctx->intervals) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, iv.a, iv.b) == cudaSuccess && iv.id >= 0 && iv.id < ORPH_N_TIMED_KERNELS) {
+            if (ms) ms[iv.id] += t;
+            if (launches) launches[iv.id]++;
+        }
+        cudaEventDestroy(iv.a);
+        cudaEventDestroy(iv.b);
+    }
+    ctx->intervals.clear();
     return ORPH_OK;
 }
 
@@ -576,7 +627,10 @@ static int launch_score_frames(orph_ctx *ctx, const ScoreParams &P, const uint32
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
     if (per_sm < 1) per_sm = 1;
-    kern<<<ctx->sm_count * per_sm, warps * 32, smem, ctx->stream>>>(P, packed32, d_offsets, pbase0, queue, counters, d_out);
+    {
+        Timed timed(ctx, 2);
+        kern<<<ctx->sm_count * per_sm, warps * 32, smem, ctx->stream>>>(P, packed32, d_offsets, pbase0, queue, counters, d_out);
+    }
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return ORPH_OK;
@@ -622,6 +676,7 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
         CUDA_TRY(cudaMemsetAsync(ctx->needs_bytes.p, 0, n_reads, s));
         pbase0 = abase0;
         if (n_words) {
+            Timed timed(ctx, 0);
             pack_ascii_kernel<<<grid_for(n_words, 256, ctx->sm_count, 16), 256, 0, s>>>(
                 d_ascii, abase0, d_offsets, n_reads, pbase0, total_bases_ascii, (uint64_t *)ctx->packed.p, (uint8_t *)ctx->needs_bytes.p);
             ctx->launches++;
@@ -631,9 +686,12 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
         d_needs = (const uint8_t *)ctx->needs_bytes.p;
     }
 
-    prefilter_kernel<<<grid_for(n_reads, 256, ctx->sm_count, 16), 256, 0, s>>>(
-        d_packed, d_offsets, pbase0, n_reads, d_needs, P.k, fast_len, bound, d_out, (uint32_t *)ctx->queue.p,
-        (uint32_t *)ctx->bytes_queue.p, counters);
+    {
+        Timed timed(ctx, 1);
+        prefilter_kernel<<<grid_for(n_reads, 256, ctx->sm_count, 16), 256, 0, s>>>(
+            d_packed, d_offsets, pbase0, n_reads, d_needs, P.k, fast_len, bound, d_out, (uint32_t *)ctx->queue.p,
+            (uint32_t *)ctx->bytes_queue.p, counters);
+    }
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
 
@@ -659,6 +717,7 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
         const uint32_t per_warp = (B.slots * 8 + B.pep_bytes + B.slots * 2 + 15) & ~15u;
         int warps = (int)std::min<size_t>(8, std::max<size_t>(1, (size_t)96 * 1024 / per_warp));
         const size_t smem = (size_t)per_warp * warps;
+        Timed timed(ctx, 3);
         if (d_ascii) {
             auto kern = score_bytes_kernel<false>;
             CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -50,6 +50,18 @@ class Context:
     def set_force_exact_dedup(self, on):
         check(self._lib.orph_ctx_set_force_exact_dedup(self._h, int(bool(on))))
 
+    KERNEL_NAMES = ("pack_ascii", "prefilter", "score_frames", "score_bytes")
+
+    def set_kernel_timing(self, on):
+        check(self._lib.orph_ctx_set_kernel_timing(self._h, int(bool(on))))
+
+    def kernel_times(self):
+        """{kernel: (total_ms, launches)} since the last call; synchronizes."""
+        ms = np.zeros(4, dtype=np.float64)
+        n = np.zeros(4, dtype=np.uint64)
+        check(self._lib.orph_ctx_kernel_times(self._h, ptr(ms), ptr(n)))
+        return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(self.KERNEL_NAMES)}
+
     @property
     def launch_count(self):
         return int(self._lib.orph_ctx_launch_count(self._h))
