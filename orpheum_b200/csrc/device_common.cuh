@@ -29,6 +29,8 @@ struct FilterDev {
     uint64_t size[ORPH_MAX_TABLES];   // bits (primes)
     uint64_t magic[ORPH_MAX_TABLES];  // floor((2^64-1) / size)
     const uint8_t *table[ORPH_MAX_TABLES];
+    uint32_t small;                   // every size < 2^31: remainders fit 32-bit arithmetic
+    uint32_t pad;
 };
 
 __device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
@@ -97,12 +99,29 @@ struct SmemKeyWords {
     }
 };
 
-// exact h % p
+// exact h % p.  With magic = floor((2^64-1)/p), q = umulhi(h, magic) is floor(h/p) or one less for every
+// p >= 2, so a single conditional subtraction finishes the reduction.
 __device__ __forceinline__ uint64_t mod_prime(uint64_t h, uint64_t p, uint64_t magic)
 {
     const uint64_t q = __umul64hi(h, magic);
     uint64_t r = h - q * p;
-    while (r >= p) r -= p;
+    if (r >= p) r -= p;
+    return r;
+}
+
+// bin of hash h in table t.  F lives in shared memory (uniform, conflict-free broadcast reads).
+__device__ __forceinline__ uint64_t filter_bin(const FilterDev &F, uint32_t t, uint64_t h)
+{
+    const uint64_t q = __umul64hi(h, F.magic[t]);
+    if (F.small) {  // the remainder before correction is < 2p < 2^32: low words suffice
+        const uint32_t p = (uint32_t)F.size[t];
+        uint32_t r = (uint32_t)h - (uint32_t)q * p;
+        if (r >= p) r -= p;
+        return r;
+    }
+    const uint64_t p = F.size[t];
+    uint64_t r = h - q * p;
+    if (r >= p) r -= p;
     return r;
 }
 
@@ -116,10 +135,35 @@ __device__ __forceinline__ bool filter_contains(const FilterDev &F, uint64_t h)
 {
     bool present = true;
     for (uint32_t t = 0; t < F.n_tables && present; t++) {
-        const uint64_t bin = mod_prime(h, F.size[t], F.magic[t]);
+        const uint64_t bin = filter_bin(F, t, h);
         present = (ld_table_byte(F.table[t] + (bin >> 3)) >> (bin & 7)) & 1u;
     }
     return present;
+}
+
+// Tables 1.. of Nodegraph.get once table 0 is known to hit.  For the usual 4-table filter the three
+// remaining probes are issued back to back so their L2 latencies overlap.
+__device__ __forceinline__ bool filter_contains_rest(const FilterDev &F, uint64_t h)
+{
+    if (F.n_tables == 4) {
+        const uint64_t b1 = filter_bin(F, 1, h), b2 = filter_bin(F, 2, h), b3 = filter_bin(F, 3, h);
+        const uint32_t v1 = ld_table_byte(F.table[1] + (b1 >> 3));
+        const uint32_t v2 = ld_table_byte(F.table[2] + (b2 >> 3));
+        const uint32_t v3 = ld_table_byte(F.table[3] + (b3 >> 3));
+        return ((v1 >> (b1 & 7)) & (v2 >> (b2 & 7)) & (v3 >> (b3 & 7)) & 1u) != 0;
+    }
+    bool present = true;
+    for (uint32_t t = 1; t < F.n_tables && present; t++) {
+        const uint64_t bin = filter_bin(F, t, h);
+        present = (ld_table_byte(F.table[t] + (bin >> 3)) >> (bin & 7)) & 1u;
+    }
+    return present;
+}
+
+// block-wide copy of the kernel-parameter filter description into shared memory
+__device__ __forceinline__ void stage_filter(FilterDev *dst, const FilterDev &src)
+{
+    if (threadIdx.x == 0) *dst = src;
 }
 
 // ---- genetic code --------------------------------------------------------------------------

@@ -123,11 +123,14 @@ static FilterDev filter_dev(const orph_filter *f)
     memset(&F, 0, sizeof(F));
     F.ksize = f->ksize;
     F.n_tables = f->n_tables;
+    bool small = true;
     for (uint32_t i = 0; i < f->n_tables; i++) {
         F.size[i] = f->sizes[i];
         F.magic[i] = ~0ULL / f->sizes[i];
         F.table[i] = f->buf + f->offsets[i];
+        if (f->sizes[i] >= (1ULL << 31)) small = false;
     }
+    F.small = small ? 1u : 0u;
     return F;
 }
 
@@ -644,7 +647,7 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
                              const uint64_t *d_offsets, uint64_t n_reads, uint32_t max_read_len, const uint8_t lut[256],
                              double thr, orph_read_result *d_out)
 {
-    if (n_reads >= (1ULL << 32)) return fail(ORPH_E_INVALID, "more than 2^32-1 reads in one call");
+    if (n_reads > (1ULL << 26)) return fail(ORPH_E_INVALID, "internal: more than 2^26 reads in one launch");
     cudaStream_t s = ctx->stream;
     int rc;
     const uint32_t bound = (max_read_len == 0 || max_read_len > ORPH_MAX_READ_LEN) ? ORPH_MAX_READ_LEN : max_read_len;
@@ -757,17 +760,27 @@ extern "C" int orph_score_reads_device(orph_ctx *ctx, const orph_filter *f, cons
     if (n_reads == 0) return ORPH_OK;
     if (reinterpret_cast<uintptr_t>(d_reads) & 15) return fail(ORPH_E_INVALID, "orph_score_reads_device: reads must be 16-byte aligned");
     DeviceGuard guard(ctx->device);
-    if (reads_format == ORPH_READS_PACKED2)
-        return score_device_impl(ctx, f, nullptr, 0, (const uint64_t *)d_reads, 0, 0, d_offsets, n_reads, max_read_len, lut, jaccard_threshold, d_out);
-    // ASCII: the size of the packed scratch depends on the first and last offset, which live on the device
-    uint64_t ends[2];
-    CUDA_TRY(cudaMemcpyAsync(&ends[0], d_offsets, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(&ends[1], d_offsets + n_reads, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    if (ends[1] < ends[0]) return fail(ORPH_E_INVALID, "orph_score_reads_device: offsets are not monotonic");
-    // d_reads[0] is absolute base 0; pack only [ends[0], ends[1])
-    return score_device_impl(ctx, f, (const uint8_t *)d_reads + ends[0], ends[0], nullptr, 0, ends[1] - ends[0], d_offsets, n_reads,
-                             max_read_len, lut, jaccard_threshold, d_out);
+    // one launch set per 2^26 reads (queue entries keep 6 bits for the open-frame mask)
+    const uint64_t kMaxLaunchReads = 1ULL << 26;
+    for (uint64_t lo = 0; lo < n_reads; lo += kMaxLaunchReads) {
+        const uint64_t m = std::min(kMaxLaunchReads, n_reads - lo);
+        if (reads_format == ORPH_READS_PACKED2) {
+            rc = score_device_impl(ctx, f, nullptr, 0, (const uint64_t *)d_reads, 0, 0, d_offsets + lo, m, max_read_len, lut,
+                                   jaccard_threshold, d_out + lo);
+        } else {
+            // ASCII: the size of the packed scratch depends on the first and last offset, which live on the device
+            uint64_t ends[2];
+            CUDA_TRY(cudaMemcpyAsync(&ends[0], d_offsets + lo, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(&ends[1], d_offsets + lo + m, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            if (ends[1] < ends[0]) return fail(ORPH_E_INVALID, "orph_score_reads_device: offsets are not monotonic");
+            // d_reads[0] is absolute base 0; pack only [ends[0], ends[1])
+            rc = score_device_impl(ctx, f, (const uint8_t *)d_reads + ends[0], ends[0], nullptr, 0, ends[1] - ends[0], d_offsets + lo, m,
+                                   max_read_len, lut, jaccard_threshold, d_out + lo);
+        }
+        if (rc != ORPH_OK) return rc;
+    }
+    return ORPH_OK;
 }
 
 extern "C" int orph_score_reads(orph_ctx *ctx, const orph_filter *f, const void *reads, int reads_format,

@@ -96,7 +96,10 @@ __device__ __forceinline__ void score_frame(const uint8_t *enc, uint32_t plen, u
     uint32_t mask = 63;
     while (mask + 1 < 2 * n) mask = 2 * mask + 1;
     if (mask >= slots) mask = slots - 1;
-    for (uint32_t s = lane; s <= mask; s += kWarp) keys[s] = kEmptyKey;
+    {
+        ulonglong2 *k2 = reinterpret_cast<ulonglong2 *>(keys);  // keys is 16-byte aligned, slot count is even
+        for (uint32_t s = lane; s <= (mask >> 1); s += kWarp) k2[s] = make_ulonglong2(kEmptyKey, kEmptyKey);
+    }
     __syncwarp();
 
     uint32_t nd = 0, nh = 0;
@@ -107,9 +110,13 @@ __device__ __forceinline__ void score_frame(const uint8_t *enc, uint32_t plen, u
         const bool active = j < n;
         uint64_t h = 0;
         bool winner = false, dup = false;
-        uint32_t slot = 0;
+        uint32_t slot = 0, v0 = 0, sh0 = 0;
         if (active) {
             h = murmur3_h1(SmemKeyWords{encw, j, k}, k);
+            // table-0 probe first: its L2 latency overlaps the de-duplication below
+            const uint64_t bin0 = filter_bin(F, 0, h);
+            v0 = ld_table_byte(F.table[0] + (bin0 >> 3));
+            sh0 = (uint32_t)bin0 & 7u;
             if (h == kEmptyKey) need_exact = true;  // cannot be stored: take the exact path for this frame
             slot = (uint32_t)h & mask;
             while (true) {
@@ -123,7 +130,8 @@ __device__ __forceinline__ void score_frame(const uint8_t *enc, uint32_t plen, u
         if (winner) pos[slot] = (uint16_t)j;
         __syncwarp();
         if (dup && !kmer_bytes_equal(enc, pos[slot], j, k)) need_exact = true;  // true 64-bit collision
-        const bool hit = winner && filter_contains(F, h);
+        bool hit = winner && ((v0 >> sh0) & 1u);
+        if (hit && F.n_tables > 1) hit = filter_contains_rest(F, h);
         nd += __popc(__ballot_sync(0xffffffffu, winner));
         nh += __popc(__ballot_sync(0xffffffffu, hit));
     }
@@ -247,6 +255,7 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
         const uint64_t r = r0 + lane;
         const bool in_range = r < n_reads;
         bool to_queue = false, to_bytes = false;
+        uint32_t open_bits = 0;
         if (in_range) {
             const uint64_t o0 = offsets[r], o1 = offsets[r + 1];
             const uint64_t L = o1 - o0;
@@ -331,6 +340,7 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
                         else open |= 8u << f;
                     }
                     rec.flags = (uint8_t)open;
+                    open_bits = open;
                     to_queue = open != 0;
                 }
             }
@@ -351,7 +361,7 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
         base_q = __shfl_sync(0xffffffffu, base_q, 0);
         base_b = __shfl_sync(0xffffffffu, base_b, 0);
         const uint32_t below = (1u << lane) - 1;
-        if (to_queue) queue[base_q + __popc(mq & below)] = (uint32_t)r;
+        if (to_queue) queue[base_q + __popc(mq & below)] = ((uint32_t)r << 6) | open_bits;
         if (to_bytes) bytes_queue[base_b + __popc(mb & below)] = (uint32_t)r;
     }
 }
@@ -359,6 +369,8 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
 // ------------------------------------------------------------------------------------------------
 // score_frames_kernel: persistent warps, dynamic fetch from the queue written by prefilter_kernel
 // ------------------------------------------------------------------------------------------------
+constexpr int kFetchBatch = 16;  // queue entries a warp claims per atomic
+
 template <int K>
 __global__ void __launch_bounds__(256)
 score_frames_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, const uint64_t *__restrict__ offsets,
@@ -366,8 +378,10 @@ score_frames_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, 
                     orph_read_result *__restrict__ out)
 {
     extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ FilterDev sF;
     __shared__ uint8_t lut_fwd[64], lut_rev[64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    stage_filter(&sF, P.F);
     if (threadIdx.x < 64) {
         const int t = threadIdx.x, b0 = t & 3, b1 = (t >> 2) & 3, b2 = t >> 4;
         lut_fwd[t] = P.lut[translate_codes(b0, b1, b2)];
@@ -382,48 +396,64 @@ score_frames_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, 
     uint8_t *pep = mine + P.slots * 8 + P.read_words * 4;
     uint16_t *pos = reinterpret_cast<uint16_t *>(pep + P.pep_bytes);
     const uint32_t k = K > 0 ? (uint32_t)K : P.k;
+    const double thr = P.jaccard_threshold;
+    const bool force_exact = P.force_exact != 0;
+    const uint32_t n_queue = counters->n_queue;
 
     while (true) {
-        uint32_t item = 0;
-        if (lane == 0) item = atomicAdd(&counters->next_queue, 1u);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= counters->n_queue) break;
-        const uint32_t r = queue[item];
-        const uint64_t o0 = offsets[r];
-        const uint32_t L = (uint32_t)(offsets[r + 1] - o0);
-        const uint64_t bitpos = 2 * (o0 - base0);
-        const uint64_t w0 = bitpos >> 5;
-        const uint32_t bit0 = (uint32_t)(bitpos & 31);
-        const uint32_t n_words = (bit0 + 2 * L + 31) / 32;
-        __syncwarp();
-        for (uint32_t t = lane; t <= n_words; t += kWarp) rd[t] = t < n_words ? __ldg(packed32 + w0 + t) : 0u;
-        const uint32_t open = out[r].flags & ORPH_FLAG_OPEN_MASK;
-        __syncwarp();
-        BestFrame best;
-        for (int f = 0; f < 6; f++) {
-            if (!((open >> f) & 1u)) continue;
-            const uint32_t phase = f % 3;
-            const uint32_t plen = (L - phase) / 3;
-            // translate + re-encode this frame only
-            for (uint32_t i = lane; i < plen; i += kWarp) {
-                const uint32_t p = f < 3 ? phase + 3 * i : L - 3 - phase - 3 * i;
-                const uint32_t bit = bit0 + 2 * p;
-                const uint32_t c = __funnelshift_r(rd[bit >> 5], rd[(bit >> 5) + 1], bit & 31) & 63u;
-                pep[i] = f < 3 ? lut_fwd[c] : lut_rev[c];
-            }
-            __syncwarp();
-            uint32_t nd, nh;
-            score_frame<K>(pep, plen, k, P.F, keys, pos, P.slots, lane, P.force_exact != 0, nd, nh);
-            const uint8_t cat = scored_category(nd, nh, plen, k, P.jaccard_threshold);
-            if (lane == 0) {
-                out[r].n_kmers[f] = (uint16_t)nd;
-                out[r].n_hits[f] = (uint16_t)nh;
-                out[r].category[f] = cat;
-            }
-            best.offer(nh, nd, cat, frame_key(f));
-            __syncwarp();
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&counters->next_queue, (uint32_t)kFetchBatch);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n_queue) break;
+        const uint32_t cnt = min((uint32_t)kFetchBatch, n_queue - base);
+        // lanes < cnt fetch one entry each together with its read's extent, so the latencies overlap
+        uint32_t my_entry = 0, my_len = 0;
+        uint64_t my_o0 = 0;
+        if (lane < cnt) {
+            my_entry = queue[base + lane];
+            const uint32_t r = my_entry >> 6;
+            my_o0 = offsets[r];
+            my_len = (uint32_t)(offsets[r + 1] - my_o0);
         }
-        if (lane == 0) out[r].best_frame = (int8_t)best.frame;
+        for (uint32_t it = 0; it < cnt; it++) {
+            const uint32_t entry = __shfl_sync(0xffffffffu, my_entry, it);
+            const uint64_t o0 = __shfl_sync(0xffffffffu, my_o0, it);
+            const uint32_t L = __shfl_sync(0xffffffffu, my_len, it);
+            const uint32_t r = entry >> 6, open = entry & 63u;
+            const uint64_t bitpos = 2 * (o0 - base0);
+            const uint64_t w0 = bitpos >> 5;
+            const uint32_t bit0 = (uint32_t)(bitpos & 31);
+            const uint32_t n_words = (bit0 + 2 * L + 31) / 32;
+            __syncwarp();
+            for (uint32_t t = lane; t <= n_words; t += kWarp) rd[t] = t < n_words ? __ldg(packed32 + w0 + t) : 0u;
+            __syncwarp();
+            BestFrame best;
+#pragma unroll 1
+            for (int f = 0; f < 6; f++) {
+                if (!((open >> f) & 1u)) continue;
+                const uint32_t phase = f % 3;
+                const uint32_t plen = (L - phase) / 3;
+                // translate + re-encode this frame only
+                for (uint32_t i = lane; i < plen; i += kWarp) {
+                    const uint32_t p = f < 3 ? phase + 3 * i : L - 3 - phase - 3 * i;
+                    const uint32_t bit = bit0 + 2 * p;
+                    const uint32_t c = __funnelshift_r(rd[bit >> 5], rd[(bit >> 5) + 1], bit & 31) & 63u;
+                    pep[i] = f < 3 ? lut_fwd[c] : lut_rev[c];
+                }
+                __syncwarp();
+                uint32_t nd, nh;
+                score_frame<K>(pep, plen, k, sF, keys, pos, P.slots, lane, force_exact, nd, nh);
+                const uint8_t cat = scored_category(nd, nh, plen, k, thr);
+                if (lane == 0) {
+                    out[r].n_kmers[f] = (uint16_t)nd;
+                    out[r].n_hits[f] = (uint16_t)nh;
+                    out[r].category[f] = cat;
+                }
+                best.offer(nh, nd, cat, frame_key(f));
+                __syncwarp();
+            }
+            if (lane == 0) out[r].best_frame = (int8_t)best.frame;
+        }
     }
 }
 
@@ -448,7 +478,12 @@ score_bytes_kernel(const ScoreParams P, const void *__restrict__ src, const uint
                    ScoreCounters *__restrict__ counters, orph_read_result *__restrict__ out)
 {
     extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ FilterDev sF;
+    __shared__ uint8_t s_lut[256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    stage_filter(&sF, P.F);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = P.lut[i];
+    __syncthreads();
     const uint32_t per_warp = P.slots * 8 + P.pep_bytes + P.slots * 2;
     uint8_t *mine = smem + (size_t)warp * ((per_warp + 15) & ~15u);
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(mine);
@@ -515,10 +550,10 @@ score_bytes_kernel(const ScoreParams P, const void *__restrict__ src, const uint
                                                  complement_byte(read_base<PACKED_SRC>(src, base0, g + 1)),
                                                  complement_byte(read_base<PACKED_SRC>(src, base0, g)));
                         }
-                        pep[i] = P.lut[aa];
+                        pep[i] = s_lut[aa];
                     }
                     __syncwarp();
-                    score_frame<0>(pep, plen, k, P.F, keys, pos, P.slots, lane, P.force_exact != 0, nk[f], nh[f]);
+                    score_frame<0>(pep, plen, k, sF, keys, pos, P.slots, lane, P.force_exact != 0, nk[f], nh[f]);
                     cat[f] = scored_category(nk[f], nh[f], plen, k, P.jaccard_threshold);
                     best.offer(nh[f], nk[f], cat[f], frame_key(f));
                 }
