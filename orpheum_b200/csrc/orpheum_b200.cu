@@ -622,7 +622,7 @@ static int launch_score_frames(orph_ctx *ctx, const ScoreParams &P, const uint32
                                uint64_t pbase0, const uint32_t *queue, ScoreCounters *counters, orph_read_result *d_out)
 {
     const int warps = 8;
-    const uint32_t per_warp = (P.slots * 8 + P.read_words * 4 + P.pep_bytes + P.slots * 2 + 15) & ~15u;
+    const uint32_t per_warp = (P.slots * 4 + P.read_words * 4 + P.pep_bytes + 15) & ~15u;
     const size_t smem = (size_t)per_warp * warps;
     if (smem > (size_t)ctx->max_smem_optin) return fail(ORPH_E_INVALID, "score_frames: %zu bytes of shared memory needed", smem);
     auto kern = score_frames_kernel<K>;
@@ -699,7 +699,7 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
     CUDA_TRY(cudaGetLastError());
 
     // fast path: open frames of clean reads
-    P.slots = std::max(64u, next_pow2(2 * std::max(1u, fast_len / 3)));
+    P.slots = std::max(128u, next_pow2(4 * std::max(1u, fast_len / 3)));
     P.pep_bytes = (fast_len / 3 + kPepPad + 3) & ~3u;
     P.read_words = (2 * fast_len + 62) / 32 + 2;
     const uint32_t *packed32 = reinterpret_cast<const uint32_t *>(d_packed);
@@ -714,10 +714,10 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
     // byte-exact path for whatever prefilter routed away (non-ACGT bytes, reads longer than the fast path)
     if (d_ascii || bound > fast_len) {
         ScoreParams B = P;
-        B.slots = std::max(64u, next_pow2(2 * std::max(1u, bound / 3)));
+        B.slots = std::max(128u, next_pow2(2 * std::max(1u, bound / 3)));
         B.pep_bytes = (bound / 3 + kPepPad + 3) & ~3u;
         B.read_words = 0;
-        const uint32_t per_warp = (B.slots * 8 + B.pep_bytes + B.slots * 2 + 15) & ~15u;
+        const uint32_t per_warp = (B.slots * 4 + B.pep_bytes + 15) & ~15u;
         int warps = (int)std::min<size_t>(8, std::max<size_t>(1, (size_t)96 * 1024 / per_warp));
         const size_t smem = (size_t)per_warp * warps;
         Timed timed(ctx, 3);

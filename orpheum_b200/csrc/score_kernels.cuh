@@ -31,7 +31,7 @@ struct ScoreParams {
     uint32_t k;                // peptide k-mer size (== F.ksize)
     uint32_t max_len;          // declared upper bound of read length in this batch
     uint32_t fast_max_len;     // reads longer than this skip the packed fast path
-    uint32_t slots;            // dedup table slots per warp (power of two, >= 2 * max k-mers per frame)
+    uint32_t slots;            // dedup table slots per warp (power of two >= 128, >= 2 * max k-mers per frame)
     uint32_t pep_bytes;        // peptide buffer bytes per warp (multiple of 4, incl. kPepPad)
     uint32_t read_words;       // staged read words per warp (fast path)
     uint32_t force_exact;      // test hook: always take the exact all-pairs dedup path
@@ -85,58 +85,62 @@ __device__ __noinline__ void score_frame_exact(const uint8_t *enc, uint32_t plen
     n_hits = nh;
 }
 
+// De-duplication table entry: [ 21-bit tag of the k-mer's hash | 11-bit k-mer position ].  A slot whose
+// tag matches is only a duplicate if the k-mer bytes at the stored position equal ours, so the set is
+// exact with no fallback; 0xFFFFFFFF (position 2047 cannot occur, see kMaxPeptide) marks an empty slot.
+constexpr uint32_t kPosBits = 11;
+constexpr uint32_t kEmptySlot = 0xFFFFFFFFu;
+constexpr uint32_t kMaxPeptide = ORPH_MAX_READ_LEN / 3;  // 2048 residues: positions <= 2048 - k < 2047
+
 template <int K>  // K > 0: compile-time k-mer size; K == 0: runtime k
 __device__ __forceinline__ void score_frame(const uint8_t *enc, uint32_t plen, uint32_t k_rt, const FilterDev &F,
-                                            unsigned long long *keys, uint16_t *pos, uint32_t slots, int lane,
-                                            bool force_exact, uint32_t &n_distinct, uint32_t &n_hits)
+                                            uint32_t *tab, uint32_t slots, int lane, bool force_exact,
+                                            uint32_t &n_distinct, uint32_t &n_hits)
 {
     const uint32_t k = K > 0 ? (uint32_t)K : k_rt;
     const uint32_t n = plen - k + 1;
-    // smallest power-of-two table with load <= 1/2 for this frame
-    uint32_t mask = 63;
-    while (mask + 1 < 2 * n) mask = 2 * mask + 1;
-    if (mask >= slots) mask = slots - 1;
+    if (force_exact) {  // test hook: the all-pairs restatement instead of the hash set
+        score_frame_exact(enc, plen, k, F, lane, n_distinct, n_hits);
+        return;
+    }
+    // smallest power-of-two table with load <= 1/4 for this frame (never larger than the carve-out,
+    // which the host sizes for load <= 1/2 at the longest admissible peptide)
+    uint32_t mask = 127;
+    while (mask + 1 < 4 * n && mask + 1 < slots) mask = 2 * mask + 1;
     {
-        ulonglong2 *k2 = reinterpret_cast<ulonglong2 *>(keys);  // keys is 16-byte aligned, slot count is even
-        for (uint32_t s = lane; s <= (mask >> 1); s += kWarp) k2[s] = make_ulonglong2(kEmptyKey, kEmptyKey);
+        uint4 *t4 = reinterpret_cast<uint4 *>(tab);  // 16-byte aligned, slot count is a multiple of 128
+        for (uint32_t s = lane; s <= (mask >> 2); s += kWarp) t4[s] = make_uint4(kEmptySlot, kEmptySlot, kEmptySlot, kEmptySlot);
     }
     __syncwarp();
 
     uint32_t nd = 0, nh = 0;
-    bool need_exact = force_exact;
     const uint32_t *encw = reinterpret_cast<const uint32_t *>(enc);
     for (uint32_t j0 = 0; j0 < n; j0 += kWarp) {
         const uint32_t j = j0 + lane;
-        const bool active = j < n;
+        bool winner = false;
         uint64_t h = 0;
-        bool winner = false, dup = false;
-        uint32_t slot = 0, v0 = 0, sh0 = 0;
-        if (active) {
+        uint32_t v0 = 0, sh0 = 0;
+        if (j < n) {
             h = murmur3_h1(SmemKeyWords{encw, j, k}, k);
             // table-0 probe first: its L2 latency overlaps the de-duplication below
             const uint64_t bin0 = filter_bin(F, 0, h);
             v0 = ld_table_byte(F.table[0] + (bin0 >> 3));
             sh0 = (uint32_t)bin0 & 7u;
-            if (h == kEmptyKey) need_exact = true;  // cannot be stored: take the exact path for this frame
-            slot = (uint32_t)h & mask;
+            const uint32_t tag = (uint32_t)(h >> 40) & ((1u << (32 - kPosBits)) - 1);
+            const uint32_t mine = (tag << kPosBits) | j;
+            uint32_t slot = (uint32_t)h & mask;
+            const uint32_t step = ((uint32_t)(h >> 20) & mask) | 1u;  // odd: visits every slot
             while (true) {
-                const unsigned long long old = atomicCAS(&keys[slot], (unsigned long long)kEmptyKey, (unsigned long long)h);
-                if (old == kEmptyKey) { winner = true; break; }
-                if (old == h) { dup = true; break; }
-                slot = (slot + 1) & mask;
+                const uint32_t old = atomicCAS(&tab[slot], kEmptySlot, mine);
+                if (old == kEmptySlot) { winner = true; break; }
+                if ((old >> kPosBits) == tag && kmer_bytes_equal(enc, old & ((1u << kPosBits) - 1), j, k)) break;
+                slot = (slot + step) & mask;
             }
         }
-        __syncwarp();
-        if (winner) pos[slot] = (uint16_t)j;
-        __syncwarp();
-        if (dup && !kmer_bytes_equal(enc, pos[slot], j, k)) need_exact = true;  // true 64-bit collision
         bool hit = winner && ((v0 >> sh0) & 1u);
         if (hit && F.n_tables > 1) hit = filter_contains_rest(F, h);
         nd += __popc(__ballot_sync(0xffffffffu, winner));
         nh += __popc(__ballot_sync(0xffffffffu, hit));
-    }
-    if (__any_sync(0xffffffffu, need_exact)) {
-        score_frame_exact(enc, plen, k, F, lane, nd, nh);
     }
     n_distinct = nd;
     n_hits = nh;
@@ -150,6 +154,18 @@ __device__ __forceinline__ uint8_t scored_category(uint32_t n_distinct, uint32_t
     if ((double)n_distinct <= (double)(plen - k + 1) / 2.0) return ORPH_CAT_LOW_COMPLEXITY_PEPTIDE;
     const double jaccard = (double)n_hits / (double)n_distinct;  // translate.py:204
     return jaccard > thr ? ORPH_CAT_CODING : ORPH_CAT_NON_CODING;
+}
+
+// smallest hit count h in [0, n] with (double)h / (double)n > thr, or n + 1 if there is none: the
+// reference's `jaccard > threshold` (translate.py:204,271) as an integer compare, decided by the very
+// same IEEE division (monotone in h, so the first h that passes is exact).
+__device__ __forceinline__ uint32_t min_hits_for(uint32_t n, double thr)
+{
+    const double dn = (double)n;
+    double est = floor(thr * dn) - 2.0;
+    uint32_t h = est > 0.0 ? (est < dn ? (uint32_t)est : n) : 0u;
+    while (h <= n && !((double)h / dn > thr)) h++;
+    return h;
 }
 
 struct BestFrame {
@@ -369,7 +385,8 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
 // ------------------------------------------------------------------------------------------------
 // score_frames_kernel: persistent warps, dynamic fetch from the queue written by prefilter_kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int kFetchBatch = 16;  // queue entries a warp claims per atomic
+constexpr int kFetchBatch = 16;          // queue entries a warp claims per atomic
+constexpr uint32_t kFastMaxKmers = kFastMaxLen / 3;  // 512: bound of the per-block min-hits table
 
 template <int K>
 __global__ void __launch_bounds__(256)
@@ -380,6 +397,7 @@ score_frames_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, 
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ FilterDev sF;
     __shared__ uint8_t lut_fwd[64], lut_rev[64];
+    __shared__ uint16_t s_min_hits[kFastMaxKmers + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     stage_filter(&sF, P.F);
     if (threadIdx.x < 64) {
@@ -387,16 +405,17 @@ score_frames_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, 
         lut_fwd[t] = P.lut[translate_codes(b0, b1, b2)];
         lut_rev[t] = P.lut[translate_codes(b2 ^ 2, b1 ^ 2, b0 ^ 2)];  // complement = code ^ 2, order reversed
     }
-    __syncthreads();
-    // per-warp carve-out: [keys | read words | peptide | pos]
-    const uint32_t per_warp = P.slots * 8 + P.read_words * 4 + P.pep_bytes + P.slots * 2;
-    uint8_t *mine = smem + (size_t)warp * ((per_warp + 15) & ~15u);
-    unsigned long long *keys = reinterpret_cast<unsigned long long *>(mine);
-    uint32_t *rd = reinterpret_cast<uint32_t *>(mine + P.slots * 8);
-    uint8_t *pep = mine + P.slots * 8 + P.read_words * 4;
-    uint16_t *pos = reinterpret_cast<uint16_t *>(pep + P.pep_bytes);
-    const uint32_t k = K > 0 ? (uint32_t)K : P.k;
     const double thr = P.jaccard_threshold;
+    for (uint32_t n = threadIdx.x; n <= P.fast_max_len / 3; n += blockDim.x)
+        s_min_hits[n] = n ? (uint16_t)min_hits_for(n, thr) : (uint16_t)1;
+    __syncthreads();
+    // per-warp carve-out: [dedup slots | read words | peptide]
+    const uint32_t per_warp = P.slots * 4 + P.read_words * 4 + P.pep_bytes;
+    uint8_t *mine = smem + (size_t)warp * ((per_warp + 15) & ~15u);
+    uint32_t *tab = reinterpret_cast<uint32_t *>(mine);
+    uint32_t *rd = reinterpret_cast<uint32_t *>(mine + P.slots * 4);
+    uint8_t *pep = mine + P.slots * 4 + P.read_words * 4;
+    const uint32_t k = K > 0 ? (uint32_t)K : P.k;
     const bool force_exact = P.force_exact != 0;
     const uint32_t n_queue = counters->n_queue;
 
@@ -419,7 +438,8 @@ score_frames_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, 
             const uint32_t entry = __shfl_sync(0xffffffffu, my_entry, it);
             const uint64_t o0 = __shfl_sync(0xffffffffu, my_o0, it);
             const uint32_t L = __shfl_sync(0xffffffffu, my_len, it);
-            const uint32_t r = entry >> 6, open = entry & 63u;
+            const uint32_t r = entry >> 6;
+            uint32_t open = entry & 63u;
             const uint64_t bitpos = 2 * (o0 - base0);
             const uint64_t w0 = bitpos >> 5;
             const uint32_t bit0 = (uint32_t)(bitpos & 31);
@@ -428,22 +448,25 @@ score_frames_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, 
             for (uint32_t t = lane; t <= n_words; t += kWarp) rd[t] = t < n_words ? __ldg(packed32 + w0 + t) : 0u;
             __syncwarp();
             BestFrame best;
-#pragma unroll 1
-            for (int f = 0; f < 6; f++) {
-                if (!((open >> f) & 1u)) continue;
-                const uint32_t phase = f % 3;
+            while (open) {
+                const int f = __ffs(open) - 1;
+                open &= open - 1;
+                const uint32_t phase = f >= 3 ? f - 3 : f;
                 const uint32_t plen = (L - phase) / 3;
                 // translate + re-encode this frame only
+                const uint8_t *lut = f < 3 ? lut_fwd : lut_rev;
+                const int p0 = f < 3 ? (int)phase : (int)(L - 3 - phase), dp = f < 3 ? 3 : -3;
                 for (uint32_t i = lane; i < plen; i += kWarp) {
-                    const uint32_t p = f < 3 ? phase + 3 * i : L - 3 - phase - 3 * i;
-                    const uint32_t bit = bit0 + 2 * p;
+                    const uint32_t bit = bit0 + 2 * (uint32_t)(p0 + dp * (int)i);
                     const uint32_t c = __funnelshift_r(rd[bit >> 5], rd[(bit >> 5) + 1], bit & 31) & 63u;
-                    pep[i] = f < 3 ? lut_fwd[c] : lut_rev[c];
+                    pep[i] = lut[c];
                 }
                 __syncwarp();
                 uint32_t nd, nh;
-                score_frame<K>(pep, plen, k, sF, keys, pos, P.slots, lane, force_exact, nd, nh);
-                const uint8_t cat = scored_category(nd, nh, plen, k, thr);
+                score_frame<K>(pep, plen, k, sF, tab, P.slots, lane, force_exact, nd, nh);
+                // evaluate_is_kmer_low_complexity: n_kmers <= (len - k + 1) / 2  (translate.py:98-100), in integers
+                const uint8_t cat = 2 * nd <= plen - k + 1 ? ORPH_CAT_LOW_COMPLEXITY_PEPTIDE
+                                    : (nh >= s_min_hits[nd] ? ORPH_CAT_CODING : ORPH_CAT_NON_CODING);
                 if (lane == 0) {
                     out[r].n_kmers[f] = (uint16_t)nd;
                     out[r].n_hits[f] = (uint16_t)nh;
@@ -484,11 +507,10 @@ score_bytes_kernel(const ScoreParams P, const void *__restrict__ src, const uint
     stage_filter(&sF, P.F);
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = P.lut[i];
     __syncthreads();
-    const uint32_t per_warp = P.slots * 8 + P.pep_bytes + P.slots * 2;
+    const uint32_t per_warp = P.slots * 4 + P.pep_bytes;
     uint8_t *mine = smem + (size_t)warp * ((per_warp + 15) & ~15u);
-    unsigned long long *keys = reinterpret_cast<unsigned long long *>(mine);
-    uint8_t *pep = mine + P.slots * 8;
-    uint16_t *pos = reinterpret_cast<uint16_t *>(pep + P.pep_bytes);
+    uint32_t *tab = reinterpret_cast<uint32_t *>(mine);
+    uint8_t *pep = mine + P.slots * 4;
     const uint32_t k = P.k;
 
     while (true) {
@@ -553,7 +575,7 @@ score_bytes_kernel(const ScoreParams P, const void *__restrict__ src, const uint
                         pep[i] = s_lut[aa];
                     }
                     __syncwarp();
-                    score_frame<0>(pep, plen, k, sF, keys, pos, P.slots, lane, P.force_exact != 0, nk[f], nh[f]);
+                    score_frame<0>(pep, plen, k, sF, tab, P.slots, lane, P.force_exact != 0, nk[f], nh[f]);
                     cat[f] = scored_category(nk[f], nh[f], plen, k, P.jaccard_threshold);
                     best.offer(nh[f], nk[f], cat[f], frame_key(f));
                 }
