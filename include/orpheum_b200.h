@@ -101,11 +101,15 @@ int orph_ctx_check(orph_ctx *ctx);
 /* Test hook: force the exact all-pairs de-duplication path in the scoring kernels (normally only
  * taken on a 64-bit MurmurHash collision between two different k-mers of one frame). */
 int orph_ctx_set_force_exact_dedup(orph_ctx *ctx, int on);
+/* Test hook: on = 0 routes short reads through the warp-per-read kernel instead of the thread-per-frame
+ * kernel (both must give identical results). */
+int orph_ctx_set_thread_path(orph_ctx *ctx, int on);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t orph_ctx_launch_count(const orph_ctx *ctx);
 /* Per-kernel device timing (CUDA events on the context's stream around every scoring kernel), for
- * bench.py's roofline.  Kernel ids: 0 pack_ascii, 1 prefilter, 2 score_frames, 3 score_bytes. */
-#define ORPH_N_TIMED_KERNELS 4
+ * bench.py's roofline.  Kernel ids: 0 pack_ascii, 1 prefilter, 2 score_frames (warp per read),
+ * 3 score_bytes, 4 score_tasks (thread per frame), 5 finalize_best. */
+#define ORPH_N_TIMED_KERNELS 6
 int orph_ctx_set_kernel_timing(orph_ctx *ctx, int on);
 /* Adds up (and clears) the intervals recorded so far: ms[i] total milliseconds and launches[i] count of
  * kernel i.  Synchronizes the stream. */

@@ -40,6 +40,7 @@ PROTOTYPES = {
     "orph_ctx_synchronize": (ctypes.c_int, [_vp]),
     "orph_ctx_check": (ctypes.c_int, [_vp]),
     "orph_ctx_set_force_exact_dedup": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "orph_ctx_set_thread_path": (ctypes.c_int, [_vp, ctypes.c_int]),
     "orph_ctx_launch_count": (ctypes.c_uint64, [_vp]),
     "orph_ctx_set_kernel_timing": (ctypes.c_int, [_vp, ctypes.c_int]),
     "orph_ctx_kernel_times": (ctypes.c_int, [_vp, _vp, _u64p]),

@@ -125,9 +125,13 @@ __device__ __forceinline__ uint64_t filter_bin(const FilterDev &F, uint32_t t, u
     return r;
 }
 
+// Bloom-table probe: read-only path, no L1 allocation (random 1-byte gathers over >= 50 MB would only
+// evict the lines the kernel actually re-uses); the tables live in L2.
 __device__ __forceinline__ uint32_t ld_table_byte(const uint8_t *p)
 {
-    return (uint32_t)__ldg(p);
+    uint32_t v;
+    asm("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
 }
 
 // Nodegraph.get: AND over tables with early exit.

@@ -14,6 +14,7 @@
 
 #include "bloom_kernels.cuh"
 #include "score_kernels.cuh"
+#include "task_kernels.cuh"
 
 using namespace orph;
 
@@ -76,10 +77,12 @@ struct orph_ctx {
     size_t l2_persist_max = 0, l2_window_max = 0;
     const void *l2_window_base = nullptr;  // filter buffer the access-policy window currently covers
     bool force_exact = false;
+    bool disable_task_kernel = false;  // test hook: route every read through the warp-per-read kernel
     uint64_t launches = 0;
     uint32_t sticky_status = 0;  // device status bits folded in by the host-buffer entry points
     DevBuf counters;             // ScoreCounters (one per in-flight call; calls on a ctx are serialised on its stream)
     DevBuf queue, bytes_queue;   // uint32 read indices
+    DevBuf task_queue;           // uint32 (read << 3 | frame), up to 6 per read
     DevBuf needs_bytes;          // uint8 per read (ASCII input)
     DevBuf packed;               // 2-bit stream built from ASCII input
     DevBuf in_reads, in_offsets, out_results;  // staging for the host-buffer entry points
@@ -198,7 +201,7 @@ extern "C" void orph_ctx_destroy(orph_ctx *ctx)
     if (!ctx) return;
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf *b : {&ctx->counters, &ctx->queue, &ctx->bytes_queue, &ctx->needs_bytes, &ctx->packed, &ctx->in_reads,
+    for (DevBuf *b : {&ctx->counters, &ctx->queue, &ctx->bytes_queue, &ctx->task_queue, &ctx->needs_bytes, &ctx->packed, &ctx->in_reads,
                       &ctx->in_offsets, &ctx->out_results, &ctx->misc, &ctx->seen})
         b->release();
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -285,6 +288,13 @@ extern "C" int orph_ctx_kernel_times(orph_ctx *ctx, double *ms, uint64_t *launch
         cudaEventDestroy(iv.b);
     }
     ctx->intervals.clear();
+    return ORPH_OK;
+}
+
+extern "C" int orph_ctx_set_thread_path(orph_ctx *ctx, int on)
+{
+    if (!ctx) return fail(ORPH_E_INVALID, "ctx is NULL");
+    ctx->disable_task_kernel = on == 0;
     return ORPH_OK;
 }
 
@@ -639,6 +649,38 @@ static int launch_score_frames(orph_ctx *ctx, const ScoreParams &P, const uint32
     return ORPH_OK;
 }
 
+template <int K>
+static int launch_score_tasks(orph_ctx *ctx, const ScoreParams &P_in, uint32_t thread_len, const uint64_t *packed,
+                              const uint64_t *d_offsets, uint64_t pbase0, const uint32_t *tasks, ScoreCounters *counters,
+                              orph_read_result *d_out)
+{
+    ScoreParams P = P_in;
+    P.read_words = (2 * thread_len + 62) / 32 + 2;  // words of the longest admissible read + one zero word
+    const size_t smem = (size_t)kTaskBlock * (kSeenWords64 * 8 + P.read_words * 4);
+    auto kern = score_tasks_kernel<K>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTaskBlock, smem));
+    if (per_sm < 1) per_sm = 1;
+    {
+        Timed timed(ctx, 4);
+        kern<<<ctx->sm_count * per_sm, kTaskBlock, smem, ctx->stream>>>(P, reinterpret_cast<const uint32_t *>(packed), d_offsets,
+                                                                          pbase0, tasks, counters, d_out);
+    }
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ORPH_OK;
+}
+
+// k-mer sizes with a compiled thread-per-frame kernel (the defaults of every alphabet, sequence_encodings.py:402-419)
+static bool has_task_kernel(uint32_t k)
+{
+    switch (k) {
+    case 7: case 8: case 9: case 10: case 11: case 12: case 16: case 21: case 31: return true;
+    default: return false;
+    }
+}
+
 // Core pipeline on device-resident inputs.  Exactly one of (d_ascii, d_packed_in) is the source:
 //   ASCII : pack_ascii -> prefilter -> score_frames -> score_bytes<ASCII> on flagged reads
 //   PACKED: prefilter -> score_frames -> score_bytes<PACKED> on over-long reads
@@ -654,6 +696,8 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
     const uint32_t fast_len = std::min(bound, kFastMaxLen);
     if ((rc = ctx->queue.ensure(n_reads * 4)) != ORPH_OK) return rc;
     if ((rc = ctx->bytes_queue.ensure(n_reads * 4)) != ORPH_OK) return rc;
+    const uint32_t thread_len = has_task_kernel(f->ksize) && !ctx->disable_task_kernel ? std::min(bound, kThreadMaxLen) : 0u;
+    if (thread_len && (rc = ctx->task_queue.ensure(n_reads * 6 * 4)) != ORPH_OK) return rc;
     ScoreCounters *counters = (ScoreCounters *)ctx->counters.p;
     // status is sticky across calls until orph_ctx_check; everything else restarts
     CUDA_TRY(cudaMemsetAsync(counters, 0, offsetof(ScoreCounters, status), s));
@@ -667,6 +711,7 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
     P.k = f->ksize;
     P.max_len = bound;
     P.fast_max_len = fast_len;
+    P.thread_max_len = thread_len;
     P.force_exact = ctx->force_exact ? 1u : 0u;
 
     const uint64_t *d_packed = d_packed_in;
@@ -692,13 +737,38 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
     {
         Timed timed(ctx, 1);
         prefilter_kernel<<<grid_for(n_reads, 256, ctx->sm_count, 16), 256, 0, s>>>(
-            d_packed, d_offsets, pbase0, n_reads, d_needs, P.k, fast_len, bound, d_out, (uint32_t *)ctx->queue.p,
-            (uint32_t *)ctx->bytes_queue.p, counters);
+            d_packed, d_offsets, pbase0, n_reads, d_needs, P.k, fast_len, thread_len, bound, d_out, (uint32_t *)ctx->queue.p,
+            (uint32_t *)ctx->task_queue.p, (uint32_t *)ctx->bytes_queue.p, counters);
     }
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
 
-    // fast path: open frames of clean reads
+    // short reads: one thread per open frame
+    if (thread_len) {
+        const uint32_t *tq = (const uint32_t *)ctx->task_queue.p;
+        switch (P.k) {
+        case 7: rc = launch_score_tasks<7>(ctx, P, thread_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
+        case 8: rc = launch_score_tasks<8>(ctx, P, thread_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
+        case 9: rc = launch_score_tasks<9>(ctx, P, thread_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
+        case 10: rc = launch_score_tasks<10>(ctx, P, thread_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
+        case 11: rc = launch_score_tasks<11>(ctx, P, thread_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
+        case 12: rc = launch_score_tasks<12>(ctx, P, thread_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
+        case 16: rc = launch_score_tasks<16>(ctx, P, thread_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
+        case 21: rc = launch_score_tasks<21>(ctx, P, thread_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
+        case 31: rc = launch_score_tasks<31>(ctx, P, thread_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
+        default: rc = fail(ORPH_E_INVALID, "internal: no task kernel for k=%u", P.k); break;
+        }
+        if (rc != ORPH_OK) return rc;
+        {
+            Timed timed(ctx, 5);
+            finalize_best_kernel<<<grid_for(n_reads, 256, ctx->sm_count, 16), 256, 0, s>>>(d_out, n_reads);
+        }
+        ctx->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+
+    // medium reads (or k without a task kernel): one warp per read
+    if (bound > thread_len) {
     P.slots = std::max(128u, next_pow2(4 * std::max(1u, fast_len / 3)));
     P.pep_bytes = (fast_len / 3 + kPepPad + 3) & ~3u;
     P.read_words = (2 * fast_len + 62) / 32 + 2;
@@ -710,6 +780,7 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
     default: rc = launch_score_frames<0>(ctx, P, packed32, d_offsets, pbase0, (const uint32_t *)ctx->queue.p, counters, d_out); break;
     }
     if (rc != ORPH_OK) return rc;
+    }
 
     // byte-exact path for whatever prefilter routed away (non-ACGT bytes, reads longer than the fast path)
     if (d_ascii || bound > fast_len) {

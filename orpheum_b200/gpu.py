@@ -50,15 +50,19 @@ class Context:
     def set_force_exact_dedup(self, on):
         check(self._lib.orph_ctx_set_force_exact_dedup(self._h, int(bool(on))))
 
-    KERNEL_NAMES = ("pack_ascii", "prefilter", "score_frames", "score_bytes")
+    KERNEL_NAMES = ("pack_ascii", "prefilter", "score_frames", "score_bytes", "score_tasks", "finalize_best")
+
+    def set_thread_path(self, on):
+        """Test hook: False sends short reads through the warp-per-read kernel."""
+        check(self._lib.orph_ctx_set_thread_path(self._h, int(bool(on))))
 
     def set_kernel_timing(self, on):
         check(self._lib.orph_ctx_set_kernel_timing(self._h, int(bool(on))))
 
     def kernel_times(self):
         """{kernel: (total_ms, launches)} since the last call; synchronizes."""
-        ms = np.zeros(4, dtype=np.float64)
-        n = np.zeros(4, dtype=np.uint64)
+        ms = np.zeros(len(self.KERNEL_NAMES), dtype=np.float64)
+        n = np.zeros(len(self.KERNEL_NAMES), dtype=np.uint64)
         check(self._lib.orph_ctx_kernel_times(self._h, ptr(ms), ptr(n)))
         return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(self.KERNEL_NAMES)}
 

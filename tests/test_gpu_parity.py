@@ -267,6 +267,13 @@ def test_synthetic_r150_vs_oracle(gpu, enc, orc, refdata, alphabet, ksize, thr):
     res2 = gpu.score_reads(gg, packed, offsets, lut, thr, reads_format=1)
     assert res2.tobytes() == res.tobytes()
     assert not (res["flags"] & 0x80).any()
+    # the warp-per-read kernel (used for reads longer than 320 nt) must agree with the thread-per-frame kernel
+    gg.ctx.set_thread_path(False)
+    try:
+        res3 = gpu.score_reads(gg, packed, offsets, lut, thr, reads_format=1)
+    finally:
+        gg.ctx.set_thread_path(True)
+    assert res3.tobytes() == res.tobytes()
 
 
 @pytest.mark.parametrize("alphabet,ksize,thr", [("protein", 7, 0.5), ("dayhoff", 12, 0.5), ("hp", 31, 0.8)])
@@ -278,6 +285,12 @@ def test_synthetic_mixed_vs_oracle(gpu, enc, orc, refdata, alphabet, ksize, thr)
     assert n_empty == 0
     res = gpu.score_reads(gg, flat, offsets, enc.encode_lut(alphabet), thr)
     assert_same_as_oracle(res, ora, f"mixed {alphabet}")
+    gg.ctx.set_thread_path(False)
+    try:
+        res_warp = gpu.score_reads(gg, flat, offsets, enc.encode_lut(alphabet), thr)
+    finally:
+        gg.ctx.set_thread_path(True)
+    assert res_warp.tobytes() == res.tobytes()
     cats = set(np.unique(ora["category"]).tolist())
     assert {0, 1, 2, 3, 4, 5} <= cats or alphabet == "hp"
     assert (res["flags"] & 0x80).any() and not (res["flags"] & 0x80).all()
