@@ -106,7 +106,8 @@ struct ReadColumn {
 // Exact answer behind a seen-filter alarm: does the k-mer ending at residue s (window `cur`) also end
 // at an earlier residue of the same frame?  Walks backwards, so a tandem repeat answers after one period.
 template <int K>
-__device__ __noinline__ bool kmer_seen_before(ReadColumn rc, const uint8_t *lut, int p0, int dp, int s, KmerWindow<K> cur)
+__device__ __forceinline__ bool kmer_seen_before(const ReadColumn &rc, const uint8_t *lut, int p0, int dp, int s,
+                                                 const KmerWindow<K> &cur)
 {
     KmerWindow<K> win = cur;
     for (int e = s - 1; e >= K - 1; e--) {
@@ -142,7 +143,12 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
         s_min_hits[n] = n ? (uint16_t)min_hits_for(n, thr) : (uint16_t)1;
     __syncthreads();
     const bool force_exact = P.force_exact != 0;
-    const bool single_table = sF.n_tables == 1;
+    const uint32_t n_tables = sF.n_tables;
+    const bool single_table = n_tables == 1;
+    // table 0 is probed once per k-mer: keep its description in registers
+    const uint64_t t0_size = sF.size[0], t0_magic = sF.magic[0];
+    const uint8_t *t0_table = sF.table[0];
+    const bool t0_small = sF.small != 0;
     const uint32_t n_tasks = counters->n_tasks;
     unsigned long long *seen = reinterpret_cast<unsigned long long *>(dyn_smem) + threadIdx.x;
     uint32_t *rd_col = reinterpret_cast<uint32_t *>(dyn_smem + (size_t)kSeenWords64 * 8 * kTaskBlock) + threadIdx.x;
@@ -185,21 +191,58 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
         const uint32_t max_plen = __reduce_max_sync(0xffffffffu, plen);
         __syncwarp();
 
-        // software pipeline: iteration s hashes k-mer s and issues its table-0 probe, then consumes the probe
-        // of k-mer s-1
+        // Software pipeline.  Iteration s: (1) if 32 survivors are queued, issue their table 1..3 probes;
+        // (2) roll in residue s (fetched one iteration ahead), hash k-mer s, issue its table-0 probe, update
+        // the seen filter; (3) consume the probes of step 1; (4) consume the table-0 probe of k-mer s-1 and
+        // queue it if it survived.  Every global load has a full hash between issue and use.
         bool prev_new = false;
         uint64_t prev_h = 0;
         uint32_t prev_v0 = 0, prev_sh = 0;
+        uint32_t res_next = plen ? rc.residue(lut, p0, dp, 0) : 0u;
         for (uint32_t s = 0; s <= max_plen; s++) {
+            // (1)
+            const bool draining = !single_table && qlen >= 32;
+            uint32_t d_hit = 0, d_owner = 0;
+            uint64_t d_b1 = 0, d_b2 = 0, d_b3 = 0;
+            uint32_t d_v1 = 0, d_v2 = 0, d_v3 = 0;
+            bool d_generic = false;
+            uint64_t d_h = 0;
+            if (draining) {
+                qlen -= 32;
+                d_h = q_hash[warp][qlen + lane];
+                d_owner = q_lane[warp][qlen + lane];
+                if (n_tables == 4) {
+                    d_b1 = filter_bin(sF, 1, d_h); d_b2 = filter_bin(sF, 2, d_h); d_b3 = filter_bin(sF, 3, d_h);
+                    d_v1 = ld_table_byte(sF.table[1] + (d_b1 >> 3));
+                    d_v2 = ld_table_byte(sF.table[2] + (d_b2 >> 3));
+                    d_v3 = ld_table_byte(sF.table[3] + (d_b3 >> 3));
+                } else {
+                    d_generic = true;
+                }
+            }
+            // (2)
             bool cur_new = false;
             uint64_t h = 0;
             uint32_t v0 = 0, sh = 0;
             if (s < plen) {
-                win.push(rc.residue(lut, p0, dp, (int)s));
+                win.push(res_next);
+                if (s + 1 < plen) res_next = rc.residue(lut, p0, dp, (int)s + 1);
                 if (s + 1 >= (uint32_t)K) {
                     h = win.hash();
-                    const uint64_t bin0 = filter_bin(sF, 0, h);
-                    v0 = ld_table_byte(sF.table[0] + (bin0 >> 3));
+                    uint64_t bin0;
+                    {
+                        const uint64_t q = __umul64hi(h, t0_magic);
+                        if (t0_small) {
+                            uint32_t rr = (uint32_t)h - (uint32_t)q * (uint32_t)t0_size;
+                            if (rr >= (uint32_t)t0_size) rr -= (uint32_t)t0_size;
+                            bin0 = rr;
+                        } else {
+                            uint64_t rr = h - q * t0_size;
+                            if (rr >= t0_size) rr -= t0_size;
+                            bin0 = rr;
+                        }
+                    }
+                    v0 = ld_table_byte(t0_table + (bin0 >> 3));
                     sh = (uint32_t)bin0 & 7u;
                     // seen filter: word chosen by 4 hash bits, three bit positions inside it by 18 more
                     const uint32_t hw = (uint32_t)(h >> 32);
@@ -212,6 +255,14 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
                     nd += cur_new ? 1u : 0u;
                 }
             }
+            // (3)
+            if (draining) {
+                if (d_generic) d_hit = filter_contains_rest(sF, d_h) ? 1u : 0u;
+                else d_hit = (d_v1 >> (d_b1 & 7)) & (d_v2 >> (d_b2 & 7)) & (d_v3 >> (d_b3 & 7)) & 1u;
+                if (d_hit) atomicAdd(&s_hits[warp][d_owner], 1u);
+                __syncwarp();
+            }
+            // (4)
             const bool hit0 = prev_new && ((prev_v0 >> prev_sh) & 1u);
             const uint64_t hq = prev_h;
             prev_new = cur_new; prev_h = h; prev_v0 = v0; prev_sh = sh;
@@ -219,7 +270,6 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
                 nh_direct += hit0 ? 1u : 0u;
                 continue;
             }
-            // survivors of table 0 go to the warp's queue and are finished 32 at a time
             const uint32_t m = __ballot_sync(0xffffffffu, hit0);
             if (m) {
                 if (hit0) {
@@ -229,14 +279,14 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
                 }
                 qlen += __popc(m);
                 __syncwarp();
-                if (qlen >= 32) {
-                    qlen -= 32;
-                    const uint64_t qh = q_hash[warp][qlen + lane];
-                    const uint32_t ql = q_lane[warp][qlen + lane];
-                    if (filter_contains_rest(sF, qh)) atomicAdd(&s_hits[warp][ql], 1u);
-                    __syncwarp();
-                }
             }
+        }
+        // at most 63 survivors are left: one full batch, then the remainder
+        if (qlen >= 32) {
+            qlen -= 32;
+            const uint64_t qh = q_hash[warp][qlen + lane];
+            const uint32_t ql = q_lane[warp][qlen + lane];
+            if (filter_contains_rest(sF, qh)) atomicAdd(&s_hits[warp][ql], 1u);
         }
         if (qlen) {
             if ((uint32_t)lane < qlen) {
