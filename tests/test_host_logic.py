@@ -1,0 +1,169 @@
+"""CPU tests of the host-side mirror of the reference interface (no GPU work): alphabets, constants,
+emission-side translation, FASTA/FASTQ reading, output writers, click wiring.  Modelled on the
+reference's tests/test_sequence_encodings.py, test_translate_single_seq.py, test_create_save_summary.py,
+test_index.py:7-22,152-190 and test_translate.py:62-149,236-252."""
+import gzip
+import json
+import math
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+from click.testing import CliRunner
+
+from orpheum_b200 import constants_index, constants_translate, fastx, sequence_encodings as enc
+from orpheum_b200.create_save_summary import CreateSaveSummary
+from orpheum_b200.translate_single_seq import TranslateSingleSeq
+from tests.conftest import load_score_vector
+
+SEQ = "CGCTTGCTTAATACTGACATCAATAATATTAGGAAAATCGCAATATAACTGTAAATCCTGTTCTGTC"
+
+
+def test_alphabets_match_reference(misc_kats):
+    probe = "ACDEFGHIKLMNPQRSTVWYXUBZOJ*acdxy"
+    for name, encoded in misc_kats["alphabets"].items():
+        assert enc.encode_peptide(probe, name) == encoded, name
+        lut = enc.encode_lut(name)
+        assert bytes(lut[np.frombuffer(probe.encode(), dtype=np.uint8)]).decode() == encoded
+    with pytest.raises(ValueError):
+        enc.encode_peptide("ACD", "not-an-alphabet")
+    with pytest.raises(ValueError):
+        enc.encode_lut("not-an-alphabet")
+    assert enc.encode_peptide("SASHAFIERCE", "dayhoff") == "bbbdbfecdac"  # tests/test_sequence_encodings.py
+    assert enc.encode_peptide("SASHAFIERCE", "hp") == "phpphhhpppp"
+    assert enc.BEST_KSIZES == misc_kats["best_ksizes"]
+    assert constants_translate.LOW_COMPLEXITY_CATEGORIES == misc_kats["low_complexity_categories"]
+    for aa in "RHKDESTNQCGPAVILMFYW":
+        for mapping in (enc.DAYHOFF_MAPPING, enc.HP_MAPPING, enc.BOTVINNIK_MAPPING, enc.AA9_MAPPING, enc.GBMR4_MAPPING,
+                        enc.SDM12_MAPPING, enc.HSDM17_MAPPING, enc.DAYHOFF_V2_MAPPING):
+            assert aa in mapping
+
+
+def test_translate_single_seq(misc_kats):
+    t = TranslateSingleSeq(SEQ, True)
+    for codon, aa in misc_kats["codons"].items():
+        assert t._translate_codon(codon) == aa
+    assert t._translate_codon("AC") == ""
+    assert t._reverse_complement("AACCGGTT") == "AACCGGTT" and t._reverse_complement("AACC") == "GGTT"
+    for seq, frames in misc_kats["six_frame"].items():
+        got = TranslateSingleSeq(seq, False).six_frame_translation()
+        assert {str(k): v for k, v in got.items()} == frames
+        assert list(got) == [1, 2, 3, -1, -2, -3]
+        for f, pep in got.items():
+            assert TranslateSingleSeq(seq, False).frame_translation(f) == pep
+    assert TranslateSingleSeq(SEQ, True).six_frame_translation_no_stops() == {
+        2: "ACLILTSIILGKSQYNCKSCSV", -2: "TEQDLQLYCDFPNIIDVSIKQA", -3: "QNRIYSYIAIFLILLMSVLSK"}
+
+
+def test_thresholds_and_helpers(misc_kats):
+    from orpheum_b200 import translate
+
+    for alphabet, thr in misc_kats["thresholds"].items():
+        assert translate.get_jaccard_threshold(None, alphabet) == thr
+    assert translate.get_jaccard_threshold(0.5, "hp") == 0.5
+    for seq, value in misc_kats["fastp_complexity"].items():
+        assert translate.compute_fastp_complexity(seq) == value
+    low = "CCCCCCCCCACCACCACCCCCCCCACCCCCCCCCCCCCCCCCCCCCCCCCCACCCCCCCACACACCCCCAACACCC"
+    assert not translate.evaluate_is_fastp_low_complexity(SEQ) and translate.evaluate_is_fastp_low_complexity(low)
+    assert translate.compute_kmer_complexity(SEQ, 7) == 30.5 and translate.compute_kmer_complexity(low, 7) == 35.0
+    assert translate.evaluate_is_kmer_low_complexity(SEQ, 7) is False
+    assert translate.evaluate_is_kmer_low_complexity(low, 7) is True
+
+
+def test_index_helpers(misc_kats):
+    from orpheum_b200 import index
+
+    assert index.per_translation_false_positive_rate(14, 4e7) == misc_kats["fpr"]["per_translation_14_4e7"] == 3.275785921922898e-06
+    assert index.per_read_false_positive_coding_rate(60, 7) == misc_kats["fpr"]["per_read_60_7"] == 3.884682410293139e-05
+    assert index.get_peptide_ksize("protein") == 7 and index.get_peptide_ksize("dayhoff") == 12
+    assert index.get_peptide_ksize("hydrophobic-polar") == 31 and index.get_peptide_ksize("protein", 11) == 11
+    with pytest.raises(ValueError):
+        index.get_peptide_ksize("not-a-molecule")
+    assert constants_index.BASED_INT.convert("1e8", None, None) == 100000000
+    assert constants_index.BASED_INT.convert("12345", None, None) == 12345
+    assert constants_index.BASED_INT.convert(77, None, None) == 77
+
+
+def test_fastx_reader(refdata, tmp_path):
+    fq = os.path.join(refdata, "SRR306838_GSM752691_hsa_br_F_1_trimmed_subsampled_n22.fq")
+    recs = list(fastx.open(fq))
+    assert len(recs) == 23
+    assert recs[0]["name"].startswith("SRR306838.") and " " in recs[0]["name"]  # full header line, not split
+    gz = list(fastx.open(fq + ".gz"))
+    # the gzipped fixture predates the 23rd (adversarial) read
+    assert [(r["name"], r["sequence"]) for r in gz] == [(r["name"], r["sequence"]) for r in recs[:22]]
+    fa = list(fastx.open(os.path.join(refdata, "index", "Homo_sapiens.GRCh38.pep.first1000lines.fa")))
+    assert len(fa) > 100 and all("\n" not in r["sequence"] for r in fa)
+    assert list(fastx.open(os.path.join(refdata, "empty_fasta.fasta"))) == []
+    with pytest.raises(ValueError):
+        fastx.open(os.path.join(refdata, "index", "Homo_sapiens.GRCh38.pep.subset.alphabet-protein_ksize-7.bloomfilter.nodegraph"))
+    mixed = tmp_path / "lower.fa"
+    mixed.write_text(">a b c\nacgt\nACGT\n>second\nNNNN\n")
+    assert [(r["name"], r["sequence"]) for r in fastx.open(str(mixed))] == [("a b c", "acgtACGT"), ("second", "NNNN")]
+    names, flat, offsets = next(fastx.read_batches(str(mixed)))
+    assert names == ["a b c", "second"] and flat.tobytes() == b"acgtACGTNNNN" and offsets.tolist() == [0, 8, 12]
+    batches = list(fastx.read_batches(fq, max_records=10))
+    assert [len(b[0]) for b in batches] == [10, 10, 3]
+
+
+def golden_rows(path):
+    """Rows as Translate produces them (float / NaN jaccard, int / NaN n_kmers), from a golden CSV."""
+    df = pd.read_csv(path, keep_default_na=True, float_precision="round_trip")
+    rows = []
+    for t in df.itertuples():
+        j = float(t.jaccard_in_peptide_db)
+        n = t.n_kmers
+        rows.append([t.read_id, j, (np.nan if (isinstance(n, float) and math.isnan(n)) else int(n)), t.category,
+                     int(t.translation_frame), t.filename])
+    return rows
+
+
+@pytest.mark.parametrize("tag,alphabet,ksize", [("n22_protein7", "protein", 7), ("n22_dayhoff12", "dayhoff", 12),
+                                                ("synth_protein7", "protein", 7), ("synth_hp21", "hp", 21)])
+def test_create_save_summary_against_reference_outputs(golden_dir, tmp_path, tag, alphabet, ksize):
+    """CSV text and JSON summary written by the unmodified reference CLI (tests/golden/ref_cli) from the same rows."""
+    ref_csv = os.path.join(golden_dir, "ref_cli", tag + ".csv")
+    ref_json = json.load(open(os.path.join(golden_dir, "ref_cli", tag + ".json")))
+    rows = golden_rows(ref_csv)
+    out_csv, out_json, out_pq = tmp_path / "o.csv", tmp_path / "o.json", tmp_path / "o.parquet"
+    summary = CreateSaveSummary([ref_json["input_files"][0]], str(out_csv), str(out_pq), str(out_json),
+                                ref_json["peptide_bloom_filter"], alphabet, ksize, ref_json["jaccard_threshold"], rows)
+    summary.maybe_write_csv()
+    summary.maybe_write_parquet()
+    summary.maybe_write_json_summary()
+    assert out_csv.read_text() == open(ref_csv).read()
+    got = json.load(open(out_json))
+    assert got == ref_json
+    pd.testing.assert_frame_equal(pd.read_parquet(out_pq), pd.read_csv(ref_csv))
+
+
+def test_json_summary_kat_and_empty(golden_dir, tmp_path):
+    # tests/test_create_save_summary.py:193-261 known answers for the 23 golden reads, protein k=7
+    ref = json.load(open(os.path.join(golden_dir, "ref_cli", "n22_protein7.json")))
+    assert ref["categorization_counts"]["Coding"] == 3 and ref["categorization_counts"]["Non-coding"] == 14
+    assert ref["jaccard_info"]["count"] == 44
+    out = tmp_path / "empty.json"
+    s = CreateSaveSummary(["empty_fasta.fasta"], None, None, str(out), "f.nodegraph", "protein", 7, 0.5, [])
+    s.maybe_write_csv()
+    s.maybe_write_parquet()
+    summary = s.maybe_write_json_summary()
+    assert summary["jaccard_info"] == {"count": 0, "mean": None, "std": None, "min": None, "25%": None, "50%": None,
+                                       "75%": None, "max": None}
+    assert summary["categorization_counts"]["Coding"] == 0 and json.load(open(out)) == summary
+
+
+def test_cli_wiring_errors():
+    from orpheum_b200 import commandline, translate
+
+    runner = CliRunner()
+    assert runner.invoke(commandline.cli, ["--help"]).exit_code == 0
+    assert runner.invoke(commandline.cli, ["translate", "--help"]).exit_code == 0
+    assert runner.invoke(commandline.cli, ["index", "--help"]).exit_code == 0
+    r = runner.invoke(translate.cli, ["--jaccard-threshold", "3.14", "pep.fa", "reads.fq"])
+    assert r.exit_code == 2
+    assert "--jaccard-threshold needs to be a number between 0 and 1, but 3.14 was provided" in r.output
+    r = runner.invoke(translate.cli, ["--jaccard-threshold", "beyonce", "pep.fa", "reads.fq"])
+    assert r.exit_code == 2 and "'beyonce' is not a valid float" in r.output
+    r = runner.invoke(translate.cli, ["--long-reads", "pep.fa", "reads.fq"])
+    assert isinstance(r.exception, NotImplementedError)
