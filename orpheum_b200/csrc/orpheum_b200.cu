@@ -85,7 +85,11 @@ struct orph_ctx {
     DevBuf task_queue;           // uint32 (read << 3 | frame), up to 6 per read
     DevBuf needs_bytes;          // uint8 per read (ASCII input)
     DevBuf packed;               // 2-bit stream built from ASCII input
-    DevBuf in_reads, in_offsets, out_results;  // staging for the host-buffer entry points
+    DevBuf in_reads, in_offsets, out_results;  // staging for the index build
+    DevBuf in_reads2[2], in_offsets2[2], out_results2[2];  // double-buffered staging of orph_score_reads
+    cudaStream_t s_in = nullptr, s_out = nullptr;        // copy streams of the host-buffer pipeline
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_kernels[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    bool pipe_ready = false;
     DevBuf misc;                 // small transfers (hash batches, ...)
     bool timing = false;
     struct Interval { cudaEvent_t a, b; int id; };
@@ -202,8 +206,18 @@ extern "C" void orph_ctx_destroy(orph_ctx *ctx)
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf *b : {&ctx->counters, &ctx->queue, &ctx->bytes_queue, &ctx->task_queue, &ctx->needs_bytes, &ctx->packed, &ctx->in_reads,
-                      &ctx->in_offsets, &ctx->out_results, &ctx->misc, &ctx->seen})
+                      &ctx->in_offsets, &ctx->out_results, &ctx->misc, &ctx->seen, &ctx->in_reads2[0], &ctx->in_reads2[1],
+                      &ctx->in_offsets2[0], &ctx->in_offsets2[1], &ctx->out_results2[0], &ctx->out_results2[1]})
         b->release();
+    if (ctx->pipe_ready) {
+        cudaStreamDestroy(ctx->s_in);
+        cudaStreamDestroy(ctx->s_out);
+        for (int b = 0; b < 2; b++) {
+            cudaEventDestroy(ctx->ev_in[b]);
+            cudaEventDestroy(ctx->ev_kernels[b]);
+            cudaEventDestroy(ctx->ev_out[b]);
+        }
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -854,6 +868,10 @@ extern "C" int orph_score_reads_device(orph_ctx *ctx, const orph_filter *f, cons
     return ORPH_OK;
 }
 
+// Host-buffer entry point.  The batch is cut into chunks that flow through a three-stage pipeline on three
+// streams -- H2D of chunk c+1, kernels of chunk c and D2H of chunk c-1 overlap (PCIe is full duplex) -- with
+// double-buffered device staging.  With pinned host memory the call is bound by the larger of the H2D time
+// and the kernel time instead of their sum.
 extern "C" int orph_score_reads(orph_ctx *ctx, const orph_filter *f, const void *reads, int reads_format,
                                 const uint64_t *offsets, uint64_t n_reads, const uint8_t lut[256], double jaccard_threshold,
                                 orph_read_result *out)
@@ -863,50 +881,87 @@ extern "C" int orph_score_reads(orph_ctx *ctx, const orph_filter *f, const void 
     if (n_reads == 0) return ORPH_OK;
     DeviceGuard guard(ctx->device);
     cudaStream_t s = ctx->stream;
-    // chunks bounded by reads and by bases so that scratch stays modest
-    const uint64_t kMaxChunkReads = 1ULL << 24;
-    const uint64_t kMaxChunkBases = 1ULL << 31;
-    uint32_t status_bits = 0;
+    if (!ctx->pipe_ready) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) {
+            CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_in[b], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_kernels[b], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_out[b], cudaEventDisableTiming));
+        }
+        ctx->pipe_ready = true;
+    }
+    // chunk boundaries: <= 2^20 reads and <= 2^28 bases each (a single longer read still forms a chunk)
+    const uint64_t kMaxChunkReads = 1ULL << 20, kMaxChunkBases = 1ULL << 28;
     uint64_t lo = 0;
+    int c = 0;
+    bool used[2] = {false, false};
     while (lo < n_reads) {
-        uint64_t hi = std::min(n_reads, lo + kMaxChunkReads);
-        while (hi > lo + 1 && offsets[hi] - offsets[lo] > kMaxChunkBases) hi = lo + (hi - lo) / 2;
-        const uint64_t m = hi - lo;
-        uint32_t max_len = 0;
-        for (uint64_t r = lo; r < hi; r++) {
-            if (offsets[r + 1] < offsets[r]) return fail(ORPH_E_INVALID, "orph_score_reads: offsets are not monotonic at read %llu", (unsigned long long)r);
-            const uint64_t L = offsets[r + 1] - offsets[r];
-            if (L > max_len) max_len = (uint32_t)std::min<uint64_t>(L, 0xFFFFFFFFu);
+        // one pass over this chunk's offsets (overlaps the GPU work of the previous chunks): extent, validity, longest read
+        uint64_t hi = lo;
+        uint32_t max_len = 1;
+        bool bad = false;
+        while (hi < n_reads && hi - lo < kMaxChunkReads) {
+            if (offsets[hi + 1] < offsets[hi]) { bad = true; break; }
+            if (hi > lo && offsets[hi + 1] - offsets[lo] > kMaxChunkBases) break;
+            max_len = (uint32_t)std::max<uint64_t>(max_len, std::min<uint64_t>(offsets[hi + 1] - offsets[hi], ORPH_MAX_READ_LEN + 1));
+            hi++;
+        }
+        if (bad) {
+            cudaDeviceSynchronize();
+            return fail(ORPH_E_INVALID, "orph_score_reads: offsets are not monotonic at read %llu", (unsigned long long)hi);
         }
         if (max_len > ORPH_MAX_READ_LEN) max_len = ORPH_MAX_READ_LEN;  // over-long reads are reported through the status
-        if (max_len == 0) max_len = 1;
-        if ((rc = ctx->in_offsets.ensure((m + 1) * 8)) != ORPH_OK) return rc;
-        if ((rc = ctx->out_results.ensure(m * sizeof(orph_read_result))) != ORPH_OK) return rc;
-        CUDA_TRY(cudaMemcpyAsync(ctx->in_offsets.p, offsets + lo, (m + 1) * 8, cudaMemcpyHostToDevice, s));
+        const uint64_t m = hi - lo;
+        const int b = c & 1;
         const uint64_t b0 = offsets[lo], b1 = offsets[hi];
+        // the staging buffers of slot b are free once the kernels (inputs) and the D2H (results) of chunk c-2 are done
+        if (used[b]) {
+            CUDA_TRY(cudaStreamWaitEvent(ctx->s_in, ctx->ev_kernels[b], 0));
+            CUDA_TRY(cudaEventSynchronize(ctx->ev_out[b]));  // also bounds how far the host runs ahead
+        }
+        if ((rc = ctx->in_offsets2[b].ensure((m + 1) * 8)) != ORPH_OK) return rc;
+        if ((rc = ctx->out_results2[b].ensure(m * sizeof(orph_read_result))) != ORPH_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(ctx->in_offsets2[b].p, offsets + lo, (m + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        const uint8_t *d_ascii = nullptr;
+        const uint64_t *d_packed = nullptr;
+        uint64_t pbase0 = 0, n_ascii = 0;
         if (reads_format == ORPH_READS_ASCII) {
-            const uint64_t nbytes = b1 - b0;
-            if ((rc = ctx->in_reads.ensure(nbytes + 64)) != ORPH_OK) return rc;
-            if (nbytes) CUDA_TRY(cudaMemcpyAsync(ctx->in_reads.p, (const uint8_t *)reads + b0, nbytes, cudaMemcpyHostToDevice, s));
-            rc = score_device_impl(ctx, f, (const uint8_t *)ctx->in_reads.p, b0, nullptr, 0, nbytes, (const uint64_t *)ctx->in_offsets.p, m,
-                                   max_len, lut, jaccard_threshold, (orph_read_result *)ctx->out_results.p);
+            n_ascii = b1 - b0;
+            if ((rc = ctx->in_reads2[b].ensure(n_ascii + 64)) != ORPH_OK) return rc;
+            if (n_ascii) CUDA_TRY(cudaMemcpyAsync(ctx->in_reads2[b].p, (const uint8_t *)reads + b0, n_ascii, cudaMemcpyHostToDevice, ctx->s_in));
+            d_ascii = (const uint8_t *)ctx->in_reads2[b].p;
         } else {
             const uint64_t w0 = b0 / 32, w1 = (b1 + 31) / 32;
-            if ((rc = ctx->in_reads.ensure((w1 - w0 + 2) * 8)) != ORPH_OK) return rc;
-            if (w1 > w0) CUDA_TRY(cudaMemcpyAsync(ctx->in_reads.p, (const uint64_t *)reads + w0, (w1 - w0) * 8, cudaMemcpyHostToDevice, s));
-            rc = score_device_impl(ctx, f, nullptr, 0, (const uint64_t *)ctx->in_reads.p, w0 * 32, 0, (const uint64_t *)ctx->in_offsets.p, m,
-                                   max_len, lut, jaccard_threshold, (orph_read_result *)ctx->out_results.p);
+            if ((rc = ctx->in_reads2[b].ensure((w1 - w0 + 2) * 8)) != ORPH_OK) return rc;
+            if (w1 > w0) CUDA_TRY(cudaMemcpyAsync(ctx->in_reads2[b].p, (const uint64_t *)reads + w0, (w1 - w0) * 8, cudaMemcpyHostToDevice, ctx->s_in));
+            d_packed = (const uint64_t *)ctx->in_reads2[b].p;
+            pbase0 = w0 * 32;
         }
-        if (rc != ORPH_OK) return rc;
-        CUDA_TRY(cudaMemcpyAsync(out + lo, ctx->out_results.p, m * sizeof(orph_read_result), cudaMemcpyDeviceToHost, s));
-        ScoreCounters c;
-        CUDA_TRY(cudaMemcpyAsync(&c, ctx->counters.p, sizeof(c), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaStreamSynchronize(s));
-        status_bits |= c.status;
+        CUDA_TRY(cudaEventRecord(ctx->ev_in[b], ctx->s_in));
+        CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_in[b], 0));
+        if (used[b]) CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_out[b], 0));
+        rc = score_device_impl(ctx, f, d_ascii, b0, d_packed, pbase0, n_ascii, (const uint64_t *)ctx->in_offsets2[b].p, m, max_len, lut,
+                               jaccard_threshold, (orph_read_result *)ctx->out_results2[b].p);
+        if (rc != ORPH_OK) {
+            cudaDeviceSynchronize();
+            return rc;
+        }
+        CUDA_TRY(cudaEventRecord(ctx->ev_kernels[b], s));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->ev_kernels[b], 0));
+        CUDA_TRY(cudaMemcpyAsync(out + lo, ctx->out_results2[b].p, m * sizeof(orph_read_result), cudaMemcpyDeviceToHost, ctx->s_out));
+        CUDA_TRY(cudaEventRecord(ctx->ev_out[b], ctx->s_out));
+        used[b] = true;
         lo = hi;
+        c++;
     }
+    ScoreCounters counters;
+    CUDA_TRY(cudaMemcpyAsync(&counters, ctx->counters.p, sizeof(counters), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_out));
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_in));
     CUDA_TRY(cudaMemsetAsync((uint8_t *)ctx->counters.p + offsetof(ScoreCounters, status), 0, sizeof(uint32_t), s));
-    return status_to_code(status_bits);
+    return status_to_code(counters.status);
 }
 
 extern "C" double orph_jaccard(const orph_read_result *r, int frame_index)
