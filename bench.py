@@ -111,7 +111,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.005)
 
     def __enter__(self):
         if self._nv is not None:
@@ -191,18 +191,11 @@ def run_reference(args):
     }))
 
 
-class CudaArrayView:
-    """Expose a raw device pointer to torch (for the NCCL broadcast of the filter)."""
-
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-
-
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from orpheum_b200 import _lib, build, gpu, sequence_encodings as enc
+    from orpheum_b200 import _lib, build, gpu, parallel, sequence_encodings as enc
 
     build.build()
     rank = int(os.environ.get("RANK", "0"))
@@ -230,10 +223,7 @@ def run_ours(args):
     ctx.synchronize()
     t_build = time.perf_counter() - t_build
     if world > 1:
-        ptr, nbytes, _ = graph.device_buffer()
-        view = torch.as_tensor(CudaArrayView(ptr, nbytes), device=dev)
-        dist.broadcast(view, src=0)
-        torch.cuda.synchronize()
+        parallel.broadcast_filter(graph, src=0)
     fill = graph.n_occupied(0) / graph.hashsizes()[0]
 
     # ---- device-resident inputs (kernel-level number) ----
@@ -286,6 +276,18 @@ def run_ours(args):
     parity = None
     pmin_mean = None
     cpu = None
+    if rank != 0:
+        # every rank checks a prefix of its own shard against the oracle
+        from oracle import oracle as orc
+
+        n_chk = min(20_000, args.reads)
+        _, ora = time_oracle(args, oracle_filter(args, residues, poffs), flat, offsets, n_chk, 2)
+        sub, scored = res_dev[:n_chk], ora["n_kmers"] >= 0
+        ok = bool((sub["category"].astype(np.int64) == ora["category"]).all()
+                  and (sub["n_kmers"][scored] == ora["n_kmers"][scored]).all()
+                  and (sub["n_hits"][scored] == ora["n_hits"][scored]).all())
+        if not ok:
+            raise SystemExit(f"bench: rank {rank}: GPU results differ from the oracle on the checked prefix")
     if rank == 0:
         from oracle import oracle as orc
 
