@@ -669,7 +669,7 @@ static int launch_score_tasks(orph_ctx *ctx, const ScoreParams &P_in, uint32_t t
                               orph_read_result *d_out)
 {
     ScoreParams P = P_in;
-    P.read_words = (2 * thread_len + 62) / 32 + 2;  // words of the longest admissible read + one zero word
+    P.read_words = (2 * thread_len + 10) / 32 + 2;  // aligned strand words incl. the word the last 30-bit refill may touch
     const size_t smem = (size_t)kTaskBlock * (kSeenWords64 * 8 + P.read_words * 4);
     auto kern = score_tasks_kernel<K>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -89,29 +89,41 @@ struct KmerWindow {
     }
 };
 
-// one thread's view of its read: 32-bit words of the 2-bit stream in a shared-memory column
-struct ReadColumn {
-    const uint32_t *col;  // word t at col[t * kTaskBlock]
-    uint32_t bit0;        // bit of base 0 inside word 0
-    // encoded residue i of the frame that starts at base p0 and advances by dp (= +3 forward, -3 reverse strand)
-    __device__ __forceinline__ uint32_t residue(const uint8_t *lut, int p0, int dp, int i) const
+// One thread's strand, staged in shared memory: the bases of the strand the frame lives on (the read itself
+// or its reverse complement), re-aligned so that base 0 sits at bit 0 of word 0.  Word t at col[t * kTaskBlock].
+// With the strand materialised every frame is a forward walk: residue i of frame phase ph is the codon at
+// bits [2*ph + 6*i, +6), looked up in ONE table (forward codon x alphabet).
+struct StrandColumn {
+    const uint32_t *col;
+    // 32 bits of the strand starting at `bit`
+    __device__ __forceinline__ uint32_t window(uint32_t bit) const
     {
-        const uint32_t bit = bit0 + 2u * (uint32_t)(p0 + dp * i);
         const uint32_t wi = bit >> 5;
-        const uint32_t c = __funnelshift_r(col[wi * kTaskBlock], col[(wi + 1) * kTaskBlock], bit & 31u) & 63u;
-        return lut[c];
+        return __funnelshift_r(col[wi * kTaskBlock], col[(wi + 1) * kTaskBlock], bit & 31u);
+    }
+    __device__ __forceinline__ uint32_t residue(const uint8_t *lut, uint32_t phase, uint32_t i) const
+    {
+        return lut[window(2u * phase + 6u * i) & 63u];
     }
 };
+
+// reverse complement of 16 packed bases: reverse the 2-bit fields, complement = code ^ 2
+__device__ __forceinline__ uint32_t revcomp_word(uint32_t x)
+{
+    uint32_t y = __brev(x);
+    y = ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
+    return y ^ 0xAAAAAAAAu;
+}
 
 // Exact answer behind a seen-filter alarm: does the k-mer ending at residue s (window `cur`) also end
 // at an earlier residue of the same frame?  Walks backwards, so a tandem repeat answers after one period.
 template <int K>
-__device__ __forceinline__ bool kmer_seen_before(const ReadColumn &rc, const uint8_t *lut, int p0, int dp, int s,
+__device__ __forceinline__ bool kmer_seen_before(const StrandColumn &sc, const uint8_t *lut, uint32_t phase, int s,
                                                  const KmerWindow<K> &cur)
 {
     KmerWindow<K> win = cur;
     for (int e = s - 1; e >= K - 1; e--) {
-        win.push_front(rc.residue(lut, p0, dp, e - K + 1));
+        win.push_front(sc.residue(lut, phase, (uint32_t)(e - K + 1)));
         if (win.equals(cur)) return true;
     }
     return false;
@@ -123,36 +135,44 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
                    uint64_t base0, const uint32_t *__restrict__ tasks, ScoreCounters *__restrict__ counters,
                    orph_read_result *__restrict__ out)
 {
-    constexpr int kWarps = kTaskBlock / 32;
-    extern __shared__ __align__(16) uint8_t dyn_smem[];  // [seen: 16 u64 x 256][read words: P.read_words u32 x 256]
+    extern __shared__ __align__(16) uint8_t dyn_smem[];  // [seen: 16 u64 x 256][strand words: P.read_words u32 x 256]
     __shared__ FilterDev sF;
-    __shared__ uint8_t lut_fwd[64], lut_rev[64];
+    __shared__ uint8_t lut_fwd[64];
     __shared__ uint16_t s_min_hits[kThreadMaxLen / 3 + 2];
-    __shared__ unsigned long long q_hash[kWarps][64];
-    __shared__ uint8_t q_lane[kWarps][64];
-    __shared__ uint32_t s_hits[kWarps][32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     stage_filter(&sF, P.F);
     if (threadIdx.x < 64) {
-        const int t = threadIdx.x, b0 = t & 3, b1 = (t >> 2) & 3, b2 = t >> 4;
-        lut_fwd[t] = P.lut[translate_codes(b0, b1, b2)];
-        lut_rev[t] = P.lut[translate_codes(b2 ^ 2, b1 ^ 2, b0 ^ 2)];
+        const int t = threadIdx.x;
+        lut_fwd[t] = P.lut[translate_codes(t & 3, (t >> 2) & 3, t >> 4)];
     }
     const double thr = P.jaccard_threshold;
     for (uint32_t n = threadIdx.x; n <= kThreadMaxLen / 3 + 1; n += blockDim.x)
         s_min_hits[n] = n ? (uint16_t)min_hits_for(n, thr) : (uint16_t)1;
     __syncthreads();
     const bool force_exact = P.force_exact != 0;
-    const uint32_t n_tables = sF.n_tables;
-    const bool single_table = n_tables == 1;
-    // table 0 is probed once per k-mer: keep its description in registers
-    const uint64_t t0_size = sF.size[0], t0_magic = sF.magic[0];
-    const uint8_t *t0_table = sF.table[0];
-    const bool t0_small = sF.small != 0;
+    const uint32_t n_tables = P.F.n_tables;
+    const bool four_tables = n_tables == 4;
+    const bool small = P.F.small != 0;
+    // bin of hash h in table T (static index: the geometry comes straight from the constant bank)
+#define ORPH_BIN(T, h, out)                                                                   \
+    {                                                                                         \
+        const uint64_t q__ = __umul64hi((h), P.F.magic[T]);                                   \
+        if (small) {                                                                          \
+            const uint32_t p__ = (uint32_t)P.F.size[T];                                       \
+            uint32_t r__ = (uint32_t)(h) - (uint32_t)q__ * p__;                               \
+            if (r__ >= p__) r__ -= p__;                                                       \
+            (out) = r__;                                                                      \
+        } else {                                                                              \
+            uint64_t r__ = (h) - q__ * P.F.size[T];                                           \
+            if (r__ >= P.F.size[T]) r__ -= P.F.size[T];                                       \
+            (out) = r__;                                                                      \
+        }                                                                                     \
+    }
     const uint32_t n_tasks = counters->n_tasks;
     unsigned long long *seen = reinterpret_cast<unsigned long long *>(dyn_smem) + threadIdx.x;
-    uint32_t *rd_col = reinterpret_cast<uint32_t *>(dyn_smem + (size_t)kSeenWords64 * 8 * kTaskBlock) + threadIdx.x;
-    const uint32_t read_words = P.read_words;
+    uint32_t *strand = reinterpret_cast<uint32_t *>(dyn_smem + (size_t)kSeenWords64 * 8 * kTaskBlock) + threadIdx.x;
+    const uint32_t strand_words = P.read_words;
+    const StrandColumn sc{strand};
 
     while (true) {
         uint32_t base = 0;
@@ -171,133 +191,96 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
         }
         const uint32_t phase = f >= 3 ? f - 3 : f;
         if (valid) plen = (L - phase) / 3;
-        const int p0 = f < 3 ? (int)phase : (int)L - 3 - (int)phase, dp = f < 3 ? 3 : -3;
-        const uint8_t *lut = f < 3 ? lut_fwd : lut_rev;
-        // stage this read's words (plus one zero word) into the thread's shared-memory column
-        const uint64_t bitpos = 2 * (o0 - base0);
-        const uint32_t bit0 = (uint32_t)(bitpos & 31);
+        // ---- stage the strand: aligned copy of the read (frames 1..3) or of its reverse complement (-1..-3)
         {
+            const uint64_t bitpos = 2 * (o0 - base0);
+            const uint32_t bit0 = (uint32_t)(bitpos & 31);
             const uint32_t *src = packed32 + (bitpos >> 5);
-            const uint32_t n_words = valid ? (bit0 + 2 * L + 31) / 32 : 0;
-            for (uint32_t t = 0; t < read_words; t++) rd_col[t * kTaskBlock] = t < n_words ? __ldg(src + t) : 0u;
+            const uint32_t n_src = valid ? (bit0 + 2 * L + 31) / 32 : 0;  // source words that hold bases of this read
+            auto src_word = [&](uint32_t i) { return i < n_src ? __ldg(src + i) : 0u; };
+            // 32 bits of the read starting at (possibly negative) read-relative bit `start`
+            auto read_bits = [&](int start) {
+                const uint32_t a = bit0 + (uint32_t)(start > 0 ? start : 0);
+                const uint32_t v = __funnelshift_r(src_word(a >> 5), src_word((a >> 5) + 1), a & 31u);
+                return start >= 0 ? v : v << (uint32_t)(-start);
+            };
+            const uint32_t n_need = valid ? (2 * L + 31) / 32 : 0;
+            for (uint32_t t = 0; t < strand_words; t++) {
+                uint32_t w = 0;
+                if (t < n_need) w = f < 3 ? read_bits((int)(32 * t)) : revcomp_word(read_bits(2 * (int)L - 32 * (int)(t + 1)));
+                strand[t * kTaskBlock] = w;
+            }
         }
-        const ReadColumn rc{rd_col, bit0};
         KmerWindow<K> win;
         win.clear();
 #pragma unroll
         for (uint32_t w = 0; w < kSeenWords64; w++) seen[w * kTaskBlock] = 0ull;
-        s_hits[warp][lane] = 0;
-        uint32_t nd = 0, nh_direct = 0, qlen = 0;
+        uint32_t nd = 0, nh = 0;
         const uint32_t max_plen = __reduce_max_sync(0xffffffffu, plen);
         __syncwarp();
 
-        // Software pipeline.  Iteration s: (1) if 32 survivors are queued, issue their table 1..3 probes;
-        // (2) roll in residue s (fetched one iteration ahead), hash k-mer s, issue its table-0 probe, update
-        // the seen filter; (3) consume the probes of step 1; (4) consume the table-0 probe of k-mer s-1 and
-        // queue it if it survived.  Every global load has a full hash between issue and use.
-        bool prev_new = false;
+        // Software pipeline over residues.  Iteration s: (A) consume the table 1..3 probes of k-mer s-2;
+        // (B) the table-0 probe of k-mer s-1 has landed: if it hit, issue its table 1..3 probes; (C) roll in
+        // residue s, hash k-mer s, issue its table-0 probe, update the seen filter.  Every gather has a whole
+        // iteration between issue and use; nothing is staged in shared memory, hits are counted in a register.
+        bool prev_new = false, pend = false;
         uint64_t prev_h = 0;
         uint32_t prev_v0 = 0, prev_sh = 0;
-        uint32_t res_next = plen ? rc.residue(lut, p0, dp, 0) : 0u;
-        for (uint32_t s = 0; s <= max_plen; s++) {
-            // (1)
-            const bool draining = !single_table && qlen >= 32;
-            uint32_t d_hit = 0, d_owner = 0;
-            uint64_t d_b1 = 0, d_b2 = 0, d_b3 = 0;
-            uint32_t d_v1 = 0, d_v2 = 0, d_v3 = 0;
-            bool d_generic = false;
-            uint64_t d_h = 0;
-            if (draining) {
-                qlen -= 32;
-                d_h = q_hash[warp][qlen + lane];
-                d_owner = q_lane[warp][qlen + lane];
-                if (n_tables == 4) {
-                    d_b1 = filter_bin(sF, 1, d_h); d_b2 = filter_bin(sF, 2, d_h); d_b3 = filter_bin(sF, 3, d_h);
-                    d_v1 = ld_table_byte(sF.table[1] + (d_b1 >> 3));
-                    d_v2 = ld_table_byte(sF.table[2] + (d_b2 >> 3));
-                    d_v3 = ld_table_byte(sF.table[3] + (d_b3 >> 3));
+        uint32_t pend_v1 = 0, pend_v2 = 0, pend_v3 = 0, pend_sh = 0;
+        uint32_t win32 = 0, in_win = 5;  // 5 codons (30 bits) are fetched at a time, uniformly across the warp
+        for (uint32_t s = 0; s < max_plen + 2; s++) {
+            // (A)
+            if (pend) nh += (pend_v1 >> (pend_sh & 7u)) & (pend_v2 >> ((pend_sh >> 3) & 7u)) & (pend_v3 >> (pend_sh >> 6)) & 1u;
+            pend = false;
+            // (B)
+            if (prev_new && ((prev_v0 >> prev_sh) & 1u)) {
+                if (n_tables == 1) {
+                    nh += 1;
+                } else if (four_tables) {
+                    uint64_t b1, b2, b3;
+                    ORPH_BIN(1, prev_h, b1);
+                    ORPH_BIN(2, prev_h, b2);
+                    ORPH_BIN(3, prev_h, b3);
+                    pend_v1 = ld_table_byte(P.F.table[1] + (b1 >> 3));
+                    pend_v2 = ld_table_byte(P.F.table[2] + (b2 >> 3));
+                    pend_v3 = ld_table_byte(P.F.table[3] + (b3 >> 3));
+                    pend_sh = ((uint32_t)b1 & 7u) | (((uint32_t)b2 & 7u) << 3) | (((uint32_t)b3 & 7u) << 6);
+                    pend = true;
                 } else {
-                    d_generic = true;
+                    nh += filter_contains_rest(sF, prev_h) ? 1u : 0u;
                 }
             }
-            // (2)
-            bool cur_new = false;
-            uint64_t h = 0;
-            uint32_t v0 = 0, sh = 0;
+            // (C)
+            prev_new = false;
+            if (in_win == 5) {
+                win32 = sc.window(2u * phase + 6u * s);
+                in_win = 0;
+            }
+            const uint32_t codon = (win32 >> (6u * in_win)) & 63u;
+            in_win++;
             if (s < plen) {
-                win.push(res_next);
-                if (s + 1 < plen) res_next = rc.residue(lut, p0, dp, (int)s + 1);
+                win.push(lut_fwd[codon]);
                 if (s + 1 >= (uint32_t)K) {
-                    h = win.hash();
+                    const uint64_t h = win.hash();
                     uint64_t bin0;
-                    {
-                        const uint64_t q = __umul64hi(h, t0_magic);
-                        if (t0_small) {
-                            uint32_t rr = (uint32_t)h - (uint32_t)q * (uint32_t)t0_size;
-                            if (rr >= (uint32_t)t0_size) rr -= (uint32_t)t0_size;
-                            bin0 = rr;
-                        } else {
-                            uint64_t rr = h - q * t0_size;
-                            if (rr >= t0_size) rr -= t0_size;
-                            bin0 = rr;
-                        }
-                    }
-                    v0 = ld_table_byte(t0_table + (bin0 >> 3));
-                    sh = (uint32_t)bin0 & 7u;
+                    ORPH_BIN(0, h, bin0);
+                    prev_v0 = ld_table_byte(P.F.table[0] + (bin0 >> 3));
+                    prev_sh = (uint32_t)bin0 & 7u;
+                    prev_h = h;
                     // seen filter: word chosen by 4 hash bits, three bit positions inside it by 18 more
                     const uint32_t hw = (uint32_t)(h >> 32);
                     const unsigned long long bits = (1ull << (hw & 63u)) | (1ull << ((hw >> 6) & 63u)) | (1ull << ((hw >> 12) & 63u));
                     unsigned long long *slot = seen + ((hw >> 18) & (kSeenWords64 - 1)) * kTaskBlock;
                     const unsigned long long old = *slot;
                     *slot = old | bits;
-                    cur_new = true;
-                    if ((old & bits) == bits || force_exact) cur_new = !kmer_seen_before<K>(rc, lut, p0, dp, (int)s, win);
-                    nd += cur_new ? 1u : 0u;
+                    prev_new = true;
+                    if ((old & bits) == bits || force_exact) prev_new = !kmer_seen_before<K>(sc, lut_fwd, phase, (int)s, win);
+                    nd += prev_new ? 1u : 0u;
                 }
             }
-            // (3)
-            if (draining) {
-                if (d_generic) d_hit = filter_contains_rest(sF, d_h) ? 1u : 0u;
-                else d_hit = (d_v1 >> (d_b1 & 7)) & (d_v2 >> (d_b2 & 7)) & (d_v3 >> (d_b3 & 7)) & 1u;
-                if (d_hit) atomicAdd(&s_hits[warp][d_owner], 1u);
-                __syncwarp();
-            }
-            // (4)
-            const bool hit0 = prev_new && ((prev_v0 >> prev_sh) & 1u);
-            const uint64_t hq = prev_h;
-            prev_new = cur_new; prev_h = h; prev_v0 = v0; prev_sh = sh;
-            if (single_table) {
-                nh_direct += hit0 ? 1u : 0u;
-                continue;
-            }
-            const uint32_t m = __ballot_sync(0xffffffffu, hit0);
-            if (m) {
-                if (hit0) {
-                    const uint32_t idx = qlen + __popc(m & ((1u << lane) - 1));
-                    q_hash[warp][idx] = hq;
-                    q_lane[warp][idx] = (uint8_t)lane;
-                }
-                qlen += __popc(m);
-                __syncwarp();
-            }
         }
-        // at most 63 survivors are left: one full batch, then the remainder
-        if (qlen >= 32) {
-            qlen -= 32;
-            const uint64_t qh = q_hash[warp][qlen + lane];
-            const uint32_t ql = q_lane[warp][qlen + lane];
-            if (filter_contains_rest(sF, qh)) atomicAdd(&s_hits[warp][ql], 1u);
-        }
-        if (qlen) {
-            if ((uint32_t)lane < qlen) {
-                const uint64_t qh = q_hash[warp][lane];
-                const uint32_t ql = q_lane[warp][lane];
-                if (filter_contains_rest(sF, qh)) atomicAdd(&s_hits[warp][ql], 1u);
-            }
-        }
-        __syncwarp();
+#undef ORPH_BIN
         if (valid) {
-            const uint32_t nh = single_table ? nh_direct : s_hits[warp][lane];
             const uint32_t n = plen - (uint32_t)K + 1;
             // evaluate_is_kmer_low_complexity: n_kmers <= (len - k + 1) / 2  (translate.py:98-100), in integers
             const uint8_t cat = 2 * nd <= n ? ORPH_CAT_LOW_COMPLEXITY_PEPTIDE
