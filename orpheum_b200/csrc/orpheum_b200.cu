@@ -669,7 +669,7 @@ static int launch_score_tasks(orph_ctx *ctx, const ScoreParams &P_in, uint32_t t
                               orph_read_result *d_out)
 {
     ScoreParams P = P_in;
-    P.read_words = (2 * thread_len + 10) / 32 + 2;  // aligned strand words incl. the word the last 30-bit refill may touch
+    P.read_words = (2 * thread_len + 34) / 32 + 2;  // aligned strand words incl. the words the look-ahead window fetch may touch
     const size_t smem = (size_t)kTaskBlock * (kSeenWords64 * 8 + P.read_words * 4);
     auto kern = score_tasks_kernel<K>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

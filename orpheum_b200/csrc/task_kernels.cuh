@@ -219,65 +219,98 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
         const uint32_t max_plen = __reduce_max_sync(0xffffffffu, plen);
         __syncwarp();
 
-        // Software pipeline over residues.  Iteration s: (A) consume the table 1..3 probes of k-mer s-2;
-        // (B) the table-0 probe of k-mer s-1 has landed: if it hit, issue its table 1..3 probes; (C) roll in
-        // residue s, hash k-mer s, issue its table-0 probe, update the seen filter.  Every gather has a whole
-        // iteration between issue and use; nothing is staged in shared memory, hits are counted in a register.
-        bool prev_new = false, pend = false;
-        uint64_t prev_h = 0;
-        uint32_t prev_v0 = 0, prev_sh = 0;
-        uint32_t pend_v1 = 0, pend_v2 = 0, pend_v3 = 0, pend_sh = 0;
-        uint32_t win32 = 0, in_win = 5;  // 5 codons (30 bits) are fetched at a time, uniformly across the warp
+        // Software pipeline over residues: no result of a shared- or global-memory load is consumed in the
+        // iteration that issues it (shared-memory loads queue behind the 32-cycle gathers in the same LSU pipe,
+        // so their latency is hundreds of cycles here).  Iteration s, in program order:
+        //   (1) seen filter of k-mer s-1: its word has arrived -> store word|bits, decide new / duplicate
+        //       (exact backward walk on an alarm; `win` is still the window of k-mer s-1);
+        //   (2) consume the table 1..3 probes of k-mer s-2;
+        //   (3) table-0 probe of k-mer s-1 has arrived: if it is new and hit, issue its table 1..3 probes;
+        //   (4) push residue s (looked up during iteration s-1), hash k-mer s, issue its table-0 probe and the
+        //       load of its seen-filter word;
+        //   (5) look up residue s+1; codons come 5 at a time from a 30-bit window that is itself loaded two
+        //       iterations before it is needed.
+        bool t0_pending = false, s2_pending = false, seen_pending = false;
+        uint64_t t0_h = 0;
+        uint32_t t0_v = 0, t0_sh = 0;
+        uint32_t s2_v1 = 0, s2_v2 = 0, s2_v3 = 0, s2_sh = 0;
+        unsigned long long *seen_slot = seen;
+        unsigned long long seen_bits = 0, seen_old = 0;
+        // window state: win32 holds codons of residues [5*g, 5*g+5); raw words of the next group are fetched early
+        uint32_t win32 = sc.window(2u * phase), win_next = 0, raw_a = 0, raw_b = 0, raw_sh = 0;
+        uint32_t res_cur = lut_fwd[win32 & 63u];  // residue 0
+        uint32_t mod5 = 0;                         // s % 5, uniform
         for (uint32_t s = 0; s < max_plen + 2; s++) {
-            // (A)
-            if (pend) nh += (pend_v1 >> (pend_sh & 7u)) & (pend_v2 >> ((pend_sh >> 3) & 7u)) & (pend_v3 >> (pend_sh >> 6)) & 1u;
-            pend = false;
-            // (B)
-            if (prev_new && ((prev_v0 >> prev_sh) & 1u)) {
+            // (1)
+            bool kmer_new = false;
+            if (seen_pending) {
+                *seen_slot = seen_old | seen_bits;
+                kmer_new = true;
+                if ((seen_old & seen_bits) == seen_bits || force_exact)
+                    kmer_new = !kmer_seen_before<K>(sc, lut_fwd, phase, (int)s - 1, win);
+                nd += kmer_new ? 1u : 0u;
+                seen_pending = false;
+            }
+            // (2)
+            if (s2_pending) nh += (s2_v1 >> (s2_sh & 7u)) & (s2_v2 >> ((s2_sh >> 3) & 7u)) & (s2_v3 >> (s2_sh >> 6)) & 1u;
+            s2_pending = false;
+            // (3)
+            if (t0_pending && kmer_new && ((t0_v >> t0_sh) & 1u)) {
                 if (n_tables == 1) {
                     nh += 1;
                 } else if (four_tables) {
                     uint64_t b1, b2, b3;
-                    ORPH_BIN(1, prev_h, b1);
-                    ORPH_BIN(2, prev_h, b2);
-                    ORPH_BIN(3, prev_h, b3);
-                    pend_v1 = ld_table_byte(P.F.table[1] + (b1 >> 3));
-                    pend_v2 = ld_table_byte(P.F.table[2] + (b2 >> 3));
-                    pend_v3 = ld_table_byte(P.F.table[3] + (b3 >> 3));
-                    pend_sh = ((uint32_t)b1 & 7u) | (((uint32_t)b2 & 7u) << 3) | (((uint32_t)b3 & 7u) << 6);
-                    pend = true;
+                    ORPH_BIN(1, t0_h, b1);
+                    ORPH_BIN(2, t0_h, b2);
+                    ORPH_BIN(3, t0_h, b3);
+                    s2_v1 = ld_table_byte(P.F.table[1] + (b1 >> 3));
+                    s2_v2 = ld_table_byte(P.F.table[2] + (b2 >> 3));
+                    s2_v3 = ld_table_byte(P.F.table[3] + (b3 >> 3));
+                    s2_sh = ((uint32_t)b1 & 7u) | (((uint32_t)b2 & 7u) << 3) | (((uint32_t)b3 & 7u) << 6);
+                    s2_pending = true;
                 } else {
-                    nh += filter_contains_rest(sF, prev_h) ? 1u : 0u;
+                    nh += filter_contains_rest(sF, t0_h) ? 1u : 0u;
                 }
             }
-            // (C)
-            prev_new = false;
-            if (in_win == 5) {
-                win32 = sc.window(2u * phase + 6u * s);
-                in_win = 0;
-            }
-            const uint32_t codon = (win32 >> (6u * in_win)) & 63u;
-            in_win++;
+            t0_pending = false;
+            // (4)
             if (s < plen) {
-                win.push(lut_fwd[codon]);
+                win.push(res_cur);
                 if (s + 1 >= (uint32_t)K) {
                     const uint64_t h = win.hash();
                     uint64_t bin0;
                     ORPH_BIN(0, h, bin0);
-                    prev_v0 = ld_table_byte(P.F.table[0] + (bin0 >> 3));
-                    prev_sh = (uint32_t)bin0 & 7u;
-                    prev_h = h;
+                    t0_v = ld_table_byte(P.F.table[0] + (bin0 >> 3));
+                    t0_sh = (uint32_t)bin0 & 7u;
+                    t0_h = h;
+                    t0_pending = true;
                     // seen filter: word chosen by 4 hash bits, three bit positions inside it by 18 more
                     const uint32_t hw = (uint32_t)(h >> 32);
-                    const unsigned long long bits = (1ull << (hw & 63u)) | (1ull << ((hw >> 6) & 63u)) | (1ull << ((hw >> 12) & 63u));
-                    unsigned long long *slot = seen + ((hw >> 18) & (kSeenWords64 - 1)) * kTaskBlock;
-                    const unsigned long long old = *slot;
-                    *slot = old | bits;
-                    prev_new = true;
-                    if ((old & bits) == bits || force_exact) prev_new = !kmer_seen_before<K>(sc, lut_fwd, phase, (int)s, win);
-                    nd += prev_new ? 1u : 0u;
+                    seen_bits = (1ull << (hw & 63u)) | (1ull << ((hw >> 6) & 63u)) | (1ull << ((hw >> 12) & 63u));
+                    seen_slot = seen + ((hw >> 18) & (kSeenWords64 - 1)) * kTaskBlock;
+                    seen_old = *seen_slot;
+                    seen_pending = true;
                 }
             }
+            // (5) residue s+1
+            if (mod5 == 1) {  // fetch the raw words of the next group of five codons
+                const uint32_t bit = 2u * phase + 6u * (s + 4);
+                raw_a = strand[(bit >> 5) * kTaskBlock];
+                raw_b = strand[((bit >> 5) + 1) * kTaskBlock];
+                raw_sh = bit & 31u;
+            } else if (mod5 == 3) {
+                win_next = __funnelshift_r(raw_a, raw_b, raw_sh);
+            }
+            uint32_t codon;
+            if (mod5 == 4) {
+                win32 = win_next;
+                mod5 = 0;
+                codon = win32 & 63u;
+            } else {
+                mod5++;
+                codon = (win32 >> (6u * mod5)) & 63u;
+            }
+            res_cur = lut_fwd[codon];
         }
 #undef ORPH_BIN
         if (valid) {
