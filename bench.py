@@ -46,12 +46,18 @@ def parse_args():
     ap.add_argument("--n-tables", type=int, default=4)
     ap.add_argument("--proteins", type=int, default=20000)
     ap.add_argument("--cpu-sample", type=int, default=400_000, help="reads in the bounded CPU-baseline sample")
+    ap.add_argument("--workload", default="r150", choices=["r150", "mixed"],
+                    help="r150 = cfg2/cfg3 (fixed 150-nt reads); mixed = cfg5 (50-300 nt, homopolymers, repeats, N, short)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
 
 def workload_name(args):
+    if args.workload == "mixed":
+        return (f"cfg5: {args.reads} synthetic mixed reads/GPU (50-300 nt; 45% coding, 45% random, 4% homopolymer, 3% "
+                f"triplet repeats, 2% with N, 1% short) vs {args.proteins}-protein synthetic proteome Bloom filter, "
+                f"{args.alphabet} k={args.ksize}, tablesize {int(args.tablesize):.0e} x {args.n_tables}")
     return (f"cfg2: {args.reads} synthetic {READ_LEN}-nt reads/GPU (50% back-translated, 1% subst.) vs "
             f"{args.proteins}-protein synthetic proteome Bloom filter, {args.alphabet} k={args.ksize}, "
             f"tablesize {int(args.tablesize):.0e} x {args.n_tables}")
@@ -137,8 +143,11 @@ def make_inputs(args, rank):
     from orpheum_b200 import synth
 
     residues, poffs = synth.make_proteome(n_proteins=args.proteins, seed=1001)
-    reads2d = synth.make_reads_fixed(args.reads, residues, poffs, length=READ_LEN, seed=2002 + rank)
-    flat, offsets = synth.concat_fixed(reads2d)
+    if args.workload == "mixed":
+        flat, offsets = synth.make_reads_mixed(args.reads, residues, poffs, ksize=args.ksize, seed=5005 + rank)
+    else:
+        reads2d = synth.make_reads_fixed(args.reads, residues, poffs, length=READ_LEN, seed=2002 + rank)
+        flat, offsets = synth.concat_fixed(reads2d)
     return residues, poffs, flat, offsets
 
 
@@ -228,15 +237,19 @@ def run_ours(args):
 
     # ---- device-resident inputs (kernel-level number) ----
     packed, needs = gpu.pack_reads(flat, offsets)
-    assert not needs.any()
-    d_packed = torch.from_numpy(packed.view(np.int64)).to(dev)
     d_offsets = torch.from_numpy(offsets.view(np.int64)).to(dev)
     d_out = torch.zeros(args.reads * 32, dtype=torch.uint8, device=dev)
+    max_len = int(np.diff(offsets.astype(np.int64)).max())
+    if needs.any():
+        # reads with N / lower case cannot be 2-bit packed: the device-resident input is the ASCII stream
+        d_reads, fmt = torch.from_numpy(flat).to(dev), _lib.READS_ASCII
+    else:
+        d_reads, fmt = torch.from_numpy(packed.view(np.int64)).to(dev), _lib.READS_PACKED2
     torch.cuda.synchronize()
 
     def step_device():
-        gpu.score_reads_device(graph, d_packed.data_ptr(), d_offsets.data_ptr(), args.reads, READ_LEN, lut, thr,
-                               d_out.data_ptr(), ctx=ctx)
+        gpu.score_reads_device(graph, d_reads.data_ptr(), d_offsets.data_ptr(), args.reads, max_len, lut, thr,
+                               d_out.data_ptr(), reads_format=fmt, ctx=ctx)
 
     def barrier():
         if world > 1:
@@ -368,13 +381,14 @@ def run_ours(args):
     sf_ms, sf_n = ktimes[dominant]
     sf_ms_per_launch = sf_ms / max(1, sf_n)
     # algorithmic bytes of one score_frames launch: stream bytes of every read + 32 B per required probe
-    algo_bytes = args.reads * (STREAM_BYTES_PER_READ + 32.0 * pmin_mean)
+    stream_bytes = ((packed.nbytes if fmt == _lib.READS_PACKED2 else flat.nbytes) / args.reads) + 4 + 32
+    algo_bytes = args.reads * (stream_bytes + 32.0 * pmin_mean)
     achieved = algo_bytes / (sf_ms_per_launch * 1e-3) / 1e9
     roofline = {
         "kernel": dominant + "_kernel", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
         "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
         "ms_per_launch": sf_ms_per_launch, "share_of_step": sf_ms_per_launch / ms_per_step,
-        "algorithmic_bytes_per_read": STREAM_BYTES_PER_READ + 32.0 * pmin_mean,
+        "algorithmic_bytes_per_read": stream_bytes + 32.0 * pmin_mean,
         "probes_min_per_read": pmin_mean, "probes_max_per_read": pmax_mean,
         "probe_sectors_per_s": args.reads * pmin_mean / (sf_ms_per_launch * 1e-3),
         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items()},

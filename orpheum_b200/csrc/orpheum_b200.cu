@@ -664,26 +664,38 @@ static int launch_score_frames(orph_ctx *ctx, const ScoreParams &P, const uint32
 }
 
 template <int K>
-static int launch_score_tasks(orph_ctx *ctx, const ScoreParams &P_in, uint32_t thread_len, const uint64_t *packed,
+static int launch_score_tasks(orph_ctx *ctx, const ScoreParams &P_in, uint32_t tier_len, int long_tier, const uint64_t *packed,
                               const uint64_t *d_offsets, uint64_t pbase0, const uint32_t *tasks, ScoreCounters *counters,
                               orph_read_result *d_out)
 {
     ScoreParams P = P_in;
-    P.read_words = (2 * thread_len + 34) / 32 + 2;  // aligned strand words incl. the words the look-ahead window fetch may touch
-    const size_t smem = (size_t)kTaskBlock * (kSeenWords64 * 8 + P.read_words * 4);
+    P.read_words = (2 * tier_len + 34) / 32 + 2;  // aligned strand words incl. the words the look-ahead window fetch may touch
+    P.seen_words = long_tier ? kSeenWordsLong : kSeenWordsShort;
+    const size_t smem = (size_t)kTaskBlock * (P.seen_words * 8 + P.read_words * 4);
     auto kern = score_tasks_kernel<K>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kTaskBlock * (kSeenWordsLong * 8 + ((2 * kThreadMaxLenLong + 34) / 32 + 2) * 4))));
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTaskBlock, smem));
     if (per_sm < 1) per_sm = 1;
     {
         Timed timed(ctx, 4);
         kern<<<ctx->sm_count * per_sm, kTaskBlock, smem, ctx->stream>>>(P, reinterpret_cast<const uint32_t *>(packed), d_offsets,
-                                                                          pbase0, tasks, counters, d_out);
+                                                                          pbase0, tasks, long_tier, counters, d_out);
     }
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return ORPH_OK;
+}
+
+template <int K>
+static int launch_score_task_tiers(orph_ctx *ctx, const ScoreParams &P, uint32_t thread_len, uint32_t short_len, const uint64_t *packed,
+                                   const uint64_t *d_offsets, uint64_t pbase0, const uint32_t *tasks, ScoreCounters *counters,
+                                   orph_read_result *d_out)
+{
+    int rc = launch_score_tasks<K>(ctx, P, short_len, 0, packed, d_offsets, pbase0, tasks, counters, d_out);
+    if (rc == ORPH_OK && thread_len > short_len)
+        rc = launch_score_tasks<K>(ctx, P, thread_len, 1, packed, d_offsets, pbase0, tasks, counters, d_out);
+    return rc;
 }
 
 // k-mer sizes with a compiled thread-per-frame kernel (the defaults of every alphabet, sequence_encodings.py:402-419)
@@ -711,6 +723,7 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
     if ((rc = ctx->queue.ensure(n_reads * 4)) != ORPH_OK) return rc;
     if ((rc = ctx->bytes_queue.ensure(n_reads * 4)) != ORPH_OK) return rc;
     const uint32_t thread_len = has_task_kernel(f->ksize) && !ctx->disable_task_kernel ? std::min(bound, kThreadMaxLen) : 0u;
+    const uint32_t short_len = std::min(thread_len, kThreadMaxLenShort);
     if (thread_len && (rc = ctx->task_queue.ensure(n_reads * 6 * 4)) != ORPH_OK) return rc;
     ScoreCounters *counters = (ScoreCounters *)ctx->counters.p;
     // status is sticky across calls until orph_ctx_check; everything else restarts
@@ -726,6 +739,8 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
     P.max_len = bound;
     P.fast_max_len = fast_len;
     P.thread_max_len = thread_len;
+    P.thread_short_len = short_len;
+    P.task_capacity = (uint32_t)(n_reads * 6);
     P.force_exact = ctx->force_exact ? 1u : 0u;
 
     const uint64_t *d_packed = d_packed_in;
@@ -751,7 +766,8 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
     {
         Timed timed(ctx, 1);
         prefilter_kernel<<<grid_for(n_reads, 256, ctx->sm_count, 16), 256, 0, s>>>(
-            d_packed, d_offsets, pbase0, n_reads, d_needs, P.k, fast_len, thread_len, bound, d_out, (uint32_t *)ctx->queue.p,
+            d_packed, d_offsets, pbase0, n_reads, d_needs, P.k, fast_len, thread_len, short_len, P.task_capacity, bound, d_out,
+            (uint32_t *)ctx->queue.p,
             (uint32_t *)ctx->task_queue.p, (uint32_t *)ctx->bytes_queue.p, counters);
     }
     ctx->launches++;
@@ -761,15 +777,15 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
     if (thread_len) {
         const uint32_t *tq = (const uint32_t *)ctx->task_queue.p;
         switch (P.k) {
-        case 7: rc = launch_score_tasks<7>(ctx, P, thread_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
-        case 8: rc = launch_score_tasks<8>(ctx, P, thread_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
-        case 9: rc = launch_score_tasks<9>(ctx, P, thread_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
-        case 10: rc = launch_score_tasks<10>(ctx, P, thread_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
-        case 11: rc = launch_score_tasks<11>(ctx, P, thread_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
-        case 12: rc = launch_score_tasks<12>(ctx, P, thread_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
-        case 16: rc = launch_score_tasks<16>(ctx, P, thread_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
-        case 21: rc = launch_score_tasks<21>(ctx, P, thread_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
-        case 31: rc = launch_score_tasks<31>(ctx, P, thread_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
+        case 7: rc = launch_score_task_tiers<7>(ctx, P, thread_len, short_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
+        case 8: rc = launch_score_task_tiers<8>(ctx, P, thread_len, short_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
+        case 9: rc = launch_score_task_tiers<9>(ctx, P, thread_len, short_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
+        case 10: rc = launch_score_task_tiers<10>(ctx, P, thread_len, short_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
+        case 11: rc = launch_score_task_tiers<11>(ctx, P, thread_len, short_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
+        case 12: rc = launch_score_task_tiers<12>(ctx, P, thread_len, short_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
+        case 16: rc = launch_score_task_tiers<16>(ctx, P, thread_len, short_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
+        case 21: rc = launch_score_task_tiers<21>(ctx, P, thread_len, short_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
+        case 31: rc = launch_score_task_tiers<31>(ctx, P, thread_len, short_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
         default: rc = fail(ORPH_E_INVALID, "internal: no task kernel for k=%u", P.k); break;
         }
         if (rc != ORPH_OK) return rc;

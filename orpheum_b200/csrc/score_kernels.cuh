@@ -32,6 +32,9 @@ struct ScoreParams {
     uint32_t max_len;          // declared upper bound of read length in this batch
     uint32_t fast_max_len;     // reads longer than this skip the packed fast path
     uint32_t thread_max_len;   // reads up to this length are scored one thread per frame (0: path disabled)
+    uint32_t thread_short_len; // of those, reads up to this length use the short tier (smaller seen filter)
+    uint32_t seen_words;       // 64-bit words of the per-thread seen filter in this launch (power of two)
+    uint32_t task_capacity;    // entries in the task queue: the short tier fills it from the front, the long tier from the back
     uint32_t slots;            // dedup table slots per warp (power of two >= 128, >= 2 * max k-mers per frame)
     uint32_t pep_bytes;        // peptide buffer bytes per warp (multiple of 4, incl. kPepPad)
     uint32_t read_words;       // staged read words per warp (fast path)
@@ -44,8 +47,10 @@ struct ScoreCounters {
     uint32_t next_queue;   // dynamic work fetch
     uint32_t n_bytes;      // reads queued for score_bytes_kernel
     uint32_t next_bytes;
-    uint32_t n_tasks;      // (read, frame) tasks queued for score_tasks_kernel (thread per frame)
+    uint32_t n_tasks;      // (read, frame) tasks queued for score_tasks_kernel (thread per frame), short tier
     uint32_t next_task;
+    uint32_t n_tasks_long; // same, long tier (reads of kThreadMaxLenShort+1 .. kThreadMaxLenLong bases)
+    uint32_t next_task_long;
     uint32_t pad;
     uint32_t status;       // kStatus* bits; sticky until orph_ctx_check -- keep it last
 };
@@ -265,7 +270,8 @@ struct Planes {
 __global__ void __launch_bounds__(256)
 prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict__ offsets, uint64_t base0,
                  uint64_t n_reads, const uint8_t *__restrict__ needs_bytes, uint32_t k, uint32_t fast_max_len,
-                 uint32_t thread_max_len, uint32_t max_len, orph_read_result *__restrict__ out,
+                 uint32_t thread_max_len, uint32_t thread_short_len, uint32_t task_capacity, uint32_t max_len,
+                 orph_read_result *__restrict__ out,
                  uint32_t *__restrict__ queue, uint32_t *__restrict__ task_queue, uint32_t *__restrict__ bytes_queue,
                  ScoreCounters *__restrict__ counters)
 {
@@ -275,7 +281,7 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
         const uint64_t r = r0 + lane;
         const bool in_range = r < n_reads;
         bool to_queue = false, to_bytes = false;
-        uint32_t open_bits = 0, n_my_tasks = 0;
+        uint32_t open_bits = 0, n_my_tasks = 0, n_my_tasks_long = 0;
         if (in_range) {
             const uint64_t o0 = offsets[r], o1 = offsets[r + 1];
             const uint64_t L = o1 - o0;
@@ -361,8 +367,9 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
                     }
                     rec.flags = (uint8_t)open;
                     open_bits = open;
-                    if (L <= thread_max_len) n_my_tasks = __popc(open);  // one thread per open frame
-                    else to_queue = open != 0;                            // one warp per read
+                    if (L <= thread_short_len) n_my_tasks = __popc(open);           // one thread per open frame
+                    else if (L <= thread_max_len) n_my_tasks_long = __popc(open);  // same, long tier
+                    else to_queue = open != 0;                                      // one warp per read
                 }
             }
             // one 32-byte record per read
@@ -384,23 +391,29 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
         const uint32_t below = (1u << lane) - 1;
         if (to_queue) queue[base_q + __popc(mq & below)] = ((uint32_t)r << 6) | open_bits;
         if (to_bytes) bytes_queue[base_b + __popc(mb & below)] = (uint32_t)r;
-        // per-frame tasks: warp-wide exclusive scan of the per-read task counts, one atomic per warp
-        uint32_t incl = n_my_tasks;
+        // per-frame tasks: warp-wide scan of the per-read task counts, one atomic per warp and tier
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += up;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total) {
-            uint32_t base_t = 0;
-            if (lane == 0) base_t = atomicAdd(&counters->n_tasks, total);
-            base_t = __shfl_sync(0xffffffffu, base_t, 0) + incl - n_my_tasks;
-            uint32_t bits = n_my_tasks ? open_bits : 0u;
-            while (bits) {
-                const uint32_t f = __ffs(bits) - 1;
-                bits &= bits - 1;
-                task_queue[base_t++] = ((uint32_t)r << 3) | f;
+        for (int tier = 0; tier < 2; tier++) {
+            const uint32_t mine = tier == 0 ? n_my_tasks : n_my_tasks_long;
+            uint32_t incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total) {
+                uint32_t base_t = 0;
+                if (lane == 0) base_t = atomicAdd(tier == 0 ? &counters->n_tasks : &counters->n_tasks_long, total);
+                base_t = __shfl_sync(0xffffffffu, base_t, 0) + incl - mine;
+                uint32_t bits = mine ? open_bits : 0u;
+                while (bits) {
+                    const uint32_t f = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    // the short tier grows from the front of the queue, the long tier from the back
+                    task_queue[tier == 0 ? base_t : task_capacity - 1 - base_t] = ((uint32_t)r << 3) | f;
+                    base_t++;
+                }
             }
         }
     }

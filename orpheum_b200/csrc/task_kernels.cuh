@@ -10,7 +10,7 @@
 // at a time (tables 1..n-1), again at full occupancy.
 //
 // Distinct k-mers (kmerize returns a set, compare_kmer_content.py:116-118): each thread keeps a private
-// 1024-bit blocked three-hash "seen" filter in shared memory.  A k-mer whose three bits are not all set
+// 1024-bit (reads <= 192 nt) or 2048-bit (<= 320 nt) blocked three-hash "seen" filter in shared memory.  A k-mer whose three bits are not all set
 // is certainly new; otherwise the frame is walked backwards from the current k-mer and compared
 // byte-exactly (a tandem repeat answers after one period, a false alarm walks the whole prefix, rarely),
 // so the de-duplication is exact.
@@ -20,9 +20,11 @@
 
 namespace orph {
 
-constexpr uint32_t kThreadMaxLen = 192;  // longest read handled one-thread-per-frame
+constexpr uint32_t kThreadMaxLenShort = 192;  // short tier: 1024-bit seen filter per thread
+constexpr uint32_t kThreadMaxLenLong = 320;   // long tier: 2048-bit seen filter per thread (fewer resident blocks)
+constexpr uint32_t kThreadMaxLen = kThreadMaxLenLong;
 constexpr int kTaskBlock = 256;
-constexpr uint32_t kSeenWords64 = 16;    // 16 x 64-bit words per thread, word w of thread t at [w * kTaskBlock + t]
+constexpr uint32_t kSeenWordsShort = 16, kSeenWordsLong = 32;  // 64-bit words; word w of thread t at [w * kTaskBlock + t]
 
 // rolling window over the last K encoded residues, little-endian bytes as MurmurHash reads them
 template <int K>
@@ -132,10 +134,10 @@ __device__ __forceinline__ bool kmer_seen_before(const StrandColumn &sc, const u
 template <int K>
 __global__ void __launch_bounds__(kTaskBlock)
 score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, const uint64_t *__restrict__ offsets,
-                   uint64_t base0, const uint32_t *__restrict__ tasks, ScoreCounters *__restrict__ counters,
+                   uint64_t base0, const uint32_t *__restrict__ tasks, int long_tier, ScoreCounters *__restrict__ counters,
                    orph_read_result *__restrict__ out)
 {
-    extern __shared__ __align__(16) uint8_t dyn_smem[];  // [seen: 16 u64 x 256][strand words: P.read_words u32 x 256]
+    extern __shared__ __align__(16) uint8_t dyn_smem[];  // [seen: P.seen_words u64 x 256][strand words: P.read_words u32 x 256]
     __shared__ FilterDev sF;
     __shared__ uint8_t lut_fwd[64];
     __shared__ uint16_t s_min_hits[kThreadMaxLen / 3 + 2];
@@ -168,22 +170,24 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
             (out) = r__;                                                                      \
         }                                                                                     \
     }
-    const uint32_t n_tasks = counters->n_tasks;
+    const uint32_t n_tasks = long_tier ? counters->n_tasks_long : counters->n_tasks;
+    uint32_t *next_task = long_tier ? &counters->next_task_long : &counters->next_task;
+    const uint32_t seen_words = P.seen_words;
     unsigned long long *seen = reinterpret_cast<unsigned long long *>(dyn_smem) + threadIdx.x;
-    uint32_t *strand = reinterpret_cast<uint32_t *>(dyn_smem + (size_t)kSeenWords64 * 8 * kTaskBlock) + threadIdx.x;
+    uint32_t *strand = reinterpret_cast<uint32_t *>(dyn_smem + (size_t)seen_words * 8 * kTaskBlock) + threadIdx.x;
     const uint32_t strand_words = P.read_words;
     const StrandColumn sc{strand};
 
     while (true) {
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&counters->next_task, 32u);
+        if (lane == 0) base = atomicAdd(next_task, 32u);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n_tasks) break;
         const bool valid = base + lane < n_tasks;
         uint32_t r = 0, f = 0, L = 0, plen = 0;
         uint64_t o0 = 0;
         if (valid) {
-            const uint32_t entry = tasks[base + lane];
+            const uint32_t entry = long_tier ? tasks[P.task_capacity - 1 - (base + lane)] : tasks[base + lane];
             r = entry >> 3;
             f = entry & 7u;
             o0 = offsets[r];
@@ -213,8 +217,7 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
         }
         KmerWindow<K> win;
         win.clear();
-#pragma unroll
-        for (uint32_t w = 0; w < kSeenWords64; w++) seen[w * kTaskBlock] = 0ull;
+        for (uint32_t w = 0; w < seen_words; w++) seen[w * kTaskBlock] = 0ull;
         uint32_t nd = 0, nh = 0;
         const uint32_t max_plen = __reduce_max_sync(0xffffffffu, plen);
         __syncwarp();
@@ -287,7 +290,7 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
                     // seen filter: word chosen by 4 hash bits, three bit positions inside it by 18 more
                     const uint32_t hw = (uint32_t)(h >> 32);
                     seen_bits = (1ull << (hw & 63u)) | (1ull << ((hw >> 6) & 63u)) | (1ull << ((hw >> 12) & 63u));
-                    seen_slot = seen + ((hw >> 18) & (kSeenWords64 - 1)) * kTaskBlock;
+                    seen_slot = seen + ((hw >> 18) & (seen_words - 1)) * kTaskBlock;
                     seen_old = *seen_slot;
                     seen_pending = true;
                 }
