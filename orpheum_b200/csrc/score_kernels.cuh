@@ -298,33 +298,44 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
                 to_bytes = true;
                 rec.flags = ORPH_FLAG_BYTE_PATH;
             } else {
+                // the read as aligned 32-bit words: A[j] = bases [16j, 16j+16), one funnel shift each
                 const uint64_t bitpos = 2 * (o0 - base0);
-                const uint64_t w0 = bitpos >> 6;
-                const uint32_t sh = (uint32_t)(bitpos & 63);
-                const uint32_t n_chunks = (uint32_t)((L + 31) / 32);
-                const uint64_t last_word = (2 * (o1 - base0) - 1) >> 6;  // last word holding a base of this read
-                // aligned word m of the read = bases [32m, 32m+32)
-                uint64_t raw_cur = packed[w0];
-                uint64_t raw_nxt = (w0 + 1 <= last_word) ? packed[w0 + 1] : 0;
-                auto align = [&](uint64_t a, uint64_t b) { return sh ? (a >> sh) | (b << (64 - sh)) : a; };
-                uint64_t cur = align(raw_cur, raw_nxt);
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(packed) + (bitpos >> 5);
+                const uint32_t sh = (uint32_t)(bitpos & 31);
+                const uint32_t n_src = (sh + 2 * (uint32_t)L + 31) / 32;  // source words holding bases of this read
+                const uint32_t n_chunks = (uint32_t)((L + 31) / 32);      // 64-bit chunks of 32 bases
+                uint32_t s_prev = src[0];
+                uint32_t next_i = 1;
+                auto next_aligned = [&]() {
+                    const uint32_t s_next = next_i < n_src ? src[next_i] : 0u;
+                    const uint32_t a = next_i <= n_src ? __funnelshift_r(s_prev, s_next, sh) : 0u;
+                    s_prev = s_next;
+                    next_i++;
+                    return a;
+                };
+                uint32_t a0 = next_aligned(), a1 = next_aligned();
                 uint32_t ndiff = 0;
-                uint64_t fwd[3] = {0, 0, 0}, rev[3] = {0, 0, 0};  // stop hits by (position mod 3)
+                // stop hits by RELATIVE class: before chunk m, rel[c] collects positions p with p mod 3 == (c + 2m) mod 3
+                uint64_t fr0 = 0, fr1 = 0, fr2 = 0, rr0 = 0, rr1 = 0, rr2 = 0;
+                constexpr uint64_t kPh0 = 0x1041041041041041ULL;  // fields t = 0, 3, 6, ... of a chunk
                 for (uint32_t m = 0; m < n_chunks; m++) {
-                    // fetch aligned word m+1 (zero past the read)
-                    raw_cur = raw_nxt;
-                    raw_nxt = (w0 + m + 2 <= last_word) ? packed[w0 + m + 2] : 0;
-                    uint64_t nxt = (m + 1 < n_chunks) ? align(raw_cur, raw_nxt) : 0;
-                    const uint32_t remaining = (uint32_t)(L - 32ull * m);  // bases from this chunk's start
-                    if (remaining < 32) cur &= (1ull << (2 * remaining)) - 1;
-                    if (m + 1 < n_chunks && remaining - 32 < 32) nxt &= (1ull << (2 * (remaining - 32))) - 1;
+                    const uint32_t a2 = next_aligned(), a3 = next_aligned();
+                    uint64_t cur = (uint64_t)a0 | ((uint64_t)a1 << 32);
+                    uint64_t nxt = (uint64_t)a2 | ((uint64_t)a3 << 32);
+                    a0 = a2;
+                    a1 = a3;
+                    const uint32_t remaining = (uint32_t)L - 32u * m;  // bases from this chunk's start
+                    uint64_t m2 = kLo, m3 = kLo;                       // positions valid for a pair / a codon
+                    if (remaining < 66) {                              // only the last two chunks need masks
+                        if (remaining < 32) cur &= (1ull << (2 * remaining)) - 1;
+                        nxt = remaining > 32 ? (remaining < 64 ? nxt & ((1ull << (2 * (remaining - 32))) - 1) : nxt) : 0ull;
+                        const uint32_t v2 = remaining > 1 ? (remaining - 1 < 32 ? remaining - 1 : 32) : 0;
+                        const uint32_t v3 = remaining > 2 ? (remaining - 2 < 32 ? remaining - 2 : 32) : 0;
+                        m2 = v2 >= 32 ? kLo : (((1ull << (2 * v2)) - 1) & kLo);
+                        m3 = v3 >= 32 ? kLo : (((1ull << (2 * v3)) - 1) & kLo);
+                    }
                     const uint64_t x1 = (cur >> 2) | (nxt << 62);
                     const uint64_t x2 = (cur >> 4) | (nxt << 60);
-                    // positions p = 32m + t valid for a pair (p+1 < L) / a codon (p+2 < L)
-                    const uint32_t v2 = remaining > 1 ? (remaining - 1 < 32 ? remaining - 1 : 32) : 0;
-                    const uint32_t v3 = remaining > 2 ? (remaining - 2 < 32 ? remaining - 2 : 32) : 0;
-                    const uint64_t m2 = v2 >= 32 ? kLo : (((1ull << (2 * v2)) - 1) & kLo);
-                    const uint64_t m3 = v3 >= 32 ? kLo : (((1ull << (2 * v3)) - 1) & kLo);
                     const uint64_t d = cur ^ x1;
                     ndiff += __popcll((d | (d >> 1)) & m2);
                     const Planes b0(cur), b1(x1), b2(x2);
@@ -332,17 +343,23 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
                     const uint64_t fs = b0.isT & ((b1.isA & (b2.isA | b2.isG)) | (b1.isG & b2.isA)) & m3;
                     // triples whose reverse complement is a stop: TTA CTA TCA
                     const uint64_t rs = b2.isA & ((b1.isT & (b0.isT | b0.isC)) | (b1.isC & b0.isT)) & m3;
-                    // bit 2t of the word is position 32m + t; (32m + t) mod 3 = (2m + t) mod 3
-                    constexpr uint64_t kPh0 = 0x1041041041041041ULL;  // fields t = 0, 3, 6, ...
-                    const uint32_t rot = (2 * m) % 3;
-#pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        const uint64_t ph = kPh0 << (2 * c);  // fields t with t mod 3 == c
-                        const uint32_t cls = (c + rot) % 3;      // position class of those fields
-                        fwd[cls] |= fs & ph;
-                        rev[cls] |= rs & ph;
-                    }
-                    cur = nxt;
+                    // field t of chunk m is position 32m + t, and 32 = 2 (mod 3): rotate the accumulators instead
+                    // of computing the class of every field
+                    const uint64_t f0 = fr0 | (fs & kPh0), f1 = fr1 | (fs & (kPh0 << 2)), f2 = fr2 | (fs & (kPh0 << 4));
+                    const uint64_t r0 = rr0 | (rs & kPh0), r1 = rr1 | (rs & (kPh0 << 2)), r2 = rr2 | (rs & (kPh0 << 4));
+                    fr0 = f2; fr1 = f0; fr2 = f1;
+                    rr0 = r2; rr1 = r0; rr2 = r1;
+                }
+                // after M chunks rel[c] holds class (c + 2M) mod 3, i.e. class k sits at index (k + M) mod 3
+                uint64_t fwd[3], rev[3];
+                {
+                    const uint32_t rot = n_chunks % 3;
+                    fwd[0] = rot == 0 ? fr0 : rot == 1 ? fr1 : fr2;
+                    fwd[1] = rot == 0 ? fr1 : rot == 1 ? fr2 : fr0;
+                    fwd[2] = rot == 0 ? fr2 : rot == 1 ? fr0 : fr1;
+                    rev[0] = rot == 0 ? rr0 : rot == 1 ? rr1 : rr2;
+                    rev[1] = rot == 0 ? rr1 : rot == 1 ? rr2 : rr0;
+                    rev[2] = rot == 0 ? rr2 : rot == 1 ? rr0 : rr1;
                 }
                 // evaluate_is_fastp_low_complexity: ndiff / len < 0.3  (translate.py:75-84)
                 if ((double)ndiff / (double)L < 0.3) {
@@ -361,7 +378,8 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
                         else open |= 1u << f;
                         // reverse frame f: codons at forward positions p = (L - f) (mod 3)
                         const uint32_t cls = (uint32_t)((L + 3 - f) % 3);
-                        if (rev[cls]) rec.category[3 + f] = ORPH_CAT_STOP_CODONS;
+                        const uint64_t rev_hits = cls == 0 ? rev[0] : cls == 1 ? rev[1] : rev[2];
+                        if (rev_hits) rec.category[3 + f] = ORPH_CAT_STOP_CODONS;
                         else if (plen_ok <= k) rec.category[3 + f] = ORPH_CAT_TOO_SHORT_PEPTIDE;
                         else open |= 8u << f;
                     }
