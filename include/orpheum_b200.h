@@ -184,6 +184,14 @@ int orph_score_reads_device(orph_ctx *ctx, const orph_filter *f, const void *d_r
  * Multi-threaded on the host; n_threads <= 0 picks the hardware concurrency. */
 int orph_pack_reads(const uint8_t *reads, const uint64_t *offsets, uint64_t n_reads, uint64_t *out_packed,
                     uint8_t *needs_ascii, int n_threads);
+/* The peptides the reference emits (stdout FASTA of coding frames, low-complexity-peptide FASTA;
+ * translate.py:244-249,271-273): the UN-encoded translation of frame item_frame[i] (1,2,3,-1,-2,-3) of read
+ * item_read[i], with the reference's codon semantics (translate_single_seq.py:13-42: 64 ACGT codons, the seven
+ * xxN codons, everything else 'X', '*' for stops).  Host arrays; the caller pre-computes out_offsets (n_items+1,
+ * item i gets (len(read) - (|frame|-1)) / 3 bytes) and provides out_peptides of out_offsets[n_items] bytes. */
+int orph_translate_frames(orph_ctx *ctx, const uint8_t *reads, const uint64_t *offsets, uint64_t n_reads,
+                          const uint64_t *item_read, const int8_t *item_frame, uint64_t n_items,
+                          const uint64_t *out_offsets, uint8_t *out_peptides);
 /* jaccard of frame i of a record exactly as the reference computes it: n_hits / n_kmers in IEEE double
  * for categories 3/4, NaN otherwise (translate.py:204). */
 double orph_jaccard(const orph_read_result *r, int frame_index);

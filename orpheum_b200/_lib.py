@@ -64,6 +64,7 @@ PROTOTYPES = {
     "orph_score_reads_device": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, _u64p, ctypes.c_uint64, ctypes.c_uint32, _u8p,
                                                ctypes.c_double, _vp]),
     "orph_pack_reads": (ctypes.c_int, [_u8p, _u64p, ctypes.c_uint64, _u64p, _u8p, ctypes.c_int]),
+    "orph_translate_frames": (ctypes.c_int, [_vp, _u8p, _u64p, ctypes.c_uint64, _u64p, _vp, ctypes.c_uint64, _u64p, _u8p]),
     "orph_jaccard": (ctypes.c_double, [_vp, ctypes.c_int]),
     "orph_bench_gather_peak": (ctypes.c_int, [_vp, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int,
                                               ctypes.POINTER(ctypes.c_double)]),

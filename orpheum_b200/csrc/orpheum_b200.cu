@@ -980,6 +980,55 @@ extern "C" int orph_score_reads(orph_ctx *ctx, const orph_filter *f, const void 
     return status_to_code(counters.status);
 }
 
+extern "C" int orph_translate_frames(orph_ctx *ctx, const uint8_t *reads, const uint64_t *offsets, uint64_t n_reads,
+                                     const uint64_t *item_read, const int8_t *item_frame, uint64_t n_items,
+                                     const uint64_t *out_offsets, uint8_t *out_peptides)
+{
+    if (!ctx) return fail(ORPH_E_INVALID, "orph_translate_frames: ctx is NULL");
+    if (n_items == 0) return ORPH_OK;
+    if (!reads || !offsets || !item_read || !item_frame || !out_offsets || !out_peptides || n_reads == 0)
+        return fail(ORPH_E_INVALID, "orph_translate_frames: NULL argument");
+    for (uint64_t i = 0; i < n_items; i++) {
+        const int f = item_frame[i];
+        if (item_read[i] >= n_reads || f == 0 || f < -3 || f > 3)
+            return fail(ORPH_E_INVALID, "orph_translate_frames: item %llu is (read %llu, frame %d)", (unsigned long long)i,
+                        (unsigned long long)item_read[i], f);
+        const uint64_t L = offsets[item_read[i] + 1] - offsets[item_read[i]];
+        const uint64_t phase = (uint64_t)(f > 0 ? f - 1 : -f - 1);
+        const uint64_t plen = L >= phase ? (L - phase) / 3 : 0;
+        if (out_offsets[i + 1] - out_offsets[i] != plen)
+            return fail(ORPH_E_INVALID, "orph_translate_frames: out_offsets of item %llu holds %llu bytes, the frame has %llu residues",
+                        (unsigned long long)i, (unsigned long long)(out_offsets[i + 1] - out_offsets[i]), (unsigned long long)plen);
+    }
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = ctx->stream;
+    const uint64_t b0 = offsets[0], n_bytes = offsets[n_reads] - b0, n_out = out_offsets[n_items] - out_offsets[0];
+    int rc;
+    if ((rc = ctx->in_reads.ensure(n_bytes + 64)) != ORPH_OK) return rc;
+    if ((rc = ctx->in_offsets.ensure((n_reads + 1) * 8)) != ORPH_OK) return rc;
+    // items: [read u64 | out offset u64 (n+1) | frame i8], then the output bytes
+    const uint64_t items_bytes = n_items * 8 + (n_items + 1) * 8 + ((n_items + 15) & ~15ULL);
+    if ((rc = ctx->misc.ensure(items_bytes + n_out + 64)) != ORPH_OK) return rc;
+    uint8_t *base = (uint8_t *)ctx->misc.p;
+    uint64_t *d_item_read = (uint64_t *)base;
+    uint64_t *d_out_off = (uint64_t *)(base + n_items * 8);
+    int8_t *d_item_frame = (int8_t *)(base + n_items * 8 + (n_items + 1) * 8);
+    uint8_t *d_out = base + items_bytes;
+    if (n_bytes) CUDA_TRY(cudaMemcpyAsync(ctx->in_reads.p, reads + b0, n_bytes, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(ctx->in_offsets.p, offsets, (n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_item_read, item_read, n_items * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_out_off, out_offsets, (n_items + 1) * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_item_frame, item_frame, n_items, cudaMemcpyHostToDevice, s));
+    translate_frames_kernel<<<grid_for(n_items * 32, 256, ctx->sm_count, 16), 256, 0, s>>>(
+        (const uint8_t *)ctx->in_reads.p, b0, (const uint64_t *)ctx->in_offsets.p, d_item_read, d_item_frame, n_items, d_out_off,
+        d_out - out_offsets[0]);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (n_out) CUDA_TRY(cudaMemcpyAsync(out_peptides, d_out, n_out, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return ORPH_OK;
+}
+
 extern "C" double orph_jaccard(const orph_read_result *r, int frame_index)
 {
     if (!r || frame_index < 0 || frame_index > 5) return NAN;

@@ -648,4 +648,40 @@ score_bytes_kernel(const ScoreParams P, const void *__restrict__ src, const uint
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// translate_frames_kernel: the peptides the reference EMITS (stdout FASTA of coding frames, the
+// low-complexity-peptide FASTA; translate.py:244-249, 271-273): un-encoded amino acids of one frame per
+// item, byte-exact codon semantics (translate_single_seq.py:13-42).  One warp per (read, frame) item.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+translate_frames_kernel(const uint8_t *__restrict__ ascii, uint64_t abase0, const uint64_t *__restrict__ offsets,
+                        const uint64_t *__restrict__ item_read, const int8_t *__restrict__ item_frame, uint64_t n_items,
+                        const uint64_t *__restrict__ out_offsets, uint8_t *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t it = warp0; it < n_items; it += n_warps) {
+        const uint64_t r = item_read[it];
+        const int key = item_frame[it];  // 1,2,3,-1,-2,-3
+        const uint64_t o0 = offsets[r];
+        const uint32_t L = (uint32_t)(offsets[r + 1] - o0);
+        const uint32_t phase = (uint32_t)(key > 0 ? key - 1 : -key - 1);
+        const uint32_t plen = L >= phase ? (L - phase) / 3 : 0;
+        const uint8_t *seq = ascii + (o0 - abase0);
+        uint8_t *dst = out + out_offsets[it];
+        for (uint32_t i = lane; i < plen; i += kWarp) {
+            uint8_t aa;
+            if (key > 0) {
+                const uint32_t p = phase + 3 * i;
+                aa = translate_bytes(seq[p], seq[p + 1], seq[p + 2]);
+            } else {
+                const uint32_t p = L - 3 - phase - 3 * i;  // forward position of the reverse codon's last base
+                aa = translate_bytes(complement_byte(seq[p + 2]), complement_byte(seq[p + 1]), complement_byte(seq[p]));
+            }
+            dst[i] = aa;
+        }
+    }
+}
+
 }  // namespace orph

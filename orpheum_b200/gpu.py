@@ -300,6 +300,28 @@ def score_reads_device(graph, d_reads_ptr, d_offsets_ptr, n_reads, max_read_len,
                                               float(jaccard_threshold), ctypes.c_void_p(d_out_ptr)))
 
 
+def translate_frames(ctx, reads, offsets, item_read, item_frame):
+    """Un-encoded peptides of the listed (read index, frame key) pairs, translated on the GPU with the
+    reference's codon semantics -> list of str in item order."""
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    item_read = np.ascontiguousarray(item_read, dtype=np.uint64)
+    item_frame = np.ascontiguousarray(item_frame, dtype=np.int8)
+    n = len(item_read)
+    if n == 0:
+        return []
+    lengths = (offsets[item_read + 1] - offsets[item_read]).astype(np.int64)
+    phase = np.abs(item_frame.astype(np.int64)) - 1
+    plen = np.maximum(lengths - phase, 0) // 3
+    out_offsets = np.zeros(n + 1, dtype=np.uint64)
+    out_offsets[1:] = np.cumsum(plen)
+    out = np.zeros(max(int(out_offsets[-1]), 1), dtype=np.uint8)
+    check(_lib.load().orph_translate_frames(ctx._h, ptr(reads), ptr(offsets), len(offsets) - 1, ptr(item_read),
+                                            ptr(item_frame), n, ptr(out_offsets), ptr(out)))
+    blob = out.tobytes()
+    return [blob[int(out_offsets[i]):int(out_offsets[i + 1])].decode("latin-1") for i in range(n)]
+
+
 def jaccard_column(results):
     """float64 [n, 6] jaccard exactly as the reference computes it (NaN where it reports NaN)."""
     cat = results["category"]

@@ -15,10 +15,10 @@ import numpy as np
 from . import _lib, constants_index, constants_translate, fastx
 from .constants_translate import FRAMES, SingleReadScore, category_text
 from .create_save_summary import CreateSaveSummary
-from .gpu import concat_reads, score_reads
+from .gpu import concat_reads, score_reads, translate_frames
 from .index import maybe_make_peptide_bloom_filter, maybe_save_peptide_bloom_filter
 from .sequence_encodings import encode_lut, encode_peptide
-from .translate_single_seq import TranslateSingleSeq
+from .translate_single_seq import TranslateSingleSeq  # noqa: F401  (re-exported: part of the reference's surface)
 
 NAN = np.nan
 
@@ -140,11 +140,21 @@ class Translate:
         n_in_db = int(self.peptide_bloom_filter.get_many(hashes).sum())
         return n_in_db / len(kmers), len(kmers)
 
-    def _expand(self, description, sequence, result):
+    def _emitted_peptides(self, flat, offsets, results):
+        """Peptides of every frame the reference would print (coding -> stdout, low-complexity -> FASTA),
+        translated on the GPU in one call: {(read index, frame key): peptide}."""
+        cat = results["category"]
+        reads_idx, frames_idx = np.nonzero((cat == _lib.CAT_CODING) | (cat == _lib.CAT_LOW_COMPLEXITY_PEPTIDE))
+        if len(reads_idx) == 0:
+            return {}
+        keys = np.asarray(FRAMES, dtype=np.int8)[frames_idx]
+        peptides = translate_frames(self.peptide_bloom_filter.ctx, flat, offsets, reads_idx, keys)
+        return {(int(r), int(k)): p for r, k, p in zip(reads_idx, keys, peptides)}
+
+    def _expand(self, description, sequence, result, peptides, index=0):
         """orph_read_result of one read -> the six SingleReadScore tuples, with the reference's side effects
         (stdout FASTA for coding frames, optional FASTA files), in frame order 1,2,3,-1,-2,-3."""
         scores = []
-        translator = None
         for f, frame in enumerate(FRAMES):
             code = int(result["category"][f])
             text = category_text(code, self.alphabet)
@@ -152,19 +162,17 @@ class Translate:
                 scores.append(SingleReadScore(NAN, NAN, text, frame))
                 continue
             n_kmers = int(result["n_kmers"][f])
-            if translator is None:
-                translator = TranslateSingleSeq(sequence, self.verbose)
             if code == 2:
                 # the reference's header literally contains the unformatted "{}.format(frame)" (translate.py:247)
                 self.maybe_write_fasta(self.file_handles["low_complexity_peptide"],
                                        description + " translation_frame: {}.format(frame)",
-                                       translator.frame_translation(frame))
+                                       peptides[(index, frame)])
                 scores.append(SingleReadScore(NAN, n_kmers, text, frame))
                 continue
             jaccard = int(result["n_hits"][f]) / n_kmers  # the one IEEE division (translate.py:204)
             seqname = ("{}__translation_frame:{}".format(description, frame) + "__jaccard:{}".format(jaccard)).replace(" ", "__")
             if code == 3:
-                write_fasta(sys.stdout, seqname, translator.frame_translation(frame))
+                write_fasta(sys.stdout, seqname, peptides[(index, frame)])
                 sys.stdout.flush()
                 self.maybe_write_fasta(self.file_handles["coding_nucleotide"], seqname, sequence)
             else:
@@ -174,8 +182,9 @@ class Translate:
 
     def maybe_score_single_read(self, description, sequence):
         """Six per-frame scores of one read (translate.py:323-331) -- a batch of one through the GPU."""
-        result = self.score_batch([sequence])[0]
-        return self._expand(description, sequence, result)
+        flat, offsets = concat_reads([sequence])
+        results = score_reads(self.peptide_bloom_filter, flat, offsets, self._lut, self.jaccard_threshold)
+        return self._expand(description, sequence, results[0], self._emitted_peptides(flat, offsets, results))
 
     # kept for interface parity; both are answered by the same GPU call
     def check_peptide_content(self, description, sequence):
@@ -213,10 +222,11 @@ class Translate:
         scoring_lines = []
         for names, flat, offsets in fastx.read_batches(reads):
             results = score_reads(self.peptide_bloom_filter, flat, offsets, self._lut, self.jaccard_threshold)
+            peptides = self._emitted_peptides(flat, offsets, results)
             data = flat.tobytes()
             for i, name in enumerate(names):
                 sequence = data[int(offsets[i]):int(offsets[i + 1])].decode("latin-1")
-                scoring_lines.extend(self._lines(reads, name, self._expand(name, sequence, results[i])))
+                scoring_lines.extend(self._lines(reads, name, self._expand(name, sequence, results[i], peptides, i)))
         return scoring_lines
 
     def set_coding_scores_all_files(self):

@@ -357,3 +357,25 @@ def test_edge_cases(gpu, enc, orc, refdata):
     # mismatched arguments fail loudly
     with pytest.raises(ValueError):
         gpu.score_reads(gg, flat, offsets, lut, float("nan"))
+
+
+def test_emitted_peptides_on_gpu(gpu, orc, misc_kats):
+    """orph_translate_frames: the un-encoded peptides the reference prints, incl. N / lower-case / IUPAC codons."""
+    vec = load_score_vector("protein", 7)
+    seqs = [r["seq"] for r in vec["reads"]] + list(misc_kats["six_frame"].keys())
+    flat, offsets = gpu.concat_reads(seqs)
+    item_read = np.repeat(np.arange(len(seqs)), 6)
+    item_frame = np.tile(np.array([1, 2, 3, -1, -2, -3], dtype=np.int8), len(seqs))
+    got = gpu.translate_frames(gpu.default_context(), flat, offsets, item_read, item_frame)
+    for i, seq in enumerate(seqs):
+        want = orc.six_frame_translation(seq)
+        assert got[6 * i: 6 * i + 6] == [want[f] for f in (1, 2, 3, -1, -2, -3)], seq
+    for seq, frames in misc_kats["six_frame"].items():  # produced by the unmodified reference
+        i = seqs.index(seq)
+        assert got[6 * i: 6 * i + 6] == [frames[str(f)] for f in (1, 2, 3, -1, -2, -3)]
+    # a sub-batch view (offsets[0] != 0) and an empty item list
+    sub = gpu.translate_frames(gpu.default_context(), flat, offsets[5:9], [0, 2], [2, -3])
+    assert sub == [orc.six_frame_translation(seqs[5])[2], orc.six_frame_translation(seqs[7])[-3]]
+    assert gpu.translate_frames(gpu.default_context(), flat, offsets, [], []) == []
+    with pytest.raises(ValueError):
+        gpu.translate_frames(gpu.default_context(), flat, offsets, [0], [4])
