@@ -196,6 +196,33 @@ int orph_translate_frames(orph_ctx *ctx, const uint8_t *reads, const uint64_t *o
  * for categories 3/4, NaN otherwise (translate.py:204). */
 double orph_jaccard(const orph_read_result *r, int frame_index);
 
+/* ---- host ingest: FASTA / FASTQ (plain or gzip) with screed's record semantics ------------------- */
+/* Stands in for `screed.open(path)` (translate.py:370, index.py:83): name = the whole header line, sequence
+ * untouched, empty file = no records.  ORPH_E_INVALID if the file is neither FASTA nor FASTQ (the reference
+ * sees screed's ValueError), ORPH_E_IO if it cannot be read or a FASTQ record is malformed. */
+typedef struct orph_fastx orph_fastx;
+int orph_fastx_open(const char *path, orph_fastx **out);
+/* Parses up to max_records records / about max_bases bases and exposes them in the scoring ABI's layout:
+ * concatenated sequence bytes + offsets[n+1], concatenated names + offsets[n+1].  The pointers stay valid
+ * until the next call on the same handle.  *n_records == 0 means end of file. */
+int orph_fastx_next_batch(orph_fastx *fx, uint64_t max_records, uint64_t max_bases, uint64_t *n_records,
+                          const uint8_t **seq_bytes, const uint64_t **seq_offsets, const uint8_t **name_bytes,
+                          const uint64_t **name_offsets);
+void orph_fastx_close(orph_fastx *fx);
+
+/* ---- score CSV straight from the result records -------------------------------------------------- */
+/* The rows of Translate.score_reads_per_record (translate.py:342-365) in the exact text csv.writer produces for
+ * them (create_save_summary.py:52-64): `read_id,jaccard,n_kmers,category,frame,filename`, 6 rows per read,
+ * jaccard as Python's repr(float) of n_hits / n_kmers or `nan`, n_kmers as an int or `nan`.  name_fields holds
+ * the read ids ALREADY rendered as CSV fields (the caller quotes the rare ids that need it), category_text[c]
+ * the CSV field of category code c (NULL where the alphabet has none), filename_field likewise.
+ * Does not write the header line. */
+int orph_csv_write_scores(const char *path, int append, const uint8_t *name_fields, const uint64_t *name_offsets,
+                          uint64_t n_reads, const orph_read_result *results, const char *const *category_text,
+                          const char *filename_field);
+/* Python's repr(float) (the formatting the CSV uses), exposed for tests.  out32 must hold 32 bytes. */
+int orph_format_float_repr(double v, char *out32);
+
 /* ---- measurement helpers (bench.py) ---------------------------------------------------------- */
 /* Random 32-byte-sector gather micro-benchmark over `footprint_bytes` of device memory: every thread
  * issues `loads_per_thread` dependent-free byte loads at pseudo-random addresses.  Returns sectors/s

@@ -66,6 +66,11 @@ PROTOTYPES = {
     "orph_pack_reads": (ctypes.c_int, [_u8p, _u64p, ctypes.c_uint64, _u64p, _u8p, ctypes.c_int]),
     "orph_translate_frames": (ctypes.c_int, [_vp, _u8p, _u64p, ctypes.c_uint64, _u64p, _vp, ctypes.c_uint64, _u64p, _u8p]),
     "orph_jaccard": (ctypes.c_double, [_vp, ctypes.c_int]),
+    "orph_fastx_open": (ctypes.c_int, [ctypes.c_char_p, _pp]),
+    "orph_fastx_next_batch": (ctypes.c_int, [_vp, ctypes.c_uint64, ctypes.c_uint64, _u64p, _pp, _pp, _pp, _pp]),
+    "orph_fastx_close": (None, [_vp]),
+    "orph_csv_write_scores": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, _u8p, _u64p, ctypes.c_uint64, _vp, _vp, ctypes.c_char_p]),
+    "orph_format_float_repr": (ctypes.c_int, [ctypes.c_double, ctypes.c_char_p]),
     "orph_bench_gather_peak": (ctypes.c_int, [_vp, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int,
                                               ctypes.POINTER(ctypes.c_double)]),
 }

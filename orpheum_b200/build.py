@@ -6,8 +6,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "liborpheum_b200.so")
-SOURCES = ["orpheum_b200.cu"]
-HEADERS = ["device_common.cuh", "score_kernels.cuh", "bloom_kernels.cuh", "../../include/orpheum_b200.h"]
+SOURCES = ["orpheum_b200.cu", "fastx.cpp"]
+HEADERS = ["device_common.cuh", "score_kernels.cuh", "task_kernels.cuh", "bloom_kernels.cuh", "../../include/orpheum_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -36,7 +36,7 @@ def build(force=False, verbose=False, extra_flags=()):
     """Compile csrc/*.cu into csrc/liborpheum_b200.so."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [nvcc(), *NVCC_FLAGS, *extra_flags, "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc(), *NVCC_FLAGS, *extra_flags, "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lz"]
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)

@@ -1,0 +1,198 @@
+"""Columnar outputs straight from the GPU result records.
+
+The reference materialises six Python lists per read (``orpheum/translate.py:342-365``) and hands them to
+``CreateSaveSummary`` (``orpheum/create_save_summary.py:42-240``); that cannot scale to the read counts the
+GPU path scores.  ``ScoreTable`` keeps the per-read records as numpy arrays and writes the same files from
+them -- the CSV byte for byte as ``csv.writer`` would (``nan``, ``repr(float)``, minimal quoting, ``\\n``), the
+parquet with the same schema, the JSON summary with the same keys, values and key order.
+"""
+import json
+import os
+
+import numpy as np
+
+from . import _lib
+from .constants_translate import FRAMES, LOW_COMPLEXITY_CATEGORIES, PROTEIN_CODING_CATEGORIES, SCORING_DF_COLUMNS, category_text
+
+_FRAMES = np.asarray(FRAMES, dtype=np.int64)
+
+
+class ScoreTable:
+    """Accumulates (names, orph_read_result records, file name) batches in read order."""
+
+    def __init__(self, alphabet):
+        self.alphabet = alphabet
+        self._names, self._records, self._files = [], [], []
+
+    def append(self, names, records, filename):
+        if len(names):
+            self._names.append(np.asarray(names, dtype=object))
+            self._records.append(records)
+            self._files.append((filename, len(names)))
+
+    def __len__(self):
+        return sum(len(n) for n in self._names)
+
+    # -- flat per-row columns (6 rows per read, frame order 1,2,3,-1,-2,-3) ------------------------------
+    def _columns(self):
+        if not self._names:
+            return None
+        names = np.concatenate(self._names)
+        rec = np.concatenate(self._records)
+        cat = rec["category"].reshape(-1).astype(np.int64)
+        n_kmers = rec["n_kmers"].reshape(-1).astype(np.int64)
+        n_hits = rec["n_hits"].reshape(-1).astype(np.int64)
+        scored = (cat == _lib.CAT_CODING) | (cat == _lib.CAT_NON_CODING)
+        has_n = scored | (cat == _lib.CAT_LOW_COMPLEXITY_PEPTIDE)
+        jaccard = np.full(cat.shape, np.nan)
+        np.divide(n_hits, n_kmers, out=jaccard, where=scored)  # the one IEEE division of translate.py:204
+        files = np.concatenate([np.full(6 * n, i, dtype=np.int64) for i, (_, n) in enumerate(self._files)])
+        return {
+            "names": names, "read_index": np.repeat(np.arange(len(names)), 6), "category": cat, "n_kmers": n_kmers,
+            "n_hits": n_hits, "scored": scored, "has_n": has_n, "jaccard": jaccard,
+            "frame": np.tile(_FRAMES, len(names)), "file_index": files, "file_names": [f for f, _ in self._files],
+        }
+
+    def _category_texts(self, present_codes):
+        # low-complexity text only if such a frame exists (the reference raises KeyError lazily, translate.py:254-256)
+        return {int(c): category_text(int(c), self.alphabet) for c in present_codes}
+
+    # -- arrow / parquet ---------------------------------------------------------------------------------
+    def to_arrow(self):
+        import pyarrow as pa
+
+        c = self._columns()
+        if c is None:
+            return None
+        texts = self._category_texts(np.unique(c["category"]))
+        codes = sorted(texts)
+        remap = np.zeros(256, dtype=np.int32)
+        for i, code in enumerate(codes):
+            remap[code] = i
+        category = pa.DictionaryArray.from_arrays(pa.array(remap[c["category"]], type=pa.int32()),
+                                                  pa.array([texts[k] for k in codes])).cast(pa.string())
+        read_id = pa.DictionaryArray.from_arrays(pa.array(c["read_index"], type=pa.int64()),
+                                                 pa.array(c["names"].tolist(), type=pa.string())).cast(pa.string())
+        filename = pa.DictionaryArray.from_arrays(pa.array(c["file_index"], type=pa.int64()),
+                                                  pa.array(c["file_names"], type=pa.string())).cast(pa.string())
+        if c["has_n"].all():
+            n_kmers = pa.array(c["n_kmers"], type=pa.int64())  # python ints only -> int64, as pyarrow infers for the reference
+        else:
+            n_kmers = pa.array(np.where(c["has_n"], c["n_kmers"].astype(np.float64), np.nan), type=pa.float64())
+        return pa.table([read_id, pa.array(c["jaccard"], type=pa.float64()), n_kmers, category,
+                         pa.array(c["frame"], type=pa.int64()), filename], names=SCORING_DF_COLUMNS)
+
+    def write_parquet(self, path):
+        import pyarrow.parquet as pq
+
+        table = self.to_arrow()
+        if table is not None:
+            pq.write_table(table, path)
+
+    # -- CSV -----------------------------------------------------------------------------------------------
+    @staticmethod
+    def _csv_field(text):
+        """One CSV field exactly as csv.writer renders it (minimal quoting)."""
+        if any(ch in text for ch in ',"\r\n'):
+            return '"' + text.replace('"', '""') + '"'
+        return text
+
+    def write_csv(self, path):
+        """Byte-identical to ``csv.writer(lineterminator="\n")`` over the reference's row lists; the rows are
+        formatted by the native writer (orph_csv_write_scores) batch by batch."""
+        import ctypes
+
+        lib = _lib.load()
+        with open(path, "wb") as out:
+            out.write((",".join(SCORING_DF_COLUMNS) + "\n").encode())
+        for names, records, (filename, _) in zip(self._names, self._records, self._files):
+            present = np.unique(records["category"])
+            texts = [None] * 6
+            for code in present:
+                texts[int(code)] = self._csv_field(category_text(int(code), self.alphabet)).encode()
+            fields = [self._csv_field(n).encode("latin-1") for n in names.tolist()]
+            offsets = np.zeros(len(fields) + 1, dtype=np.uint64)
+            offsets[1:] = np.cumsum([len(f) for f in fields])
+            blob = np.frombuffer(b"".join(fields), dtype=np.uint8) if offsets[-1] else np.zeros(1, dtype=np.uint8)
+            records = np.ascontiguousarray(records)
+            arr = (ctypes.c_char_p * 6)(*texts)
+            _lib.check(lib.orph_csv_write_scores(os.fsencode(path), 1, _lib.ptr(blob), _lib.ptr(offsets), len(fields),
+                                                 _lib.ptr(records), arr, self._csv_field(filename).encode()))
+
+    # -- JSON summary --------------------------------------------------------------------------------------
+    def empty_categories(self):
+        counts = dict.fromkeys(PROTEIN_CODING_CATEGORIES.values(), 0)
+        counts[LOW_COMPLEXITY_CATEGORIES[self.alphabet]] = 0
+        return counts
+
+    def summary(self, filenames, peptide_bloom_filter_filename, peptide_ksize, jaccard_threshold):
+        """The dict ``CreateSaveSummary.maybe_write_json_summary`` dumps (create_save_summary.py:91-240)."""
+        unique_filenames = [os.path.basename(f) for f in ([filenames] if isinstance(filenames, str) else filenames)]
+        c = self._columns()
+        if c is None:
+            empty = self.empty_categories()
+            zero_hist = {str(i): 0 for i in range(len(empty))}
+            return {
+                "input_files": unique_filenames,
+                "jaccard_info": {"count": 0, "mean": None, "std": None, "min": None, "25%": None, "50%": None, "75%": None,
+                                 "max": None},
+                "categorization_counts": empty, "categorization_percentages": empty,
+                "histogram_n_coding_frames_per_read": zero_hist,
+                "histogram_n_coding_frames_per_read_percentages": dict(zero_hist),
+            }
+        names, cat = c["names"], c["category"].reshape(-1, 6)
+        # the reference groups CONSECUTIVE rows with equal read ids (itertools.groupby, :180-182)
+        new_group = np.ones(len(names), dtype=bool)
+        if len(names) > 1:
+            new_group[1:] = names[1:] != names[:-1]
+        group = np.cumsum(new_group) - 1
+        n_groups = int(group[-1]) + 1
+        present = np.zeros((n_groups, 6), dtype=bool)  # category code present in the group
+        np.logical_or.at(present, (np.repeat(group, 6), cat.reshape(-1)), True)
+        counts = self.empty_categories()
+        coding = present[:, _lib.CAT_CODING]
+        short_pep = ~coding & present[:, _lib.CAT_TOO_SHORT_PEPTIDE]
+        short_read = ~coding & ~short_pep & present[:, _lib.CAT_LOW_COMPLEXITY_NUCLEOTIDE]
+        rest = ~coding & ~short_pep & ~short_read
+        single = rest & (present.sum(axis=1) == 1)
+        counts["Coding"] += int(coding.sum())
+        counts[PROTEIN_CODING_CATEGORIES["too_short_peptide"]] += int(short_pep.sum())
+        counts[PROTEIN_CODING_CATEGORIES["too_short_nucleotide"]] += int(short_read.sum())
+        for code in np.unique(np.argmax(present[single], axis=1)) if single.any() else []:
+            counts[category_text(int(code), self.alphabet)] += int((np.argmax(present[single], axis=1) == code).sum())
+        counts["Non-coding"] += int((rest & ~single).sum())
+        total = sum(counts.values())
+        percentages = {k: 100 * v / total for k, v in counts.items()}
+        # histogram of coding frames per read id (Counter over read ids, :216-222): ids are merged by VALUE here
+        is_coding = cat == _lib.CAT_CODING
+        per_read = is_coding.sum(axis=1)
+        coding_names = names[per_read > 0]
+        label = "Number of reads with {} putative protein-coding translations".format
+        hist_counts, hist_pct = {}, {}
+        if len(coding_names):
+            per_name = {}
+            for name, n in zip(coding_names.tolist(), per_read[per_read > 0].tolist()):
+                per_name[name] = per_name.get(name, 0) + n
+            hist = {}
+            for n in per_name.values():
+                hist[n] = hist.get(n, 0) + 1
+            tot = sum(hist.values())
+            hist_counts = {label(k): v for k, v in hist.items()}
+            hist_pct = {label(k): 100 * v / tot for k, v in hist.items()}
+        j = c["jaccard"]  # the reference hands numpy a python list of the same doubles
+        jaccard_info = {
+            "count": int(np.count_nonzero(~np.isnan(j))), "mean": np.nanmean(j), "std": np.nanstd(j), "min": np.nanmin(j),
+            "25%": np.nanpercentile(j, 25), "50%": np.nanpercentile(j, 50), "75%": np.nanpercentile(j, 75), "max": np.nanmax(j),
+        }
+        return {
+            "input_files": unique_filenames, "jaccard_info": jaccard_info, "categorization_counts": counts,
+            "categorization_percentages": percentages, "histogram_n_coding_frames_per_read": hist_counts,
+            "histogram_n_coding_frames_per_read_percentages": hist_pct, "peptide_bloom_filter": peptide_bloom_filter_filename,
+            "peptide_alphabet": self.alphabet, "peptide_ksize": peptide_ksize, "jaccard_threshold": jaccard_threshold,
+        }
+
+    def write_json_summary(self, path, filenames, peptide_bloom_filter_filename, peptide_ksize, jaccard_threshold):
+        summary = self.summary(filenames, peptide_bloom_filter_filename, peptide_ksize, jaccard_threshold)
+        with open(path, "w") as handle:
+            json.dump(summary, fp=handle)
+        return summary

@@ -32,6 +32,16 @@ static int fail(int code, const char *fmt, ...)
     return code;
 }
 
+// shared with fastx.cpp
+int orph_set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
 #define CUDA_TRY(expr)                                                                              \
     do {                                                                                            \
         cudaError_t e__ = (expr);                                                                   \

@@ -5,6 +5,7 @@ untouched (no upper-casing), an empty file yields nothing, anything else raises 
 import bz2
 import gzip
 import io
+import os
 
 import numpy as np
 
@@ -47,13 +48,12 @@ class _Reader:
         if self._kind == ">":
             name, parts = None, []
             for line in f:
-                line = line.rstrip("\r\n")
                 if line[:1] == ">":
                     if name is not None:
                         yield Record(name=name, sequence="".join(parts))
-                    name, parts = line[1:], []
-                else:
-                    parts.append(line)
+                    name, parts = line[1:].strip(), []
+                elif name is not None:
+                    parts.append(line.strip())
             if name is not None:
                 yield Record(name=name, sequence="".join(parts))
         elif self._kind == "@":
@@ -61,20 +61,112 @@ class _Reader:
                 header = f.readline()
                 if not header:
                     return
-                seq = f.readline().rstrip("\r\n")
-                f.readline()
-                qual = f.readline().rstrip("\r\n")
-                yield Record(name=header.rstrip("\r\n")[1:], sequence=seq, quality=qual)
+                if not header.strip():
+                    continue
+                if header[0] != "@":
+                    raise OSError("bad FASTQ: no '@' at the beginning of a record")
+                parts = []
+                line = f.readline()
+                while line and line[0] not in "+#":
+                    parts.append(line.strip())
+                    line = f.readline()
+                seq = "".join(parts)
+                qual, line = [], ""
+                while sum(map(len, qual)) < len(seq):
+                    line = f.readline()
+                    if not line:
+                        break
+                    qual.append(line.strip())
+                if sum(map(len, qual)) != len(seq):
+                    raise OSError("bad FASTQ: quality and sequence lengths differ")
+                yield Record(name=header[1:].strip(), sequence=seq, quality="".join(qual))
 
 
-def open(path):  # noqa: A001 - same public name as screed.open
+class _NativeReader:
+    """The C++ parser of csrc/fastx.cpp (plain and gzip input): same records, an order of magnitude faster."""
+
+    def __init__(self, path):
+        import ctypes
+
+        from . import _lib
+
+        self._ct = ctypes
+        self._lib = _lib.load()
+        handle = ctypes.c_void_p()
+        rc = self._lib.orph_fastx_open(os.fsencode(path), ctypes.byref(handle))
+        if rc == _lib.ORPH_E_INVALID:
+            raise ValueError(f"unknown file format for '{path}'")
+        if rc != 0:
+            raise OSError(_lib.last_error())
+        self._h = handle
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def close(self):
+        if self._h:
+            self._lib.orph_fastx_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def batches(self, max_records=1 << 20, max_bases=1 << 28):
+        ct = self._ct
+        n = ct.c_uint64()
+        seq, seq_off, names, name_off = ct.c_void_p(), ct.c_void_p(), ct.c_void_p(), ct.c_void_p()
+        while True:
+            rc = self._lib.orph_fastx_next_batch(self._h, max_records, max_bases, ct.byref(n), ct.byref(seq), ct.byref(seq_off),
+                                                 ct.byref(names), ct.byref(name_off))
+            if rc != 0:
+                from . import _lib
+
+                raise OSError(_lib.last_error())
+            if n.value == 0:
+                return
+            m = int(n.value)
+            offsets = np.ctypeslib.as_array(ct.cast(seq_off, ct.POINTER(ct.c_uint64)), shape=(m + 1,)).copy()
+            noffs = np.ctypeslib.as_array(ct.cast(name_off, ct.POINTER(ct.c_uint64)), shape=(m + 1,)).copy()
+            total = int(offsets[-1])
+            flat = (np.ctypeslib.as_array(ct.cast(seq, ct.POINTER(ct.c_uint8)), shape=(total,)).copy()
+                    if total else np.zeros(0, dtype=np.uint8))
+            blob = ct.string_at(names, int(noffs[-1])) if noffs[-1] else b""
+            name_list = [blob[int(noffs[i]):int(noffs[i + 1])].decode("latin-1") for i in range(m)]
+            yield name_list, flat, offsets
+
+    def __iter__(self):
+        for names, flat, offsets in self.batches():
+            data = flat.tobytes()
+            for i, name in enumerate(names):
+                yield Record(name=name, sequence=data[int(offsets[i]):int(offsets[i + 1])].decode("latin-1"))
+
+
+def _is_bz2(path):
+    with io.open(path, "rb") as f:
+        return f.read(3) == b"BZh"
+
+
+def open(path, native=True):  # noqa: A001 - same public name as screed.open
+    """Record iterator.  gzip / plain files go through the native parser; bzip2 through Python."""
+    if native and not _is_bz2(path):
+        return _NativeReader(path)
     return _Reader(path)
 
 
-def read_batches(path, max_records=1 << 20, max_bases=1 << 28):
+def read_batches(path, max_records=1 << 20, max_bases=1 << 28, native=True):
     """Yield (names, flat uint8 bytes, uint64 offsets[n+1]) batches in file order, in the layout the C ABI takes."""
+    if native and not _is_bz2(path):
+        with _NativeReader(path) as reader:
+            yield from reader.batches(max_records, max_bases)
+        return
     names, seqs, n_bases = [], [], 0
-    with open(path) as records:
+    with _Reader(path) as records:
         for rec in records:
             names.append(rec["name"])
             s = rec["sequence"].encode("latin-1")

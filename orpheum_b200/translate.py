@@ -229,6 +229,60 @@ class Translate:
                 scoring_lines.extend(self._lines(reads, name, self._expand(name, sequence, results[i], peptides, i)))
         return scoring_lines
 
+    # -- columnar path (what the CLI uses): no per-row python objects ---------------------------------------
+    def _emit_batch(self, names, flat, offsets, results):
+        """stdout / FASTA side effects of one batch, in read order then frame order (translate.py:244-298)."""
+        cat = results["category"]
+        want = cat == _lib.CAT_CODING
+        if self.file_handles["low_complexity_peptide"] is not None:
+            want |= cat == _lib.CAT_LOW_COMPLEXITY_PEPTIDE
+        if self.file_handles["noncoding_nucleotide"] is not None:
+            want |= cat == _lib.CAT_NON_CODING
+        reads_idx, frames_idx = np.nonzero(want)
+        if len(reads_idx) == 0:
+            return
+        codes = cat[reads_idx, frames_idx]
+        need_pep = (codes == _lib.CAT_CODING) | (codes == _lib.CAT_LOW_COMPLEXITY_PEPTIDE)
+        keys = np.asarray(FRAMES, dtype=np.int8)[frames_idx]
+        peptides = iter(translate_frames(self.peptide_bloom_filter.ctx, flat, offsets, reads_idx[need_pep], keys[need_pep]))
+        data = flat.tobytes()
+        hits, n_kmers = results["n_hits"], results["n_kmers"]
+        out = []
+        handles = self.file_handles
+        for r, f, code, key in zip(reads_idx.tolist(), frames_idx.tolist(), codes.tolist(), keys.tolist()):
+            name = names[r]
+            if code == _lib.CAT_LOW_COMPLEXITY_PEPTIDE:
+                write_fasta(handles["low_complexity_peptide"], name + " translation_frame: {}.format(frame)", next(peptides))
+                continue
+            jaccard = int(hits[r, f]) / int(n_kmers[r, f])
+            seqname = ("{}__translation_frame:{}".format(name, key) + "__jaccard:{}".format(jaccard)).replace(" ", "__")
+            if code == _lib.CAT_CODING:
+                out.append(">{}\n{}\n".format(seqname, next(peptides)))
+                if handles["coding_nucleotide"] is not None:
+                    write_fasta(handles["coding_nucleotide"], seqname, data[int(offsets[r]):int(offsets[r + 1])].decode("latin-1"))
+            else:
+                write_fasta(handles["noncoding_nucleotide"], seqname, data[int(offsets[r]):int(offsets[r + 1])].decode("latin-1"))
+        if out:
+            sys.stdout.write("".join(out))
+            sys.stdout.flush()
+
+    def score_all_files_columnar(self):
+        """Score every input file and return a columnar ``ScoreTable`` (same information as ``coding_scores``,
+        6 rows per read, without building python rows); stdout / FASTA outputs are written on the way."""
+        from .columnar import ScoreTable
+
+        table = ScoreTable(self.alphabet)
+        self.maybe_open_fastas()
+        try:
+            for reads in self.reads:
+                for names, flat, offsets in fastx.read_batches(reads):
+                    results = score_reads(self.peptide_bloom_filter, flat, offsets, self._lut, self.jaccard_threshold)
+                    self._emit_batch(names, flat, offsets, results)
+                    table.append(names, results, reads)
+        finally:
+            self.maybe_close_fastas()
+        return table
+
     def set_coding_scores_all_files(self):
         self.maybe_open_fastas()
         try:
@@ -282,13 +336,14 @@ def cli(peptides, reads, peptide_ksize=None, save_peptide_bloom_filter=True, pep
         n_tables=constants_index.DEFAULT_N_TABLES, long_reads=False, verbose=False):
     """Writes coding peptides from reads to standard output"""
     translate_obj = Translate(locals())
-    translate_obj.set_coding_scores_all_files()
-    summary = CreateSaveSummary(reads, csv, parquet, json_summary, translate_obj.peptide_bloom_filter_filename, alphabet,
-                                translate_obj.peptide_ksize, translate_obj.jaccard_threshold, translate_obj.coding_scores)
-    del translate_obj.coding_scores
-    summary.maybe_write_csv()
-    summary.maybe_write_parquet()
-    summary.maybe_write_json_summary()
+    table = translate_obj.score_all_files_columnar()
+    if csv:
+        table.write_csv(csv)
+    if parquet and len(table):
+        table.write_parquet(parquet)
+    if json_summary:
+        table.write_json_summary(json_summary, reads, translate_obj.peptide_bloom_filter_filename,
+                                 translate_obj.peptide_ksize, translate_obj.jaccard_threshold)
 
 
 if __name__ == "__main__":

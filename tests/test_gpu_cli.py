@@ -155,3 +155,43 @@ def test_index_cli(workdir, refdata, monkeypatch):
     index.maybe_make_peptide_bloom_filter(
         "reference_data/index/Homo_sapiens.GRCh38.pep.subset.alphabet-protein_ksize-7.bloomfilter.nodegraph", 7, "protein",
         peptides_are_bloom_filter=True)
+
+
+def test_columnar_outputs_equal_row_list_outputs(workdir, monkeypatch, tmp_path):
+    """ScoreTable (arrays) vs CreateSaveSummary (python rows) on awkward read ids: commas, quotes, empty name,
+    duplicated consecutive ids, duplicated non-consecutive ids."""
+    import json as js
+
+    from orpheum_b200 import constants_index, translate
+    from orpheum_b200.create_save_summary import CreateSaveSummary
+
+    monkeypatch.chdir(workdir)
+    coding = "CGCTTGCTTAATACTGACATCAATAATATTAGGAAAATCGCAATATAACTGTAAATCCTGTTCTGTC"
+    reads = [("plain", coding), ('with,comma "and quotes"', coding), ("dup", coding), ("dup", "ACGT" * 20), ("", "CAG" * 30),
+             ("other", "C" * 50), ("dup", coding), ("tab\there", coding[:30])]
+    fq = tmp_path / "awkward.fq"
+    fq.write_text("".join(f"@{n}\n{s}\n+\n{'I' * len(s)}\n" for n, s in reads))
+    args = dict(reads=[str(fq)], peptides="reference_data/index/Homo_sapiens.GRCh38.pep.subset.alphabet-protein_ksize-7.bloomfilter.nodegraph",
+                peptide_ksize=7, save_peptide_bloom_filter=False, peptides_are_bloom_filter=True, jaccard_threshold=None,
+                alphabet="protein", csv=False, parquet=False, json_summary=False, coding_nucleotide_fasta=None,
+                noncoding_nucleotide_fasta=None, low_complexity_nucleotide_fasta=None, low_complexity_peptide_fasta=None,
+                tablesize=constants_index.DEFAULT_MAX_TABLESIZE, n_tables=4, long_reads=False, verbose=False)
+    t = translate.Translate(args)
+    t.set_coding_scores_all_files()
+    rows = t.coding_scores
+    ref = CreateSaveSummary([str(fq)], str(tmp_path / "r.csv"), str(tmp_path / "r.parquet"), str(tmp_path / "r.json"), "f.nodegraph",
+                            "protein", 7, 0.5, rows)
+    ref.maybe_write_csv()
+    ref.maybe_write_parquet()
+    ref.maybe_write_json_summary()
+    table = translate.Translate(args).score_all_files_columnar()
+    assert len(table) == len(reads)
+    table.write_csv(str(tmp_path / "c.csv"))
+    table.write_parquet(str(tmp_path / "c.parquet"))
+    table.write_json_summary(str(tmp_path / "c.json"), [str(fq)], "f.nodegraph", 7, 0.5)
+    assert (tmp_path / "c.csv").read_text() == (tmp_path / "r.csv").read_text()
+    assert js.load(open(tmp_path / "c.json")) == js.load(open(tmp_path / "r.json"))
+    import pyarrow.parquet as pq
+
+    a, b = pq.read_table(str(tmp_path / "c.parquet")), pq.read_table(str(tmp_path / "r.parquet"))
+    assert a.schema.equals(b.schema) and a.to_pandas().equals(b.to_pandas())

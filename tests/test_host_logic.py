@@ -167,3 +167,73 @@ def test_cli_wiring_errors():
     assert r.exit_code == 2 and "'beyonce' is not a valid float" in r.output
     r = runner.invoke(translate.cli, ["--long-reads", "pep.fa", "reads.fq"])
     assert isinstance(r.exception, NotImplementedError)
+
+
+def test_native_parser_matches_python_reader(refdata, golden_dir, tmp_path):
+    """csrc/fastx.cpp against the pure-Python reader on every fixture and on awkward files."""
+    import gzip as gz
+
+    from orpheum_b200 import build
+
+    build.build()
+    files = [os.path.join(refdata, "SRR306838_GSM752691_hsa_br_F_1_trimmed_subsampled_n22.fq"),
+             os.path.join(refdata, "SRR306838_GSM752691_hsa_br_F_1_trimmed_subsampled_n22.fq.gz"),
+             os.path.join(refdata, "SRR306838_GSM752691_hsa_br_F_1_trimmed_subsampled_first20.fq.gz"),
+             os.path.join(refdata, "low_complexity_nucleotides.fastq"), os.path.join(refdata, "low_complexity_peptides.fastq"),
+             os.path.join(refdata, "index", "Homo_sapiens.GRCh38.pep.first1000lines.fa"),
+             os.path.join(refdata, "index", "Homo_sapiens.GRCh38.pep.subset.fa.gz"),
+             os.path.join(refdata, "empty_fasta.fasta"), os.path.join(golden_dir, "ref_cli", "synth_mixed.fq")]
+    odd = tmp_path / "odd.fa"
+    odd.write_bytes(b">crlf header  \r\nACGT\r\nacgtn\r\n\r\n>no-sequence\n>last one\nAC\nGT")  # CRLF, blank line, no final newline
+    wrapped = tmp_path / "wrapped.fq"
+    wrapped.write_text("@r1 x\nACGT\nACGT\n+\nIIII\nIIII\n@r2\nNN\n+r2\n@@\n")  # multi-line record, '@' in the quality line
+    files += [str(odd), str(wrapped)]
+    with gz.open(tmp_path / "wrapped.fq.gz", "wt") as f:
+        f.write(wrapped.read_text())
+    files.append(str(tmp_path / "wrapped.fq.gz"))
+    for path in files:
+        py = [(r["name"], r["sequence"]) for r in fastx.open(path, native=False)]
+        native = [(r["name"], r["sequence"]) for r in fastx.open(path, native=True)]
+        assert native == py, path
+        # batch form, small batches to exercise the resume logic
+        names, seqs = [], []
+        for n, flat, offsets in fastx.read_batches(path, max_records=7, native=True):
+            data = flat.tobytes()
+            names += n
+            seqs += [data[int(offsets[i]):int(offsets[i + 1])].decode("latin-1") for i in range(len(n))]
+        assert list(zip(names, seqs)) == py, path
+    assert [(r["name"], r["sequence"]) for r in fastx.open(str(odd))] == [("crlf header", "ACGTacgtn"), ("no-sequence", ""), ("last one", "ACGT")]
+    assert [(r["name"], r["sequence"]) for r in fastx.open(str(wrapped))] == [("r1 x", "ACGTACGT"), ("r2", "NN")]
+    with pytest.raises(ValueError):
+        fastx.open(os.path.join(refdata, "index", "Homo_sapiens.GRCh38.pep.subset.alphabet-protein_ksize-7.bloomfilter.nodegraph"))
+    bad = tmp_path / "bad.fq"
+    bad.write_text("@r1\nACGT\n+\nII\n")
+    with pytest.raises(OSError):
+        list(fastx.open(str(bad)))
+    with pytest.raises(OSError):
+        list(fastx.open(str(bad), native=False))
+
+
+def test_native_float_repr_matches_python():
+    """The CSV's float text: every jaccard ratio h/n the 16-bit counters can form for n <= 400, plus extremes."""
+    import ctypes
+
+    from orpheum_b200 import _lib, build
+
+    build.build()
+    lib = _lib.load()
+    buf = ctypes.create_string_buffer(32)
+
+    def native(v):
+        assert lib.orph_format_float_repr(v, buf) == 0
+        return buf.value.decode()
+
+    for n in range(1, 401):
+        for h in range(0, n + 1):
+            assert native(h / n) == repr(h / n), (h, n)
+    for n in (65535, 65521, 4099, 12345):
+        for h in (0, 1, 2, 3, 7, n // 3, n - 1, n):
+            assert native(h / n) == repr(h / n), (h, n)
+    for v in (0.0, 1.0, 0.5, 1e-4, 1e-5, 9.999e-5, 123456.789, 1e15, 1e16, 1.5e17, 2.0**-40, 3.0, 100.0, -0.25, 1e22, 5e-324):
+        assert native(v) == repr(v), v
+    assert native(float("nan")) == "nan"
