@@ -25,8 +25,9 @@ class ScoreTable:
         self._names, self._records, self._files = [], [], []
 
     def append(self, names, records, filename):
+        """names: a list of str or a fastx.NameList (byte blob + offsets, kept as is for the CSV writer)."""
         if len(names):
-            self._names.append(np.asarray(names, dtype=object))
+            self._names.append(names)
             self._records.append(records)
             self._files.append((filename, len(names)))
 
@@ -37,7 +38,7 @@ class ScoreTable:
     def _columns(self):
         if not self._names:
             return None
-        names = np.concatenate(self._names)
+        names = np.concatenate([np.asarray(n.tolist() if hasattr(n, "tolist") else n, dtype=object) for n in self._names])
         rec = np.concatenate(self._records)
         cat = rec["category"].reshape(-1).astype(np.int64)
         n_kmers = rec["n_kmers"].reshape(-1).astype(np.int64)
@@ -110,13 +111,21 @@ class ScoreTable:
             texts = [None] * 6
             for code in present:
                 texts[int(code)] = self._csv_field(category_text(int(code), self.alphabet)).encode()
-            fields = [self._csv_field(n).encode("latin-1") for n in names.tolist()]
-            offsets = np.zeros(len(fields) + 1, dtype=np.uint64)
-            offsets[1:] = np.cumsum([len(f) for f in fields])
-            blob = np.frombuffer(b"".join(fields), dtype=np.uint8) if offsets[-1] else np.zeros(1, dtype=np.uint8)
+            raw = getattr(names, "blob", None)
+            if raw is not None and not any(ch in raw for ch in b',"\r\n'):
+                # the usual case: no read id needs quoting, the parser's name blob IS the column of CSV fields
+                blob = np.frombuffer(raw, dtype=np.uint8) if len(raw) else np.zeros(1, dtype=np.uint8)
+                offsets = np.ascontiguousarray(names.offsets, dtype=np.uint64)
+                n_fields = len(names)
+            else:
+                fields = [self._csv_field(n).encode("latin-1") for n in (names.tolist() if hasattr(names, "tolist") else names)]
+                offsets = np.zeros(len(fields) + 1, dtype=np.uint64)
+                offsets[1:] = np.cumsum([len(f) for f in fields])
+                blob = np.frombuffer(b"".join(fields), dtype=np.uint8) if offsets[-1] else np.zeros(1, dtype=np.uint8)
+                n_fields = len(fields)
             records = np.ascontiguousarray(records)
             arr = (ctypes.c_char_p * 6)(*texts)
-            _lib.check(lib.orph_csv_write_scores(os.fsencode(path), 1, _lib.ptr(blob), _lib.ptr(offsets), len(fields),
+            _lib.check(lib.orph_csv_write_scores(os.fsencode(path), 1, _lib.ptr(blob), _lib.ptr(offsets), n_fields,
                                                  _lib.ptr(records), arr, self._csv_field(filename).encode()))
 
     # -- JSON summary --------------------------------------------------------------------------------------

@@ -82,6 +82,40 @@ class _Reader:
                 yield Record(name=header[1:].strip(), sequence=seq, quality="".join(qual))
 
 
+class NameList:
+    """Record names of one batch as one byte blob + offsets; behaves like a list of str, decoding lazily."""
+
+    def __init__(self, blob, offsets):
+        self.blob = blob
+        self.offsets = offsets
+        self._list = None
+
+    def __len__(self):
+        return len(self.offsets) - 1
+
+    def __getitem__(self, i):
+        if self._list is not None:
+            return self._list[i]
+        if isinstance(i, slice):
+            return self.tolist()[i]
+        if i < 0:
+            i += len(self)
+        return self.blob[int(self.offsets[i]):int(self.offsets[i + 1])].decode("latin-1")
+
+    def __iter__(self):
+        return iter(self.tolist())
+
+    def __eq__(self, other):
+        return self.tolist() == (other.tolist() if isinstance(other, NameList) else list(other))
+
+    def tolist(self):
+        if self._list is None:
+            text = self.blob.decode("latin-1")
+            offs = self.offsets.tolist()
+            self._list = [text[offs[i]:offs[i + 1]] for i in range(len(offs) - 1)]
+        return self._list
+
+
 class _NativeReader:
     """The C++ parser of csrc/fastx.cpp (plain and gzip input): same records, an order of magnitude faster."""
 
@@ -137,8 +171,7 @@ class _NativeReader:
             flat = (np.ctypeslib.as_array(ct.cast(seq, ct.POINTER(ct.c_uint8)), shape=(total,)).copy()
                     if total else np.zeros(0, dtype=np.uint8))
             blob = ct.string_at(names, int(noffs[-1])) if noffs[-1] else b""
-            name_list = [blob[int(noffs[i]):int(noffs[i + 1])].decode("latin-1") for i in range(m)]
-            yield name_list, flat, offsets
+            yield NameList(blob, noffs), flat, offsets
 
     def __iter__(self):
         for names, flat, offsets in self.batches():

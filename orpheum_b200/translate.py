@@ -246,16 +246,16 @@ class Translate:
         keys = np.asarray(FRAMES, dtype=np.int8)[frames_idx]
         peptides = iter(translate_frames(self.peptide_bloom_filter.ctx, flat, offsets, reads_idx[need_pep], keys[need_pep]))
         data = flat.tobytes()
-        hits, n_kmers = results["n_hits"], results["n_kmers"]
+        hits = results["n_hits"][reads_idx, frames_idx].tolist()
+        n_kmers = results["n_kmers"][reads_idx, frames_idx].tolist()
         out = []
         handles = self.file_handles
-        for r, f, code, key in zip(reads_idx.tolist(), frames_idx.tolist(), codes.tolist(), keys.tolist()):
+        for r, code, key, h, n in zip(reads_idx.tolist(), codes.tolist(), keys.tolist(), hits, n_kmers):
             name = names[r]
             if code == _lib.CAT_LOW_COMPLEXITY_PEPTIDE:
                 write_fasta(handles["low_complexity_peptide"], name + " translation_frame: {}.format(frame)", next(peptides))
                 continue
-            jaccard = int(hits[r, f]) / int(n_kmers[r, f])
-            seqname = ("{}__translation_frame:{}".format(name, key) + "__jaccard:{}".format(jaccard)).replace(" ", "__")
+            seqname = f"{name}__translation_frame:{key}__jaccard:{h / n}".replace(" ", "__")
             if code == _lib.CAT_CODING:
                 out.append(">{}\n{}\n".format(seqname, next(peptides)))
                 if handles["coding_nucleotide"] is not None:

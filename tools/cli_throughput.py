@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""End-to-end throughput of the `translate` CLI from a FASTQ file on disk to CSV + JSON summary + coding
+peptides (stdout discarded): the whole user-visible path (parse -> GPU -> outputs).  Usage:
+    python tools/cli_throughput.py [n_reads] [--gz]"""
+import contextlib
+import io
+import json
+import os
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from click.testing import CliRunner  # noqa: E402
+
+from orpheum_b200 import gpu, sequence_encodings as enc, synth, translate  # noqa: E402
+
+
+def main():
+    n_reads = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 1_000_000
+    use_gz = "--gz" in sys.argv
+    tmp = tempfile.mkdtemp(prefix="orph_cli_")
+    residues, poffs = synth.make_proteome(n_proteins=20000, seed=1001)
+    g = gpu.GpuNodegraph(7, int(1e8), 4)
+    g.add_peptides(residues, poffs, enc.encode_lut("protein"))
+    filt = os.path.join(tmp, "proteome.nodegraph")
+    g.save(filt)
+    reads = synth.make_reads_fixed(n_reads, residues, poffs, length=150, seed=2002)
+    fq = os.path.join(tmp, "reads.fq")
+    t = time.perf_counter()
+    with open(fq, "wb") as f:
+        qual = b"I" * 150
+        for lo in range(0, n_reads, 100000):
+            hi = min(n_reads, lo + 100000)
+            f.write(b"".join(b"@read%d lane:1/1\n%s\n+\n%s\n" % (i, reads[i].tobytes(), qual) for i in range(lo, hi)))
+    t_write = time.perf_counter() - t
+    if use_gz:
+        os.system(f"gzip -1 -f {fq}")
+        fq += ".gz"
+    size = os.path.getsize(fq)
+    csv, js = os.path.join(tmp, "scores.csv"), os.path.join(tmp, "summary.json")
+    argv = ["--peptides-are-bloom-filter", "--peptide-ksize", "7", "--csv", csv, "--json-summary", js, filt, fq]
+    for attempt in range(2):  # first run warms the page cache and the CUDA context
+        t = time.perf_counter()
+        result = CliRunner().invoke(translate.cli, argv)
+        dt = time.perf_counter() - t
+        assert result.exit_code == 0, result.exception
+    summary = json.load(open(js))
+    print(json.dumps({"n_reads": n_reads, "input": os.path.basename(fq), "input_bytes": size, "seconds": dt,
+                      "reads_per_s": n_reads / dt, "csv_bytes": os.path.getsize(csv),
+                      "coding_reads": summary["categorization_counts"]["Coding"],
+                      "stdout_bytes": len(result.output), "fastq_write_s": t_write}))
+
+
+if __name__ == "__main__":
+    main()
