@@ -108,8 +108,8 @@ int orph_ctx_set_thread_path(orph_ctx *ctx, int on);
 uint64_t orph_ctx_launch_count(const orph_ctx *ctx);
 /* Per-kernel device timing (CUDA events on the context's stream around every scoring kernel), for
  * bench.py's roofline.  Kernel ids: 0 pack_ascii, 1 prefilter, 2 score_frames (warp per read),
- * 3 score_bytes, 4 score_tasks (thread per frame), 5 finalize_best. */
-#define ORPH_N_TIMED_KERNELS 6
+ * 3 score_bytes, 4 score_tasks (thread per frame), 5 finalize_best, 6 task sort (scan + scatter). */
+#define ORPH_N_TIMED_KERNELS 7
 int orph_ctx_set_kernel_timing(orph_ctx *ctx, int on);
 /* Adds up (and clears) the intervals recorded so far: ms[i] total milliseconds and launches[i] count of
  * kernel i.  Synchronizes the stream. */

@@ -93,6 +93,7 @@ struct orph_ctx {
     DevBuf counters;             // ScoreCounters (one per in-flight call; calls on a ctx are serialised on its stream)
     DevBuf queue, bytes_queue;   // uint32 read indices
     DevBuf task_queue;           // uint32 (read << 3 | frame), up to 6 per read
+    DevBuf task_queue_sorted;    // the same entries ordered by peptide length (mixed-length batches)
     DevBuf needs_bytes;          // uint8 per read (ASCII input)
     DevBuf packed;               // 2-bit stream built from ASCII input
     DevBuf in_reads, in_offsets, out_results;  // staging for the index build
@@ -215,7 +216,7 @@ extern "C" void orph_ctx_destroy(orph_ctx *ctx)
     if (!ctx) return;
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf *b : {&ctx->counters, &ctx->queue, &ctx->bytes_queue, &ctx->task_queue, &ctx->needs_bytes, &ctx->packed, &ctx->in_reads,
+    for (DevBuf *b : {&ctx->counters, &ctx->queue, &ctx->bytes_queue, &ctx->task_queue, &ctx->task_queue_sorted, &ctx->needs_bytes, &ctx->packed, &ctx->in_reads,
                       &ctx->in_offsets, &ctx->out_results, &ctx->misc, &ctx->seen, &ctx->in_reads2[0], &ctx->in_reads2[1],
                       &ctx->in_offsets2[0], &ctx->in_offsets2[1], &ctx->out_results2[0], &ctx->out_results2[1]})
         b->release();
@@ -675,22 +676,31 @@ static int launch_score_frames(orph_ctx *ctx, const ScoreParams &P, const uint32
 
 template <int K>
 static int launch_score_tasks(orph_ctx *ctx, const ScoreParams &P_in, uint32_t tier_len, int long_tier, const uint64_t *packed,
-                              const uint64_t *d_offsets, uint64_t pbase0, const uint32_t *tasks, ScoreCounters *counters,
-                              orph_read_result *d_out)
+                              const uint64_t *d_offsets, uint64_t pbase0, const uint32_t *tasks, const uint32_t *tasks_sorted,
+                              ScoreCounters *counters, orph_read_result *d_out)
 {
     ScoreParams P = P_in;
     P.read_words = (2 * tier_len + 34) / 32 + 2;  // aligned strand words incl. the words the look-ahead window fetch may touch
     P.seen_words = long_tier ? kSeenWordsLong : kSeenWordsShort;
     const size_t smem = (size_t)kTaskBlock * (P.seen_words * 8 + P.read_words * 4);
     auto kern = score_tasks_kernel<K>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kTaskBlock * (kSeenWordsLong * 8 + ((2 * kThreadMaxLenLong + 34) / 32 + 2) * 4))));
-    int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTaskBlock, smem));
-    if (per_sm < 1) per_sm = 1;
+    // attribute + occupancy query once per (device, smem size): they cost tens of microseconds per call
+    static thread_local int cached_dev = -1, cached_per_sm[2] = {0, 0};
+    static thread_local size_t cached_smem[2] = {0, 0};
+    if (cached_dev != ctx->device || cached_smem[long_tier] != smem) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kTaskBlock * (kSeenWordsLong * 8 + ((2 * kThreadMaxLenLong + 34) / 32 + 2) * 4))));
+        int q = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, kTaskBlock, smem));
+        if (cached_dev != ctx->device) cached_smem[0] = cached_smem[1] = 0;
+        cached_dev = ctx->device;
+        cached_smem[long_tier] = smem;
+        cached_per_sm[long_tier] = q < 1 ? 1 : q;
+    }
+    const int per_sm = cached_per_sm[long_tier];
     {
         Timed timed(ctx, 4);
         kern<<<ctx->sm_count * per_sm, kTaskBlock, smem, ctx->stream>>>(P, reinterpret_cast<const uint32_t *>(packed), d_offsets,
-                                                                          pbase0, tasks, long_tier, counters, d_out);
+                                                                          pbase0, tasks, tasks_sorted, long_tier, counters, d_out);
     }
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -699,12 +709,12 @@ static int launch_score_tasks(orph_ctx *ctx, const ScoreParams &P_in, uint32_t t
 
 template <int K>
 static int launch_score_task_tiers(orph_ctx *ctx, const ScoreParams &P, uint32_t thread_len, uint32_t short_len, const uint64_t *packed,
-                                   const uint64_t *d_offsets, uint64_t pbase0, const uint32_t *tasks, ScoreCounters *counters,
-                                   orph_read_result *d_out)
+                                   const uint64_t *d_offsets, uint64_t pbase0, const uint32_t *tasks, const uint32_t *tasks_sorted,
+                                   ScoreCounters *counters, orph_read_result *d_out)
 {
-    int rc = launch_score_tasks<K>(ctx, P, short_len, 0, packed, d_offsets, pbase0, tasks, counters, d_out);
+    int rc = launch_score_tasks<K>(ctx, P, short_len, 0, packed, d_offsets, pbase0, tasks, tasks_sorted, counters, d_out);
     if (rc == ORPH_OK && thread_len > short_len)
-        rc = launch_score_tasks<K>(ctx, P, thread_len, 1, packed, d_offsets, pbase0, tasks, counters, d_out);
+        rc = launch_score_tasks<K>(ctx, P, thread_len, 1, packed, d_offsets, pbase0, tasks, tasks_sorted, counters, d_out);
     return rc;
 }
 
@@ -735,6 +745,7 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
     const uint32_t thread_len = has_task_kernel(f->ksize) && !ctx->disable_task_kernel ? std::min(bound, kThreadMaxLen) : 0u;
     const uint32_t short_len = std::min(thread_len, kThreadMaxLenShort);
     if (thread_len && (rc = ctx->task_queue.ensure(n_reads * 6 * 4)) != ORPH_OK) return rc;
+    if (thread_len && (rc = ctx->task_queue_sorted.ensure(n_reads * 6 * 4)) != ORPH_OK) return rc;
     ScoreCounters *counters = (ScoreCounters *)ctx->counters.p;
     // status is sticky across calls until orph_ctx_check; everything else restarts
     CUDA_TRY(cudaMemsetAsync(counters, 0, offsetof(ScoreCounters, status), s));
@@ -786,16 +797,25 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
     // short reads: one thread per open frame
     if (thread_len) {
         const uint32_t *tq = (const uint32_t *)ctx->task_queue.p;
+        const uint32_t *tq_sorted = (const uint32_t *)ctx->task_queue_sorted.p;
+        {
+            Timed timed(ctx, 6);
+            task_scan_kernel<<<1, 64, 0, s>>>(counters);
+            task_scatter_kernel<<<grid_for(n_reads / 8 + 1, 256, ctx->sm_count, 4), 256, 0, s>>>(d_offsets, tq, (uint32_t *)ctx->task_queue_sorted.p,
+                                                                                             P.task_capacity, counters);
+        }
+        ctx->launches += 2;
+        CUDA_TRY(cudaGetLastError());
         switch (P.k) {
-        case 7: rc = launch_score_task_tiers<7>(ctx, P, thread_len, short_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
-        case 8: rc = launch_score_task_tiers<8>(ctx, P, thread_len, short_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
-        case 9: rc = launch_score_task_tiers<9>(ctx, P, thread_len, short_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
-        case 10: rc = launch_score_task_tiers<10>(ctx, P, thread_len, short_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
-        case 11: rc = launch_score_task_tiers<11>(ctx, P, thread_len, short_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
-        case 12: rc = launch_score_task_tiers<12>(ctx, P, thread_len, short_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
-        case 16: rc = launch_score_task_tiers<16>(ctx, P, thread_len, short_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
-        case 21: rc = launch_score_task_tiers<21>(ctx, P, thread_len, short_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
-        case 31: rc = launch_score_task_tiers<31>(ctx, P, thread_len, short_len, d_packed, d_offsets, pbase0, tq, counters, d_out); break;
+        case 7: rc = launch_score_task_tiers<7>(ctx, P, thread_len, short_len, d_packed, d_offsets, pbase0, tq, tq_sorted, counters, d_out); break;
+        case 8: rc = launch_score_task_tiers<8>(ctx, P, thread_len, short_len, d_packed, d_offsets, pbase0, tq, tq_sorted, counters, d_out); break;
+        case 9: rc = launch_score_task_tiers<9>(ctx, P, thread_len, short_len, d_packed, d_offsets, pbase0, tq, tq_sorted, counters, d_out); break;
+        case 10: rc = launch_score_task_tiers<10>(ctx, P, thread_len, short_len, d_packed, d_offsets, pbase0, tq, tq_sorted, counters, d_out); break;
+        case 11: rc = launch_score_task_tiers<11>(ctx, P, thread_len, short_len, d_packed, d_offsets, pbase0, tq, tq_sorted, counters, d_out); break;
+        case 12: rc = launch_score_task_tiers<12>(ctx, P, thread_len, short_len, d_packed, d_offsets, pbase0, tq, tq_sorted, counters, d_out); break;
+        case 16: rc = launch_score_task_tiers<16>(ctx, P, thread_len, short_len, d_packed, d_offsets, pbase0, tq, tq_sorted, counters, d_out); break;
+        case 21: rc = launch_score_task_tiers<21>(ctx, P, thread_len, short_len, d_packed, d_offsets, pbase0, tq, tq_sorted, counters, d_out); break;
+        case 31: rc = launch_score_task_tiers<31>(ctx, P, thread_len, short_len, d_packed, d_offsets, pbase0, tq, tq_sorted, counters, d_out); break;
         default: rc = fail(ORPH_E_INVALID, "internal: no task kernel for k=%u", P.k); break;
         }
         if (rc != ORPH_OK) return rc;
@@ -828,7 +848,7 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
         B.slots = std::max(128u, next_pow2(2 * std::max(1u, bound / 3)));
         B.pep_bytes = (bound / 3 + kPepPad + 3) & ~3u;
         B.read_words = 0;
-        const uint32_t per_warp = (B.slots * 4 + B.pep_bytes + 15) & ~15u;
+        const uint32_t per_warp = (B.slots * 4 + B.pep_bytes + ((bound + 7) & ~3u) + 15) & ~15u;
         int warps = (int)std::min<size_t>(8, std::max<size_t>(1, (size_t)96 * 1024 / per_warp));
         const size_t smem = (size_t)per_warp * warps;
         Timed timed(ctx, 3);
@@ -870,6 +890,7 @@ extern "C" int orph_score_reads_device(orph_ctx *ctx, const orph_filter *f, cons
     if (rc != ORPH_OK) return rc;
     if (n_reads == 0) return ORPH_OK;
     if (reinterpret_cast<uintptr_t>(d_reads) & 15) return fail(ORPH_E_INVALID, "orph_score_reads_device: reads must be 16-byte aligned");
+    if (reinterpret_cast<uintptr_t>(d_out) & 15) return fail(ORPH_E_INVALID, "orph_score_reads_device: out must be 16-byte aligned");
     DeviceGuard guard(ctx->device);
     // one launch set per 2^26 reads (queue entries keep 6 bits for the open-frame mask)
     const uint64_t kMaxLaunchReads = 1ULL << 26;

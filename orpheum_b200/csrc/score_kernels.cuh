@@ -11,9 +11,9 @@
 //   score_bytes_kernel     one WARP per read with the reference's byte semantics (N, lower case,
 //                          IUPAC, over-long reads); used for the reads the two kernels above skip
 //
-// score_frame(): distinct k-mers (compare_kmer_content.py:116-118) via a per-warp shared-memory
-// hash set keyed by the k-mer's MurmurHash (verified byte-wise on equality, exact all-pairs
-// fallback on a true 64-bit collision), Bloom probes with early exit (translate.py:187-191).
+// score_frame(): distinct k-mers (compare_kmer_content.py:116-118) via a per-warp shared-memory hash
+// set of [hash tag | k-mer position] entries, every tag match confirmed on the k-mer bytes (exact),
+// Bloom probes with early exit (translate.py:187-191).  The short-read hot kernel is task_kernels.cuh.
 #pragma once
 #include "device_common.cuh"
 
@@ -23,6 +23,8 @@ constexpr int kWarp = 32;
 constexpr uint32_t kFastMaxLen = 1536;   // longest read the packed fast path handles
 constexpr uint32_t kStatusEmptyRead = 1u;
 constexpr uint32_t kStatusTooLong = 2u;
+
+constexpr uint32_t kLenBuckets = 128;  // peptide lengths of the thread-per-frame tiers (<= 320 / 3) fit
 
 struct ScoreParams {
     FilterDev F;
@@ -51,6 +53,9 @@ struct ScoreCounters {
     uint32_t next_task;
     uint32_t n_tasks_long; // same, long tier (reads of kThreadMaxLenShort+1 .. kThreadMaxLenLong bases)
     uint32_t next_task_long;
+    uint32_t sort_tier[2];        // set by task_scan_kernel: this tier's tasks are consumed from the length-sorted copy
+    uint32_t hist[2][kLenBuckets];   // tasks per peptide length, per tier (filled by prefilter_kernel)
+    uint32_t cursor[2][kLenBuckets]; // scatter cursors of the counting sort (longest peptides first)
     uint32_t pad;
     uint32_t status;       // kStatus* bits; sticky until orph_ctx_check -- keep it last
 };
@@ -276,6 +281,9 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
                  ScoreCounters *__restrict__ counters)
 {
     const int lane = threadIdx.x & 31;
+    __shared__ uint32_t s_hist[2][kLenBuckets];
+    for (uint32_t i = threadIdx.x; i < 2 * kLenBuckets; i += blockDim.x) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
     const uint64_t first = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) & ~31ull;  // warp-uniform loop bound
     for (uint64_t r0 = first; r0 < n_reads; r0 += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t r = r0 + lane;
@@ -385,9 +393,17 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
                     }
                     rec.flags = (uint8_t)open;
                     open_bits = open;
-                    if (L <= thread_short_len) n_my_tasks = __popc(open);           // one thread per open frame
-                    else if (L <= thread_max_len) n_my_tasks_long = __popc(open);  // same, long tier
-                    else to_queue = open != 0;                                      // one warp per read
+                    if (L <= thread_max_len) {  // one thread per open frame
+                        const int tier = L <= thread_short_len ? 0 : 1;
+                        if (tier == 0) n_my_tasks = __popc(open);
+                        else n_my_tasks_long = __popc(open);
+                        for (uint32_t bits = open; bits; bits &= bits - 1) {  // peptide-length histogram for the task sort
+                            const uint32_t f = __ffs(bits) - 1;
+                            atomicAdd(&s_hist[tier][min((uint32_t)((L - (f >= 3 ? f - 3 : f)) / 3), kLenBuckets - 1)], 1u);
+                        }
+                    } else {
+                        to_queue = open != 0;  // one warp per read
+                    }
                 }
             }
             // one 32-byte record per read
@@ -433,6 +449,76 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
                     base_t++;
                 }
             }
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < 2 * kLenBuckets; i += blockDim.x) {
+        const uint32_t v = (&s_hist[0][0])[i];
+        if (v) atomicAdd(&counters->hist[0][0] + i, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Counting sort of the thread-per-frame tasks by peptide length (longest first), so that the 32 frames a
+// warp walks in lock step have (nearly) the same number of residues.  Skipped when a tier's lengths span
+// at most three adjacent values (fixed-length reads), where the prefilter's read order is kept.
+// ------------------------------------------------------------------------------------------------
+__global__ void task_scan_kernel(ScoreCounters *__restrict__ counters)
+{
+    const int tier = threadIdx.x >> 5, lane = threadIdx.x & 31;  // 64 threads: one warp per tier
+    if (tier >= 2) return;
+    uint32_t lo = kLenBuckets, hi = 0;
+    for (uint32_t b = lane; b < kLenBuckets; b += 32)
+        if (counters->hist[tier][b]) { lo = min(lo, b); hi = max(hi, b); }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if (lane == 0) {
+        uint32_t run = 0;
+        for (int b = (int)kLenBuckets - 1; b >= 0; b--) {  // descending: the longest frames go first
+            counters->cursor[tier][b] = run;
+            run += counters->hist[tier][b];
+        }
+        counters->sort_tier[tier] = (lo < kLenBuckets && hi - lo >= 3) ? 1u : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+task_scatter_kernel(const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ tasks, uint32_t *__restrict__ sorted,
+                    uint32_t task_capacity, ScoreCounters *__restrict__ counters)
+{
+    // Each block sorts chunks of kChunk tasks: shared-memory histogram, ONE global atomic per (chunk, length) to
+    // reserve the output ranges, shared-memory cursors inside them.
+    constexpr uint32_t kChunk = 2048;
+    __shared__ uint32_t s_count[kLenBuckets], s_base[kLenBuckets];
+#pragma unroll
+    for (int tier = 0; tier < 2; tier++) {
+        if (!counters->sort_tier[tier]) continue;
+        const uint32_t n = tier == 0 ? counters->n_tasks : counters->n_tasks_long;
+        auto plen_of = [&](uint32_t entry) {
+            const uint32_t r = entry >> 3, f = entry & 7u;
+            const uint32_t L = (uint32_t)(offsets[r + 1] - offsets[r]);
+            return min((L - (f >= 3 ? f - 3 : f)) / 3, kLenBuckets - 1);
+        };
+        for (uint32_t c0 = blockIdx.x * kChunk; c0 < n; c0 += gridDim.x * kChunk) {
+            for (uint32_t b = threadIdx.x; b < kLenBuckets; b += blockDim.x) s_count[b] = 0;
+            __syncthreads();
+            const uint32_t c1 = min(n, c0 + kChunk);
+            for (uint32_t i = c0 + threadIdx.x; i < c1; i += blockDim.x)
+                atomicAdd(&s_count[plen_of(tasks[tier == 0 ? i : task_capacity - 1 - i])], 1u);
+            __syncthreads();
+            for (uint32_t b = threadIdx.x; b < kLenBuckets; b += blockDim.x) {
+                const uint32_t cnt = s_count[b];
+                s_base[b] = cnt ? atomicAdd(&counters->cursor[tier][b], cnt) : 0u;
+                s_count[b] = 0;
+            }
+            __syncthreads();
+            for (uint32_t i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+                const uint32_t entry = tasks[tier == 0 ? i : task_capacity - 1 - i];
+                const uint32_t b = plen_of(entry);
+                const uint32_t pos = s_base[b] + atomicAdd(&s_count[b], 1u);
+                sorted[tier == 0 ? pos : task_capacity - 1 - pos] = entry;
+            }
+            __syncthreads();
         }
     }
 }
@@ -562,10 +648,13 @@ score_bytes_kernel(const ScoreParams P, const void *__restrict__ src, const uint
     stage_filter(&sF, P.F);
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = P.lut[i];
     __syncthreads();
-    const uint32_t per_warp = P.slots * 4 + P.pep_bytes;
+    // per-warp carve-out: [dedup slots | peptide | read bytes]
+    const uint32_t rb_bytes = (P.max_len + 7) & ~3u;
+    const uint32_t per_warp = P.slots * 4 + P.pep_bytes + rb_bytes;
     uint8_t *mine = smem + (size_t)warp * ((per_warp + 15) & ~15u);
     uint32_t *tab = reinterpret_cast<uint32_t *>(mine);
     uint8_t *pep = mine + P.slots * 4;
+    uint8_t *rb = pep + P.pep_bytes;  // the read's bytes, staged once: every pass below works from shared memory
     const uint32_t k = P.k;
 
     while (true) {
@@ -587,10 +676,13 @@ score_bytes_kernel(const ScoreParams P, const void *__restrict__ src, const uint
             for (int f = 0; f < 6; f++) cat[f] = ORPH_CAT_INVALID;
         } else {
             const uint32_t L = (uint32_t)L64;
+            __syncwarp();
+            for (uint32_t i = lane; i < L; i += kWarp) rb[i] = read_base<PACKED_SRC>(src, base0, o0 + i);
+            __syncwarp();
             // compute_fastp_complexity (translate.py:79-84): case-sensitive byte compare
             uint32_t ndiff = 0;
             for (uint32_t i = lane; i + 1 < L; i += kWarp)
-                ndiff += read_base<PACKED_SRC>(src, base0, o0 + i) != read_base<PACKED_SRC>(src, base0, o0 + i + 1);
+                ndiff += rb[i] != rb[i + 1];
             ndiff = __reduce_add_sync(0xffffffffu, ndiff);
             if ((double)ndiff / (double)L < 0.3) {
                 flags |= ORPH_FLAG_LOW_COMPLEXITY;
@@ -600,8 +692,8 @@ score_bytes_kernel(const ScoreParams P, const void *__restrict__ src, const uint
                 // which frames contain a stop codon
                 uint32_t stops = 0;
                 for (uint32_t p = lane; p + 3 <= L; p += kWarp) {
-                    const uint8_t a = read_base<PACKED_SRC>(src, base0, o0 + p), b = read_base<PACKED_SRC>(src, base0, o0 + p + 1),
-                                  c = read_base<PACKED_SRC>(src, base0, o0 + p + 2);
+                    const uint8_t a = rb[p], b = rb[p + 1],
+                                  c = rb[p + 2];
                     if (translate_bytes(a, b, c) == '*') stops |= 1u << (p % 3);
                     if (translate_bytes(complement_byte(c), complement_byte(b), complement_byte(a)) == '*')
                         stops |= 8u << ((L - p) % 3);
@@ -618,14 +710,11 @@ score_bytes_kernel(const ScoreParams P, const void *__restrict__ src, const uint
                     for (uint32_t i = lane; i < plen; i += kWarp) {
                         uint8_t aa;
                         if (f < 3) {
-                            const uint64_t g = o0 + phase + 3 * i;
-                            aa = translate_bytes(read_base<PACKED_SRC>(src, base0, g), read_base<PACKED_SRC>(src, base0, g + 1),
-                                                 read_base<PACKED_SRC>(src, base0, g + 2));
+                            const uint32_t g = phase + 3 * i;
+                            aa = translate_bytes(rb[g], rb[g + 1], rb[g + 2]);
                         } else {
-                            const uint64_t g = o0 + (L - 3 - phase - 3 * i);  // forward position of the codon's last base
-                            aa = translate_bytes(complement_byte(read_base<PACKED_SRC>(src, base0, g + 2)),
-                                                 complement_byte(read_base<PACKED_SRC>(src, base0, g + 1)),
-                                                 complement_byte(read_base<PACKED_SRC>(src, base0, g)));
+                            const uint32_t g = L - 3 - phase - 3 * i;  // forward position of the codon's last base
+                            aa = translate_bytes(complement_byte(rb[g + 2]), complement_byte(rb[g + 1]), complement_byte(rb[g]));
                         }
                         pep[i] = s_lut[aa];
                     }

@@ -134,8 +134,8 @@ __device__ __forceinline__ bool kmer_seen_before(const StrandColumn &sc, const u
 template <int K>
 __global__ void __launch_bounds__(kTaskBlock)
 score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, const uint64_t *__restrict__ offsets,
-                   uint64_t base0, const uint32_t *__restrict__ tasks, int long_tier, ScoreCounters *__restrict__ counters,
-                   orph_read_result *__restrict__ out)
+                   uint64_t base0, const uint32_t *__restrict__ tasks_unsorted, const uint32_t *__restrict__ tasks_sorted,
+                   int long_tier, ScoreCounters *__restrict__ counters, orph_read_result *__restrict__ out)
 {
     extern __shared__ __align__(16) uint8_t dyn_smem[];  // [seen: P.seen_words u64 x 256][strand words: P.read_words u32 x 256]
     __shared__ FilterDev sF;
@@ -171,6 +171,7 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
         }                                                                                     \
     }
     const uint32_t n_tasks = long_tier ? counters->n_tasks_long : counters->n_tasks;
+    const uint32_t *tasks = counters->sort_tier[long_tier ? 1 : 0] ? tasks_sorted : tasks_unsorted;
     uint32_t *next_task = long_tier ? &counters->next_task_long : &counters->next_task;
     const uint32_t seen_words = P.seen_words;
     unsigned long long *seen = reinterpret_cast<unsigned long long *>(dyn_smem) + threadIdx.x;
