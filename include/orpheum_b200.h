@@ -151,7 +151,9 @@ int orph_filter_replicate(const orph_filter *src, orph_ctx *dst_ctx, orph_filter
 /* The inner loop of index.make_peptide_bloom_filter (index.py:107-122): for each record, skip it if it
  * contains '*', re-encode through lut (encode_peptide), hash every k-mer (MurmurHash3_x64_128 seed 42,
  * low 64 bits) and OR bit (hash % size_i) into every table.  residues/offsets are HOST arrays
- * (offsets has n_records+1 entries).  n_unique_kmers_inc (optional) receives the increment. */
+ * (offsets has n_records+1 entries).  n_unique_kmers_inc (optional) receives the increment of
+ * Nodegraph.n_unique_kmers(); passing NULL skips the de-duplication set that exact count needs (the bits are
+ * the same) and orph_filter_n_unique_kmers() then over-counts k-mers that were inserted concurrently. */
 int orph_filter_add_peptides(orph_filter *f, const uint8_t *residues, const uint64_t *offsets, uint64_t n_records,
                              const uint8_t lut[256], uint64_t *n_unique_kmers_inc);
 /* Nodegraph.add(hash) for a batch of precomputed hashes (index.py:119); is_new (optional) gets 0/1. */

@@ -541,17 +541,22 @@ extern "C" int orph_filter_add_peptides(orph_filter *f, const uint8_t *residues,
         int rc;
         if ((rc = ctx->in_reads.ensure(total + 16)) != ORPH_OK) return rc;
         if ((rc = ctx->in_offsets.ensure((m + 1) * sizeof(uint64_t))) != ORPH_OK) return rc;
+        // the hash set of seen k-mers only serves n_unique_kmers: skipped when the caller does not ask for the count
+        const bool count_unique = n_unique_kmers_inc != nullptr;
         uint64_t slots = 1024;
-        while (slots < 2 * total) slots <<= 1;
-        if ((rc = ctx->seen.ensure(slots * 8)) != ORPH_OK) return rc;
-        CUDA_TRY(cudaMemsetAsync(ctx->seen.p, 0xFF, slots * 8, s));
+        if (count_unique) {
+            while (slots < 2 * total) slots <<= 1;
+            if ((rc = ctx->seen.ensure(slots * 8)) != ORPH_OK) return rc;
+            CUDA_TRY(cudaMemsetAsync(ctx->seen.p, 0xFF, slots * 8, s));
+        }
         if (total) CUDA_TRY(cudaMemcpyAsync(ctx->in_reads.p, residues + base, total, cudaMemcpyHostToDevice, s));
         CUDA_TRY(cudaMemcpyAsync(ctx->in_offsets.p, offsets + lo, (m + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
         CUDA_TRY(cudaMemsetAsync(f->d_scalars + 2, 0, sizeof(unsigned long long), s));
         const int grid = ctx->sm_count * 8;
         // the residues pointer is shifted so that the absolute offsets index it directly
         bloom_add_peptides_kernel<<<grid, 256, 0, s>>>(P, (const uint8_t *)ctx->in_reads.p - base, (const uint64_t *)ctx->in_offsets.p, m,
-                                                      f->d_scalars + 2, f->d_scalars, (unsigned long long *)ctx->seen.p, slots - 1);
+                                                      f->d_scalars + 2, f->d_scalars, count_unique ? (unsigned long long *)ctx->seen.p : nullptr,
+                                                      slots - 1);
         ctx->launches++;
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaStreamSynchronize(s));  // the staging buffers are reused by the next chunk

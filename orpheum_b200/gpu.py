@@ -174,15 +174,16 @@ class GpuNodegraph:
         check(self._lib.orph_filter_query_hashes(self._h, ptr(h), len(h), ptr(out)))
         return out
 
-    def add_peptides(self, residues, offsets, lut):
-        """The inner loop of index.make_peptide_bloom_filter for a batch of records (index.py:107-122)."""
+    def add_peptides(self, residues, offsets, lut, count_unique=True):
+        """The inner loop of index.make_peptide_bloom_filter for a batch of records (index.py:107-122).
+        count_unique=False skips the bookkeeping behind n_unique_kmers() (same bits, faster build)."""
         residues = np.ascontiguousarray(residues, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         lut = np.ascontiguousarray(lut, dtype=np.uint8)
         assert lut.shape == (256,)
         inc = ctypes.c_uint64()
         check(self._lib.orph_filter_add_peptides(self._h, ptr(residues), ptr(offsets), len(offsets) - 1, ptr(lut),
-                                                 ctypes.byref(inc)))
+                                                 ctypes.byref(inc) if count_unique else None))
         return int(inc.value)
 
     def tables(self):

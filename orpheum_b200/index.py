@@ -94,8 +94,10 @@ def make_peptide_bloom_filter(
     tablesize=constants_index.DEFAULT_MAX_TABLESIZE,
     index_dir=None,
     ctx=None,
+    count_unique=True,
 ):
-    """Bloom filter of every peptide k-mer of `peptides` (a file, or an iterable of files with index_dir)."""
+    """Bloom filter of every peptide k-mer of `peptides` (a file, or an iterable of files with index_dir).
+    count_unique=False skips the bookkeeping behind ``n_unique_kmers()`` (the saved file is identical)."""
     lut = encode_lut(molecule)  # ValueError for an unknown alphabet, like encode_peptide
     bloom = GpuNodegraph(peptide_ksize, int(tablesize), n_tables=n_tables, ctx=ctx)
     if not index_dir:
@@ -107,7 +109,7 @@ def make_peptide_bloom_filter(
                 offsets = np.zeros(len(seqs) + 1, dtype=np.uint64)
                 offsets[1:] = np.cumsum([len(s) for s in seqs])
                 residues = np.frombuffer(b"".join(seqs), dtype=np.uint8) if offsets[-1] else np.zeros(1, np.uint8)
-                bloom.add_peptides(residues, offsets, lut)
+                bloom.add_peptides(residues, offsets, lut, count_unique=count_unique)
         finally:
             if hasattr(records, "close"):
                 records.close()
@@ -178,7 +180,7 @@ def cli(peptides, peptide_ksize=None, alphabet="protein", save_as=None, tablesiz
         peptides = (os.path.join(index_dir, p) for p in os.listdir(index_dir))
     peptide_ksize = get_peptide_ksize(alphabet, peptide_ksize)
     bloom = make_peptide_bloom_filter(peptides, peptide_ksize, alphabet, n_tables=n_tables, tablesize=tablesize,
-                                      index_dir=index_dir)
+                                      index_dir=index_dir, count_unique=False)  # the CLI never reports the count
     maybe_save_peptide_bloom_filter(peptides, bloom, alphabet,
                                     save_peptide_bloom_filter=save_as if save_as is not None else True,
                                     index_dir=index_dir)
