@@ -36,7 +36,7 @@ STREAM_BYTES_PER_READ = (READ_LEN + 3) // 4 + 4 + 32  # 2-bit payload
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU per step")

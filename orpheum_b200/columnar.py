@@ -130,78 +130,95 @@ class ScoreTable:
 
     # -- JSON summary --------------------------------------------------------------------------------------
     def empty_categories(self):
-        counts = dict.fromkeys(PROTEIN_CODING_CATEGORIES.values(), 0)
-        counts[LOW_COMPLEXITY_CATEGORIES[self.alphabet]] = 0
-        return counts
+        return empty_categories(self.alphabet)
 
     def summary(self, filenames, peptide_bloom_filter_filename, peptide_ksize, jaccard_threshold):
         """The dict ``CreateSaveSummary.maybe_write_json_summary`` dumps (create_save_summary.py:91-240)."""
-        unique_filenames = [os.path.basename(f) for f in ([filenames] if isinstance(filenames, str) else filenames)]
         c = self._columns()
         if c is None:
-            empty = self.empty_categories()
-            zero_hist = {str(i): 0 for i in range(len(empty))}
-            return {
-                "input_files": unique_filenames,
-                "jaccard_info": {"count": 0, "mean": None, "std": None, "min": None, "25%": None, "50%": None, "75%": None,
-                                 "max": None},
-                "categorization_counts": empty, "categorization_percentages": empty,
-                "histogram_n_coding_frames_per_read": zero_hist,
-                "histogram_n_coding_frames_per_read_percentages": dict(zero_hist),
-            }
-        names, cat = c["names"], c["category"].reshape(-1, 6)
-        # the reference groups CONSECUTIVE rows with equal read ids (itertools.groupby, :180-182)
-        new_group = np.ones(len(names), dtype=bool)
-        if len(names) > 1:
-            new_group[1:] = names[1:] != names[:-1]
-        group = np.cumsum(new_group) - 1
-        n_groups = int(group[-1]) + 1
-        present = np.zeros((n_groups, 6), dtype=bool)  # category code present in the group
-        np.logical_or.at(present, (np.repeat(group, 6), cat.reshape(-1)), True)
-        counts = self.empty_categories()
-        coding = present[:, _lib.CAT_CODING]
-        short_pep = ~coding & present[:, _lib.CAT_TOO_SHORT_PEPTIDE]
-        short_read = ~coding & ~short_pep & present[:, _lib.CAT_LOW_COMPLEXITY_NUCLEOTIDE]
-        rest = ~coding & ~short_pep & ~short_read
-        single = rest & (present.sum(axis=1) == 1)
-        counts["Coding"] += int(coding.sum())
-        counts[PROTEIN_CODING_CATEGORIES["too_short_peptide"]] += int(short_pep.sum())
-        counts[PROTEIN_CODING_CATEGORIES["too_short_nucleotide"]] += int(short_read.sum())
-        for code in np.unique(np.argmax(present[single], axis=1)) if single.any() else []:
-            counts[category_text(int(code), self.alphabet)] += int((np.argmax(present[single], axis=1) == code).sum())
-        counts["Non-coding"] += int((rest & ~single).sum())
-        total = sum(counts.values())
-        percentages = {k: 100 * v / total for k, v in counts.items()}
-        # histogram of coding frames per read id (Counter over read ids, :216-222): ids are merged by VALUE here
-        is_coding = cat == _lib.CAT_CODING
-        per_read = is_coding.sum(axis=1)
-        coding_names = names[per_read > 0]
-        label = "Number of reads with {} putative protein-coding translations".format
-        hist_counts, hist_pct = {}, {}
-        if len(coding_names):
-            per_name = {}
-            for name, n in zip(coding_names.tolist(), per_read[per_read > 0].tolist()):
-                per_name[name] = per_name.get(name, 0) + n
-            hist = {}
-            for n in per_name.values():
-                hist[n] = hist.get(n, 0) + 1
-            tot = sum(hist.values())
-            hist_counts = {label(k): v for k, v in hist.items()}
-            hist_pct = {label(k): 100 * v / tot for k, v in hist.items()}
-        j = c["jaccard"]  # the reference hands numpy a python list of the same doubles
-        jaccard_info = {
-            "count": int(np.count_nonzero(~np.isnan(j))), "mean": np.nanmean(j), "std": np.nanstd(j), "min": np.nanmin(j),
-            "25%": np.nanpercentile(j, 25), "50%": np.nanpercentile(j, 50), "75%": np.nanpercentile(j, 75), "max": np.nanmax(j),
-        }
-        return {
-            "input_files": unique_filenames, "jaccard_info": jaccard_info, "categorization_counts": counts,
-            "categorization_percentages": percentages, "histogram_n_coding_frames_per_read": hist_counts,
-            "histogram_n_coding_frames_per_read_percentages": hist_pct, "peptide_bloom_filter": peptide_bloom_filter_filename,
-            "peptide_alphabet": self.alphabet, "peptide_ksize": peptide_ksize, "jaccard_threshold": jaccard_threshold,
-        }
+            return summarize(self.alphabet, None, filenames, peptide_bloom_filter_filename, peptide_ksize, jaccard_threshold)
+        names = c["names"]
+        group_of_read = consecutive_groups(names)
+        coding_rows = np.nonzero(c["category"] == _lib.CAT_CODING)[0]
+        rows = (np.repeat(group_of_read, 6), c["category"], names[c["read_index"][coding_rows]].tolist(), c["jaccard"])
+        return summarize(self.alphabet, rows, filenames, peptide_bloom_filter_filename, peptide_ksize, jaccard_threshold)
 
     def write_json_summary(self, path, filenames, peptide_bloom_filter_filename, peptide_ksize, jaccard_threshold):
         summary = self.summary(filenames, peptide_bloom_filter_filename, peptide_ksize, jaccard_threshold)
         with open(path, "w") as handle:
             json.dump(summary, fp=handle)
         return summary
+
+
+def empty_categories(alphabet):
+    counts = dict.fromkeys(PROTEIN_CODING_CATEGORIES.values(), 0)
+    counts[LOW_COMPLEXITY_CATEGORIES[alphabet]] = 0
+    return counts
+
+
+def consecutive_groups(names):
+    """Group index per element, a new group wherever the value differs from its predecessor: what
+    ``itertools.groupby`` does to the read ids in the reference (create_save_summary.py:180-182)."""
+    names = np.asarray(names, dtype=object)
+    start = np.ones(len(names), dtype=bool)
+    if len(names) > 1:
+        start[1:] = names[1:] != names[:-1]
+    return np.cumsum(start) - 1
+
+
+def summarize(alphabet, rows, filenames, peptide_bloom_filter_filename, peptide_ksize, jaccard_threshold):
+    """The JSON-summary dict.  rows = (group index per row, category code per row, read ids of the Coding rows in
+    row order, jaccard per row), or None when no read was scored."""
+    input_files = [os.path.basename(f) for f in ([filenames] if isinstance(filenames, str) else filenames)]
+    if rows is None:
+        empty = empty_categories(alphabet)
+        zero_hist = {str(i): 0 for i in range(len(empty))}
+        return {
+            "input_files": input_files,
+            "jaccard_info": {"count": 0, "mean": None, "std": None, "min": None, "25%": None, "50%": None, "75%": None,
+                             "max": None},
+            "categorization_counts": empty, "categorization_percentages": empty,
+            "histogram_n_coding_frames_per_read": zero_hist,
+            "histogram_n_coding_frames_per_read_percentages": dict(zero_hist),
+        }
+    group, codes, coding_ids, jaccard = rows
+    # one category per group of rows: Coding > too-short peptide > too-short read > the only category > Non-coding
+    present = np.zeros((int(group[-1]) + 1, 6), dtype=bool)
+    present[group, codes] = True
+    coding = present[:, _lib.CAT_CODING]
+    short_pep = ~coding & present[:, _lib.CAT_TOO_SHORT_PEPTIDE]
+    short_read = ~coding & ~short_pep & present[:, _lib.CAT_LOW_COMPLEXITY_NUCLEOTIDE]
+    undecided = ~coding & ~short_pep & ~short_read
+    single = undecided & (present.sum(axis=1) == 1)
+    counts = empty_categories(alphabet)
+    counts["Coding"] += int(coding.sum())
+    counts[PROTEIN_CODING_CATEGORIES["too_short_peptide"]] += int(short_pep.sum())
+    counts[PROTEIN_CODING_CATEGORIES["too_short_nucleotide"]] += int(short_read.sum())
+    only = np.argmax(present[single], axis=1)
+    for code in np.unique(only):
+        counts[category_text(int(code), alphabet)] += int((only == code).sum())
+    counts["Non-coding"] += int((undecided & ~single).sum())
+    total = sum(counts.values())
+    # coding frames per read id; ids are merged by value here, as collections.Counter does (:216-222)
+    per_id = {}
+    for read_id in coding_ids:
+        per_id[read_id] = per_id.get(read_id, 0) + 1
+    histogram = {}
+    for n in per_id.values():
+        histogram[n] = histogram.get(n, 0) + 1
+    n_coding_ids = sum(histogram.values())
+    label = "Number of reads with {} putative protein-coding translations".format
+    return {
+        "input_files": input_files,
+        "jaccard_info": {
+            "count": int(np.count_nonzero(~np.isnan(jaccard))), "mean": np.nanmean(jaccard), "std": np.nanstd(jaccard),
+            "min": np.nanmin(jaccard), "25%": np.nanpercentile(jaccard, 25), "50%": np.nanpercentile(jaccard, 50),
+            "75%": np.nanpercentile(jaccard, 75), "max": np.nanmax(jaccard),
+        },
+        "categorization_counts": counts,
+        "categorization_percentages": {k: 100 * v / total for k, v in counts.items()},
+        "histogram_n_coding_frames_per_read": {label(k): v for k, v in histogram.items()},
+        "histogram_n_coding_frames_per_read_percentages": {label(k): 100 * v / n_coding_ids for k, v in histogram.items()},
+        "peptide_bloom_filter": peptide_bloom_filter_filename, "peptide_alphabet": alphabet, "peptide_ksize": peptide_ksize,
+        "jaccard_threshold": jaccard_threshold,
+    }
