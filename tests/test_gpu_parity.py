@@ -379,3 +379,53 @@ def test_emitted_peptides_on_gpu(gpu, orc, misc_kats):
     assert gpu.translate_frames(gpu.default_context(), flat, offsets, [], []) == []
     with pytest.raises(ValueError):
         gpu.translate_frames(gpu.default_context(), flat, offsets, [0], [4])
+
+
+@pytest.mark.parametrize("ksize,n_tables,tablesize", [
+    (7, 1, 1e6), (7, 2, 30011), (7, 7, 1e6), (5, 4, 1e5), (13, 3, 1e6), (8, 4, 1e6), (20, 4, 1e6), (32, 2, 1e6), (40, 4, 1e6),
+])
+def test_other_geometries_and_ksizes(gpu, enc, orc, refdata, ksize, n_tables, tablesize):
+    """k-mer sizes with and without a compiled thread-per-frame kernel (generic warp kernel otherwise), 1 / 2 / 3 / 7
+    tables (the non-unrolled probe loops), tiny over-full tables."""
+    from orpheum_b200 import synth
+
+    fasta = os.path.join(refdata, "index", "Homo_sapiens.GRCh38.pep.first1000lines.fa")
+    res_, offs_ = fasta_arrays(fasta)
+    lut = enc.encode_lut("dayhoff" if ksize >= 13 else "protein")
+    olut = orc.encode_lut("dayhoff" if ksize >= 13 else "protein")
+    go = orc.Nodegraph(ksize, tablesize, n_tables)
+    go.add_peptides(res_, offs_, olut)
+    gg = gpu.GpuNodegraph(ksize, tablesize, n_tables)
+    gg.add_peptides(res_, offs_, lut)
+    assert [gg.n_occupied(i) for i in range(n_tables)] == [go.n_occupied(i) for i in range(n_tables)]
+    standard = np.zeros(256, dtype=bool)
+    standard[np.frombuffer(synth.AMINO_ACIDS.encode(), dtype=np.uint8)] = True
+    keep = [i for i in range(len(offs_) - 1) if offs_[i + 1] - offs_[i] >= 120 and standard[res_[int(offs_[i]):int(offs_[i + 1])]].all()]
+    residues = np.concatenate([res_[int(offs_[i]):int(offs_[i + 1])] for i in keep])
+    poffs = np.zeros(len(keep) + 1, dtype=np.uint64)
+    poffs[1:] = np.cumsum([int(offs_[i + 1] - offs_[i]) for i in keep])
+    flat, offsets = synth.make_reads_mixed(3000, residues, poffs, ksize=ksize, seed=11 + ksize, min_len=30, max_len=400)
+    ora, n_empty = orc.score_reads(go, flat, offsets, olut, 0.5, n_threads=0)
+    assert n_empty == 0
+    res = gpu.score_reads(gg, flat, offsets, lut, 0.5)
+    assert_same_as_oracle(res, ora, f"k={ksize} tables={n_tables}")
+
+
+def test_table_larger_than_2_31_bits(gpu, enc, orc):
+    """Tables of more than 2^31 bits take the 64-bit remainder path of the Barrett reduction."""
+    from orpheum_b200 import synth
+
+    residues, poffs = synth.make_proteome(n_proteins=300, seed=21)
+    tablesize = 2_300_000_000
+    gg = gpu.GpuNodegraph(7, tablesize, 1)
+    assert gg.hashsizes()[0] > 2**31
+    gg.add_peptides(residues, poffs, enc.encode_lut("protein"))
+    go = orc.Nodegraph(7, tablesize, 1)
+    go.add_peptides(residues, poffs, orc.encode_lut("protein"))
+    assert gg.n_occupied(0) == go.n_occupied(0)
+    flat, offsets = synth.concat_fixed(synth.make_reads_fixed(4000, residues, poffs, length=150, seed=22))
+    ora, _ = orc.score_reads(go, flat, offsets, orc.encode_lut("protein"), 0.5, n_threads=0)
+    res = gpu.score_reads(gg, flat, offsets, enc.encode_lut("protein"), 0.5)
+    assert_same_as_oracle(res, ora, "2^31")
+    hashes = np.random.default_rng(5).integers(0, 2**64, 5000, dtype=np.uint64)
+    np.testing.assert_array_equal(gg.get_many(hashes), np.array([go.get(int(h)) for h in hashes], dtype=np.uint8))
