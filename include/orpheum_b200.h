@@ -84,7 +84,8 @@ typedef enum orph_reads_format {
                               through an ASCII batch (orph_pack_reads reports which). */
 } orph_reads_format;
 
-#define ORPH_MAX_READ_LEN 6144u /* longest read the byte-exact path scores (over-long -> ORPH_E_TOO_LONG) */
+#define ORPH_MAX_READ_LEN 196607u /* longest read scored (over-long -> ORPH_E_TOO_LONG): a frame of 65535 residues is the
+                                     most whose distinct k-mer count fits the record's 16-bit fields */
 
 typedef struct orph_ctx orph_ctx;
 typedef struct orph_filter orph_filter;
@@ -108,8 +109,9 @@ int orph_ctx_set_thread_path(orph_ctx *ctx, int on);
 uint64_t orph_ctx_launch_count(const orph_ctx *ctx);
 /* Per-kernel device timing (CUDA events on the context's stream around every scoring kernel), for
  * bench.py's roofline.  Kernel ids: 0 pack_ascii, 1 prefilter, 2 score_frames (warp per read),
- * 3 score_bytes, 4 score_tasks (thread per frame), 5 finalize_best, 6 task sort (scan + scatter). */
-#define ORPH_N_TIMED_KERNELS 7
+ * 3 score_bytes, 4 score_tasks (thread per frame), 5 finalize_best, 6 task sort (scan + scatter),
+ * 7 score_long (block per read). */
+#define ORPH_N_TIMED_KERNELS 8
 int orph_ctx_set_kernel_timing(orph_ctx *ctx, int on);
 /* Adds up (and clears) the intervals recorded so far: ms[i] total milliseconds and launches[i] count of
  * kernel i.  Synchronizes the stream. */

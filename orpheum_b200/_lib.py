@@ -16,7 +16,7 @@ ORPH_OK = 0
 ORPH_E_INVALID, ORPH_E_CUDA, ORPH_E_NOMEM, ORPH_E_TOO_LONG, ORPH_E_EMPTY_READ, ORPH_E_IO = -1, -2, -3, -4, -5, -6
 READS_ASCII, READS_PACKED2 = 0, 1
 MAX_TABLES = 16
-MAX_READ_LEN = 6144
+MAX_READ_LEN = 196607
 
 CAT_STOP_CODONS, CAT_TOO_SHORT_PEPTIDE, CAT_LOW_COMPLEXITY_PEPTIDE, CAT_CODING, CAT_NON_CODING, \
     CAT_LOW_COMPLEXITY_NUCLEOTIDE = range(6)

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "bloom_kernels.cuh"
+#include "long_kernels.cuh"
 #include "score_kernels.cuh"
 #include "task_kernels.cuh"
 
@@ -106,6 +107,7 @@ struct orph_ctx {
     struct Interval { cudaEvent_t a, b; int id; };
     std::vector<Interval> intervals;
     DevBuf seen;                 // hash set of k-mer hashes seen during one index-build chunk
+    DevBuf long_scratch;         // per-block peptide + de-duplication table of score_long_kernel
 };
 
 struct orph_filter {
@@ -217,7 +219,7 @@ extern "C" void orph_ctx_destroy(orph_ctx *ctx)
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf *b : {&ctx->counters, &ctx->queue, &ctx->bytes_queue, &ctx->task_queue, &ctx->task_queue_sorted, &ctx->needs_bytes, &ctx->packed, &ctx->in_reads,
-                      &ctx->in_offsets, &ctx->out_results, &ctx->misc, &ctx->seen, &ctx->in_reads2[0], &ctx->in_reads2[1],
+                      &ctx->in_offsets, &ctx->out_results, &ctx->misc, &ctx->seen, &ctx->long_scratch, &ctx->in_reads2[0], &ctx->in_reads2[1],
                       &ctx->in_offsets2[0], &ctx->in_offsets2[1], &ctx->out_results2[0], &ctx->out_results2[1]})
         b->release();
     if (ctx->pipe_ready) {
@@ -792,7 +794,7 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
     {
         Timed timed(ctx, 1);
         prefilter_kernel<<<grid_for(n_reads, 256, ctx->sm_count, 16), 256, 0, s>>>(
-            d_packed, d_offsets, pbase0, n_reads, d_needs, P.k, fast_len, thread_len, short_len, P.task_capacity, bound, d_out,
+            d_packed, d_offsets, pbase0, n_reads, d_needs, P.k, fast_len, thread_len, short_len, P.task_capacity, bound, kBytesMaxLen, d_out,
             (uint32_t *)ctx->queue.p,
             (uint32_t *)ctx->task_queue.p, (uint32_t *)ctx->bytes_queue.p, counters);
     }
@@ -850,10 +852,12 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
     // byte-exact path for whatever prefilter routed away (non-ACGT bytes, reads longer than the fast path)
     if (d_ascii || bound > fast_len) {
         ScoreParams B = P;
-        B.slots = std::max(128u, next_pow2(2 * std::max(1u, bound / 3)));
-        B.pep_bytes = (bound / 3 + kPepPad + 3) & ~3u;
+        const uint32_t bbound = std::min(bound, kBytesMaxLen);
+        B.max_len = bbound;
+        B.slots = std::max(128u, next_pow2(2 * std::max(1u, bbound / 3)));
+        B.pep_bytes = (bbound / 3 + kPepPad + 3) & ~3u;
         B.read_words = 0;
-        const uint32_t per_warp = (B.slots * 4 + B.pep_bytes + ((bound + 7) & ~3u) + 15) & ~15u;
+        const uint32_t per_warp = (B.slots * 4 + B.pep_bytes + ((bbound + 7) & ~3u) + 15) & ~15u;
         int warps = (int)std::min<size_t>(8, std::max<size_t>(1, (size_t)96 * 1024 / per_warp));
         const size_t smem = (size_t)per_warp * warps;
         Timed timed(ctx, 3);
@@ -870,6 +874,21 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
             kern<<<ctx->sm_count * std::max(1, per_sm), warps * 32, smem, s>>>(B, d_packed, d_offsets, pbase0, n_reads, (const uint32_t *)ctx->bytes_queue.p, counters, d_out);
         }
+        ctx->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+
+    // reads beyond the warp kernel's shared-memory staging: one block per read, scratch in global memory
+    if (bound > kBytesMaxLen) {
+        const int grid = ctx->sm_count;
+        if ((rc = ctx->long_scratch.ensure(long_scratch_bytes(bound) * grid)) != ORPH_OK) return rc;
+        Timed timed(ctx, 7);
+        if (d_ascii)
+            score_long_kernel<false><<<grid, kLongBlock, 0, s>>>(P, d_ascii, d_offsets, abase0, (const uint32_t *)ctx->bytes_queue.p, (uint32_t)n_reads,
+                                                              counters, d_out, (uint8_t *)ctx->long_scratch.p);
+        else
+            score_long_kernel<true><<<grid, kLongBlock, 0, s>>>(P, d_packed, d_offsets, pbase0, (const uint32_t *)ctx->bytes_queue.p, (uint32_t)n_reads,
+                                                             counters, d_out, (uint8_t *)ctx->long_scratch.p);
         ctx->launches++;
         CUDA_TRY(cudaGetLastError());
     }

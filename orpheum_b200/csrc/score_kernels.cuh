@@ -21,6 +21,7 @@ namespace orph {
 
 constexpr int kWarp = 32;
 constexpr uint32_t kFastMaxLen = 1536;   // longest read the packed fast path handles
+constexpr uint32_t kBytesMaxLen = 6144;  // longest read the warp-per-read byte path stages in shared memory; beyond: block per read
 constexpr uint32_t kStatusEmptyRead = 1u;
 constexpr uint32_t kStatusTooLong = 2u;
 
@@ -56,6 +57,8 @@ struct ScoreCounters {
     uint32_t sort_tier[2];        // set by task_scan_kernel: this tier's tasks are consumed from the length-sorted copy
     uint32_t hist[2][kLenBuckets];   // tasks per peptide length, per tier (filled by prefilter_kernel)
     uint32_t cursor[2][kLenBuckets]; // scatter cursors of the counting sort (longest peptides first)
+    uint32_t n_long;       // reads queued for score_long_kernel (block per read), from the back of the byte queue
+    uint32_t next_long;
     uint32_t pad;
     uint32_t status;       // kStatus* bits; sticky until orph_ctx_check -- keep it last
 };
@@ -103,7 +106,7 @@ __device__ __noinline__ void score_frame_exact(const uint8_t *enc, uint32_t plen
 // exact with no fallback; 0xFFFFFFFF (position 2047 cannot occur, see kMaxPeptide) marks an empty slot.
 constexpr uint32_t kPosBits = 11;
 constexpr uint32_t kEmptySlot = 0xFFFFFFFFu;
-constexpr uint32_t kMaxPeptide = ORPH_MAX_READ_LEN / 3;  // 2048 residues: positions <= 2048 - k < 2047
+constexpr uint32_t kMaxPeptide = kBytesMaxLen / 3;  // 2048 residues: positions <= 2048 - k < 2047
 
 template <int K>  // K > 0: compile-time k-mer size; K == 0: runtime k
 __device__ __forceinline__ void score_frame(const uint8_t *enc, uint32_t plen, uint32_t k_rt, const FilterDev &F,
@@ -276,7 +279,7 @@ __global__ void __launch_bounds__(256)
 prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict__ offsets, uint64_t base0,
                  uint64_t n_reads, const uint8_t *__restrict__ needs_bytes, uint32_t k, uint32_t fast_max_len,
                  uint32_t thread_max_len, uint32_t thread_short_len, uint32_t task_capacity, uint32_t max_len,
-                 orph_read_result *__restrict__ out,
+                 uint32_t bytes_max_len, orph_read_result *__restrict__ out,
                  uint32_t *__restrict__ queue, uint32_t *__restrict__ task_queue, uint32_t *__restrict__ bytes_queue,
                  ScoreCounters *__restrict__ counters)
 {
@@ -288,7 +291,7 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
     for (uint64_t r0 = first; r0 < n_reads; r0 += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t r = r0 + lane;
         const bool in_range = r < n_reads;
-        bool to_queue = false, to_bytes = false;
+        bool to_queue = false, to_bytes = false, to_long = false;
         uint32_t open_bits = 0, n_my_tasks = 0, n_my_tasks_long = 0;
         if (in_range) {
             const uint64_t o0 = offsets[r], o1 = offsets[r + 1];
@@ -302,6 +305,9 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
                 atomicOr(&counters->status, kStatusEmptyRead);
             } else if (L > max_len) {
                 atomicOr(&counters->status, kStatusTooLong);
+            } else if (L > bytes_max_len) {
+                to_long = true;
+                rec.flags = ORPH_FLAG_BYTE_PATH;
             } else if ((needs_bytes && needs_bytes[r]) || L > fast_max_len) {
                 to_bytes = true;
                 rec.flags = ORPH_FLAG_BYTE_PATH;
@@ -425,6 +431,8 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
         const uint32_t below = (1u << lane) - 1;
         if (to_queue) queue[base_q + __popc(mq & below)] = ((uint32_t)r << 6) | open_bits;
         if (to_bytes) bytes_queue[base_b + __popc(mb & below)] = (uint32_t)r;
+        if (to_long)  // rare: the byte queue is filled from the back, one atomic per read
+            bytes_queue[(uint32_t)n_reads - 1 - atomicAdd(&counters->n_long, 1u)] = (uint32_t)r;
         // per-frame tasks: warp-wide scan of the per-read task counts, one atomic per warp and tier
 #pragma unroll
         for (int tier = 0; tier < 2; tier++) {

@@ -50,7 +50,7 @@ class Context:
     def set_force_exact_dedup(self, on):
         check(self._lib.orph_ctx_set_force_exact_dedup(self._h, int(bool(on))))
 
-    KERNEL_NAMES = ("pack_ascii", "prefilter", "score_frames", "score_bytes", "score_tasks", "finalize_best", "task_sort")
+    KERNEL_NAMES = ("pack_ascii", "prefilter", "score_frames", "score_bytes", "score_tasks", "finalize_best", "task_sort", "score_long")
 
     def set_thread_path(self, on):
         """Test hook: False sends short reads through the warp-per-read kernel."""

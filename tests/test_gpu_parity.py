@@ -343,6 +343,7 @@ def test_edge_cases(gpu, enc, orc, refdata):
     with pytest.raises(ZeroDivisionError):
         gpu.score_reads(gg, flat, offsets, lut, 0.5)
     # long reads: beyond the packed fast path (1536) -> byte path; beyond ORPH_MAX_READ_LEN -> ValueError
+    # (reads between 6144 and ORPH_MAX_READ_LEN: test_long_reads_block_kernel)
     rng = np.random.default_rng(3)
     long_reads = ["".join(rng.choice(list("ACGT"), size=n)) for n in (1536, 1537, 3000, 6144)]
     # make one of them free of stop codons in frame 1 so it is actually scored
@@ -351,7 +352,7 @@ def test_edge_cases(gpu, enc, orc, refdata):
     res = gpu.score_reads(gg, flat, offsets, lut, 0.5)
     ora, _ = orc.score_reads(go, flat, offsets, orc.encode_lut("protein"), 0.5)
     assert_same_as_oracle(res, ora, "long")
-    flat, offsets = gpu.concat_reads(["A" * 6145])
+    flat, offsets = gpu.concat_reads(["ACGT" * 49152])  # 196608 = ORPH_MAX_READ_LEN + 1
     with pytest.raises(ValueError):
         gpu.score_reads(gg, flat, offsets, lut, 0.5)
     # mismatched arguments fail loudly
@@ -429,3 +430,132 @@ def test_table_larger_than_2_31_bits(gpu, enc, orc):
     assert_same_as_oracle(res, ora, "2^31")
     hashes = np.random.default_rng(5).integers(0, 2**64, 5000, dtype=np.uint64)
     np.testing.assert_array_equal(gg.get_many(hashes), np.array([go.get(int(h)) for h in hashes], dtype=np.uint8))
+
+
+def _orf_read(rng, residues, poffs, n_codons, subst=0.0):
+    """A read with one long open frame: back-translated proteome residues (one fixed codon per amino acid)."""
+    codon = {"A": "GCT", "R": "CGT", "N": "AAC", "D": "GAC", "C": "TGC", "Q": "CAG", "E": "GAA", "G": "GGT", "H": "CAC",
+             "I": "ATC", "L": "CTG", "K": "AAA", "M": "ATG", "F": "TTC", "P": "CCG", "S": "TCT", "T": "ACC", "W": "TGG",
+             "Y": "TAC", "V": "GTT"}
+    out = []
+    while len(out) < n_codons:
+        p = int(rng.integers(0, len(poffs) - 1))
+        seq = residues[int(poffs[p]):int(poffs[p + 1])].tobytes().decode()
+        out.extend(codon.get(a, "GCT") for a in seq)
+    s = np.frombuffer("".join(out[:n_codons]).encode(), dtype=np.uint8).copy()
+    if subst:
+        hit = rng.random(s.size) < subst
+        s[hit] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, int(hit.sum()))]
+    return s.tobytes().decode()
+
+
+@pytest.mark.parametrize("reads_format", ["ascii", "packed"])
+@pytest.mark.parametrize("alphabet,ksize", [("protein", 7), ("dayhoff", 12), ("hp", 31)])
+def test_long_reads_block_kernel(gpu, enc, orc, refdata, alphabet, ksize, reads_format):
+    """Reads of 6145 .. ORPH_MAX_READ_LEN bases (the reference has no length limit) take the block-per-read kernel:
+    long open reading frames with thousands of distinct and repeated k-mers, random reads, N bytes, lower case, a
+    low-complexity read, the maximum length, mixed with short reads in one batch."""
+    from orpheum_b200 import _lib, synth
+
+    residues, poffs = synth.make_proteome(n_proteins=400, seed=31)
+    lut, olut = enc.encode_lut(alphabet), orc.encode_lut(alphabet)
+    gg = gpu.GpuNodegraph(ksize, 2e6, 4)
+    gg.add_peptides(residues, poffs, lut)
+    go = orc.Nodegraph(ksize, 2e6, 4)
+    go.add_peptides(residues, poffs, olut)
+    rng = np.random.default_rng(17)
+    rand = lambda n: "".join(rng.choice(list("ACGT"), size=n))
+    reads = [
+        _orf_read(rng, residues, poffs, 2049),            # 6147 nt, open frame 1, every k-mer in the filter
+        _orf_read(rng, residues, poffs, 3000, 0.002),     # a few substitutions: some frames may close
+        rand(6145), rand(20000),                          # random: stops everywhere
+        "ACGTAC" + _orf_read(rng, residues, poffs, 7000), # open frame 1 again (6 = 0 mod 3), 21 kb
+        "G" + _orf_read(rng, residues, poffs, 5000),      # open frame 2
+        _orf_read(rng, residues, poffs, 1200) * 3,        # tandem repeat of a 3.6 kb unit: 2/3 duplicates
+        "GCTGAAAAGCTGGTT" * 1000,                         # 15 kb of a 5-residue repeat: low-complexity peptide
+        "A" * 5000 + "C" * 5000,                          # fastp low complexity
+        rand(150), _orf_read(rng, residues, poffs, 50),   # short reads in the same batch
+        _orf_read(rng, residues, poffs, 65535) + "AC",    # ORPH_MAX_READ_LEN = 196607 bases, 65535-residue frames
+    ]
+    if reads_format == "ascii":
+        with_n = list(_orf_read(rng, residues, poffs, 4000))
+        for pos in rng.integers(0, len(with_n), 40):
+            with_n[int(pos)] = "N"
+        reads.append("".join(with_n))                     # N inside codons: X residues and xxN codons
+        reads.append(_orf_read(rng, residues, poffs, 2500).lower())
+        reads.append(_orf_read(rng, residues, poffs, 2500)[:7000] + "acgtnRYK" * 10)
+    flat, offsets = gpu.concat_reads(reads)
+    ora, _ = orc.score_reads(go, flat, offsets, olut, 0.5, n_threads=0)
+    assert (ora["n_kmers"] > 50000).any() and (ora["n_kmers"] > 2000).sum() >= 5  # the long frames were really scored
+    if reads_format == "ascii":
+        res = gpu.score_reads(gg, flat, offsets, lut, 0.5)
+    else:
+        packed, needs = gpu.pack_reads(flat, offsets)
+        assert not needs.any()
+        res = gpu.score_reads(gg, packed, offsets, lut, 0.5, reads_format=_lib.READS_PACKED2)
+    assert_same_as_oracle(res, ora, f"long {alphabet} {reads_format}")
+    # the exact all-pairs restatement of the de-duplication agrees (without the 196 kb read: O(n^2))
+    if reads_format == "ascii":
+        flat2, offsets2 = gpu.concat_reads(reads[:4])
+        gg.ctx.set_force_exact_dedup(True)
+        try:
+            res2 = gpu.score_reads(gg, flat2, offsets2, lut, 0.5)
+        finally:
+            gg.ctx.set_force_exact_dedup(False)
+        assert res2.tobytes() == res[:4].tobytes()
+
+
+def test_full_size_properties_cfg2(gpu, enc, orc):
+    """BASELINE configs[1] at full size (10 M x 150 nt, protein k=7, tablesize 1e8 x 4) through size-independent
+    properties: (1) every input form and kernel path gives byte-identical records (host ASCII, host 2-bit, warp-per-read
+    instead of thread-per-frame on a 1 M slice); (2) scoring uneven sub-batches and concatenating equals scoring the
+    whole batch; (3) reverse-complement symmetry: frame f of rc(read) is frame f+3 of the read; (4) a random sample
+    drawn from the whole batch equals the oracle."""
+    from orpheum_b200 import _lib, synth
+
+    n = 10_000_000
+    residues, poffs = synth.make_proteome(n_proteins=20000, seed=1001)
+    reads2d = synth.make_reads_fixed(n, residues, poffs, length=150, seed=2002)
+    flat, offsets = synth.concat_fixed(reads2d)
+    lut = enc.encode_lut("protein")
+    gg = gpu.GpuNodegraph(7, 1e8, 4)
+    gg.add_peptides(residues, poffs, lut, count_unique=False)
+    res = gpu.score_reads(gg, flat, offsets, lut, 0.5)
+    # the batch is not degenerate: every category of an ACGT read occurs, and many frames were scored
+    cats = np.bincount(res["category"].reshape(-1), minlength=6)
+    assert cats[_lib.CAT_CODING] > 4_000_000 and cats[_lib.CAT_NON_CODING] > 1_000_000 and cats[0] > 30_000_000
+    digest = lambda a: (int(a.view(np.uint64).sum(dtype=np.uint64)), int(np.bitwise_xor.reduce(a.view(np.uint64))))
+    want = digest(res)
+    # (1) 2-bit host input
+    packed, needs = gpu.pack_reads(flat, offsets)
+    assert not needs.any()
+    assert digest(gpu.score_reads(gg, packed, offsets, lut, 0.5, reads_format=_lib.READS_PACKED2)) == want
+    # (1) warp-per-read kernel on a slice
+    lo, hi = 3_000_000, 4_000_000
+    gg.ctx.set_thread_path(False)
+    try:
+        sl = gpu.score_reads(gg, flat, offsets[lo:hi + 1], lut, 0.5)
+    finally:
+        gg.ctx.set_thread_path(True)
+    assert sl.tobytes() == res[lo:hi].tobytes()
+    # (2) uneven sub-batches
+    cuts = [0, 1, 31, 32, 1000, 1_048_577, 2_500_001, 7_000_003, n]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        assert gpu.score_reads(gg, flat, offsets[a:b + 1], lut, 0.5).tobytes() == res[a:b].tobytes(), (a, b)
+    # (3) reverse complement: forward frames of rc(read) are the read's reverse frames and vice versa
+    m = 2_000_000
+    comp = np.zeros(256, dtype=np.uint8)
+    comp[np.frombuffer(b"ACGT", dtype=np.uint8)] = np.frombuffer(b"TGCA", dtype=np.uint8)
+    rc = np.ascontiguousarray(comp[reads2d[:m, ::-1]])
+    rres = gpu.score_reads(gg, rc.reshape(-1), offsets[:m + 1], lut, 0.5)
+    swap = [3, 4, 5, 0, 1, 2]
+    for field in ("n_kmers", "n_hits", "category"):
+        np.testing.assert_array_equal(rres[field], res[field][:m][:, swap], err_msg=field)
+    np.testing.assert_array_equal(rres["flags"] & 0x40, res["flags"][:m] & 0x40)
+    # (4) random sample against the oracle
+    pick = np.sort(np.random.default_rng(9).choice(n, 50_000, replace=False))
+    sflat, soffs = synth.concat_fixed(reads2d[pick])
+    go = orc.Nodegraph(7, int(1e8), 4)
+    go.add_peptides(residues, poffs, orc.encode_lut("protein"))
+    ora, _ = orc.score_reads(go, sflat, soffs, orc.encode_lut("protein"), 0.5, n_threads=0)
+    assert_same_as_oracle(res[pick], ora, "full-size sample")
