@@ -116,6 +116,16 @@ int orph_ctx_set_kernel_timing(orph_ctx *ctx, int on);
 /* Adds up (and clears) the intervals recorded so far: ms[i] total milliseconds and launches[i] count of
  * kernel i.  Synchronizes the stream. */
 int orph_ctx_kernel_times(orph_ctx *ctx, double *ms, uint64_t *launches);
+/* Host ingest of orph_score_reads (ASCII batches): the call is PCIe-bound at 1 byte per base, so the library packs part
+ * of each large batch to 2 bits per base on `n_threads` host threads while the copy engine ships the rest as ASCII
+ * (a pinned input buffer is needed for that overlap; a pageable one is always packed).  n_threads < 0 (default): the
+ * cores this process may run on, divided by LOCAL_WORLD_SIZE when that is set; 0: never pack on the host.  Results do
+ * not depend on the setting. */
+int orph_ctx_set_host_threads(orph_ctx *ctx, int n_threads);
+/* Counters of the ingest pipeline since the context was created (any output may be NULL): chunks packed on the host,
+ * chunks sent as ASCII, size of the host pool, measured host packing rate in input bytes/s, measured H2D rate. */
+int orph_ctx_ingest_stats(orph_ctx *ctx, uint64_t *chunks_packed_on_host, uint64_t *chunks_sent_ascii, int *host_threads,
+                          double *pack_bytes_per_s, double *h2d_bytes_per_s);
 const char *orph_last_error(void);
 int orph_abi_version(void);
 

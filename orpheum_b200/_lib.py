@@ -44,6 +44,8 @@ PROTOTYPES = {
     "orph_ctx_launch_count": (ctypes.c_uint64, [_vp]),
     "orph_ctx_set_kernel_timing": (ctypes.c_int, [_vp, ctypes.c_int]),
     "orph_ctx_kernel_times": (ctypes.c_int, [_vp, _vp, _u64p]),
+    "orph_ctx_set_host_threads": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "orph_ctx_ingest_stats": (ctypes.c_int, [_vp, _u64p, _u64p, _vp, _vp, _vp]),
     "orph_last_error": (ctypes.c_char_p, []),
     "orph_abi_version": (ctypes.c_int, []),
     "orph_table_sizes": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint32, _u64p]),

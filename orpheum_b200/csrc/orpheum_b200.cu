@@ -9,10 +9,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <sched.h>
 #include <thread>
 #include <vector>
 
 #include "bloom_kernels.cuh"
+#include "hostpack.h"
 #include "long_kernels.cuh"
 #include "score_kernels.cuh"
 #include "task_kernels.cuh"
@@ -79,6 +81,31 @@ struct DevBuf {
     }
 };
 
+// pinned host buffer
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t need)
+    {
+        if (need <= cap) return ORPH_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = need + need / 8 + 256;
+        CUDA_TRY(cudaHostAlloc(&p, want, cudaHostAllocDefault));
+        cap = want;
+        return ORPH_OK;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+constexpr int kPipeSlots = 4;  // chunks in flight in the host-buffer pipeline
+
 struct orph_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -98,10 +125,18 @@ struct orph_ctx {
     DevBuf needs_bytes;          // uint8 per read (ASCII input)
     DevBuf packed;               // 2-bit stream built from ASCII input
     DevBuf in_reads, in_offsets, out_results;  // staging for the index build
-    DevBuf in_reads2[2], in_offsets2[2], out_results2[2];  // double-buffered staging of orph_score_reads
+    DevBuf in_reads2[kPipeSlots], in_offsets2[kPipeSlots], out_results2[kPipeSlots];  // staging slots of orph_score_reads
+    PinnedBuf h_packed[kPipeSlots];                      // host-packed 2-bit words of a chunk, pinned for the async H2D
     cudaStream_t s_in = nullptr, s_out = nullptr;        // copy streams of the host-buffer pipeline
-    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_kernels[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    cudaEvent_t ev_in[kPipeSlots] = {}, ev_kernels[kPipeSlots] = {}, ev_out[kPipeSlots] = {};
+    cudaEvent_t ev_h2d_begin[kPipeSlots] = {}, ev_h2d_end[kPipeSlots] = {};  // timed: calibrate the H2D rate the planner uses
+    uint64_t h2d_bytes[kPipeSlots] = {};
     bool pipe_ready = false;
+    int host_threads = -1;                               // host packing threads: -1 auto, 0 = never pack on the host
+    orph_host::Pool *pool = nullptr;
+    double pack_s_per_byte = 0;                          // measured host packing cost (running average)
+    double h2d_bytes_per_s = 50e9;                       // planning estimate of the H2D rate
+    uint64_t chunks_packed_on_host = 0, chunks_sent_ascii = 0;
     DevBuf misc;                 // small transfers (hash batches, ...)
     bool timing = false;
     struct Interval { cudaEvent_t a, b; int id; };
@@ -219,16 +254,24 @@ extern "C" void orph_ctx_destroy(orph_ctx *ctx)
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf *b : {&ctx->counters, &ctx->queue, &ctx->bytes_queue, &ctx->task_queue, &ctx->task_queue_sorted, &ctx->needs_bytes, &ctx->packed, &ctx->in_reads,
-                      &ctx->in_offsets, &ctx->out_results, &ctx->misc, &ctx->seen, &ctx->long_scratch, &ctx->in_reads2[0], &ctx->in_reads2[1],
-                      &ctx->in_offsets2[0], &ctx->in_offsets2[1], &ctx->out_results2[0], &ctx->out_results2[1]})
+                      &ctx->in_offsets, &ctx->out_results, &ctx->misc, &ctx->seen, &ctx->long_scratch})
         b->release();
+    for (int b = 0; b < kPipeSlots; b++) {
+        ctx->in_reads2[b].release();
+        ctx->in_offsets2[b].release();
+        ctx->out_results2[b].release();
+        ctx->h_packed[b].release();
+    }
+    delete ctx->pool;
     if (ctx->pipe_ready) {
         cudaStreamDestroy(ctx->s_in);
         cudaStreamDestroy(ctx->s_out);
-        for (int b = 0; b < 2; b++) {
+        for (int b = 0; b < kPipeSlots; b++) {
             cudaEventDestroy(ctx->ev_in[b]);
             cudaEventDestroy(ctx->ev_kernels[b]);
             cudaEventDestroy(ctx->ev_out[b]);
+            cudaEventDestroy(ctx->ev_h2d_begin[b]);
+            cudaEventDestroy(ctx->ev_h2d_end[b]);
         }
     }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -939,88 +982,221 @@ extern "C" int orph_score_reads_device(orph_ctx *ctx, const orph_filter *f, cons
     return ORPH_OK;
 }
 
-// Host-buffer entry point.  The batch is cut into chunks that flow through a three-stage pipeline on three
-// streams -- H2D of chunk c+1, kernels of chunk c and D2H of chunk c-1 overlap (PCIe is full duplex) -- with
-// double-buffered device staging.  With pinned host memory the call is bound by the larger of the H2D time
-// and the kernel time instead of their sum.
-extern "C" int orph_score_reads(orph_ctx *ctx, const orph_filter *f, const void *reads, int reads_format,
-                                const uint64_t *offsets, uint64_t n_reads, const uint8_t lut[256], double jaccard_threshold,
-                                orph_read_result *out)
+// max over i of off[i+1] - off[i] for i in [0, m); a decreasing pair wraps to >= 2^63.  Four independent accumulators
+// per thread, spread over the pool when there is one (1 M offsets in well under 0.1 ms).
+static uint64_t scan_read_lengths(orph_host::Pool *pool, const uint64_t *off, uint64_t m)
 {
-    int rc = check_score_args(ctx, f, reads, reads_format, offsets, n_reads, lut, jaccard_threshold, out);
-    if (rc != ORPH_OK) return rc;
-    if (n_reads == 0) return ORPH_OK;
-    DeviceGuard guard(ctx->device);
+    auto part = [&](uint64_t a, uint64_t b) {
+        uint64_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+        uint64_t i = a;
+        for (; i + 4 <= b; i += 4) {
+            m0 = std::max(m0, off[i + 1] - off[i]);
+            m1 = std::max(m1, off[i + 2] - off[i + 1]);
+            m2 = std::max(m2, off[i + 3] - off[i + 2]);
+            m3 = std::max(m3, off[i + 4] - off[i + 3]);
+        }
+        for (; i < b; i++) m0 = std::max(m0, off[i + 1] - off[i]);
+        return std::max(std::max(m0, m1), std::max(m2, m3));
+    };
+    constexpr uint64_t kBlock = 1 << 16;
+    if (!pool || m <= 2 * kBlock) return part(0, m);
+    const uint64_t n_blocks = (m + kBlock - 1) / kBlock;
+    std::vector<uint64_t> partial(n_blocks, 0);
+    pool->run(n_blocks, [&](uint64_t blk) { partial[blk] = part(blk * kBlock, std::min(m, (blk + 1) * kBlock)); });
+    uint64_t best = 0;
+    for (uint64_t v : partial) best = std::max(best, v);
+    return best;
+}
+
+// Host-buffer pipeline.  The batch is cut into chunks that flow through three stages on three streams -- H2D of
+// chunk c+1, kernels of chunk c and D2H of chunk c-1 overlap (PCIe is full duplex) -- over kPipeSlots staging slots.
+//
+// ASCII batches are PCIe-bound (150 B per 150-nt read against 37.5 B as 2-bit codes), so when `allow_pack` is set the
+// host cores pack part of the chunks (SIMD, thread pool) while the copy engine ships the others as ASCII: before
+// each chunk the H2D backlog is compared with the time the host needs to pack the chunk, and the chunk goes out as
+// ASCII whenever the copy engine would otherwise run dry.  Reads that cannot be 2-bit packed (N, lower case, ...)
+// are scored a second time from their bytes (`exceptions`, filled with their indices) and overwrite the record of the
+// first pass; a chunk where more than 1/8 of the reads are of that kind is sent as ASCII instead.
+static int score_host_pipeline(orph_ctx *ctx, const orph_filter *f, const void *reads, int reads_format, const uint64_t *offsets,
+                               uint64_t n_reads, const uint8_t lut[256], double jaccard_threshold, orph_read_result *out,
+                               bool allow_pack, std::vector<uint64_t> *exceptions)
+{
+    using clk = std::chrono::steady_clock;
+    int rc;
     cudaStream_t s = ctx->stream;
     if (!ctx->pipe_ready) {
         CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
-        for (int b = 0; b < 2; b++) {
+        for (int b = 0; b < kPipeSlots; b++) {
             CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_in[b], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_kernels[b], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_out[b], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreate(&ctx->ev_h2d_begin[b]));
+            CUDA_TRY(cudaEventCreate(&ctx->ev_h2d_end[b]));
         }
         ctx->pipe_ready = true;
     }
-    // chunk boundaries: <= 2^20 reads and <= 2^28 bases each (a single longer read still forms a chunk)
-    const uint64_t kMaxChunkReads = 1ULL << 20, kMaxChunkBases = 1ULL << 28;
+    bool input_pinned = false;
+    if (!ctx->pool && (allow_pack || n_reads >= (1ULL << 18))) {  // the pool also scans the offsets of large batches
+        int n = ctx->host_threads;
+        if (n <= 0) {  // auto: the cores this process may run on, shared between the ranks of one node
+            cpu_set_t set;
+            n = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+            const char *lws = getenv("LOCAL_WORLD_SIZE");
+            const int ranks = lws ? atoi(lws) : 1;
+            if (ranks > 1) n /= ranks;
+            n = std::max(1, std::min(n, 64));
+        }
+        ctx->pool = new (std::nothrow) orph_host::Pool(n);
+        if (!ctx->pool) return fail(ORPH_E_NOMEM, "out of host memory");
+    }
+    if (allow_pack) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, reads) == cudaSuccess) input_pinned = attr.type == cudaMemoryTypeHost;
+        else cudaGetLastError();
+    }
+    // ORPHEUM_B200_TRACE=1: per-chunk timeline of the three stages on stderr (development aid)
+    static const bool trace = getenv("ORPHEUM_B200_TRACE") != nullptr;
+    struct ChunkTrace { cudaEvent_t e[6]; double host_enqueue_s, host_pack_s; int packed; uint64_t m; };
+    std::vector<ChunkTrace> tr;
+    const auto t_call = clk::now();
+    auto mark = [&](int which, cudaStream_t st) {
+        if (trace) { cudaEventCreate(&tr.back().e[which]); cudaEventRecord(tr.back().e[which], st); }
+    };
+    // the H2D rate actually achieved by a finished slot (PCIe generation, NUMA placement and contention with the
+    // running kernels all move it) replaces the planner's estimate
+    auto calibrate_h2d = [&](int slot) {
+        float ms = 0;
+        if (ctx->h2d_bytes[slot] >= (1u << 20) && cudaEventElapsedTime(&ms, ctx->ev_h2d_begin[slot], ctx->ev_h2d_end[slot]) == cudaSuccess && ms > 0) {
+            const double rate = (double)ctx->h2d_bytes[slot] / (1e-3 * ms);
+            ctx->h2d_bytes_per_s = 0.75 * ctx->h2d_bytes_per_s + 0.25 * rate;
+        } else {
+            cudaGetLastError();
+        }
+        ctx->h2d_bytes[slot] = 0;
+    };
+    std::vector<uint8_t> needs;
+    // chunk boundaries: <= 2^19 reads and <= 2^27 bases each (a single longer read still forms a chunk)
+    const uint64_t kMaxChunkReads = 1ULL << 19, kMaxChunkBases = 1ULL << 27;
     uint64_t lo = 0;
     int c = 0;
-    bool used[2] = {false, false};
+    bool used[kPipeSlots] = {};
+    int ascii_streak = 0;  // chunks still to be sent as ASCII after one with many unpackable reads
+    clk::time_point h2d_free_at = clk::now();  // planning estimate: when the copy engine runs out of queued work
     while (lo < n_reads) {
-        // one pass over this chunk's offsets (overlaps the GPU work of the previous chunks): extent, validity, longest read
-        uint64_t hi = lo;
-        uint32_t max_len = 1;
-        bool bad = false;
-        while (hi < n_reads && hi - lo < kMaxChunkReads) {
-            if (offsets[hi + 1] < offsets[hi]) { bad = true; break; }
-            if (hi > lo && offsets[hi + 1] - offsets[lo] > kMaxChunkBases) break;
-            max_len = (uint32_t)std::max<uint64_t>(max_len, std::min<uint64_t>(offsets[hi + 1] - offsets[hi], ORPH_MAX_READ_LEN + 1));
-            hi++;
+        // this chunk's extent, validity and longest read (overlaps the GPU work of the previous chunks)
+        uint64_t hi = std::min(n_reads, lo + kMaxChunkReads);
+        uint64_t longest = scan_read_lengths(ctx->pool, offsets + lo, hi - lo);
+        if (longest < (1ULL << 63) && offsets[hi] - offsets[lo] > kMaxChunkBases) {
+            hi = (uint64_t)(std::upper_bound(offsets + lo + 1, offsets + hi + 1, offsets[lo] + kMaxChunkBases) - offsets) - 1;
+            if (hi <= lo) hi = lo + 1;
+            longest = scan_read_lengths(ctx->pool, offsets + lo, hi - lo);
         }
-        if (bad) {
+        if (longest >= (1ULL << 63)) {  // a decreasing pair wraps around
+            uint64_t at = lo;
+            while (at < hi && offsets[at + 1] >= offsets[at]) at++;
             cudaDeviceSynchronize();
-            return fail(ORPH_E_INVALID, "orph_score_reads: offsets are not monotonic at read %llu", (unsigned long long)hi);
+            return fail(ORPH_E_INVALID, "orph_score_reads: offsets are not monotonic at read %llu", (unsigned long long)at);
         }
+        uint32_t max_len = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(longest, ORPH_MAX_READ_LEN + 1));
         if (max_len > ORPH_MAX_READ_LEN) max_len = ORPH_MAX_READ_LEN;  // over-long reads are reported through the status
         const uint64_t m = hi - lo;
-        const int b = c & 1;
+        const int b = c % kPipeSlots;
         const uint64_t b0 = offsets[lo], b1 = offsets[hi];
-        // the staging buffers of slot b are free once the kernels (inputs) and the D2H (results) of chunk c-2 are done
+        // the staging buffers of slot b are free once the kernels (inputs) and the D2H (results) of its previous chunk are done
         if (used[b]) {
             CUDA_TRY(cudaStreamWaitEvent(ctx->s_in, ctx->ev_kernels[b], 0));
             CUDA_TRY(cudaEventSynchronize(ctx->ev_out[b]));  // also bounds how far the host runs ahead
+            calibrate_h2d(b);
         }
         if ((rc = ctx->in_offsets2[b].ensure((m + 1) * 8)) != ORPH_OK) return rc;
         if ((rc = ctx->out_results2[b].ensure(m * sizeof(orph_read_result))) != ORPH_OK) return rc;
-        CUDA_TRY(cudaMemcpyAsync(ctx->in_offsets2[b].p, offsets + lo, (m + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
         const uint8_t *d_ascii = nullptr;
         const uint64_t *d_packed = nullptr;
         uint64_t pbase0 = 0, n_ascii = 0;
-        if (reads_format == ORPH_READS_ASCII) {
-            n_ascii = b1 - b0;
-            if ((rc = ctx->in_reads2[b].ensure(n_ascii + 64)) != ORPH_OK) return rc;
-            if (n_ascii) CUDA_TRY(cudaMemcpyAsync(ctx->in_reads2[b].p, (const uint8_t *)reads + b0, n_ascii, cudaMemcpyHostToDevice, ctx->s_in));
-            d_ascii = (const uint8_t *)ctx->in_reads2[b].p;
-        } else {
-            const uint64_t w0 = b0 / 32, w1 = (b1 + 31) / 32;
-            if ((rc = ctx->in_reads2[b].ensure((w1 - w0 + 2) * 8)) != ORPH_OK) return rc;
-            if (w1 > w0) CUDA_TRY(cudaMemcpyAsync(ctx->in_reads2[b].p, (const uint64_t *)reads + w0, (w1 - w0) * 8, cudaMemcpyHostToDevice, ctx->s_in));
-            d_packed = (const uint64_t *)ctx->in_reads2[b].p;
-            pbase0 = w0 * 32;
+        bool pack_here = false;
+        if (trace) { tr.push_back(ChunkTrace{}); tr.back().m = m; tr.back().host_pack_s = 0; }
+        if (reads_format == ORPH_READS_ASCII && allow_pack && b1 > b0 && ascii_streak == 0) {
+            // pack on the host unless the copy engine would run dry meanwhile (only a pinned buffer can be sent asynchronously)
+            const double backlog = std::chrono::duration<double>(h2d_free_at - clk::now()).count();
+            const double pack_s = ctx->pack_s_per_byte * (double)(b1 - b0);
+            if (!input_pinned) pack_here = true;                       // pageable input: the CPU reads it faster than a staged copy
+            else if (ctx->pack_s_per_byte == 0) pack_here = c > 0;    // rate not measured yet: chunk 0 feeds the copy engine
+            else pack_here = backlog >= pack_s;
         }
+        if (ascii_streak > 0) ascii_streak--;
+        if (pack_here) {
+            const uint64_t n_words = (b1 - b0 + 31) / 32;
+            // pinned allocations cost milliseconds and synchronise the device: size every slot at once, for a full chunk
+            for (int q = 0; q < kPipeSlots; q++)
+                if ((rc = ctx->h_packed[q].ensure((n_words + 2) * 8)) != ORPH_OK) return rc;
+            needs.assign(m, 0);
+            const auto t0 = clk::now();
+            orph_host::pack_stream(ctx->pool, (const uint8_t *)reads + b0, b0, b1 - b0, offsets + lo, m, (uint64_t *)ctx->h_packed[b].p, needs.data());
+            const double dt = std::chrono::duration<double>(clk::now() - t0).count() / (double)(b1 - b0);
+            ctx->pack_s_per_byte = ctx->pack_s_per_byte == 0 ? dt : 0.75 * ctx->pack_s_per_byte + 0.25 * dt;
+            if (trace) tr.back().host_pack_s = dt * (double)(b1 - b0);
+            uint64_t n_flagged = 0;
+            for (uint64_t i = 0; i < m; i++) n_flagged += needs[i];
+            if (n_flagged * 8 > m) {  // mostly unpackable input (soft-masked genome, ...): ASCII is the cheaper route
+                pack_here = false;
+                ascii_streak = 8;
+            } else {
+                if (n_flagged && exceptions)
+                    for (uint64_t i = 0; i < m; i++)
+                        if (needs[i]) exceptions->push_back(lo + i);
+                if ((rc = ctx->in_reads2[b].ensure((n_words + 2) * 8)) != ORPH_OK) return rc;
+                d_packed = (const uint64_t *)ctx->in_reads2[b].p;
+                pbase0 = b0;
+                ctx->chunks_packed_on_host++;
+                h2d_free_at = std::max(h2d_free_at, clk::now()) +
+                              std::chrono::duration_cast<clk::duration>(std::chrono::duration<double>((double)(n_words * 8 + (m + 1) * 8) / ctx->h2d_bytes_per_s));
+            }
+        }
+        if (trace) { tr.back().packed = pack_here; tr.back().host_enqueue_s = std::chrono::duration<double>(clk::now() - t_call).count(); }
+        mark(0, ctx->s_in);
+        CUDA_TRY(cudaEventRecord(ctx->ev_h2d_begin[b], ctx->s_in));
+        ctx->h2d_bytes[b] = (m + 1) * 8 + (pack_here ? ((b1 - b0 + 31) / 32) * 8 : reads_format == ORPH_READS_ASCII ? b1 - b0 : (b1 - b0) / 4);
+        if (pack_here) {
+            const uint64_t n_words = (b1 - b0 + 31) / 32;
+            CUDA_TRY(cudaMemcpyAsync(ctx->in_reads2[b].p, ctx->h_packed[b].p, n_words * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        }
+        CUDA_TRY(cudaMemcpyAsync(ctx->in_offsets2[b].p, offsets + lo, (m + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        if (!pack_here) {
+            if (reads_format == ORPH_READS_ASCII) {
+                n_ascii = b1 - b0;
+                if ((rc = ctx->in_reads2[b].ensure(n_ascii + 64)) != ORPH_OK) return rc;
+                if (n_ascii) CUDA_TRY(cudaMemcpyAsync(ctx->in_reads2[b].p, (const uint8_t *)reads + b0, n_ascii, cudaMemcpyHostToDevice, ctx->s_in));
+                d_ascii = (const uint8_t *)ctx->in_reads2[b].p;
+                ctx->chunks_sent_ascii++;
+                h2d_free_at = std::max(h2d_free_at, clk::now()) +
+                              std::chrono::duration_cast<clk::duration>(std::chrono::duration<double>((double)(n_ascii + (m + 1) * 8) / ctx->h2d_bytes_per_s));
+            } else {
+                const uint64_t w0 = b0 / 32, w1 = (b1 + 31) / 32;
+                if ((rc = ctx->in_reads2[b].ensure((w1 - w0 + 2) * 8)) != ORPH_OK) return rc;
+                if (w1 > w0) CUDA_TRY(cudaMemcpyAsync(ctx->in_reads2[b].p, (const uint64_t *)reads + w0, (w1 - w0) * 8, cudaMemcpyHostToDevice, ctx->s_in));
+                d_packed = (const uint64_t *)ctx->in_reads2[b].p;
+                pbase0 = w0 * 32;
+            }
+        }
+        mark(1, ctx->s_in);
+        CUDA_TRY(cudaEventRecord(ctx->ev_h2d_end[b], ctx->s_in));
         CUDA_TRY(cudaEventRecord(ctx->ev_in[b], ctx->s_in));
         CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_in[b], 0));
         if (used[b]) CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_out[b], 0));
+        mark(2, s);
         rc = score_device_impl(ctx, f, d_ascii, b0, d_packed, pbase0, n_ascii, (const uint64_t *)ctx->in_offsets2[b].p, m, max_len, lut,
                                jaccard_threshold, (orph_read_result *)ctx->out_results2[b].p);
         if (rc != ORPH_OK) {
             cudaDeviceSynchronize();
             return rc;
         }
+        mark(3, s);
         CUDA_TRY(cudaEventRecord(ctx->ev_kernels[b], s));
         CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->ev_kernels[b], 0));
+        mark(4, ctx->s_out);
         CUDA_TRY(cudaMemcpyAsync(out + lo, ctx->out_results2[b].p, m * sizeof(orph_read_result), cudaMemcpyDeviceToHost, ctx->s_out));
+        mark(5, ctx->s_out);
         CUDA_TRY(cudaEventRecord(ctx->ev_out[b], ctx->s_out));
         used[b] = true;
         lo = hi;
@@ -1031,8 +1207,78 @@ extern "C" int orph_score_reads(orph_ctx *ctx, const orph_filter *f, const void 
     CUDA_TRY(cudaStreamSynchronize(s));
     CUDA_TRY(cudaStreamSynchronize(ctx->s_out));
     CUDA_TRY(cudaStreamSynchronize(ctx->s_in));
+    for (int q = 0; q < kPipeSlots; q++)
+        if (used[q]) calibrate_h2d(q);
+    if (trace && !tr.empty()) {
+        fprintf(stderr, "[orph trace] call of %llu reads, %.3f ms on the host clock\n", (unsigned long long)n_reads,
+                1e3 * std::chrono::duration<double>(clk::now() - t_call).count());
+        fprintf(stderr, "[orph trace] chunk reads mode host_enq host_pack | h2d_start h2d_end | k_start k_end | d2h_start d2h_end (ms, device times relative to chunk 0's h2d_start)\n");
+        for (size_t i = 0; i < tr.size(); i++) {
+            float t[6];
+            for (int k = 0; k < 6; k++) cudaEventElapsedTime(&t[k], tr[0].e[0], tr[i].e[k]);
+            fprintf(stderr, "[orph trace] %3zu %8llu %s %8.3f %8.3f | %8.3f %8.3f | %8.3f %8.3f | %8.3f %8.3f\n", i, (unsigned long long)tr[i].m,
+                    tr[i].packed ? "pack " : "plain", 1e3 * tr[i].host_enqueue_s, 1e3 * tr[i].host_pack_s, t[0], t[1], t[2], t[3], t[4], t[5]);
+        }
+        for (auto &ct : tr)
+            for (int k = 0; k < 6; k++) cudaEventDestroy(ct.e[k]);
+    }
     CUDA_TRY(cudaMemsetAsync((uint8_t *)ctx->counters.p + offsetof(ScoreCounters, status), 0, sizeof(uint32_t), s));
     return status_to_code(counters.status);
+}
+
+extern "C" int orph_score_reads(orph_ctx *ctx, const orph_filter *f, const void *reads, int reads_format,
+                                const uint64_t *offsets, uint64_t n_reads, const uint8_t lut[256], double jaccard_threshold,
+                                orph_read_result *out)
+{
+    int rc = check_score_args(ctx, f, reads, reads_format, offsets, n_reads, lut, jaccard_threshold, out);
+    if (rc != ORPH_OK) return rc;
+    if (n_reads == 0) return ORPH_OK;
+    DeviceGuard guard(ctx->device);
+    // host packing pays once a batch is large enough to keep the pool busy; small batches go out as they are
+    const bool allow_pack = reads_format == ORPH_READS_ASCII && ctx->host_threads != 0 && offsets[n_reads] - offsets[0] >= (1ULL << 22);
+    std::vector<uint64_t> exceptions;
+    rc = score_host_pipeline(ctx, f, reads, reads_format, offsets, n_reads, lut, jaccard_threshold, out, allow_pack, &exceptions);
+    if (rc != ORPH_OK && rc != ORPH_E_EMPTY_READ && rc != ORPH_E_TOO_LONG) return rc;
+    if (!exceptions.empty()) {
+        // second pass over the reads the 2-bit stream cannot represent: their bytes, gathered into one small ASCII batch
+        const uint64_t n_exc = exceptions.size();
+        std::vector<uint64_t> eoff(n_exc + 1);
+        eoff[0] = 0;
+        for (uint64_t i = 0; i < n_exc; i++) eoff[i + 1] = eoff[i] + (offsets[exceptions[i] + 1] - offsets[exceptions[i]]);
+        std::vector<uint8_t> ebytes(eoff[n_exc] + 64);
+        for (uint64_t i = 0; i < n_exc; i++)
+            memcpy(ebytes.data() + eoff[i], (const uint8_t *)reads + offsets[exceptions[i]], eoff[i + 1] - eoff[i]);
+        std::vector<orph_read_result> eout(n_exc);
+        const int rc2 = score_host_pipeline(ctx, f, ebytes.data(), ORPH_READS_ASCII, eoff.data(), n_exc, lut, jaccard_threshold, eout.data(), false, nullptr);
+        if (rc2 != ORPH_OK && rc2 != ORPH_E_EMPTY_READ && rc2 != ORPH_E_TOO_LONG) return rc2;
+        for (uint64_t i = 0; i < n_exc; i++) out[exceptions[i]] = eout[i];
+        if (rc == ORPH_OK) rc = rc2;
+    }
+    return rc;
+}
+
+extern "C" int orph_ctx_set_host_threads(orph_ctx *ctx, int n_threads)
+{
+    if (!ctx) return fail(ORPH_E_INVALID, "ctx is NULL");
+    if (ctx->pool && n_threads != ctx->host_threads) {  // re-created at the new size on the next large batch
+        delete ctx->pool;
+        ctx->pool = nullptr;
+    }
+    ctx->host_threads = n_threads;
+    ctx->pack_s_per_byte = 0;
+    return ORPH_OK;
+}
+
+extern "C" int orph_ctx_ingest_stats(orph_ctx *ctx, uint64_t *chunks_packed_on_host, uint64_t *chunks_sent_ascii, int *host_threads,
+                                     double *pack_bytes_per_s, double *h2d_bytes_per_s)
+{
+    if (!ctx) return fail(ORPH_E_INVALID, "ctx is NULL");
+    if (chunks_packed_on_host) *chunks_packed_on_host = ctx->chunks_packed_on_host;
+    if (chunks_sent_ascii) *chunks_sent_ascii = ctx->chunks_sent_ascii;
+    if (host_threads) *host_threads = ctx->pool ? ctx->pool->size() : ctx->host_threads;
+    if (pack_bytes_per_s) *pack_bytes_per_s = ctx->pack_s_per_byte > 0 ? 1.0 / ctx->pack_s_per_byte : 0.0;
+    if (h2d_bytes_per_s) *h2d_bytes_per_s = ctx->h2d_bytes_per_s;
+    return ORPH_OK;
 }
 
 extern "C" int orph_translate_frames(orph_ctx *ctx, const uint8_t *reads, const uint64_t *offsets, uint64_t n_reads,
@@ -1104,44 +1350,12 @@ extern "C" int orph_pack_reads(const uint8_t *reads, const uint64_t *offsets, ui
     const uint64_t n_words = (total + 31) / 32;
     if (needs_ascii) memset(needs_ascii, 0, n_reads);
     if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
-    n_threads = (int)std::min<uint64_t>(n_threads, std::max<uint64_t>(1, n_words / 4096));
-    uint8_t valid[256];
-    memset(valid, 0, sizeof(valid));
-    valid['A'] = valid['C'] = valid['G'] = valid['T'] = 1;
-    auto work = [&](uint64_t w_lo, uint64_t w_hi) {
-        for (uint64_t w = w_lo; w < w_hi; w++) {
-            const uint64_t g0 = 32 * w;
-            const uint32_t count = (uint32_t)std::min<uint64_t>(32, total - g0);
-            const uint8_t *p = reads + b0 + g0;
-            uint64_t bits = 0;
-            uint32_t bad = 0;
-            for (uint32_t i = 0; i < count; i++) {
-                bits |= (uint64_t)((p[i] >> 1) & 3u) << (2 * i);
-                bad |= (uint32_t)(valid[p[i]] ^ 1u) << i;
-            }
-            out_packed[w] = bits;
-            if (bad && needs_ascii) {
-                for (uint32_t i = 0; i < count; i++) {
-                    if (!((bad >> i) & 1u)) continue;
-                    const uint64_t g = b0 + g0 + i;
-                    const uint64_t *it = std::upper_bound(offsets, offsets + n_reads + 1, g);
-                    uint64_t r = (uint64_t)(it - offsets) - 1;
-                    if (r >= n_reads) r = n_reads - 1;
-                    needs_ascii[r] = 1;
-                }
-            }
-        }
-    };
+    n_threads = (int)std::min<uint64_t>(n_threads, std::max<uint64_t>(1, n_words / 8192));
     if (n_threads <= 1) {
-        work(0, n_words);
+        orph_host::pack_stream(nullptr, reads + b0, b0, total, offsets, n_reads, out_packed, needs_ascii);
     } else {
-        std::vector<std::thread> pool;
-        const uint64_t per = (n_words + n_threads - 1) / n_threads;
-        for (int t = 0; t < n_threads; t++) {
-            const uint64_t lo = std::min(n_words, per * t), hi = std::min(n_words, per * (t + 1));
-            if (lo < hi) pool.emplace_back(work, lo, hi);
-        }
-        for (auto &th : pool) th.join();
+        orph_host::Pool pool(n_threads);
+        orph_host::pack_stream(&pool, reads + b0, b0, total, offsets, n_reads, out_packed, needs_ascii);
     }
     return ORPH_OK;
 }

@@ -56,6 +56,17 @@ class Context:
         """Test hook: False sends short reads through the warp-per-read kernel."""
         check(self._lib.orph_ctx_set_thread_path(self._h, int(bool(on))))
 
+    def set_host_threads(self, n):
+        """Host threads that 2-bit pack ASCII batches inside score_reads (<0 auto, 0 never pack on the host)."""
+        check(self._lib.orph_ctx_set_host_threads(self._h, int(n)))
+
+    def ingest_stats(self):
+        packed, ascii_, threads, rate, h2d = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_int(), ctypes.c_double(), ctypes.c_double()
+        check(self._lib.orph_ctx_ingest_stats(self._h, ctypes.byref(packed), ctypes.byref(ascii_), ctypes.byref(threads),
+                                              ctypes.byref(rate), ctypes.byref(h2d)))
+        return {"chunks_packed_on_host": int(packed.value), "chunks_sent_ascii": int(ascii_.value),
+                "host_threads": int(threads.value), "pack_bytes_per_s": float(rate.value), "h2d_bytes_per_s": float(h2d.value)}
+
     def set_kernel_timing(self, on):
         check(self._lib.orph_ctx_set_kernel_timing(self._h, int(bool(on))))
 

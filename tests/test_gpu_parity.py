@@ -559,3 +559,57 @@ def test_full_size_properties_cfg2(gpu, enc, orc):
     go.add_peptides(residues, poffs, orc.encode_lut("protein"))
     ora, _ = orc.score_reads(go, sflat, soffs, orc.encode_lut("protein"), 0.5, n_threads=0)
     assert_same_as_oracle(res[pick], ora, "full-size sample")
+
+
+def test_host_packing_ingest_paths(gpu, enc, orc):
+    """orph_score_reads on large ASCII batches: chunks packed to 2 bits on the host threads, chunks sent as ASCII,
+    the second pass over unpackable reads (N, lower case), the mostly-unpackable fallback, pageable and pinned input --
+    every route must give the records of the plain ASCII path (host_threads = 0) and of the oracle."""
+    import torch
+
+    from orpheum_b200 import synth
+
+    residues, poffs = synth.make_proteome(n_proteins=2000, seed=41)
+    lut, olut = enc.encode_lut("protein"), orc.encode_lut("protein")
+    gg = gpu.GpuNodegraph(7, 1e7, 4)
+    gg.add_peptides(residues, poffs, lut)
+    go = orc.Nodegraph(7, int(1e7), 4)
+    go.add_peptides(residues, poffs, olut)
+    ctx = gg.ctx
+    # 2.6 M mixed reads (~450 MB of ASCII, 2 % with N, several chunks): every category, three kernel tiers, byte path
+    flat, offsets = synth.make_reads_mixed(2_600_000, residues, poffs, ksize=7, seed=77)
+    flat = flat.copy()
+    lower = np.random.default_rng(5).choice(len(offsets) - 1, 3000, replace=False)  # plus some soft-masked reads
+    for r in lower:
+        a, b = int(offsets[r]), int(offsets[r + 1])
+        flat[a:b] = np.frombuffer(flat[a:b].tobytes().lower(), dtype=np.uint8)
+    try:
+        ctx.set_host_threads(0)
+        want = gpu.score_reads(gg, flat, offsets, lut, 0.5)
+        before = ctx.ingest_stats()
+        assert before["chunks_packed_on_host"] == 0
+        pinned = torch.empty(flat.size, dtype=torch.uint8).pin_memory()
+        pinned.numpy()[:] = flat
+        for threads, buf in ((1, flat), (4, flat), (-1, flat), (-1, pinned.numpy()), (3, pinned.numpy())):
+            ctx.set_host_threads(threads)
+            got = gpu.score_reads(gg, buf, offsets, lut, 0.5)
+            assert got.tobytes() == want.tobytes(), threads
+        after = ctx.ingest_stats()
+        assert after["chunks_packed_on_host"] >= 6 and after["pack_bytes_per_s"] > 0
+        # sub-range with a non-zero first offset and a non-multiple-of-32 start
+        ctx.set_host_threads(-1)
+        a, b = 12_345, 2_222_222
+        assert gpu.score_reads(gg, flat, offsets[a:b + 1], lut, 0.5).tobytes() == want[a:b].tobytes()
+        # mostly unpackable input: soft-masked everything
+        low = np.frombuffer(flat.tobytes().lower(), dtype=np.uint8)
+        ctx.set_host_threads(0)
+        want_low = gpu.score_reads(gg, low, offsets, lut, 0.5)
+        ctx.set_host_threads(-1)
+        assert gpu.score_reads(gg, low, offsets, lut, 0.5).tobytes() == want_low.tobytes()
+    finally:
+        ctx.set_host_threads(-1)
+    sample = np.sort(np.random.default_rng(6).choice(len(offsets) - 1, 30_000, replace=False))
+    sample = np.union1d(sample, lower[:500])
+    sflat, soffs = gpu.concat_reads([flat[int(offsets[r]):int(offsets[r + 1])].tobytes() for r in sample])
+    ora, _ = orc.score_reads(go, sflat, soffs, olut, 0.5, n_threads=0)
+    assert_same_as_oracle(want[sample], ora, "ingest sample")
