@@ -245,6 +245,16 @@ int orph_format_float_repr(double v, char *out32);
 int orph_bench_gather_peak(orph_ctx *ctx, uint64_t footprint_bytes, uint32_t loads_per_thread, int persist_l2,
                            double *sectors_per_second);
 
+/* Counter-based synthetic reads generated in HBM (BASELINE configs[3]: 1e9 reads are too many to stage from the host).
+ * Read i = first_index + t is a pure function of (seed, i): even i is back-translated from the proteome (random
+ * synonymous codons from d_syn_table, 1 % substitutions, random phase and strand), odd i is uniform ACGT;
+ * orpheum_b200/synth.py:counter_reads is the host twin.  All pointers are DEVICE pointers; d_packed_out receives the
+ * ORPH_READS_PACKED2 stream of n_reads reads of read_len bases ((n_reads * read_len + 31) / 32 + 1 u64 words).
+ * d_syn_table[aa]: bits 0..2 = number of sense codons of amino-acid byte aa, codon c at bits [4 + 6c, +6). */
+int orph_synth_reads_device(orph_ctx *ctx, uint64_t seed, uint64_t first_index, uint64_t n_reads, uint32_t read_len,
+                            const uint8_t *d_residues, const uint64_t *d_prot_offsets, uint64_t n_proteins,
+                            const uint64_t *d_syn_table, void *d_packed_out);
+
 #ifdef __cplusplus
 }
 #endif

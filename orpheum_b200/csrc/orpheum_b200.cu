@@ -17,6 +17,7 @@
 #include "hostpack.h"
 #include "long_kernels.cuh"
 #include "score_kernels.cuh"
+#include "synth_kernels.cuh"
 #include "task_kernels.cuh"
 
 using namespace orph;
@@ -1361,8 +1362,25 @@ extern "C" int orph_pack_reads(const uint8_t *reads, const uint64_t *offsets, ui
 }
 
 // ------------------------------------------------------------------------------------------------
-// measurement helper
+// measurement helpers
 // ------------------------------------------------------------------------------------------------
+extern "C" int orph_synth_reads_device(orph_ctx *ctx, uint64_t seed, uint64_t first_index, uint64_t n_reads, uint32_t read_len,
+                                       const uint8_t *d_residues, const uint64_t *d_prot_offsets, uint64_t n_proteins,
+                                       const uint64_t *d_syn_table, void *d_packed_out)
+{
+    if (!ctx || !d_residues || !d_prot_offsets || !d_syn_table || !d_packed_out || n_proteins == 0)
+        return fail(ORPH_E_INVALID, "orph_synth_reads_device: NULL argument");
+    if (read_len < 3 || read_len > kSynthMaxLen) return fail(ORPH_E_INVALID, "orph_synth_reads_device: read_len %u not in 3..%u", read_len, kSynthMaxLen);
+    if (n_reads == 0) return ORPH_OK;
+    DeviceGuard guard(ctx->device);
+    const uint64_t n_words = (n_reads * read_len + 31) / 32 + 1;
+    CUDA_TRY(cudaMemsetAsync(d_packed_out, 0, n_words * 8, ctx->stream));
+    synth_reads_kernel<<<grid_for(n_reads, 256, ctx->sm_count, 16), 256, 0, ctx->stream>>>(seed, first_index, n_reads, read_len, d_residues, d_prot_offsets,
+                                                                                        n_proteins, d_syn_table, (uint32_t *)d_packed_out);
+    CUDA_TRY(cudaGetLastError());
+    return ORPH_OK;
+}
+
 extern "C" int orph_bench_gather_peak(orph_ctx *ctx, uint64_t footprint_bytes, uint32_t loads_per_thread, int persist_l2,
                                       double *sectors_per_second)
 {

@@ -136,3 +136,78 @@ def concat_fixed(reads2d):
     n, L = reads2d.shape
     offsets = np.arange(n + 1, dtype=np.uint64) * np.uint64(L)
     return np.ascontiguousarray(reads2d).reshape(-1), offsets
+
+
+# ---- counter-based reads (cfg4): read i is a pure function of (seed, i) --------------------------------------
+# numpy twin of csrc/synth_kernels.cuh; both must produce the same bases for every index.
+_GOLD, _STEP = np.uint64(0x9E3779B97F4A7C15), np.uint64(0xD1B54A32D192ED03)
+_CODE_OF = np.zeros(256, dtype=np.uint8)          # ASCII -> 2-bit read code (ascii >> 1) & 3: A0 C1 T2 G3
+_CODE_OF[_ACGT] = (_ACGT >> 1) & 3
+_BASE_OF = np.frombuffer(b"ACTG", dtype=np.uint8)  # 2-bit read code -> ASCII
+
+
+def syn_table():
+    """uint64[256] synonymous-codon table in the layout orph_synth_reads_device takes: bits 0..2 = number of sense
+    codons of the amino-acid byte, codon c at bits [4 + 6c, +6) as three 2-bit read codes (first base lowest)."""
+    table = np.zeros(256, dtype=np.uint64)
+    for aa in range(256):
+        n = int(_SYN_COUNTS[aa])
+        v = n
+        for c in range(n):
+            codes = _CODE_OF[_SYN_CODONS[aa, c]]
+            v |= (int(codes[0]) | (int(codes[1]) << 2) | (int(codes[2]) << 4)) << (4 + 6 * c)
+        table[aa] = v
+    return table
+
+
+def _mix(z):
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def _draw(seed, idx, d):
+    with np.errstate(over="ignore"):
+        return _mix(np.uint64(seed) + idx * _GOLD + np.uint64(d + 1) * _STEP)
+
+
+def counter_reads(indices, residues, prot_offsets, seed=3003, length=150):
+    """Reads with the given GLOBAL indices: uint8 [m, length] ASCII.  Even index: back-translated; odd: uniform."""
+    idx = np.ascontiguousarray(indices, dtype=np.uint64)
+    m, n_res = len(idx), length // 3 + 2
+    codes = np.zeros((m, length), dtype=np.uint8)
+    with np.errstate(over="ignore"):
+        odd = (idx & np.uint64(1)) == 1
+        b = np.arange(length)
+        if odd.any():
+            draws = np.stack([_draw(seed, idx[odd], q) for q in range((length + 31) // 32)], axis=1)  # [mo, words]
+            codes[odd] = ((draws[:, b // 32] >> (2 * (b % 32)).astype(np.uint64)) & np.uint64(3)).astype(np.uint8)
+        ev = ~odd
+        if ev.any():
+            ie = idx[ev]
+            n_prot = len(prot_offsets) - 1
+            plen = (prot_offsets[1:] - prot_offsets[:-1]).astype(np.uint64)
+            d0, d1 = _draw(seed, ie, 0), _draw(seed, ie, 1)
+            p = (d0 % np.uint64(n_prot)).astype(np.int64)
+            while True:
+                short = plen[p] < n_res
+                if not short.any():
+                    break
+                p[short] = (p[short] + 1) % n_prot
+            start = prot_offsets[p].astype(np.uint64) + (d0 >> np.uint64(32)) % (plen[p] - np.uint64(n_res) + np.uint64(1))
+            phase = (d1 % np.uint64(3)).astype(np.int64)
+            flip = ((d1 >> np.uint64(8)) & np.uint64(1)).astype(bool)
+            j = np.arange(n_res)
+            aa = residues[start.astype(np.int64)[:, None] + j[None, :]]                               # [me, n_res]
+            picks = np.stack([_draw(seed, ie, 2 + q) for q in range((n_res + 7) // 8)], axis=1)       # [me, groups]
+            pick = ((picks[:, j // 8] >> (8 * (j % 8)).astype(np.uint64)) & np.uint64(0xFF)).astype(np.int64)
+            choice = pick % _SYN_COUNTS[aa]
+            nt = _CODE_OF[_SYN_CODONS[aa, choice].reshape(len(ie), n_res * 3)]                        # 2-bit codes
+            rd = np.take_along_axis(nt, phase[:, None] + b[None, :], axis=1)
+            subs = np.stack([_draw(seed, ie, 16 + q) for q in range((length + 3) // 4)], axis=1)
+            v = ((subs[:, b // 4] >> (16 * (b % 4)).astype(np.uint64)) & np.uint64(0xFFFF)).astype(np.int64)
+            hit = v < 655
+            rd = np.where(hit, (rd + 1 + v % 3) & 3, rd).astype(np.uint8)
+            rd[flip] = rd[flip][:, ::-1] ^ 2
+            codes[ev] = rd
+    return _BASE_OF[codes]

@@ -613,3 +613,93 @@ def test_host_packing_ingest_paths(gpu, enc, orc):
     sflat, soffs = gpu.concat_reads([flat[int(offsets[r]):int(offsets[r + 1])].tobytes() for r in sample])
     ora, _ = orc.score_reads(go, sflat, soffs, olut, 0.5, n_threads=0)
     assert_same_as_oracle(want[sample], ora, "ingest sample")
+
+
+def test_full_size_cfg4_index_build(gpu, enc, orc):
+    """BASELINE configs[3], index side: Bloom build from the 1e8-residue synthetic proteome (P100M) on the GPU at
+    tablesize 1e8 (L2 regime, ~63 % fill) and 1e9 (HBM regime).  Bit-exact against the oracle on a 1e6-residue prefix
+    proteome with the same geometry; at full size through properties: the build is idempotent and order-independent
+    (two halves in either order, with and without the n_unique_kmers bookkeeping), every bit of the prefix filter is set
+    in the full one, and every k-mer of sampled proteins is found (no false negatives)."""
+    from orpheum_b200 import synth
+
+    residues, poffs = synth.make_proteome(n_proteins=187000, seed=1004)
+    assert 9.5e7 < int(poffs[-1]) < 1.1e8
+    lut, olut = enc.encode_lut("protein"), orc.encode_lut("protein")
+    n_prefix = int(np.searchsorted(poffs, 1_000_000))
+    half = len(poffs) // 2
+    for tablesize in (int(1e8), int(1e9)):
+        full = gpu.GpuNodegraph(7, tablesize, 4)
+        full.add_peptides(residues, poffs, lut)
+        pops = [full.n_occupied(i) for i in range(4)]
+        # order independence + idempotence
+        other = gpu.GpuNodegraph(7, tablesize, 4)
+        other.add_peptides(residues, poffs[half:], lut, count_unique=False)
+        other.add_peptides(residues, poffs[: half + 1], lut, count_unique=False)
+        other.add_peptides(residues, poffs[: n_prefix + 1], lut)
+        assert [other.n_occupied(i) for i in range(4)] == pops
+        ta, _ = full.tables()
+        tb, _ = other.tables()
+        assert all((a == b).all() for a, b in zip(ta, tb))
+        del other, tb
+        # prefix proteome: identical to the oracle, and a subset of the full filter
+        small = gpu.GpuNodegraph(7, tablesize, 4)
+        small.add_peptides(residues, poffs[: n_prefix + 1], lut)
+        o_small = orc.Nodegraph(7, tablesize, 4)
+        o_small.add_peptides(residues, poffs[: n_prefix + 1], olut)
+        ts, _ = small.tables()
+        for i in range(4):
+            assert (ts[i] == o_small.table(i)).all(), (tablesize, i)
+            assert ((ts[i] & ta[i]) == ts[i]).all()
+        assert abs(small.n_unique_kmers() - o_small.n_unique_kmers()) <= 1e-3 * o_small.n_unique_kmers()  # tests/test_index.py:54 rtol
+        # no false negatives on proteins sampled from the whole proteome
+        rng = np.random.default_rng(tablesize % 1000)
+        kmers = []
+        for p in rng.choice(len(poffs) - 1, 300, replace=False):
+            seq = residues[int(poffs[p]):int(poffs[p + 1])].tobytes().decode()
+            kmers.extend(seq[j:j + 7] for j in range(0, len(seq) - 6, 5))
+        assert full.get_many(full.ctx.hash_kmers(kmers)).all()
+        del full, small, ta, ts, o_small
+
+
+def test_counter_based_read_generator(gpu, enc, orc):
+    """The HBM read generator of bench.py --workload cfg4 (orph_synth_reads_device) and its numpy twin
+    (synth.counter_reads) produce the same bases for the same global indices, for any split of the index range, and the
+    generated batch scores identically to the host copy."""
+    import torch
+
+    from orpheum_b200 import _lib, synth
+
+    residues, poffs = synth.make_proteome(n_proteins=3000, seed=8)
+    ctx = gpu.default_context()
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    d_res = torch.from_numpy(residues).to(dev)
+    d_poffs = torch.from_numpy(poffs.view(np.int64)).to(dev)
+    d_syn = torch.from_numpy(synth.syn_table().view(np.int64)).to(dev)
+    for length, first, n in ((150, 0, 50_000), (150, 999_999_999_000, 4097), (149, 12_345, 1000), (64, 7, 333), (320, 1 << 40, 200)):
+        d_reads = torch.zeros((n * length + 31) // 32 + 2, dtype=torch.int64, device=dev)
+        _lib.check(lib.orph_synth_reads_device(ctx._h, 3003, first, n, length, d_res.data_ptr(), d_poffs.data_ptr(), len(poffs) - 1,
+                                               d_syn.data_ptr(), d_reads.data_ptr()))
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        host = synth.counter_reads(np.arange(first, first + n, dtype=np.uint64), residues, poffs, seed=3003, length=length)
+        flat, offs = synth.concat_fixed(host)
+        want, needs = gpu.pack_reads(flat, offs)
+        assert not needs.any()
+        got = d_reads.cpu().numpy().view(np.uint64)
+        n_words = (n * length + 31) // 32
+        np.testing.assert_array_equal(got[:n_words], want[:n_words], err_msg=f"L={length} first={first}")
+    # half of the reads are coding: the generated batch is a meaningful workload
+    lut = enc.encode_lut("protein")
+    gg = gpu.GpuNodegraph(7, 1e7, 4)
+    gg.add_peptides(residues, poffs, lut)
+    host = synth.counter_reads(np.arange(0, 20_000, dtype=np.uint64), residues, poffs, seed=3003, length=150)
+    flat, offs = synth.concat_fixed(host)
+    res = gpu.score_reads(gg, flat, offs, lut, 0.5)
+    coding = (res["category"] == _lib.CAT_CODING).any(axis=1)
+    assert coding[0::2].mean() > 0.9 and coding[1::2].mean() < 0.05
+    go = orc.Nodegraph(7, int(1e7), 4)
+    go.add_peptides(residues, poffs, orc.encode_lut("protein"))
+    ora, _ = orc.score_reads(go, flat, offs, orc.encode_lut("protein"), 0.5, n_threads=0)
+    assert_same_as_oracle(res, ora, "counter reads")
