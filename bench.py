@@ -440,6 +440,8 @@ def run_ours(args):
     roofline = {
         "kernel": dominant + "_kernel", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
         "frac": achieved / peak_gbs,
+        "note": "achieved counts 32 B per required Bloom probe; the probes are served by the L2-resident filter, not HBM, so frac can "
+                "exceed 1 -- gather_frac (required probe sectors/s over the measured random-gather ceiling) grades the kernel",
         # DRAM bytes of this kernel per launch: 115.8 B/read measured by `ncu --set full` on a 2 M-read launch of the
         # same workload (profiles/r01_ncu_full_final_score_tasks.csv: dram read 187.4 MB + write 44.2 MB), scaled by reads.
         # Far below the algorithmic bytes because the probes are served by the L2-resident filter.
