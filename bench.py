@@ -52,6 +52,7 @@ def parse_args():
                          "generated in HBM and sharded over the GPUs (strong scaling)")
     ap.add_argument("--total-reads", type=float, default=1e9, help="cfg4: reads of the whole job, split over the GPUs")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fastq", action="store_true", help="skip the FASTQ-file end-to-end leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -409,6 +410,45 @@ def run_ours(args):
             e2e["packed_input"] = {"value": world * args.reads * args.steps / dtp, "ms_per_step": 1e3 * dtp / args.steps,
                                    "h2d_bytes_per_step": int(packed.nbytes + offsets.nbytes),
                                    "identical_to_device_path": bool(h_out.numpy().view(_lib.READ_RESULT_DTYPE).tobytes() == res_dev.tobytes())}
+
+    # ---- from a FASTQ file: parse (native parallel parser, next batch prefetched) -> orph_score_reads -> records ----
+    if e2e is not None and rank == 0 and world == 1 and args.workload == "r150" and not args.no_fastq:
+        import shutil
+        import tempfile
+
+        from orpheum_b200 import fastx
+
+        n_fq = min(args.reads, 4_000_000)
+        tmpdir = tempfile.mkdtemp(prefix="orph_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            fq = os.path.join(tmpdir, "reads.fq")
+            qual = b"I" * READ_LEN
+            rows = flat[: n_fq * READ_LEN].reshape(n_fq, READ_LEN)
+            with open(fq, "wb") as fh:
+                for lo in range(0, n_fq, 200_000):
+                    fh.write(b"".join(b"@read%d 1:N:0\n%s\n+\n%s\n" % (i, rows[i].tobytes(), qual) for i in range(lo, min(n_fq, lo + 200_000))))
+            fq_bytes = os.path.getsize(fq)
+
+            def pass_fastq():
+                got, parts = 0, []
+                for _names, b_flat, b_offs in fastx.read_batches(fq, prefetch=1):
+                    parts.append(gpu.score_reads(graph, b_flat, b_offs, lut, thr, ctx=ctx))
+                    got += len(b_offs) - 1
+                return got, parts
+
+            pass_fastq()
+            reps = 3
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                got, parts = pass_fastq()
+            dtf = (time.perf_counter() - t0) / reps
+            same_fq = got == n_fq and np.concatenate(parts).tobytes() == res_dev[:n_fq].tobytes()
+            e2e["from_fastq"] = {"value": n_fq / dtf, "unit": UNIT, "reads": n_fq, "fastq_bytes": fq_bytes, "ms": 1e3 * dtf,
+                                 "fastq_GBps": fq_bytes / dtf / 1e9, "identical_to_device_path": bool(same_fq),
+                                 "path": "uncompressed four-line FASTQ on tmpfs -> orph_fastx_* (mmap, parallel parse, one batch "
+                                         "prefetched) -> orph_score_reads (pageable host ASCII, packed on the host) -> records"}
+        finally:
+            shutil.rmtree(tmpdir, ignore_errors=True)
 
     # ---- measured random-gather ceiling for this filter footprint ----
     gather = None

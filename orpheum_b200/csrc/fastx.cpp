@@ -4,6 +4,10 @@
 // header line without the leading '>' / '@' (no split at white space), sequence lines are concatenated
 // as they are (no upper-casing), FASTQ may wrap its sequence over several lines, an empty file has no
 // records, and a file that starts with anything else is not a sequence file.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <cstdint>
@@ -12,22 +16,62 @@
 #include <string>
 #include <vector>
 
+#include <algorithm>
+#include <cstdlib>
+#include <thread>
+
 #include "../../include/orpheum_b200.h"
+#include "hostpack.h"
 
 extern int orph_set_error(int code, const char *fmt, ...);  // defined in orpheum_b200.cu
+
+// Text window of the input.  gzip: a malloc'ed buffer refilled through gzread (grown with realloc, never
+// zero-filled).  Plain files: the whole file mapped read-only, so that the parallel parser touches the page cache
+// directly (no copy, page faults spread over the threads).
+struct TextBuf {
+    char *p = nullptr;
+    size_t cap = 0;
+    bool mapped = false;
+    char *data() const { return p; }
+    size_t size() const { return cap; }
+    bool grow(size_t want)
+    {
+        if (mapped) return false;
+        char *q = (char *)realloc(p, want);
+        if (!q) return false;
+        p = q;
+        cap = want;
+        return true;
+    }
+    void release()
+    {
+        if (mapped && p) munmap(p, cap);
+        else free(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
 
 struct orph_fastx {
     gzFile gz = nullptr;
     char kind = 0;  // '>' FASTA, '@' FASTQ, 0 empty file
-    std::vector<char> buf;
+    TextBuf buf;
     size_t pos = 0, end = 0;
     bool eof = false;
+    double bytes_per_record = 400;  // running estimate, sizes the window of the FASTQ fast path
     std::string pending;  // FASTA: header line of the next record, already consumed
     bool have_pending = false;
     // current batch
     std::vector<uint8_t> seq, names;
     std::vector<uint64_t> seq_off, name_off;
     std::string line;  // scratch
+    // fast path for strict four-line FASTQ (parallel over the host cores); any other layout takes the general parser
+    bool fast_ok = true;
+    orph_host::Pool *pool = nullptr;
+    std::vector<uint64_t> nl;               // newline positions of the buffered text
+    std::vector<uint32_t> seq_len, name_len;
+    std::vector<uint64_t> seq_src, name_src;
+    ~orph_fastx() { delete pool; buf.release(); }
 };
 
 static bool fill(orph_fastx *fx)
@@ -36,7 +80,10 @@ static bool fill(orph_fastx *fx)
     if (fx->pos > 0 && fx->pos < fx->end) memmove(fx->buf.data(), fx->buf.data() + fx->pos, fx->end - fx->pos);
     fx->end -= fx->pos;
     fx->pos = 0;
-    if (fx->end == fx->buf.size()) fx->buf.resize(fx->buf.size() * 2);
+    if (fx->end == fx->buf.size() && !fx->buf.grow(fx->buf.size() * 2)) {
+        fx->eof = true;  // out of memory: stop reading; the callers report a truncated record
+        return false;
+    }
     const int n = gzread(fx->gz, fx->buf.data() + fx->end, (unsigned)(fx->buf.size() - fx->end));
     if (n <= 0) {
         fx->eof = true;
@@ -88,12 +135,36 @@ extern "C" int orph_fastx_open(const char *path, orph_fastx **out)
     gzbuffer(gz, 1 << 20);
     orph_fastx *fx = new orph_fastx();
     fx->gz = gz;
-    fx->buf.resize(4 << 20);
-    fill(fx);
+    bool mapped = false;
+    if (gzdirect(gz)) {  // not compressed: map the file instead of copying it through gzread
+        const int fd = open(path, O_RDONLY);
+        struct stat st;
+        if (fd >= 0 && fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+            void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m != MAP_FAILED) {
+                madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+                fx->buf.p = (char *)m;
+                fx->buf.cap = (size_t)st.st_size;
+                fx->buf.mapped = true;
+                fx->end = (size_t)st.st_size;
+                fx->eof = true;
+                mapped = true;
+            }
+        }
+        if (fd >= 0) close(fd);
+    }
+    if (!mapped) {
+        if (!fx->buf.grow(4 << 20)) {
+            gzclose(gz);
+            delete fx;
+            return orph_set_error(ORPH_E_NOMEM, "out of host memory");
+        }
+        fill(fx);
+    }
     if (fx->end == 0) {
         fx->kind = 0;  // empty file: no records
-    } else if (fx->buf[0] == '>' || fx->buf[0] == '@') {
-        fx->kind = fx->buf[0];
+    } else if (fx->buf.p[0] == '>' || fx->buf.p[0] == '@') {
+        fx->kind = fx->buf.p[0];
     } else {
         gzclose(gz);
         delete fx;
@@ -115,6 +186,142 @@ static void begin_record(orph_fastx *fx, const char *name, size_t len)
     strip(&name, &len);
     fx->names.insert(fx->names.end(), (const uint8_t *)name, (const uint8_t *)name + len);
     fx->name_off.push_back(fx->names.size());
+}
+
+// ------------------------------------------------------------------------------------------------
+// Strict four-line FASTQ, parsed in parallel: index the newlines of the buffered text, check every record
+// (line 0 starts with '@', line 2 with '+', sequence non-empty and not starting with '+' / '#', quality as long
+// as the sequence), then copy names and sequences to their places.  Returns false -- with nothing consumed --
+// whenever the text is not of that shape (wrapped records, blank lines, a truncated tail, ...): the general
+// parser below then produces the records or the error.
+// ------------------------------------------------------------------------------------------------
+static inline void strip_range(const char *base, uint64_t &a, uint64_t &b)
+{
+    while (b > a && (base[b - 1] == '\r' || base[b - 1] == ' ' || base[b - 1] == '\t' || base[b - 1] == '\n')) b--;
+    while (b > a && (base[a] == ' ' || base[a] == '\t' || base[a] == '\r')) a++;
+}
+
+#include <chrono>
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+static bool fastq_fast_batch(orph_fastx *fx, uint64_t max_records, uint64_t max_bases, uint64_t *n_out)
+{
+    static const bool trace = getenv("ORPHEUM_B200_TRACE") != nullptr;
+    const double t_begin = now_s();
+    // a window of text that should hold the batch, sized from the bytes per record seen so far
+    uint64_t want = (uint64_t)std::min<double>(1024.0 * (1 << 20), std::min<double>((double)max_records * fx->bytes_per_record, (double)max_bases * 3.0)) + (1 << 16);
+    while (!fx->eof && fx->end - fx->pos < want)
+        if (!fill(fx)) break;
+    const char *base = fx->buf.data();
+    const uint64_t lo = fx->pos;
+    if (fx->end <= lo) return false;
+    const uint64_t hi = std::min<uint64_t>(fx->end, lo + want);  // the rest of a mapped file waits for the next batches
+    const bool at_end = fx->eof && hi == fx->end;
+    const uint64_t n_bytes = hi - lo;
+    const double t_filled = now_s();
+    if (!fx->pool && n_bytes >= (8u << 20)) {
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        fx->pool = new (std::nothrow) orph_host::Pool((int)std::min(hw, 32u));
+    }
+    auto parallel_for = [&](uint64_t n_items, const std::function<void(uint64_t)> &fn) {
+        if (fx->pool) fx->pool->run(n_items, fn);
+        else
+            for (uint64_t i = 0; i < n_items; i++) fn(i);
+    };
+    // ---- newline index
+    constexpr uint64_t kSeg = 4u << 20;
+    const uint64_t n_seg = (n_bytes + kSeg - 1) / kSeg;
+    std::vector<uint64_t> seg_count(n_seg + 1, 0);
+    parallel_for(n_seg, [&](uint64_t sgm) {
+        const char *p = base + lo + sgm * kSeg, *e = base + std::min(hi, lo + (sgm + 1) * kSeg);
+        uint64_t c = 0;
+        while (p < e && (p = (const char *)memchr(p, '\n', (size_t)(e - p))) != nullptr) { c++; p++; }
+        seg_count[sgm + 1] = c;
+    });
+    for (uint64_t sgm = 0; sgm < n_seg; sgm++) seg_count[sgm + 1] += seg_count[sgm];
+    uint64_t n_lines = seg_count[n_seg];
+    const bool tail_line = at_end && base[hi - 1] != '\n';  // last line of the file without a terminator
+    fx->nl.resize(n_lines + 1);
+    parallel_for(n_seg, [&](uint64_t sgm) {
+        const char *p = base + lo + sgm * kSeg, *e = base + std::min(hi, lo + (sgm + 1) * kSeg);
+        uint64_t at = seg_count[sgm];
+        while (p < e && (p = (const char *)memchr(p, '\n', (size_t)(e - p))) != nullptr) { fx->nl[at++] = (uint64_t)(p - base); p++; }
+    });
+    if (tail_line) fx->nl[n_lines++] = hi;
+    const double t_indexed = now_s();
+    if (at_end && n_lines % 4 != 0) return false;  // odd tail: let the general parser decide
+    uint64_t n_avail = n_lines / 4;
+    if (n_avail == 0) {
+        // not even one record in the window (long reads): widen it, unless it already spans everything there is
+        if (at_end || want >= (1ull << 30)) return false;
+        fx->bytes_per_record = std::max(8.0 * fx->bytes_per_record, 8.0 * (double)want / (double)std::max<uint64_t>(1, max_records));
+        return fastq_fast_batch(fx, max_records, max_bases, n_out);
+    }
+    uint64_t n_take = std::min(n_avail, max_records);
+    const uint64_t *nl = fx->nl.data();
+    auto line_begin = [&](uint64_t k) { return k == 0 ? lo : nl[k - 1] + 1; };
+    // ---- validate + measure
+    fx->seq_len.resize(n_take);
+    fx->name_len.resize(n_take);
+    fx->seq_src.resize(n_take);
+    fx->name_src.resize(n_take);
+    constexpr uint64_t kRecBlock = 1 << 14;
+    const uint64_t n_blk = (n_take + kRecBlock - 1) / kRecBlock;
+    std::vector<uint8_t> blk_bad(n_blk, 0);
+    parallel_for(n_blk, [&](uint64_t blk) {
+        const uint64_t r1 = std::min(n_take, (blk + 1) * kRecBlock);
+        for (uint64_t r = blk * kRecBlock; r < r1; r++) {
+            uint64_t h0 = line_begin(4 * r), h1 = nl[4 * r];
+            uint64_t s0 = h1 + 1, s1 = nl[4 * r + 1];
+            const uint64_t p0 = s1 + 1, p1 = nl[4 * r + 2];
+            uint64_t q0 = p1 + 1, q1 = nl[4 * r + 3];
+            if (h1 == h0 || base[h0] != '@' || p1 == p0 || base[p0] != '+' || s1 == s0 || base[s0] == '+' || base[s0] == '#') { blk_bad[blk] = 1; return; }
+            h0++;
+            strip_range(base, h0, h1);
+            strip_range(base, s0, s1);
+            strip_range(base, q0, q1);
+            if (s1 == s0 || q1 - q0 != s1 - s0 || s1 - s0 > 0xFFFFFFFFull || h1 - h0 > 0xFFFFFFFFull) { blk_bad[blk] = 1; return; }
+            fx->seq_src[r] = s0;
+            fx->seq_len[r] = (uint32_t)(s1 - s0);
+            fx->name_src[r] = h0;
+            fx->name_len[r] = (uint32_t)(h1 - h0);
+        }
+    });
+    for (uint64_t blk = 0; blk < n_blk; blk++)
+        if (blk_bad[blk]) return false;
+    const double t_validated = now_s();
+    // ---- offsets (records are taken while the bases collected so far are below max_bases, like the general parser)
+    fx->seq_off.resize(n_take + 1);
+    fx->name_off.resize(n_take + 1);
+    fx->seq_off[0] = fx->name_off[0] = 0;
+    uint64_t n = 0;
+    while (n < n_take && fx->seq_off[n] < max_bases) {
+        fx->seq_off[n + 1] = fx->seq_off[n] + fx->seq_len[n];
+        fx->name_off[n + 1] = fx->name_off[n] + fx->name_len[n];
+        n++;
+    }
+    n_take = n;
+    fx->seq_off.resize(n_take + 1);
+    fx->name_off.resize(n_take + 1);
+    fx->seq.resize(fx->seq_off[n_take]);
+    fx->names.resize(fx->name_off[n_take]);
+    // ---- copy
+    const uint64_t n_cblk = (n_take + kRecBlock - 1) / kRecBlock;
+    parallel_for(n_cblk, [&](uint64_t blk) {
+        const uint64_t r1 = std::min(n_take, (blk + 1) * kRecBlock);
+        for (uint64_t r = blk * kRecBlock; r < r1; r++) {
+            memcpy(fx->seq.data() + fx->seq_off[r], base + fx->seq_src[r], fx->seq_len[r]);
+            memcpy(fx->names.data() + fx->name_off[r], base + fx->name_src[r], fx->name_len[r]);
+        }
+    });
+    fx->pos = std::min<uint64_t>(hi, nl[4 * n_take - 1] + 1);
+    fx->bytes_per_record = 1.05 * (double)(fx->pos - lo) / (double)n_take + 8;
+    *n_out = n_take;
+    if (trace)
+        fprintf(stderr, "[orph trace] fastq batch: %llu records from %.1f MB of text: fill %.1f ms, newline index %.1f ms, validate %.1f ms, offsets + copy %.1f ms\n",
+                (unsigned long long)n_take, n_bytes / 1e6, 1e3 * (t_filled - t_begin), 1e3 * (t_indexed - t_filled), 1e3 * (t_validated - t_indexed),
+                1e3 * (now_s() - t_validated));
+    return true;
 }
 
 extern "C" int orph_fastx_next_batch(orph_fastx *fx, uint64_t max_records, uint64_t max_bases, uint64_t *n_records,
@@ -151,7 +358,14 @@ extern "C" int orph_fastx_next_batch(orph_fastx *fx, uint64_t max_records, uint6
             fx->seq_off.push_back(fx->seq.size());
             n++;
         }
+    } else if (fx->kind == '@' && fx->fast_ok && fastq_fast_batch(fx, max_records, max_bases, &n)) {
+        // done: strict four-line records, parsed in parallel
     } else if (fx->kind == '@') {
+        fx->fast_ok = false;  // some other FASTQ layout (or the tail of the file): general parser from here on
+        fx->seq.clear();
+        fx->names.clear();
+        fx->seq_off.assign(1, 0);
+        fx->name_off.assign(1, 0);
         while (n < max_records && fx->seq.size() < max_bases) {
             if (!next_line(fx, &s, &len)) break;
             if (len == 0) continue;

@@ -192,11 +192,55 @@ def open(path, native=True):  # noqa: A001 - same public name as screed.open
     return _Reader(path)
 
 
-def read_batches(path, max_records=1 << 20, max_bases=1 << 28, native=True):
-    """Yield (names, flat uint8 bytes, uint64 offsets[n+1]) batches in file order, in the layout the C ABI takes."""
+def _prefetched(make_iter, depth):
+    """Run a batch iterator in a background thread (the native parser releases the GIL), `depth` batches ahead."""
+    import queue
+    import threading
+
+    q = queue.Queue(maxsize=depth)
+    stop = threading.Event()
+
+    def work():
+        try:
+            for item in make_iter():
+                while not stop.is_set():
+                    try:
+                        q.put((item, None), timeout=0.1)
+                        break
+                    except queue.Full:
+                        continue
+                if stop.is_set():
+                    return
+            q.put((None, StopIteration()))
+        except BaseException as exc:  # re-raised in the consumer
+            q.put((None, exc))
+
+    t = threading.Thread(target=work, daemon=True)
+    t.start()
+    try:
+        while True:
+            item, exc = q.get()
+            if exc is not None:
+                if isinstance(exc, StopIteration):
+                    return
+                raise exc
+            yield item
+    finally:
+        stop.set()
+
+
+def read_batches(path, max_records=1 << 20, max_bases=1 << 28, native=True, prefetch=0):
+    """Yield (names, flat uint8 bytes, uint64 offsets[n+1]) batches in file order, in the layout the C ABI takes.
+    prefetch > 0 parses that many batches ahead in a background thread, so that parsing overlaps the GPU call."""
     if native and not _is_bz2(path):
-        with _NativeReader(path) as reader:
-            yield from reader.batches(max_records, max_bases)
+        def batches():
+            with _NativeReader(path) as reader:
+                yield from reader.batches(max_records, max_bases)
+
+        if prefetch > 0:
+            yield from _prefetched(batches, prefetch)
+        else:
+            yield from batches()
         return
     names, seqs, n_bases = [], [], 0
     with _Reader(path) as records:

@@ -275,7 +275,7 @@ class Translate:
         self.maybe_open_fastas()
         try:
             for reads in self.reads:
-                for names, flat, offsets in fastx.read_batches(reads):
+                for names, flat, offsets in fastx.read_batches(reads, prefetch=1):  # the next batch is parsed meanwhile
                     results = score_reads(self.peptide_bloom_filter, flat, offsets, self._lut, self.jaccard_threshold)
                     self._emit_batch(names, flat, offsets, results)
                     table.append(names, results, reads)

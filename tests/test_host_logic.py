@@ -237,3 +237,69 @@ def test_native_float_repr_matches_python():
     for v in (0.0, 1.0, 0.5, 1e-4, 1e-5, 9.999e-5, 123456.789, 1e15, 1e16, 1.5e17, 2.0**-40, 3.0, 100.0, -0.25, 1e22, 5e-324):
         assert native(v) == repr(v), v
     assert native(float("nan")) == "nan"
+
+
+def test_parallel_fastq_fast_path(tmp_path):
+    """The strict four-line FASTQ fast path (newline index + validation + copies spread over the host cores) against the
+    pure-Python reader: files large enough for several segments and the thread pool, CRLF, spaces around fields, no final
+    newline, '@' and '+' as first quality characters, and layouts that must fall back to the general parser in the middle
+    of a file (a wrapped record, a blank line, an empty sequence)."""
+    from orpheum_b200 import build
+
+    build.build()
+    rng = np.random.default_rng(4)
+    bases = np.frombuffer(b"ACGTN", dtype=np.uint8)
+
+    def records(n, start=0):
+        out = []
+        for i in range(start, start + n):
+            L = int(rng.integers(30, 300))
+            seq = bases[rng.integers(0, 5 if i % 50 == 0 else 4, L)].tobytes()
+            qual = bytes(rng.integers(33, 74, L, dtype=np.uint8))
+            if i % 7 == 0:
+                qual = b"@" + qual[1:]
+            if i % 11 == 0:
+                qual = b"+" + qual[1:]
+            out.append((b"read%d lane:%d  extra" % (i, i % 8), seq, qual))
+        return out
+
+    def render(recs, eol=b"\n", final=True):
+        text = b"".join(b"@" + n + eol + s + eol + b"+" + (n if i % 3 == 0 else b"") + eol + q + eol for i, (n, s, q) in enumerate(recs))
+        return text if final else text[: -len(eol)]
+
+    def check(path, **kw):
+        py = [(r["name"], r["sequence"]) for r in fastx.open(path, native=False)]
+        got_names, got_seqs = [], []
+        for names, flat, offsets in fastx.read_batches(path, native=True, **kw):
+            data = flat.tobytes()
+            got_names += names.tolist()
+            got_seqs += [data[int(offsets[i]):int(offsets[i + 1])].decode("latin-1") for i in range(len(names))]
+        assert len(py) == len(got_names)
+        assert list(zip(got_names, got_seqs)) == py, path
+        return len(py)
+
+    big = records(60_000)
+    p = tmp_path / "big.fq"
+    p.write_bytes(render(big))
+    assert p.stat().st_size > (16 << 20)
+    assert check(str(p)) == 60_000
+    assert check(str(p), max_records=25_000) == 60_000
+    assert check(str(p), max_bases=1_000_000) == 60_000
+    p.write_bytes(render(big[:5000], eol=b"\r\n", final=False))
+    assert check(str(p)) == 5000
+    # padded fields
+    p.write_bytes(b"@ r1 \t\n  ACGT \n+\n IIII\t\n@r2\nAC\n+\nII")
+    assert check(str(p)) == 2
+    # layouts the fast path must hand over to the general parser, at the start, in the middle and at the end
+    head, tail = render(big[:30_000]), render(big[30_000:40_000])
+    wrapped = b"@w x\nACGT\nACGT\n+\nIIII\nIIII\n"
+    for odd in (wrapped, b"\n", b"@empty\n\n+\n\n", b"@hash\nACGT\n#\nIIII\n"):
+        for layout in (odd + head, head + odd + tail, head + odd):
+            if layout[:1] != b"@":
+                continue  # a file that starts with a blank line is not FASTQ for either reader
+            p.write_bytes(layout)
+            check(str(p), max_records=8192)
+    # a truncated file raises like the general parser
+    p.write_bytes(head + b"@r\nACGT\n+\nII\n")
+    with pytest.raises(OSError):
+        check(str(p))
