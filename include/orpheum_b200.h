@@ -234,6 +234,19 @@ void orph_fastx_close(orph_fastx *fx);
 int orph_csv_write_scores(const char *path, int append, const uint8_t *name_fields, const uint64_t *name_offsets,
                           uint64_t n_reads, const orph_read_result *results, const char *const *category_text,
                           const char *filename_field);
+/* The FASTA records Translate emits for one batch (translate.py:244-298), in read order then frame order:
+ *   kind 0  coding peptides (the stdout stream): ">{name}__translation_frame:{f}__jaccard:{j}" with every space
+ *           replaced by "__", then the peptide;
+ *   kind 1 / 2  coding / non-coding nucleotides (--coding-nucleotide-fasta, --noncoding-nucleotide-fasta): the same
+ *           header, then the read;
+ *   kind 3  low-complexity peptides: ">{name} translation_frame: {}.format(frame)" verbatim (translate.py:247).
+ * peptides / pep_offsets: the un-encoded translations (orph_translate_frames) of every frame whose category is CODING
+ * -- and LOW_COMPLEXITY_PEPTIDE when peptides_include_low_complexity -- in read order then frame order.  Writes at
+ * most out_cap bytes and always returns the full length in *out_len (call again with a larger buffer if needed). */
+int orph_format_fasta(int kind, const uint8_t *names, const uint64_t *name_offsets, uint64_t n_reads,
+                      const orph_read_result *results, const uint8_t *reads, const uint64_t *read_offsets,
+                      const uint8_t *peptides, const uint64_t *pep_offsets, int peptides_include_low_complexity,
+                      uint8_t *out, uint64_t out_cap, uint64_t *out_len);
 /* Python's repr(float) (the formatting the CSV uses), exposed for tests.  out32 must hold 32 bytes. */
 int orph_format_float_repr(double v, char *out32);
 

@@ -72,6 +72,8 @@ PROTOTYPES = {
     "orph_fastx_next_batch": (ctypes.c_int, [_vp, ctypes.c_uint64, ctypes.c_uint64, _u64p, _pp, _pp, _pp, _pp]),
     "orph_fastx_close": (None, [_vp]),
     "orph_csv_write_scores": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, _u8p, _u64p, ctypes.c_uint64, _vp, _vp, ctypes.c_char_p]),
+    "orph_format_fasta": (ctypes.c_int, [ctypes.c_int, _u8p, _u64p, ctypes.c_uint64, _vp, _u8p, _u64p, _u8p, _u64p, ctypes.c_int, _u8p,
+                                         ctypes.c_uint64, _u64p]),
     "orph_format_float_repr": (ctypes.c_int, [ctypes.c_double, ctypes.c_char_p]),
     "orph_synth_reads_device": (ctypes.c_int, [_vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32, _vp, _vp,
                                                ctypes.c_uint64, _vp, _vp]),

@@ -315,13 +315,37 @@ def score_reads_device(graph, d_reads_ptr, d_offsets_ptr, n_reads, max_read_len,
 def translate_frames(ctx, reads, offsets, item_read, item_frame):
     """Un-encoded peptides of the listed (read index, frame key) pairs, translated on the GPU with the
     reference's codon semantics -> list of str in item order."""
+    out, out_offsets = translate_frames_raw(ctx, reads, offsets, item_read, item_frame)
+    blob = out.tobytes()
+    return [blob[int(out_offsets[i]):int(out_offsets[i + 1])].decode("latin-1") for i in range(len(out_offsets) - 1)]
+
+
+def format_fasta(kind, names_blob, name_offsets, results, reads, read_offsets, peptides, pep_offsets, peptides_include_low_complexity):
+    """orph_format_fasta -> bytes (see include/orpheum_b200.h)."""
+    lib = _lib.load()
+    names_blob = np.ascontiguousarray(names_blob, dtype=np.uint8)
+    name_offsets = np.ascontiguousarray(name_offsets, dtype=np.uint64)
+    results = np.ascontiguousarray(results)
+    n = len(results)
+    need = ctypes.c_uint64()
+    args = [int(kind), ptr(names_blob), ptr(name_offsets), n, ptr(results), ptr(reads) if reads is not None else None,
+            ptr(read_offsets) if read_offsets is not None else None, ptr(peptides) if peptides is not None else None,
+            ptr(pep_offsets) if pep_offsets is not None else None, int(bool(peptides_include_low_complexity))]
+    check(lib.orph_format_fasta(*args, None, 0, ctypes.byref(need)))
+    out = np.empty(max(int(need.value), 1), dtype=np.uint8)
+    check(lib.orph_format_fasta(*args, ptr(out), int(need.value), ctypes.byref(need)))
+    return out[: int(need.value)].tobytes()
+
+
+def translate_frames_raw(ctx, reads, offsets, item_read, item_frame):
+    """Like translate_frames, but returns (uint8 blob, uint64 offsets[n_items + 1]) without building python strings."""
     reads = np.ascontiguousarray(reads, dtype=np.uint8)
     offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
     item_read = np.ascontiguousarray(item_read, dtype=np.uint64)
     item_frame = np.ascontiguousarray(item_frame, dtype=np.int8)
     n = len(item_read)
     if n == 0:
-        return []
+        return np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.uint64)
     lengths = (offsets[item_read + 1] - offsets[item_read]).astype(np.int64)
     phase = np.abs(item_frame.astype(np.int64)) - 1
     plen = np.maximum(lengths - phase, 0) // 3
@@ -330,8 +354,7 @@ def translate_frames(ctx, reads, offsets, item_read, item_frame):
     out = np.zeros(max(int(out_offsets[-1]), 1), dtype=np.uint8)
     check(_lib.load().orph_translate_frames(ctx._h, ptr(reads), ptr(offsets), len(offsets) - 1, ptr(item_read),
                                             ptr(item_frame), n, ptr(out_offsets), ptr(out)))
-    blob = out.tobytes()
-    return [blob[int(out_offsets[i]):int(out_offsets[i + 1])].decode("latin-1") for i in range(n)]
+    return out[: int(out_offsets[-1])], out_offsets
 
 
 def jaccard_column(results):

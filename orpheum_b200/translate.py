@@ -15,7 +15,7 @@ import numpy as np
 from . import _lib, constants_index, constants_translate, fastx
 from .constants_translate import FRAMES, SingleReadScore, category_text
 from .create_save_summary import CreateSaveSummary
-from .gpu import concat_reads, score_reads, translate_frames
+from .gpu import concat_reads, format_fasta, score_reads, translate_frames, translate_frames_raw
 from .index import maybe_make_peptide_bloom_filter, maybe_save_peptide_bloom_filter
 from .sequence_encodings import encode_lut, encode_peptide
 from .translate_single_seq import TranslateSingleSeq  # noqa: F401  (re-exported: part of the reference's surface)
@@ -231,39 +231,41 @@ class Translate:
 
     # -- columnar path (what the CLI uses): no per-row python objects ---------------------------------------
     def _emit_batch(self, names, flat, offsets, results):
-        """stdout / FASTA side effects of one batch, in read order then frame order (translate.py:244-298)."""
+        """stdout / FASTA side effects of one batch, in read order then frame order (translate.py:244-298).  The records
+        are formatted by the native library (``orph_format_fasta``) straight from the result array; the peptides come from
+        one GPU call (``orph_translate_frames``)."""
         cat = results["category"]
-        want = cat == _lib.CAT_CODING
-        if self.file_handles["low_complexity_peptide"] is not None:
-            want |= cat == _lib.CAT_LOW_COMPLEXITY_PEPTIDE
-        if self.file_handles["noncoding_nucleotide"] is not None:
-            want |= cat == _lib.CAT_NON_CODING
-        reads_idx, frames_idx = np.nonzero(want)
-        if len(reads_idx) == 0:
-            return
-        codes = cat[reads_idx, frames_idx]
-        need_pep = (codes == _lib.CAT_CODING) | (codes == _lib.CAT_LOW_COMPLEXITY_PEPTIDE)
-        keys = np.asarray(FRAMES, dtype=np.int8)[frames_idx]
-        peptides = iter(translate_frames(self.peptide_bloom_filter.ctx, flat, offsets, reads_idx[need_pep], keys[need_pep]))
-        data = flat.tobytes()
-        hits = results["n_hits"][reads_idx, frames_idx].tolist()
-        n_kmers = results["n_kmers"][reads_idx, frames_idx].tolist()
-        out = []
         handles = self.file_handles
-        for r, code, key, h, n in zip(reads_idx.tolist(), codes.tolist(), keys.tolist(), hits, n_kmers):
-            name = names[r]
-            if code == _lib.CAT_LOW_COMPLEXITY_PEPTIDE:
-                write_fasta(handles["low_complexity_peptide"], name + " translation_frame: {}.format(frame)", next(peptides))
-                continue
-            seqname = f"{name}__translation_frame:{key}__jaccard:{h / n}".replace(" ", "__")
-            if code == _lib.CAT_CODING:
-                out.append(">{}\n{}\n".format(seqname, next(peptides)))
-                if handles["coding_nucleotide"] is not None:
-                    write_fasta(handles["coding_nucleotide"], seqname, data[int(offsets[r]):int(offsets[r + 1])].decode("latin-1"))
-            else:
-                write_fasta(handles["noncoding_nucleotide"], seqname, data[int(offsets[r]):int(offsets[r + 1])].decode("latin-1"))
-        if out:
-            sys.stdout.write("".join(out))
+        with_lcp = handles["low_complexity_peptide"] is not None
+        want = cat == _lib.CAT_CODING
+        if with_lcp:
+            want = want | (cat == _lib.CAT_LOW_COMPLEXITY_PEPTIDE)
+        has_noncoding = handles["noncoding_nucleotide"] is not None and bool((cat == _lib.CAT_NON_CODING).any())
+        reads_idx, frames_idx = np.nonzero(want)
+        if len(reads_idx) == 0 and not has_noncoding:
+            return
+        if isinstance(names, fastx.NameList):
+            name_blob, name_offsets = np.frombuffer(names.blob, dtype=np.uint8), names.offsets
+        else:
+            encoded = [n.encode("latin-1") for n in names]
+            name_blob = np.frombuffer(b"".join(encoded), dtype=np.uint8)
+            name_offsets = np.zeros(len(encoded) + 1, dtype=np.uint64)
+            name_offsets[1:] = np.cumsum([len(e) for e in encoded])
+        keys = np.asarray(FRAMES, dtype=np.int8)[frames_idx]
+        peptides, pep_offsets = translate_frames_raw(self.peptide_bloom_filter.ctx, flat, offsets, reads_idx, keys)
+
+        def render(kind):
+            return format_fasta(kind, name_blob, name_offsets, results, flat, offsets, peptides, pep_offsets, with_lcp).decode("latin-1")
+
+        if with_lcp:
+            handles["low_complexity_peptide"].write(render(3))
+        if handles["coding_nucleotide"] is not None:
+            handles["coding_nucleotide"].write(render(1))
+        if has_noncoding:
+            handles["noncoding_nucleotide"].write(render(2))
+        text = render(0)
+        if text:
+            sys.stdout.write(text)
             sys.stdout.flush()
 
     def score_all_files_columnar(self):
