@@ -1,0 +1,6 @@
+CMD="python bench.py --reads 2000000 --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --cpu-sample 20000"
+$CMD > gpurun_out/plain_r1r.log 2>&1 || { echo plain failed; tail -3 gpurun_out/plain_r1r.log; exit 1; }
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1r.csv $CMD > gpurun_out/ncu1_r1r.log 2>&1; echo launches rc=$?
+ncu --set full --clock-control none --import-source on -k regex:prefilter_kernel -s 3 -c 1 -o gpurun_out/prof_r1r_prefilter $CMD > gpurun_out/ncu2_r1r.log 2>&1; echo prefilter rc=$?
+ncu --set full --clock-control none --import-source on -k regex:score_tasks_kernel -s 3 -c 1 -o gpurun_out/prof_r1r_tasks $CMD > gpurun_out/ncu3_r1r.log 2>&1; echo tasks rc=$?
+ls -la gpurun_out/*r1r*
