@@ -1051,7 +1051,14 @@ static int score_host_pipeline(orph_ctx *ctx, const orph_filter *f, const void *
         ctx->pool = new (std::nothrow) orph_host::Pool(n);
         if (!ctx->pool) return fail(ORPH_E_NOMEM, "out of host memory");
     }
+    // chunk boundaries: <= 2^19 reads and <= 2^27 bases each
+    const uint64_t kMaxChunkReads = 1ULL << 19, kMaxChunkBases = 1ULL << 27;
     if (allow_pack) {
+        // pinned staging for host-packed chunks: every slot sized now, for the largest chunk this call can form (pinned
+        // allocations cost milliseconds and synchronise the device, and nothing is in flight at this point)
+        const uint64_t max_chunk_words = std::min<uint64_t>(kMaxChunkBases, offsets[n_reads] - offsets[0]) / 32 + 4;
+        for (int q = 0; q < kPipeSlots; q++)
+            if ((rc = ctx->h_packed[q].ensure(max_chunk_words * 8)) != ORPH_OK) return rc;
         cudaPointerAttributes attr;
         if (cudaPointerGetAttributes(&attr, reads) == cudaSuccess) input_pinned = attr.type == cudaMemoryTypeHost;
         else cudaGetLastError();
@@ -1077,8 +1084,6 @@ static int score_host_pipeline(orph_ctx *ctx, const orph_filter *f, const void *
         ctx->h2d_bytes[slot] = 0;
     };
     std::vector<uint8_t> needs;
-    // chunk boundaries: <= 2^19 reads and <= 2^27 bases each (a single longer read still forms a chunk)
-    const uint64_t kMaxChunkReads = 1ULL << 19, kMaxChunkBases = 1ULL << 27;
     uint64_t lo = 0;
     int c = 0;
     bool used[kPipeSlots] = {};
@@ -1126,11 +1131,9 @@ static int score_host_pipeline(orph_ctx *ctx, const orph_filter *f, const void *
             else pack_here = backlog >= pack_s;
         }
         if (ascii_streak > 0) ascii_streak--;
+        if (pack_here && ((b1 - b0 + 31) / 32 + 2) * 8 > ctx->h_packed[b].cap) pack_here = false;  // one absurdly long read: no staging for it
         if (pack_here) {
             const uint64_t n_words = (b1 - b0 + 31) / 32;
-            // pinned allocations cost milliseconds and synchronise the device: size every slot at once, for a full chunk
-            for (int q = 0; q < kPipeSlots; q++)
-                if ((rc = ctx->h_packed[q].ensure((n_words + 2) * 8)) != ORPH_OK) return rc;
             needs.assign(m, 0);
             const auto t0 = clk::now();
             orph_host::pack_stream(ctx->pool, (const uint8_t *)reads + b0, b0, b1 - b0, offsets + lo, m, (uint64_t *)ctx->h_packed[b].p, needs.data());

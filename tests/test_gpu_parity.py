@@ -601,6 +601,16 @@ def test_host_packing_ingest_paths(gpu, enc, orc):
         ctx.set_host_threads(-1)
         a, b = 12_345, 2_222_222
         assert gpu.score_reads(gg, flat, offsets[a:b + 1], lut, 0.5).tobytes() == want[a:b].tobytes()
+        # an empty read / an over-long read inside a large host-packed batch: same errors as on the small-batch route
+        cut = 1_000_000
+        offs_empty = np.concatenate([offsets[:cut + 1], offsets[cut:cut + 200_001]])  # read `cut` has length 0
+        with pytest.raises(ZeroDivisionError):
+            gpu.score_reads(gg, flat, offs_empty, lut, 0.5)
+        offs_long = np.concatenate([offsets[:cut], offsets[cut + 2000:cut + 100_000]])  # one read of ~350 k bases
+        assert int(np.diff(offs_long.astype(np.int64)).max()) > 196_607
+        with pytest.raises(ValueError):
+            gpu.score_reads(gg, flat, offs_long, lut, 0.5)
+        assert gpu.score_reads(gg, flat, offsets[:cut + 1], lut, 0.5).tobytes() == want[:cut].tobytes()  # the context recovers
         # mostly unpackable input: soft-masked everything
         low = np.frombuffer(flat.tobytes().lower(), dtype=np.uint8)
         ctx.set_host_threads(0)
