@@ -77,3 +77,39 @@ def test_no_gpu_fails_loudly(lib):
 
     with pytest.raises(Exception):
         gpu.Context(0)
+
+
+def test_host_packer_simd_against_numpy(lib):
+    """The SIMD packer (SSSE3 / AVX2, thread pool) against a numpy restatement: every byte value, reads that start and
+    end inside 32-base words, a non-zero first offset, a partial last word, one and many threads."""
+    from orpheum_b200 import gpu
+
+    rng = np.random.default_rng(7)
+    n = 40_000
+    lengths = rng.integers(1, 400, n)
+    offsets = np.zeros(n + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum(lengths)
+    offsets += np.uint64(13)  # the stream does not start at base 0 of the buffer
+    total = int(offsets[-1])
+    flat = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, total)].copy()
+    dirty = rng.choice(n, 400, replace=False)
+    for r in dirty:  # arbitrary bytes (lower case, N, IUPAC, control characters, >= 0x80) somewhere in the read
+        a, b = int(offsets[r]), int(offsets[r + 1])
+        pos = rng.integers(a, b, rng.integers(1, 4))
+        flat[pos] = rng.integers(0, 256, len(pos), dtype=np.uint8)
+    valid = np.zeros(256, dtype=bool)
+    valid[np.frombuffer(b"ACGT", dtype=np.uint8)] = True
+    body = flat[13:]
+    codes = ((body >> 1) & 3).astype(np.uint64)
+    pad = (-len(codes)) % 32
+    words = np.concatenate([codes, np.zeros(pad, dtype=np.uint64)]).reshape(-1, 32)
+    want = np.zeros(len(words), dtype=np.uint64)
+    for i in range(32):
+        want |= words[:, i] << np.uint64(2 * i)
+    bad_pos = np.nonzero(~valid[body])[0] + 13
+    want_needs = np.zeros(n, dtype=np.uint8)
+    want_needs[np.searchsorted(offsets, bad_pos, side="right") - 1] = 1
+    for threads in (1, 3, 8):
+        packed, needs = gpu.pack_reads(flat, offsets, n_threads=threads)
+        np.testing.assert_array_equal(packed[: len(want)], want)
+        np.testing.assert_array_equal(needs, want_needs)
