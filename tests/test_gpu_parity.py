@@ -719,6 +719,6 @@ def test_counter_based_read_generator(gpu, enc, orc):
 def test_host_packer_on_the_gpu_box(gpu):
     """The SIMD level is chosen at run time (AVX2 on the GPU boxes, SSSE3 in the build container): run the numpy
     comparison of the host packer on this host too."""
-    from test_cabi_symbols import test_host_packer_simd_against_numpy
+    from tests.test_cabi_symbols import test_host_packer_simd_against_numpy
 
     test_host_packer_simd_against_numpy(None)
