@@ -1128,6 +1128,9 @@ static int score_host_pipeline(orph_ctx *ctx, const orph_filter *f, const void *
             const double pack_s = ctx->pack_s_per_byte * (double)(b1 - b0);
             if (!input_pinned) pack_here = true;                       // pageable input: the CPU reads it faster than a staged copy
             else if (ctx->pack_s_per_byte == 0) pack_here = c > 0;    // rate not measured yet: chunk 0 feeds the copy engine
+            else if (ctx->pack_s_per_byte * ctx->h2d_bytes_per_s > 1.0 && (c & 15) != 15)
+                pack_here = false;  // the host packs slower than the wire carries (many ranks sharing few cores and one memory
+                                    // system): packing only adds host memory traffic; one chunk in 16 re-measures the rate
             else pack_here = backlog >= pack_s;
         }
         if (ascii_streak > 0) ascii_streak--;
