@@ -321,7 +321,58 @@ def cli_vectors():
         json.dump(manifest, f, indent=1)
 
 
+def long_reads(residues, offsets, seed=123):
+    """Reads beyond the 6144-nt bound of the warp-per-read byte path (block-per-read kernel): long open reading frames,
+    random sequence, a tandem repeat, N bytes and a soft-masked stretch."""
+    rng = np.random.default_rng(seed)
+    codon = {"A": "GCT", "R": "CGT", "N": "AAC", "D": "GAC", "C": "TGC", "Q": "CAG", "E": "GAA", "G": "GGT", "H": "CAC",
+             "I": "ATC", "L": "CTG", "K": "AAA", "M": "ATG", "F": "TTC", "P": "CCG", "S": "TCT", "T": "ACC", "W": "TGG",
+             "Y": "TAC", "V": "GTT"}
+
+    def orf(n_codons):
+        out = []
+        while len(out) < n_codons:
+            p = int(rng.integers(0, len(offsets) - 1))
+            seq = residues[int(offsets[p]):int(offsets[p + 1])].tobytes().decode()
+            out.extend(codon.get(a, "GCT") for a in seq)
+        return "".join(out[:n_codons])
+
+    rand = lambda n: "".join(rng.choice(list("ACGT"), size=n))
+    with_n = list(orf(2400))
+    for pos in rng.integers(0, len(with_n), 25):
+        with_n[int(pos)] = "N"
+    masked = orf(2300)
+    masked = masked[:3000] + masked[3000:3300].lower() + masked[3300:]
+    return [
+        ("long-orf 6150", orf(2050)),
+        ("long-orf frame2 9001", "G" + orf(3000)),
+        ("long-random 7000", rand(7000)),
+        ("long-tandem 3x2100", orf(700) * 3),
+        ("long-with-N 7200", "".join(with_n)),
+        ("long-softmasked 6900", masked),
+        ("long-lowcomplexity 8000", "A" * 4000 + "C" * 4000),
+        ("long-repeat-peptide 6300", "GCTGAAAAGCTGGTT" * 420),
+    ]
+
+
+def long_vectors():
+    data = os.path.join(GOLD, "reference_data")
+    first1000 = os.path.join(data, "index", "Homo_sapiens.GRCh38.pep.first1000lines.fa")
+    residues, offsets = proteome_arrays(first1000)
+    vec = score_vectors("protein", 7, first1000, 1000000, long_reads(residues, offsets))
+    with open(os.path.join(GOLD, "ref_scores_long_protein_k7.json"), "w") as f:
+        json.dump(vec, f, separators=(",", ":"))
+    cats = {}
+    for r in vec["reads"]:
+        for row in r["rows"]:
+            cats[row[2]] = cats.get(row[2], 0) + 1
+    print("long", len(vec["reads"]), "reads", cats, [max((row[1] or 0) for row in r["rows"]) for r in vec["reads"]])
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "long":  # only the long-read vector (added later; the others stay as they are)
+        long_vectors()
+        return
     os.makedirs(GOLD, exist_ok=True)
     copy_reference_data()
     data = os.path.join(GOLD, "reference_data")
@@ -344,6 +395,7 @@ def main():
     with open(os.path.join(GOLD, "ref_misc_kats.json"), "w") as f:
         json.dump(misc_kats(), f, indent=1)
     cli_vectors()
+    long_vectors()
 
 
 if __name__ == "__main__":

@@ -21,8 +21,9 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-def load_score_vector(alphabet, ksize):
-    with open(os.path.join(GOLDEN, f"ref_scores_{alphabet}_k{ksize}.json")) as f:
+def load_score_vector(alphabet, ksize, tag=""):
+    """tag "long_": the vector of reads beyond 6144 nt (oracle/gen_golden.py long)."""
+    with open(os.path.join(GOLDEN, f"ref_scores_{tag}{alphabet}_k{ksize}.json")) as f:
         return json.load(f)
 
 

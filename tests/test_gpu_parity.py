@@ -198,7 +198,20 @@ def test_golden_csv_23_reads(gpu, enc, refdata, reads_n22, misc_kats, alphabet, 
 def test_reference_vectors(gpu, enc, orc, refdata, misc_kats, alphabet, ksize, force_exact):
     """Rows produced by the UNMODIFIED reference (tests/golden/ref_scores_*.json): categories, n_kmers,
     integer hit counts and jaccard, for every read incl. N / lower-case / short / low-complexity ones."""
-    vec = load_score_vector(alphabet, ksize)
+    n_bytes_path, n_reads = check_reference_vector(gpu, enc, refdata, misc_kats, load_score_vector(alphabet, ksize), alphabet, ksize, force_exact)
+    assert 0 < n_bytes_path < n_reads  # both the packed fast path and the byte path were exercised
+
+
+@pytest.mark.parametrize("force_exact", [False, True])
+def test_reference_vectors_long_reads(gpu, enc, refdata, misc_kats, force_exact):
+    """Reads of 6.1 - 9 kb scored by the UNMODIFIED reference (tests/golden/ref_scores_long_protein_k7.json): the
+    block-per-read kernel against the reference itself, not only against the oracle."""
+    vec = load_score_vector("protein", 7, tag="long_")
+    n_bytes_path, n_reads = check_reference_vector(gpu, enc, refdata, misc_kats, vec, "protein", 7, force_exact)
+    assert n_bytes_path == n_reads == 8
+
+
+def check_reference_vector(gpu, enc, refdata, misc_kats, vec, alphabet, ksize, force_exact):
     g = gpu_filter(gpu, enc, os.path.join(refdata, vec["peptides"]), alphabet, ksize, vec["tablesize"], vec["n_tables"])
     assert [g.n_occupied(i) for i in range(4)] == vec["filter_popcounts"]
     flat, offsets = gpu.concat_reads([r["seq"] for r in vec["reads"]])
@@ -223,7 +236,7 @@ def test_reference_vectors(gpu, enc, orc, refdata, misc_kats, alphabet, ksize, f
                 assert math.isnan(jac[i, f])
             else:
                 assert jac[i, f] == j
-    assert 0 < n_bytes_path < len(vec["reads"])  # both the packed fast path and the byte path were exercised
+    return n_bytes_path, len(vec["reads"])
 
 
 def synthetic_case(gpu, enc, orc, refdata, alphabet, ksize, thr, n, mixed):

@@ -148,7 +148,17 @@ def test_golden_csv_23_reads(refdata, reads_n22, misc_kats, alphabet, ksize):
 
 @pytest.mark.parametrize("alphabet,ksize", SCORE_VECTORS)
 def test_against_unmodified_reference_vectors(refdata, misc_kats, alphabet, ksize):
-    vec = load_score_vector(alphabet, ksize)
+    check_reference_vector(load_score_vector(alphabet, ksize), refdata, misc_kats, alphabet, ksize)
+
+
+def test_against_unmodified_reference_long_reads(refdata, misc_kats):
+    """Reads of 6.1 - 9 kb scored by the unmodified reference (no length limit there): long ORFs, N, soft-masked, tandem repeat."""
+    vec = load_score_vector("protein", 7, tag="long_")
+    assert min(len(r["seq"]) for r in vec["reads"]) > 6144
+    check_reference_vector(vec, refdata, misc_kats, "protein", 7)
+
+
+def check_reference_vector(vec, refdata, misc_kats, alphabet, ksize):
     g = build_filter(os.path.join(refdata, vec["peptides"]), alphabet, ksize, vec["tablesize"], vec["n_tables"])
     assert [g.n_occupied(i) for i in range(4)] == vec["filter_popcounts"]
     lut = orc.encode_lut(alphabet)
