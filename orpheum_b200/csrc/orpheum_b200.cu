@@ -1091,10 +1091,13 @@ static int score_host_pipeline(orph_ctx *ctx, const orph_filter *f, const void *
     clk::time_point h2d_free_at = clk::now();  // planning estimate: when the copy engine runs out of queued work
     while (lo < n_reads) {
         // this chunk's extent, validity and longest read (overlaps the GPU work of the previous chunks)
-        uint64_t hi = std::min(n_reads, lo + kMaxChunkReads);
+        // the first chunks are small so that the pipeline fills quickly (nothing overlaps the first H2D)
+        const int ramp = std::min(c, 3);
+        const uint64_t chunk_reads = kMaxChunkReads >> (3 - ramp), chunk_bases = kMaxChunkBases >> (3 - ramp);
+        uint64_t hi = std::min(n_reads, lo + chunk_reads);
         uint64_t longest = scan_read_lengths(ctx->pool, offsets + lo, hi - lo);
-        if (longest < (1ULL << 63) && offsets[hi] - offsets[lo] > kMaxChunkBases) {
-            hi = (uint64_t)(std::upper_bound(offsets + lo + 1, offsets + hi + 1, offsets[lo] + kMaxChunkBases) - offsets) - 1;
+        if (longest < (1ULL << 63) && offsets[hi] - offsets[lo] > chunk_bases) {
+            hi = (uint64_t)(std::upper_bound(offsets + lo + 1, offsets + hi + 1, offsets[lo] + chunk_bases) - offsets) - 1;
             if (hi <= lo) hi = lo + 1;
             longest = scan_read_lengths(ctx->pool, offsets + lo, hi - lo);
         }
