@@ -187,8 +187,10 @@ int orph_score_reads(orph_ctx *ctx, const orph_filter *f, const void *reads, int
                      orph_read_result *out);
 /* Device-buffer form: same contract, but reads/offsets/out are DEVICE pointers (reads 16-byte aligned)
  * and the call only enqueues on the context's stream.  max_read_len is an upper bound on the read
- * length in this batch (reads beyond it are still scored, through the slower byte path); pass 0 if
- * unknown (assumes ORPH_MAX_READ_LEN).  Use orph_ctx_check() for the deferred status. */
+ * length in this batch: it sizes the per-read scratch of the kernels and decides which of them are launched
+ * (a read longer than the declared bound is reported through ORPH_E_TOO_LONG); pass 0 if unknown (assumes
+ * ORPH_MAX_READ_LEN, which costs scratch memory and idle launches).  Use orph_ctx_check() for the deferred
+ * status. */
 int orph_score_reads_device(orph_ctx *ctx, const orph_filter *f, const void *d_reads, int reads_format,
                             const uint64_t *d_offsets, uint64_t n_reads, uint32_t max_read_len,
                             const uint8_t lut[256], double jaccard_threshold, orph_read_result *d_out);
