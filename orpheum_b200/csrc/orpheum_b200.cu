@@ -814,6 +814,9 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
     P.thread_short_len = short_len;
     P.task_capacity = (uint32_t)(n_reads * 6);
     P.force_exact = ctx->force_exact ? 1u : 0u;
+    // the warp kernel's de-duplication slots keep 11 position bits and reserve position 2047 for "empty": with k = 1 a
+    // 2048-residue frame would reach it, so those reads take the block-per-read kernel
+    const uint32_t bytes_max_len = f->ksize == 1 ? kBytesMaxLen - 3 : kBytesMaxLen;
 
     const uint64_t *d_packed = d_packed_in;
     uint64_t pbase0 = pbase0_in;
@@ -838,7 +841,7 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
     {
         Timed timed(ctx, 1);
         prefilter_kernel<<<grid_for(n_reads, 256, ctx->sm_count, 16), 256, 0, s>>>(
-            d_packed, d_offsets, pbase0, n_reads, d_needs, P.k, fast_len, thread_len, short_len, P.task_capacity, bound, kBytesMaxLen, d_out,
+            d_packed, d_offsets, pbase0, n_reads, d_needs, P.k, fast_len, thread_len, short_len, P.task_capacity, bound, bytes_max_len, d_out,
             (uint32_t *)ctx->queue.p,
             (uint32_t *)ctx->task_queue.p, (uint32_t *)ctx->bytes_queue.p, counters);
     }
@@ -896,7 +899,7 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
     // byte-exact path for whatever prefilter routed away (non-ACGT bytes, reads longer than the fast path)
     if (d_ascii || bound > fast_len) {
         ScoreParams B = P;
-        const uint32_t bbound = std::min(bound, kBytesMaxLen);
+        const uint32_t bbound = std::min(bound, bytes_max_len);
         B.max_len = bbound;
         B.slots = std::max(128u, next_pow2(2 * std::max(1u, bbound / 3)));
         B.pep_bytes = (bbound / 3 + kPepPad + 3) & ~3u;
@@ -923,7 +926,7 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
     }
 
     // reads beyond the warp kernel's shared-memory staging: one block per read, scratch in global memory
-    if (bound > kBytesMaxLen) {
+    if (bound > bytes_max_len) {
         const int grid = ctx->sm_count;
         if ((rc = ctx->long_scratch.ensure(long_scratch_bytes(bound) * grid)) != ORPH_OK) return rc;
         Timed timed(ctx, 7);
