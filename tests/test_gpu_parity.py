@@ -735,3 +735,24 @@ def test_host_packer_on_the_gpu_box(gpu):
     from tests.test_cabi_symbols import test_host_packer_simd_against_numpy
 
     test_host_packer_simd_against_numpy(None)
+
+
+def test_ksize_one_and_two(gpu, enc, orc):
+    """Degenerate k-mer sizes through every kernel tier (no thread-per-frame kernel is compiled for them): k = 1 makes a
+    2048-residue frame reach position 2047 of the warp kernel's de-duplication slots, which is why reads of 6142+ bases
+    go to the block-per-read kernel there."""
+    from orpheum_b200 import synth
+
+    residues, poffs = synth.make_proteome(n_proteins=50, seed=61)
+    rng = np.random.default_rng(62)
+    reads = [_orf_read(rng, residues, poffs, n) for n in (50, 107, 400, 2046, 2047, 2048, 2049, 3000)]
+    reads += ["".join(rng.choice(list("ACGT"), size=n)) for n in (30, 150, 6141, 6142, 6144)]
+    flat, offsets = gpu.concat_reads(reads)
+    for ksize in (1, 2):
+        gg = gpu.GpuNodegraph(ksize, 1e4, 4)
+        gg.add_peptides(residues[:200], np.array([0, 200], dtype=np.uint64), enc.encode_lut("protein"))  # part of the alphabet only
+        go = orc.Nodegraph(ksize, int(1e4), 4)
+        go.add_peptides(residues[:200], np.array([0, 200], dtype=np.uint64), orc.encode_lut("protein"))
+        ora, _ = orc.score_reads(go, flat, offsets, orc.encode_lut("protein"), 0.5, n_threads=0)
+        res = gpu.score_reads(gg, flat, offsets, enc.encode_lut("protein"), 0.5)
+        assert_same_as_oracle(res, ora, f"k={ksize}")
