@@ -224,6 +224,9 @@ int orph_fastx_open(const char *path, orph_fastx **out);
 int orph_fastx_next_batch(orph_fastx *fx, uint64_t max_records, uint64_t max_bases, uint64_t *n_records,
                           const uint8_t **seq_bytes, const uint64_t **seq_offsets, const uint8_t **name_bytes,
                           const uint64_t **name_offsets);
+/* Copies the sequence bytes and offsets of the batch returned by the last orph_fastx_next_batch into caller-owned
+ * arrays (seq_offsets[n] bytes and n + 1 offsets), using the parser's threads. */
+int orph_fastx_copy_batch(orph_fastx *fx, uint8_t *seq_dst, uint64_t *seq_offsets_dst);
 void orph_fastx_close(orph_fastx *fx);
 
 /* ---- score CSV straight from the result records -------------------------------------------------- */

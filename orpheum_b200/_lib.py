@@ -70,6 +70,7 @@ PROTOTYPES = {
     "orph_jaccard": (ctypes.c_double, [_vp, ctypes.c_int]),
     "orph_fastx_open": (ctypes.c_int, [ctypes.c_char_p, _pp]),
     "orph_fastx_next_batch": (ctypes.c_int, [_vp, ctypes.c_uint64, ctypes.c_uint64, _u64p, _pp, _pp, _pp, _pp]),
+    "orph_fastx_copy_batch": (ctypes.c_int, [_vp, _u8p, _u64p]),
     "orph_fastx_close": (None, [_vp]),
     "orph_csv_write_scores": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, _u8p, _u64p, ctypes.c_uint64, _vp, _vp, ctypes.c_char_p]),
     "orph_format_fasta": (ctypes.c_int, [ctypes.c_int, _u8p, _u64p, ctypes.c_uint64, _vp, _u8p, _u64p, _u8p, _u64p, ctypes.c_int, _u8p,

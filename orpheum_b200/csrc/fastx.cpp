@@ -400,6 +400,22 @@ extern "C" int orph_fastx_next_batch(orph_fastx *fx, uint64_t max_records, uint6
     return ORPH_OK;
 }
 
+// Copies the current batch's sequence bytes and offsets into caller-owned arrays (numpy buffers on the Python side),
+// spread over the pool: a fresh 150 MB destination is mostly page faults, which parallelise.
+extern "C" int orph_fastx_copy_batch(orph_fastx *fx, uint8_t *seq_dst, uint64_t *seq_offsets_dst)
+{
+    if (!fx || (!seq_dst && !fx->seq.empty()) || !seq_offsets_dst) return orph_set_error(ORPH_E_INVALID, "orph_fastx_copy_batch: NULL argument");
+    memcpy(seq_offsets_dst, fx->seq_off.data(), fx->seq_off.size() * sizeof(uint64_t));
+    const uint64_t total = fx->seq.size();
+    constexpr uint64_t kBlock = 4u << 20;
+    const uint64_t n_blk = (total + kBlock - 1) / kBlock;
+    auto work = [&](uint64_t b) { memcpy(seq_dst + b * kBlock, fx->seq.data() + b * kBlock, (size_t)std::min<uint64_t>(kBlock, total - b * kBlock)); };
+    if (fx->pool && n_blk > 1) fx->pool->run(n_blk, work);
+    else
+        for (uint64_t b = 0; b < n_blk; b++) work(b);
+    return ORPH_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Score CSV writer: the rows Translate.score_reads_per_record builds (translate.py:342-365) and
 // CreateSaveSummary.maybe_write_csv writes with csv.writer(lineterminator="\n")

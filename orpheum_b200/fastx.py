@@ -165,11 +165,15 @@ class _NativeReader:
             if n.value == 0:
                 return
             m = int(n.value)
-            offsets = np.ctypeslib.as_array(ct.cast(seq_off, ct.POINTER(ct.c_uint64)), shape=(m + 1,)).copy()
             noffs = np.ctypeslib.as_array(ct.cast(name_off, ct.POINTER(ct.c_uint64)), shape=(m + 1,)).copy()
-            total = int(offsets[-1])
-            flat = (np.ctypeslib.as_array(ct.cast(seq, ct.POINTER(ct.c_uint8)), shape=(total,)).copy()
-                    if total else np.zeros(0, dtype=np.uint8))
+            total = int(ct.cast(seq_off, ct.POINTER(ct.c_uint64))[m])
+            offsets = np.empty(m + 1, dtype=np.uint64)
+            flat = np.empty(total, dtype=np.uint8)
+            # the parser's threads copy into the numpy-owned buffers (first-touch page faults in parallel)
+            if self._lib.orph_fastx_copy_batch(self._h, flat.ctypes.data if total else None, offsets.ctypes.data) != 0:
+                from . import _lib
+
+                raise OSError(_lib.last_error())
             blob = ct.string_at(names, int(noffs[-1])) if noffs[-1] else b""
             yield NameList(blob, noffs), flat, offsets
 
