@@ -339,13 +339,21 @@ def cli(peptides, reads, peptide_ksize=None, save_peptide_bloom_filter=True, pep
     """Writes coding peptides from reads to standard output"""
     translate_obj = Translate(locals())
     table = translate_obj.score_all_files_columnar()
-    if csv:
-        table.write_csv(csv)
-    if parquet and len(table):
-        table.write_parquet(parquet)
-    if json_summary:
-        table.write_json_summary(json_summary, reads, translate_obj.peptide_bloom_filter_filename,
-                                 translate_obj.peptide_ksize, translate_obj.jaccard_threshold)
+    # the three outputs are independent: the CSV is formatted by the native writer (GIL released) while the parquet
+    # table and the JSON summary are built here
+    from concurrent.futures import ThreadPoolExecutor
+
+    with ThreadPoolExecutor(max_workers=2) as pool:
+        pending = []
+        if csv:
+            pending.append(pool.submit(table.write_csv, csv))
+        if parquet and len(table):
+            pending.append(pool.submit(table.write_parquet, parquet))
+        if json_summary:
+            table.write_json_summary(json_summary, reads, translate_obj.peptide_bloom_filter_filename,
+                                     translate_obj.peptide_ksize, translate_obj.jaccard_threshold)
+        for job in pending:
+            job.result()
 
 
 if __name__ == "__main__":
