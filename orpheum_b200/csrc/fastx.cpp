@@ -368,7 +368,12 @@ extern "C" int orph_fastx_next_batch(orph_fastx *fx, uint64_t max_records, uint6
         fx->name_off.assign(1, 0);
         while (n < max_records && fx->seq.size() < max_bases) {
             if (!next_line(fx, &s, &len)) break;
-            if (len == 0) continue;
+            {
+                const char *t = s;
+                size_t tl = len;
+                strip(&t, &tl);
+                if (tl == 0) continue;  // blank line (possibly just "\r") between records
+            }
             if (s[0] != '@') return orph_set_error(ORPH_E_IO, "bad FASTQ: no '@' at the beginning of a record");
             begin_record(fx, s + 1, len - 1);
             const size_t seq_start = fx->seq.size();

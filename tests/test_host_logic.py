@@ -303,3 +303,68 @@ def test_parallel_fastq_fast_path(tmp_path):
     p.write_bytes(head + b"@r\nACGT\n+\nII\n")
     with pytest.raises(OSError):
         check(str(p))
+
+
+def test_native_parser_random_files(tmp_path):
+    """Seeded random FASTQ / FASTA files (strict and sloppy layouts mixed: CRLF, blank lines, wrapped sequences and
+    qualities, '+name' separators, '@' / '+' / '>' as first quality characters, trailing spaces, missing final newline)
+    through the native parser -- fast path, general parser and the hand-over between them -- against the Python reader,
+    at several batch sizes."""
+    from orpheum_b200 import build
+
+    build.build()
+    rng = np.random.default_rng(12)
+    alphabet = np.frombuffer(b"ACGTNacgtn", dtype=np.uint8)
+
+    def fastq(n_rec, sloppy):
+        out = []
+        for i in range(n_rec):
+            L = int(rng.integers(1, 120))
+            seq = alphabet[rng.integers(0, len(alphabet), L)].tobytes()
+            qual = bytes(rng.integers(33, 75, L, dtype=np.uint8))
+            eol = b"\r\n" if sloppy and rng.random() < 0.2 else b"\n"
+            name = b"r%d %s" % (i, bytes(rng.integers(48, 90, int(rng.integers(0, 12)), dtype=np.uint8)))
+            if sloppy and rng.random() < 0.15:  # wrapped record
+                cut = int(rng.integers(0, L + 1))
+                seq_lines = [s for s in (seq[:cut], seq[cut:]) if s]
+                qual_lines = [q for q in (qual[:cut], qual[cut:]) if q]
+            else:
+                seq_lines, qual_lines = [seq], [qual]
+            rec = b"@" + name + (b"  " if sloppy and rng.random() < 0.1 else b"") + eol
+            rec += b"".join(s + eol for s in seq_lines) + b"+" + (name if rng.random() < 0.3 else b"") + eol
+            rec += b"".join(q + eol for q in qual_lines)
+            if sloppy and rng.random() < 0.1:
+                rec += eol  # blank line between records
+            out.append(rec)
+        text = b"".join(out)
+        if rng.random() < 0.3 and text.endswith(b"\n") and not text.endswith(b"\n\n") and not text.endswith(b"\r\n"):
+            text = text[:-1]
+        return text
+
+    def fasta(n_rec):
+        out = []
+        for i in range(n_rec):
+            L = int(rng.integers(0, 200))
+            seq = alphabet[rng.integers(0, len(alphabet), L)].tobytes()
+            width = int(rng.integers(1, 80))
+            out.append(b">p%d some description\n" % i + b"".join(seq[j:j + width] + b"\n" for j in range(0, L, width)))
+        return b"".join(out)
+
+    p = tmp_path / "f.fx"
+    for case in range(120):
+        kind = case % 3
+        text = fastq(int(rng.integers(1, 400)), sloppy=False) if kind == 0 else fastq(int(rng.integers(1, 400)), sloppy=True) if kind == 1 \
+            else fasta(int(rng.integers(1, 100)))
+        p.write_bytes(text)
+        try:
+            want = [(r["name"], r["sequence"]) for r in fastx.open(str(p), native=False)]
+        except OSError:
+            with pytest.raises(OSError):
+                list(fastx.read_batches(str(p)))
+            continue
+        for max_records in (1 << 20, 37):
+            got = []
+            for names, flat, offsets in fastx.read_batches(str(p), max_records=max_records, prefetch=case % 2):
+                data = flat.tobytes()
+                got += [(names[i], data[int(offsets[i]):int(offsets[i + 1])].decode("latin-1")) for i in range(len(names))]
+            assert got == want, (case, max_records)
