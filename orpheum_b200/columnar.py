@@ -72,8 +72,12 @@ class ScoreTable:
             remap[code] = i
         category = pa.DictionaryArray.from_arrays(pa.array(remap[c["category"]], type=pa.int32()),
                                                   pa.array([texts[k] for k in codes])).cast(pa.string())
-        read_id = pa.DictionaryArray.from_arrays(pa.array(c["read_index"], type=pa.int64()),
-                                                 pa.array(c["names"].tolist(), type=pa.string())).cast(pa.string())
+        try:
+            name_values = pa.array(c["names"].tolist(), type=pa.string())
+        except (UnicodeEncodeError, pa.ArrowInvalid):  # ids that are not valid UTF-8 (kept byte-exact in the CSV): U+FFFD here
+            name_values = pa.array([n.encode("utf-8", "surrogateescape").decode("utf-8", "replace") for n in c["names"].tolist()],
+                                   type=pa.string())
+        read_id = pa.DictionaryArray.from_arrays(pa.array(c["read_index"], type=pa.int64()), name_values).cast(pa.string())
         filename = pa.DictionaryArray.from_arrays(pa.array(c["file_index"], type=pa.int64()),
                                                   pa.array(c["file_names"], type=pa.string())).cast(pa.string())
         if c["has_n"].all():
@@ -118,7 +122,7 @@ class ScoreTable:
                 offsets = np.ascontiguousarray(names.offsets, dtype=np.uint64)
                 n_fields = len(names)
             else:
-                fields = [self._csv_field(n).encode("latin-1") for n in (names.tolist() if hasattr(names, "tolist") else names)]
+                fields = [self._csv_field(n).encode("utf-8", "surrogateescape") for n in (names.tolist() if hasattr(names, "tolist") else names)]
                 offsets = np.zeros(len(fields) + 1, dtype=np.uint64)
                 offsets[1:] = np.cumsum([len(f) for f in fields])
                 blob = np.frombuffer(b"".join(fields), dtype=np.uint8) if offsets[-1] else np.zeros(1, dtype=np.uint8)

@@ -31,7 +31,7 @@ class CreateSaveSummary:
 
     def maybe_write_csv(self):
         if self.csv:
-            with open(self.csv, "w") as handle:
+            with open(self.csv, "w", encoding="utf-8", errors="surrogateescape") as handle:
                 writer = _csv.writer(handle, lineterminator="\n")
                 writer.writerow(SCORING_DF_COLUMNS)
                 writer.writerows(self.coding_scores)

@@ -9,15 +9,19 @@ import os
 
 import numpy as np
 
+# Record names travel as bytes through the native path; where they become str they are decoded as UTF-8 (what
+# screed does) with surrogateescape, so that any byte string survives the round trip into the CSV / FASTA outputs.
+TEXT_CODEC = ("utf-8", "surrogateescape")
+
 
 def _open_text(path):
     with io.open(path, "rb") as f:
         magic = f.read(3)
     if magic[:2] == b"\x1f\x8b":
-        return gzip.open(path, "rt", encoding="latin-1")
+        return gzip.open(path, "rt", encoding=TEXT_CODEC[0], errors=TEXT_CODEC[1])
     if magic == b"BZh":
-        return bz2.open(path, "rt", encoding="latin-1")
-    return io.open(path, "rt", encoding="latin-1")
+        return bz2.open(path, "rt", encoding=TEXT_CODEC[0], errors=TEXT_CODEC[1])
+    return io.open(path, "rt", encoding=TEXT_CODEC[0], errors=TEXT_CODEC[1])
 
 
 class Record(dict):
@@ -100,7 +104,7 @@ class NameList:
             return self.tolist()[i]
         if i < 0:
             i += len(self)
-        return self.blob[int(self.offsets[i]):int(self.offsets[i + 1])].decode("latin-1")
+        return self.blob[int(self.offsets[i]):int(self.offsets[i + 1])].decode(*TEXT_CODEC)
 
     def __iter__(self):
         return iter(self.tolist())
@@ -110,9 +114,12 @@ class NameList:
 
     def tolist(self):
         if self._list is None:
-            text = self.blob.decode("latin-1")
             offs = self.offsets.tolist()
-            self._list = [text[offs[i]:offs[i + 1]] for i in range(len(offs) - 1)]
+            if self.blob.isascii():  # one decode, then slices by byte offsets == character offsets
+                text = self.blob.decode("ascii")
+                self._list = [text[offs[i]:offs[i + 1]] for i in range(len(offs) - 1)]
+            else:
+                self._list = [self.blob[offs[i]:offs[i + 1]].decode(*TEXT_CODEC) for i in range(len(offs) - 1)]
         return self._list
 
 
@@ -181,7 +188,7 @@ class _NativeReader:
         for names, flat, offsets in self.batches():
             data = flat.tobytes()
             for i, name in enumerate(names):
-                yield Record(name=name, sequence=data[int(offsets[i]):int(offsets[i + 1])].decode("latin-1"))
+                yield Record(name=name, sequence=data[int(offsets[i]):int(offsets[i + 1])].decode(*TEXT_CODEC))
 
 
 def _is_bz2(path):
@@ -250,7 +257,7 @@ def read_batches(path, max_records=1 << 20, max_bases=1 << 28, native=True, pref
     with _Reader(path) as records:
         for rec in records:
             names.append(rec["name"])
-            s = rec["sequence"].encode("latin-1")
+            s = rec["sequence"].encode(*TEXT_CODEC)
             seqs.append(s)
             n_bases += len(s)
             if len(names) >= max_records or n_bases >= max_bases:

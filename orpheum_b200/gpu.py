@@ -263,7 +263,7 @@ class GpuNodegraph:
 # -- scoring ---------------------------------------------------------------------------------------
 def concat_reads(sequences):
     """list of str/bytes -> (uint8 flat, uint64 offsets[n+1])."""
-    seqs = [s.encode("latin-1") if isinstance(s, str) else bytes(s) for s in sequences]
+    seqs = [s.encode("utf-8", "surrogateescape") if isinstance(s, str) else bytes(s) for s in sequences]
     offsets = np.zeros(len(seqs) + 1, dtype=np.uint64)
     if seqs:
         offsets[1:] = np.cumsum([len(s) for s in seqs])

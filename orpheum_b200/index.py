@@ -76,7 +76,7 @@ def get_peptide_ksize(molecule, peptide_ksize=None):
 def _record_batches(records, max_residues=1 << 26):
     seqs, total = [], 0
     for record in records:
-        s = record["sequence"].encode("latin-1")
+        s = record["sequence"].encode("utf-8", "surrogateescape")
         seqs.append(s)
         total += len(s)
         if total >= max_residues:

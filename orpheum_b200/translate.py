@@ -102,7 +102,7 @@ class Translate:
 
     def open_and_announce(self, filename, seqtype):
         # the reference announces through a logger that sits at ERROR level: nothing is printed
-        return open(filename, "w")
+        return open(filename, "w", encoding=fastx.TEXT_CODEC[0], errors=fastx.TEXT_CODEC[1])
 
     def maybe_open_fastas(self):
         self.fastas = {
@@ -225,7 +225,7 @@ class Translate:
             peptides = self._emitted_peptides(flat, offsets, results)
             data = flat.tobytes()
             for i, name in enumerate(names):
-                sequence = data[int(offsets[i]):int(offsets[i + 1])].decode("latin-1")
+                sequence = data[int(offsets[i]):int(offsets[i + 1])].decode(*fastx.TEXT_CODEC)
                 scoring_lines.extend(self._lines(reads, name, self._expand(name, sequence, results[i], peptides, i)))
         return scoring_lines
 
@@ -247,7 +247,7 @@ class Translate:
         if isinstance(names, fastx.NameList):
             name_blob, name_offsets = np.frombuffer(names.blob, dtype=np.uint8), names.offsets
         else:
-            encoded = [n.encode("latin-1") for n in names]
+            encoded = [n.encode(*fastx.TEXT_CODEC) for n in names]
             name_blob = np.frombuffer(b"".join(encoded), dtype=np.uint8)
             name_offsets = np.zeros(len(encoded) + 1, dtype=np.uint64)
             name_offsets[1:] = np.cumsum([len(e) for e in encoded])
@@ -255,7 +255,7 @@ class Translate:
         peptides, pep_offsets = translate_frames_raw(self.peptide_bloom_filter.ctx, flat, offsets, reads_idx, keys)
 
         def render(kind):
-            return format_fasta(kind, name_blob, name_offsets, results, flat, offsets, peptides, pep_offsets, with_lcp).decode("latin-1")
+            return format_fasta(kind, name_blob, name_offsets, results, flat, offsets, peptides, pep_offsets, with_lcp).decode(*fastx.TEXT_CODEC)
 
         if with_lcp:
             handles["low_complexity_peptide"].write(render(3))

@@ -368,3 +368,99 @@ def test_native_parser_random_files(tmp_path):
                 data = flat.tobytes()
                 got += [(names[i], data[int(offsets[i]):int(offsets[i + 1])].decode("latin-1")) for i in range(len(names))]
             assert got == want, (case, max_records)
+
+
+def test_columnar_writers_against_row_list_writers_random(tmp_path):
+    """Random result records (every category mix, duplicate and awkward read ids, several input files) through the
+    columnar writers (native CSV formatter, arrow table, vectorised JSON summary) and through the row-list
+    CreateSaveSummary that mirrors the reference's object interface: CSV bytes, parquet tables and JSON summaries agree."""
+    import json as js
+
+    import pyarrow.parquet as pq
+
+    from orpheum_b200 import _lib, build
+    from orpheum_b200.columnar import ScoreTable
+    from orpheum_b200.constants_translate import FRAMES, category_text
+    from orpheum_b200.create_save_summary import CreateSaveSummary
+
+    build.build()
+    rng = np.random.default_rng(21)
+    for case in range(12):
+        alphabet = ["protein", "dayhoff", "hp"][case % 3]
+        table, rows, files = ScoreTable(alphabet), [], []
+        for fi in range(int(rng.integers(1, 4))):
+            filename = f"dir {fi}/reads,{fi}.fq" if case % 4 == 0 else f"reads{fi}.fq"
+            n = int(rng.integers(1, 300))
+            rec = np.zeros(n, dtype=_lib.READ_RESULT_DTYPE)
+            style = rng.integers(0, 4)
+            probs = [[.5, .1, .1, .15, .15, 0], [0, 0, 0, .5, .5, 0], [.9, .1, 0, 0, 0, 0], [.3, .1, .2, .2, .2, 0]][style]
+            cat = rng.choice(6, size=(n, 6), p=probs)
+            low = rng.random(n) < 0.1
+            cat[low] = 5  # a fastp-low-complexity read carries the same label on all six frames
+            rec["category"] = cat
+            nk = rng.integers(1, 200, size=(n, 6))
+            nh = (rng.random((n, 6)) * (nk + 1)).astype(np.int64)
+            has_n = (cat == 2) | (cat == 3) | (cat == 4)
+            scored = (cat == 3) | (cat == 4)
+            rec["n_kmers"] = np.where(has_n, nk, 0)
+            rec["n_hits"] = np.where(scored, np.minimum(nh, nk), 0)
+            names = []
+            for i in range(n):
+                kind = rng.integers(0, 12)
+                name = f"read{i} lane:{fi}"
+                if kind == 0:
+                    name = f'id,with,commas "{i}"'
+                elif kind == 1 and names:
+                    name = names[-1]  # duplicate of the previous id (groupby merges the rows)
+                elif kind == 2 and len(names) > 3:
+                    name = names[0]   # duplicate of a distant id (Counter merges the coding counts)
+                elif kind == 3:
+                    name = f"caf\xe9 \u4e2d {i}"  # UTF-8 ids keep their bytes in the CSV and their characters in the parquet
+                names.append(name)
+            table.append(names, rec, filename)
+            files.append(filename)
+            for i in range(n):
+                for f in range(6):
+                    c = int(cat[i, f])
+                    jac = int(rec["n_hits"][i, f]) / int(rec["n_kmers"][i, f]) if c in (3, 4) else np.nan
+                    rows.append([names[i], jac, int(rec["n_kmers"][i, f]) if c in (2, 3, 4) else np.nan, category_text(c, alphabet), FRAMES[f],
+                                 filename])
+        d = tmp_path / f"case{case}"
+        d.mkdir()
+        ref = CreateSaveSummary(files, str(d / "r.csv"), str(d / "r.parquet"), str(d / "r.json"), "f.nodegraph", alphabet, 7, 0.5, rows)
+        ref.maybe_write_csv()
+        ref.maybe_write_parquet()
+        ref.maybe_write_json_summary()
+        table.write_csv(str(d / "c.csv"))
+        table.write_parquet(str(d / "c.parquet"))
+        table.write_json_summary(str(d / "c.json"), files, "f.nodegraph", 7, 0.5)
+        assert (d / "c.csv").read_bytes() == (d / "r.csv").read_bytes(), case
+        a, b = pq.read_table(str(d / "c.parquet")), pq.read_table(str(d / "r.parquet"))
+        assert a.schema.equals(b.schema) and a.to_pandas().equals(b.to_pandas()), case
+        assert js.load(open(d / "c.json")) == js.load(open(d / "r.json")), case
+
+
+def test_non_ascii_read_ids_keep_their_bytes(tmp_path):
+    """Read ids are decoded as UTF-8 (screed does) with surrogateescape: UTF-8 ids come out as the same characters, any
+    other byte string survives byte for byte into the CSV."""
+    from orpheum_b200 import _lib, build
+    from orpheum_b200.columnar import ScoreTable
+
+    build.build()
+    fq = tmp_path / "n.fq"
+    fq.write_bytes("@café 中文 1\nACGT\n+\nIIII\n".encode("utf-8") + b"@raw\xe9\xff 2\nAC\n+\nII\n@plain 3\nA\n+\nI\n")
+    for native in (True, False):
+        names = [r["name"] for r in fastx.open(str(fq), native=native)]
+        assert names[0] == "café 中文 1" and names[2] == "plain 3"
+        assert names[1].encode(*fastx.TEXT_CODEC) == b"raw\xe9\xff 2"
+    (names, flat, offsets), = list(fastx.read_batches(str(fq)))
+    assert names.tolist() == [r["name"] for r in fastx.open(str(fq), native=False)]
+    rec = np.zeros(3, dtype=_lib.READ_RESULT_DTYPE)
+    rec["category"] = 1
+    for ids in (names, names.tolist()):
+        table = ScoreTable("protein")
+        table.append(ids, rec, "n.fq")
+        table.write_csv(str(tmp_path / "o.csv"))
+        text = (tmp_path / "o.csv").read_bytes()
+        assert "café 中文 1,nan".encode("utf-8") in text and b"raw\xe9\xff 2,nan" in text
+        table.write_parquet(str(tmp_path / "o.parquet"))
