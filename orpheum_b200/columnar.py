@@ -142,9 +142,16 @@ class ScoreTable:
         if c is None:
             return summarize(self.alphabet, None, filenames, peptide_bloom_filter_filename, peptide_ksize, jaccard_threshold)
         names = c["names"]
-        group_of_read = consecutive_groups(names)
-        coding_rows = np.nonzero(c["category"] == _lib.CAT_CODING)[0]
-        rows = (np.repeat(group_of_read, 6), c["category"], names[c["read_index"][coding_rows]].tolist(), c["jaccard"])
+        coding = c["category"] == _lib.CAT_CODING
+        if len(set(names.tolist())) == len(names):
+            # the usual case, every read id occurs once: groups are the reads themselves and the coding frames per id are
+            # the coding frames per read (no per-id python bookkeeping)
+            per_read = coding.reshape(-1, 6).sum(axis=1)
+            rows = (np.repeat(np.arange(len(names)), 6), c["category"], per_read[per_read > 0], c["jaccard"])
+        else:
+            group_of_read = consecutive_groups(names)
+            coding_rows = np.nonzero(coding)[0]
+            rows = (np.repeat(group_of_read, 6), c["category"], names[c["read_index"][coding_rows]].tolist(), c["jaccard"])
         return summarize(self.alphabet, rows, filenames, peptide_bloom_filter_filename, peptide_ksize, jaccard_threshold)
 
     def write_json_summary(self, path, filenames, peptide_bloom_filter_filename, peptide_ksize, jaccard_threshold):
@@ -172,7 +179,8 @@ def consecutive_groups(names):
 
 def summarize(alphabet, rows, filenames, peptide_bloom_filter_filename, peptide_ksize, jaccard_threshold):
     """The JSON-summary dict.  rows = (group index per row, category code per row, read ids of the Coding rows in
-    row order, jaccard per row), or None when no read was scored."""
+    row order -- or, when every id is unique, an int array with the number of Coding rows of each id that has any, in
+    read order --, jaccard per row), or None when no read was scored."""
     input_files = [os.path.basename(f) for f in ([filenames] if isinstance(filenames, str) else filenames)]
     if rows is None:
         empty = empty_categories(alphabet)
@@ -204,12 +212,17 @@ def summarize(alphabet, rows, filenames, peptide_bloom_filter_filename, peptide_
     counts["Non-coding"] += int((undecided & ~single).sum())
     total = sum(counts.values())
     # coding frames per read id; ids are merged by value here, as collections.Counter does (:216-222)
-    per_id = {}
-    for read_id in coding_ids:
-        per_id[read_id] = per_id.get(read_id, 0) + 1
     histogram = {}
-    for n in per_id.values():
-        histogram[n] = histogram.get(n, 0) + 1
+    if isinstance(coding_ids, np.ndarray):  # already the number of coding frames of each id that has any (unique ids)
+        values, first, counts = np.unique(coding_ids, return_index=True, return_counts=True)
+        for at in np.argsort(first):        # keys in order of first appearance, as Counter / dict insertion gives them
+            histogram[int(values[at])] = int(counts[at])
+    else:
+        per_id = {}
+        for read_id in coding_ids:
+            per_id[read_id] = per_id.get(read_id, 0) + 1
+        for n in per_id.values():
+            histogram[n] = histogram.get(n, 0) + 1
     n_coding_ids = sum(histogram.values())
     label = "Number of reads with {} putative protein-coding translations".format
     return {
