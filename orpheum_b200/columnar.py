@@ -214,9 +214,9 @@ def summarize(alphabet, rows, filenames, peptide_bloom_filter_filename, peptide_
     # coding frames per read id; ids are merged by value here, as collections.Counter does (:216-222)
     histogram = {}
     if isinstance(coding_ids, np.ndarray):  # already the number of coding frames of each id that has any (unique ids)
-        values, first, counts = np.unique(coding_ids, return_index=True, return_counts=True)
+        values, first, n_ids = np.unique(coding_ids, return_index=True, return_counts=True)
         for at in np.argsort(first):        # keys in order of first appearance, as Counter / dict insertion gives them
-            histogram[int(values[at])] = int(counts[at])
+            histogram[int(values[at])] = int(n_ids[at])
     else:
         per_id = {}
         for read_id in coding_ids:

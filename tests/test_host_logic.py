@@ -407,12 +407,12 @@ def test_columnar_writers_against_row_list_writers_random(tmp_path):
             names = []
             for i in range(n):
                 kind = rng.integers(0, 12)
-                name = f"read{i} lane:{fi}"
+                name = f"read{i} lane:{fi} file{fi}"
                 if kind == 0:
-                    name = f'id,with,commas "{i}"'
-                elif kind == 1 and names:
+                    name = f'id,with,commas "{i}" {fi}'
+                elif kind == 1 and names and case % 4 != 3:  # (every fourth case keeps all ids unique: the summary's fast path)
                     name = names[-1]  # duplicate of the previous id (groupby merges the rows)
-                elif kind == 2 and len(names) > 3:
+                elif kind == 2 and len(names) > 3 and case % 4 != 3:
                     name = names[0]   # duplicate of a distant id (Counter merges the coding counts)
                 elif kind == 3:
                     name = f"caf\xe9 \u4e2d {i}"  # UTF-8 ids keep their bytes in the CSV and their characters in the parquet
