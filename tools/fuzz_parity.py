@@ -74,6 +74,9 @@ def main():
         go = orc.Nodegraph(ksize, tablesize, n_tables)
         go.add_peptides(residues, poffs, olut)
         assert [gg.n_occupied(i) for i in range(n_tables)] == [go.n_occupied(i) for i in range(n_tables)], "filter bits differ"
+        if tablesize <= 1e6:  # the tables byte for byte
+            tabs, _ = gg.tables()
+            assert all((tabs[i] == go.table(i)).all() for i in range(n_tables)), "filter tables differ"
         n = int(rng.choice([1, 33, 1000, 20_000]))
         flat, offsets = random_reads(rng, residues, poffs, n, ksize)
         n = len(offsets) - 1
@@ -116,6 +119,16 @@ def main():
                                   "gpu": {k: got[int(bad[0])][k].tolist() for k in ("category", "n_kmers", "n_hits")},
                                   "oracle": {k: o[int(bad[0])][k].tolist() for k in ("category", "n_kmers", "n_hits")}}))
                 sys.exit(1)
+        # the peptides the reference would emit (coding / low-complexity frames of a few reads), translated on the GPU
+        if lo == 0:
+            cat = res["category"]
+            ri, fi = np.nonzero((cat[:200] == _lib.CAT_CODING) | (cat[:200] == _lib.CAT_LOW_COMPLEXITY_PEPTIDE))
+            if len(ri):
+                keys = np.asarray(_lib.FRAMES, dtype=np.int8)[fi]
+                peps = gpu.translate_frames(ctx, flat, offsets, ri, keys)
+                for r, k, pep in zip(ri.tolist(), keys.tolist(), peps):
+                    want = orc.six_frame_translation(flat[int(offsets[r]):int(offsets[r + 1])].tobytes())[k]
+                    assert pep == want, ("peptide differs", r, k)
         rounds += 1
         reads_total += n
         print(f"round {rounds}: {alphabet} k={ksize} tables={n_tables}x{tablesize:.0e} thr={thr:.3f} reads={n} max_len={int(lengths.max())} "
