@@ -464,3 +464,54 @@ def test_non_ascii_read_ids_keep_their_bytes(tmp_path):
         text = (tmp_path / "o.csv").read_bytes()
         assert "café 中文 1,nan".encode("utf-8") in text and b"raw\xe9\xff 2,nan" in text
         table.write_parquet(str(tmp_path / "o.parquet"))
+
+
+def test_native_fasta_formatter_against_python(tmp_path):
+    """orph_format_fasta (the text of the stdout / FASTA records, translate.py:244-298) against the reference's python
+    formatting on random records: every output stream, ids with spaces and UTF-8, float repr of the jaccard."""
+    from orpheum_b200 import _lib, build, gpu
+    from orpheum_b200.constants_translate import FRAMES
+
+    build.build()
+    rng = np.random.default_rng(31)
+    for with_lcp in (True, False):
+        n = 500
+        rec = np.zeros(n, dtype=_lib.READ_RESULT_DTYPE)
+        cat = rng.choice(6, size=(n, 6), p=[.4, .05, .1, .25, .2, 0])
+        rec["category"] = cat
+        nk = rng.integers(1, 300, size=(n, 6))
+        rec["n_kmers"] = np.where(np.isin(cat, (2, 3, 4)), nk, 0)
+        rec["n_hits"] = np.where(np.isin(cat, (3, 4)), (rng.random((n, 6)) * (nk + 1)).astype(np.int64).clip(0, nk), 0)
+        names = [f"read {i}  two  spaces/{i % 3}" if i % 5 else f"caf\xe9 {i}" for i in range(n)]
+        reads = ["".join(rng.choice(list("ACGTN"), size=int(rng.integers(20, 90)))) for _ in range(n)]
+        flat, offsets = gpu.concat_reads(reads)
+        name_bytes = [s.encode("utf-8") for s in names]
+        name_offsets = np.zeros(n + 1, dtype=np.uint64)
+        name_offsets[1:] = np.cumsum([len(b) for b in name_bytes])
+        name_blob = np.frombuffer(b"".join(name_bytes), dtype=np.uint8)
+        peps, pep_of = [], {}
+        for i in range(n):
+            for f in range(6):
+                if cat[i, f] == 3 or (with_lcp and cat[i, f] == 2):
+                    pep_of[(i, f)] = "".join(rng.choice(list("ACDEFGHIKLMNPQRSTVWYX*"), size=int(rng.integers(0, 30))))
+                    peps.append(pep_of[(i, f)])
+        pep_offsets = np.zeros(len(peps) + 1, dtype=np.uint64)
+        pep_offsets[1:] = np.cumsum([len(p) for p in peps])
+        pep_blob = np.frombuffer("".join(peps).encode(), dtype=np.uint8) if pep_offsets[-1] else np.zeros(1, dtype=np.uint8)
+        want = {0: [], 1: [], 2: [], 3: []}
+        for i in range(n):
+            for f, frame in enumerate(FRAMES):
+                c = int(cat[i, f])
+                if c == 2:
+                    want[3].append(">{}\n{}\n".format(names[i] + " translation_frame: {}.format(frame)", pep_of.get((i, f), "")))
+                if c in (3, 4):
+                    jaccard = int(rec["n_hits"][i, f]) / int(rec["n_kmers"][i, f])
+                    seqname = ("{}__translation_frame:{}".format(names[i], frame) + "__jaccard:{}".format(jaccard)).replace(" ", "__")
+                    if c == 3:
+                        want[0].append(">{}\n{}\n".format(seqname, pep_of[(i, f)]))
+                        want[1].append(">{}\n{}\n".format(seqname, reads[i]))
+                    else:
+                        want[2].append(">{}\n{}\n".format(seqname, reads[i]))
+        for kind in (0, 1, 2) + ((3,) if with_lcp else ()):
+            got = gpu.format_fasta(kind, name_blob, name_offsets, rec, flat, offsets, pep_blob, pep_offsets, with_lcp)
+            assert got.decode("utf-8") == "".join(want[kind]), (kind, with_lcp)
