@@ -375,8 +375,10 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
                     rev[1] = rot == 0 ? rr1 : rot == 1 ? rr2 : rr0;
                     rev[2] = rot == 0 ? rr2 : rot == 1 ? rr0 : rr1;
                 }
-                // evaluate_is_fastp_low_complexity: ndiff / len < 0.3  (translate.py:75-84)
-                if ((double)ndiff / (double)L < 0.3) {
+                // evaluate_is_fastp_low_complexity: ndiff / len < 0.3  (translate.py:75-84).  In integers: double(0.3) lies
+                // 1.1e-17 below 3/10 and the quotients of integers below 2^18 nearest to 3/10 are 1/(10 L) > 3.8e-7 away, so
+                // the IEEE compare is true exactly when 10 ndiff < 3 L (equality gives fl(3/10) < fl(3/10): false both ways)
+                if (10ull * ndiff < 3ull * L) {
                     rec.flags = ORPH_FLAG_LOW_COMPLEXITY;
 #pragma unroll
                     for (int f = 0; f < 6; f++) rec.category[f] = ORPH_CAT_LOW_COMPLEXITY_NUCLEOTIDE;
