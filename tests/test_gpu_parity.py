@@ -756,3 +756,42 @@ def test_ksize_one_and_two(gpu, enc, orc):
         ora, _ = orc.score_reads(go, flat, offsets, orc.encode_lut("protein"), 0.5, n_threads=0)
         res = gpu.score_reads(gg, flat, offsets, enc.encode_lut("protein"), 0.5)
         assert_same_as_oracle(res, ora, f"k={ksize}")
+
+
+def test_two_host_threads_two_contexts(gpu, enc, orc):
+    """The ABI is thread-compatible per orph_ctx: two host threads, each with its own context and filter replica on the
+    same GPU, score different batches at the same time (ctypes releases the GIL) and get the serial results."""
+    import threading
+
+    from orpheum_b200 import synth
+
+    residues, poffs = synth.make_proteome(n_proteins=1000, seed=71)
+    lut = enc.encode_lut("protein")
+    base = gpu.GpuNodegraph(7, 1e7, 4)
+    base.add_peptides(residues, poffs, lut)
+    batches = [synth.make_reads_mixed(300_000, residues, poffs, ksize=7, seed=72 + i) for i in range(2)]
+    want = [gpu.score_reads(base, f, o, lut, 0.5) for f, o in batches]
+    ctxs = [gpu.Context(0), gpu.Context(0)]
+    graphs = [base.replicate(c) for c in ctxs]
+    errors, got = [], [None, None]
+
+    def work(i):
+        try:
+            for _ in range(6):
+                res = gpu.score_reads(graphs[i], batches[i][0], batches[i][1], lut, 0.5, ctx=ctxs[i])
+                if res.tobytes() != want[i].tobytes():
+                    raise AssertionError(f"thread {i}: records differ")
+            got[i] = True
+        except BaseException as exc:  # noqa: BLE001 - reported in the main thread
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert got == [True, True]
+    del graphs
+    for c in ctxs:
+        c.close()
