@@ -105,32 +105,41 @@ class ScoreTable:
     def write_csv(self, path):
         """Byte-identical to ``csv.writer(lineterminator="\n")`` over the reference's row lists; the rows are
         formatted by the native writer (orph_csv_write_scores) batch by batch."""
+        self.write_csv_header(path)
+        for names, records, (filename, _) in zip(self._names, self._records, self._files):
+            self.append_csv_batch(path, names, records, filename)
+
+    @staticmethod
+    def write_csv_header(path):
+        with open(path, "wb") as out:
+            out.write((",".join(SCORING_DF_COLUMNS) + "\n").encode())
+
+    def append_csv_batch(self, path, names, records, filename):
+        """Append the 6 rows per read of one batch to the CSV (after write_csv_header).  The native formatter runs
+        with the GIL released, so the CLI streams batches to it from a worker thread while later batches are scored."""
         import ctypes
 
         lib = _lib.load()
-        with open(path, "wb") as out:
-            out.write((",".join(SCORING_DF_COLUMNS) + "\n").encode())
-        for names, records, (filename, _) in zip(self._names, self._records, self._files):
-            present = np.unique(records["category"])
-            texts = [None] * 6
-            for code in present:
-                texts[int(code)] = self._csv_field(category_text(int(code), self.alphabet)).encode()
-            raw = getattr(names, "blob", None)
-            if raw is not None and not any(ch in raw for ch in b',"\r\n'):
-                # the usual case: no read id needs quoting, the parser's name blob IS the column of CSV fields
-                blob = np.frombuffer(raw, dtype=np.uint8) if len(raw) else np.zeros(1, dtype=np.uint8)
-                offsets = np.ascontiguousarray(names.offsets, dtype=np.uint64)
-                n_fields = len(names)
-            else:
-                fields = [self._csv_field(n).encode("utf-8", "surrogateescape") for n in (names.tolist() if hasattr(names, "tolist") else names)]
-                offsets = np.zeros(len(fields) + 1, dtype=np.uint64)
-                offsets[1:] = np.cumsum([len(f) for f in fields])
-                blob = np.frombuffer(b"".join(fields), dtype=np.uint8) if offsets[-1] else np.zeros(1, dtype=np.uint8)
-                n_fields = len(fields)
-            records = np.ascontiguousarray(records)
-            arr = (ctypes.c_char_p * 6)(*texts)
-            _lib.check(lib.orph_csv_write_scores(os.fsencode(path), 1, _lib.ptr(blob), _lib.ptr(offsets), n_fields,
-                                                 _lib.ptr(records), arr, self._csv_field(filename).encode()))
+        present = np.unique(records["category"])
+        texts = [None] * 6
+        for code in present:
+            texts[int(code)] = self._csv_field(category_text(int(code), self.alphabet)).encode()
+        raw = getattr(names, "blob", None)
+        if raw is not None and not any(ch in raw for ch in b',"\r\n'):
+            # the usual case: no read id needs quoting, the parser's name blob IS the column of CSV fields
+            blob = np.frombuffer(raw, dtype=np.uint8) if len(raw) else np.zeros(1, dtype=np.uint8)
+            offsets = np.ascontiguousarray(names.offsets, dtype=np.uint64)
+            n_fields = len(names)
+        else:
+            fields = [self._csv_field(n).encode("utf-8", "surrogateescape") for n in (names.tolist() if hasattr(names, "tolist") else names)]
+            offsets = np.zeros(len(fields) + 1, dtype=np.uint64)
+            offsets[1:] = np.cumsum([len(f) for f in fields])
+            blob = np.frombuffer(b"".join(fields), dtype=np.uint8) if offsets[-1] else np.zeros(1, dtype=np.uint8)
+            n_fields = len(fields)
+        records = np.ascontiguousarray(records)
+        arr = (ctypes.c_char_p * 6)(*texts)
+        _lib.check(lib.orph_csv_write_scores(os.fsencode(path), 1, _lib.ptr(blob), _lib.ptr(offsets), n_fields,
+                                             _lib.ptr(records), arr, self._csv_field(filename).encode()))
 
     # -- JSON summary --------------------------------------------------------------------------------------
     def empty_categories(self):
