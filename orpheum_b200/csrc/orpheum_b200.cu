@@ -1023,8 +1023,9 @@ static uint64_t scan_read_lengths(orph_host::Pool *pool, const uint64_t *off, ui
 // first pass; a chunk where more than 1/8 of the reads are of that kind is sent as ASCII instead.
 static int score_host_pipeline(orph_ctx *ctx, const orph_filter *f, const void *reads, int reads_format, const uint64_t *offsets,
                                uint64_t n_reads, const uint8_t lut[256], double jaccard_threshold, orph_read_result *out,
-                               bool allow_pack, std::vector<uint64_t> *exceptions)
+                               bool allow_pack_in, std::vector<uint64_t> *exceptions)
 {
+    bool allow_pack = allow_pack_in;
     using clk = std::chrono::steady_clock;
     int rc;
     cudaStream_t s = ctx->stream;
@@ -1060,8 +1061,13 @@ static int score_host_pipeline(orph_ctx *ctx, const orph_filter *f, const void *
         // pinned staging for host-packed chunks: every slot sized now, for the largest chunk this call can form (pinned
         // allocations cost milliseconds and synchronise the device, and nothing is in flight at this point)
         const uint64_t max_chunk_words = std::min<uint64_t>(kMaxChunkBases, offsets[n_reads] - offsets[0]) / 32 + 4;
-        for (int q = 0; q < kPipeSlots; q++)
-            if ((rc = ctx->h_packed[q].ensure(max_chunk_words * 8)) != ORPH_OK) return rc;
+        for (int q = 0; q < kPipeSlots && allow_pack; q++)
+            if (ctx->h_packed[q].ensure(max_chunk_words * 8) != ORPH_OK) {
+                cudaGetLastError();  // no pinned memory to be had (locked-memory limit): every chunk goes out as it is
+                allow_pack = false;
+            }
+    }
+    if (allow_pack) {
         cudaPointerAttributes attr;
         if (cudaPointerGetAttributes(&attr, reads) == cudaSuccess) input_pinned = attr.type == cudaMemoryTypeHost;
         else cudaGetLastError();
