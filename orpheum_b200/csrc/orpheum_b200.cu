@@ -241,6 +241,13 @@ extern "C" int orph_ctx_create(int device, void *stream, orph_ctx **out)
         ctx->own_stream = true;
     }
     int rc = ctx->counters.ensure(sizeof(ScoreCounters));
+    if (rc == ORPH_OK) {
+        // cudaMalloc does not clear: the sticky status word must start at zero (recycled device memory would otherwise
+        // show up as a spurious ORPH_E_EMPTY_READ / ORPH_E_TOO_LONG on the context's first call)
+        cudaError_t e = cudaMemsetAsync(ctx->counters.p, 0, ctx->counters.cap, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(ORPH_E_CUDA, "orph_ctx_create: %s", cudaGetErrorString(e));
+    }
     if (rc != ORPH_OK) {
         orph_ctx_destroy(ctx);
         return rc;
