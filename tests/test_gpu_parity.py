@@ -795,3 +795,42 @@ def test_two_host_threads_two_contexts(gpu, enc, orc):
     del graphs
     for c in ctxs:
         c.close()
+
+
+def test_context_and_filter_lifecycle_churn(gpu, enc, orc):
+    """Contexts and filters created and destroyed over and over on recycled device memory (nothing the library reads may
+    depend on cudaMalloc returning zeroed memory): every fresh context scores correctly on its first call, small and
+    large batches alternate so that every staging buffer is re-allocated."""
+    import torch
+
+    from orpheum_b200 import synth
+
+    residues, poffs = synth.make_proteome(n_proteins=300, seed=81)
+    lut, olut = enc.encode_lut("protein"), orc.encode_lut("protein")
+    go = orc.Nodegraph(7, int(1e6), 4)
+    go.add_peptides(residues, poffs, olut)
+    small = synth.make_reads_mixed(2000, residues, poffs, ksize=7, seed=82)
+    large = synth.make_reads_mixed(120_000, residues, poffs, ksize=7, seed=83)
+    want = {}
+    for name, (flat, offs) in (("small", small), ("large", large)):
+        ora, _ = orc.score_reads(go, flat, offs, olut, 0.5, n_threads=0)
+        want[name] = ora
+    for it in range(12):
+        # dirty the allocator's free lists: a buffer full of ones, released right before the context is created
+        junk = torch.full(((64 + 16 * it) << 20,), 0xFF, dtype=torch.uint8, device="cuda:0")
+        torch.cuda.synchronize()
+        del junk
+        torch.cuda.empty_cache()
+        ctx = gpu.Context(0)
+        g = gpu.GpuNodegraph(7, 1e6, 4, ctx=ctx)
+        g.add_peptides(residues, poffs, lut)
+        order = ("small", "large") if it % 2 else ("large", "small")
+        for name in order:
+            flat, offs = small if name == "small" else large
+            res = gpu.score_reads(g, flat, offs, lut, 0.5, ctx=ctx)
+            assert_same_as_oracle(res[:3000], want[name][:3000], f"churn {it} {name}")
+            scored = want[name]["n_kmers"] >= 0
+            assert (res["n_hits"][scored] == want[name]["n_hits"][scored]).all()
+        ctx.check()
+        del g
+        ctx.close()
