@@ -72,6 +72,10 @@ struct DevBuf {
         size_t want = need + need / 8 + 256;
         CUDA_TRY(cudaMalloc(&p, want));
         cap = want;
+        // ORPHEUM_B200_POISON=1 (test aid): fill every scratch allocation with 0xCD, so that a kernel that reads memory
+        // nothing has written shows up as a parity failure instead of working by luck on zeroed pages
+        static const bool poison = getenv("ORPHEUM_B200_POISON") != nullptr;
+        if (poison) CUDA_TRY(cudaMemset(p, 0xCD, want));
         return ORPH_OK;
     }
     void release()
