@@ -60,29 +60,58 @@ extern "C" int orph_abi_version(void) { return ORPH_ABI_VERSION; }
 // ------------------------------------------------------------------------------------------------
 // handles
 // ------------------------------------------------------------------------------------------------
+// Test aids (environment variables, read once):
+//   ORPHEUM_B200_POISON=1  every scratch allocation is pre-filled with 0xCD, so that a kernel that reads memory nothing
+//                          has written shows up as a parity failure instead of working by luck on zeroed pages;
+//   ORPHEUM_B200_GUARD=1   the slack behind the requested size of every scratch buffer is filled with 0xA5 and checked
+//                          after each scoring / index call: a kernel writing past its buffer fails the call
+//                          (compute-sanitizer is not available on the GPU pool).
+static bool env_flag(const char *name)
+{
+    const char *v = getenv(name);
+    return v && *v && *v != '0';
+}
+static const bool g_poison = env_flag("ORPHEUM_B200_POISON");
+static const bool g_guard = env_flag("ORPHEUM_B200_GUARD");
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    size_t used = 0;  // bytes asked for by the last ensure(); [used, cap) is slack
     int ensure(size_t need)
     {
-        if (need <= cap) return ORPH_OK;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = need + need / 8 + 256;
-        CUDA_TRY(cudaMalloc(&p, want));
-        cap = want;
-        // ORPHEUM_B200_POISON=1 (test aid): fill every scratch allocation with 0xCD, so that a kernel that reads memory
-        // nothing has written shows up as a parity failure instead of working by luck on zeroed pages
-        static const bool poison = getenv("ORPHEUM_B200_POISON") != nullptr;
-        if (poison) CUDA_TRY(cudaMemset(p, 0xCD, want));
+        if (need > cap) {
+            if (p) cudaFree(p);
+            p = nullptr;
+            cap = 0;
+            size_t want = need + need / 8 + 256;
+            CUDA_TRY(cudaMalloc(&p, want));
+            cap = want;
+            if (g_poison) CUDA_TRY(cudaMemset(p, 0xCD, want));
+        }
+        used = need;
+        if (g_guard) {  // (synchronises: a test aid; earlier launches may still be using the part that becomes slack)
+            CUDA_TRY(cudaDeviceSynchronize());
+            CUDA_TRY(cudaMemset((uint8_t *)p + used, 0xA5, cap - used));
+        }
         return ORPH_OK;
+    }
+    // guard mode: true if nothing wrote into the slack
+    bool slack_intact() const
+    {
+        if (!g_guard || !p || cap <= used) return true;
+        std::vector<uint8_t> h(cap - used);
+        if (cudaMemcpy(h.data(), (const uint8_t *)p + used, h.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+        for (uint8_t b : h)
+            if (b != 0xA5) return false;
+        return true;
     }
     void release()
     {
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
+        used = 0;
     }
 };
 
@@ -149,6 +178,26 @@ struct orph_ctx {
     DevBuf seen;                 // hash set of k-mer hashes seen during one index-build chunk
     DevBuf long_scratch;         // per-block peptide + de-duplication table of score_long_kernel
 };
+
+// guard mode: every scratch buffer of the context, by name
+static int verify_guards(orph_ctx *ctx)
+{
+    if (!g_guard) return ORPH_OK;
+    cudaDeviceSynchronize();
+    struct Named { const char *name; const DevBuf *b; };
+    std::vector<Named> all = {{"counters", &ctx->counters}, {"queue", &ctx->queue}, {"bytes_queue", &ctx->bytes_queue}, {"task_queue", &ctx->task_queue},
+                              {"task_queue_sorted", &ctx->task_queue_sorted}, {"needs_bytes", &ctx->needs_bytes}, {"packed", &ctx->packed},
+                              {"in_reads", &ctx->in_reads}, {"in_offsets", &ctx->in_offsets}, {"out_results", &ctx->out_results}, {"misc", &ctx->misc},
+                              {"seen", &ctx->seen}, {"long_scratch", &ctx->long_scratch}};
+    for (int q = 0; q < kPipeSlots; q++) {
+        all.push_back({"in_reads2", &ctx->in_reads2[q]});
+        all.push_back({"in_offsets2", &ctx->in_offsets2[q]});
+        all.push_back({"out_results2", &ctx->out_results2[q]});
+    }
+    for (const Named &n : all)
+        if (!n.b->slack_intact()) return fail(ORPH_E_CUDA, "ORPHEUM_B200_GUARD: a kernel wrote past the end of scratch buffer '%s'", n.name);
+    return ORPH_OK;
+}
 
 struct orph_filter {
     int device = 0;
@@ -248,7 +297,7 @@ extern "C" int orph_ctx_create(int device, void *stream, orph_ctx **out)
     if (rc == ORPH_OK) {
         // cudaMalloc does not clear: the sticky status word must start at zero (recycled device memory would otherwise
         // show up as a spurious ORPH_E_EMPTY_READ / ORPH_E_TOO_LONG on the context's first call)
-        cudaError_t e = cudaMemsetAsync(ctx->counters.p, 0, ctx->counters.cap, ctx->stream);
+        cudaError_t e = cudaMemsetAsync(ctx->counters.p, 0, sizeof(ScoreCounters), ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = fail(ORPH_E_CUDA, "orph_ctx_create: %s", cudaGetErrorString(e));
     }
@@ -314,6 +363,10 @@ extern "C" int orph_ctx_check(orph_ctx *ctx)
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     uint32_t bits = c.status | ctx->sticky_status;
     ctx->sticky_status = 0;
+    if (g_guard) {
+        const int rg = verify_guards(ctx);
+        if (rg != ORPH_OK) return rg;
+    }
     CUDA_TRY(cudaMemsetAsync((uint8_t *)ctx->counters.p + offsetof(ScoreCounters, status), 0, sizeof(uint32_t), ctx->stream));
     return status_to_code(bits);
 }
@@ -622,6 +675,7 @@ extern "C" int orph_filter_add_peptides(orph_filter *f, const uint8_t *residues,
     int rc = fetch_n_unique(f, nullptr);
     if (rc != ORPH_OK) return rc;
     if (n_unique_kmers_inc) *n_unique_kmers_inc = f->n_unique - before;
+    if (g_guard && (rc = verify_guards(ctx)) != ORPH_OK) return rc;
     return ORPH_OK;
 }
 
@@ -1283,6 +1337,10 @@ extern "C" int orph_score_reads(orph_ctx *ctx, const orph_filter *f, const void 
         if (rc2 != ORPH_OK && rc2 != ORPH_E_EMPTY_READ && rc2 != ORPH_E_TOO_LONG) return rc2;
         for (uint64_t i = 0; i < n_exc; i++) out[exceptions[i]] = eout[i];
         if (rc == ORPH_OK) rc = rc2;
+    }
+    if (g_guard) {
+        const int rg = verify_guards(ctx);
+        if (rg != ORPH_OK) return rg;
     }
     return rc;
 }
