@@ -419,7 +419,9 @@ def run_ours(args):
         from orpheum_b200 import fastx
 
         n_fq = min(args.reads, 4_000_000)
-        tmpdir = tempfile.mkdtemp(prefix="orph_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        need_bytes = n_fq * (2 * READ_LEN + 40)
+        shm_ok = os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 2 * need_bytes
+        tmpdir = tempfile.mkdtemp(prefix="orph_bench_", dir="/dev/shm" if shm_ok else None)
         try:
             fq = os.path.join(tmpdir, "reads.fq")
             qual = b"I" * READ_LEN
@@ -447,6 +449,8 @@ def run_ours(args):
                                  "fastq_GBps": fq_bytes / dtf / 1e9, "identical_to_device_path": bool(same_fq),
                                  "path": "uncompressed four-line FASTQ on tmpfs -> orph_fastx_* (mmap, parallel parse, one batch "
                                          "prefetched) -> orph_score_reads (pageable host ASCII, packed on the host) -> records"}
+        except Exception as exc:  # a measurement extra: never lose the bench line over it (disk full, ...)
+            e2e["from_fastq"] = {"error": f"{type(exc).__name__}: {exc}"}
         finally:
             shutil.rmtree(tmpdir, ignore_errors=True)
 
