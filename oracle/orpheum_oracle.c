@@ -2,12 +2,12 @@
  * orpheum_oracle.c -- CPU restatement of the orpheum `translate` scoring path
  * and the `index` Bloom build.
  *
- * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, the smoke check
- * in __graft_entry__.py and bench.py's cpu_baseline / --impl reference legs may
- * load it.  The product (orpheum_b200/) never calls into this file; it fails
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/ (incl. the checker
+ * scripts under tests/scripts/), the smoke check in __graft_entry__.py and
+ * bench.py's cpu_baseline / --impl reference legs may load it.  The product (orpheum_b200/) never calls into this file; it fails
  * loudly when its CUDA library is missing.
  *
- * Parity status: PINNED.  tests/test_oracle_*.py check this file against
+ * Parity status: PINNED.  tests/test_oracle.py check this file against
  *   - the reference's golden .nodegraph files (byte-identical rebuild),
  *   - the reference's golden score CSVs / coding FASTA for the 23 test reads,
  *   - the inline known-answer tests of the reference's unit tests,

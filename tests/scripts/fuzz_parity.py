@@ -2,7 +2,7 @@
 """Randomised differential test: GPU path against the oracle over random filter geometries, alphabets, k-mer sizes,
 read-length mixes (all kernel tiers), N / lower-case density, input formats and sub-batches.
 
-    python tools/fuzz_parity.py [seconds] [seed]
+    python tests/scripts/fuzz_parity.py [seconds] [seed]
 Prints one line per round and a JSON summary; exits 1 on the first difference (after dumping the case).
 """
 import json
@@ -12,7 +12,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 from oracle import oracle as orc  # noqa: E402

@@ -5,7 +5,7 @@ parquet and JSON summary through the columnar writer -- compared with (a) the fi
 (the reference's object interface, itself pinned to the reference's golden outputs by tests/test_host_logic.py)
 writes from ORACLE scores of the same reads, and (b) the single-GPU records.
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/multi_gpu_output_parity.py [n_reads]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/scripts/multi_gpu_output_parity.py [n_reads]
 """
 import json
 import os
@@ -14,7 +14,7 @@ import tempfile
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 

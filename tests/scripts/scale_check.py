@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """cfg4 at scale on one GPU: Bloom build from a ~1e8-residue synthetic proteome (tablesize 1e8 and 1e9),
 bits checked against the CPU oracle, then scoring of synthetic reads against the HBM-resident 1e9 filter
-with a parity check on a prefix.  Prints one JSON line per stage.  Usage: python tools/scale_check.py [n_reads]"""
+with a parity check on a prefix.  Prints one JSON line per stage.  Usage: python tests/scripts/scale_check.py [n_reads]"""
 import json
 import os
 import sys
@@ -9,7 +9,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 from oracle import oracle as orc  # noqa: E402
