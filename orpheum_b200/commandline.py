@@ -1,27 +1,25 @@
-"""``orpheum`` command group: ``translate`` and ``index`` (mirror of ``orpheum/commandline.py:21-36``;
-``compare-kmers`` is a separate analysis tool outside the scoring path and is not provided)."""
-from functools import partial
+"""``orpheum`` command group with the two sub-commands on the GPU path, ``translate`` and ``index``
+(same names, options and help behaviour as ``orpheum/commandline.py:21-36``; ``compare-kmers`` is a separate
+analysis tool outside the scoring path and is not provided)."""
+import functools
 
 import click
 
-click.option = partial(click.option, show_default=True)  # as the reference does (commandline.py:16)
+# every option shows its default in --help, as in the reference's command line (commandline.py:16)
+click.option = functools.partial(click.option, show_default=True)
 
-from .index import cli as index  # noqa: E402
-from .translate import cli as translate  # noqa: E402
+from . import index as _index  # noqa: E402  (imported after the patch above, so their options inherit it)
+from . import translate as _translate  # noqa: E402
 
-settings = dict(help_option_names=["-h", "--help"])
-
-
-@click.group(options_metavar="", subcommand_metavar="<command>", context_settings=settings)
-def cli():
-    """
-    B200-native orpheum: partition sequencing reads into protein-coding and non-coding bins
-    (six-frame translation + k-mer Bloom filter of a reference proteome), scored on the GPU.
-    """
-
-
-cli.add_command(index, name="index")
-cli.add_command(translate, name="translate")
+cli = click.Group(
+    name="orpheum",
+    help="B200-native orpheum: partition sequencing reads into protein-coding and non-coding bins "
+         "(six-frame translation + k-mer Bloom filter of a reference proteome), scored on the GPU.",
+    commands={"index": _index.cli, "translate": _translate.cli},
+    options_metavar="",
+    subcommand_metavar="<command>",
+    context_settings={"help_option_names": ["-h", "--help"]},
+)
 
 if __name__ == "__main__":
     cli()
