@@ -834,3 +834,20 @@ def test_context_and_filter_lifecycle_churn(gpu, enc, orc):
         ctx.check()
         del g
         ctx.close()
+
+
+def test_randomised_differential_smoke():
+    """A short run of tests/scripts/fuzz_parity.py (random alphabets, k, geometries, read-length tiers, dirty bytes, input
+    formats, kernel routes; GPU records, filter tables and emitted peptides against the oracle) with a fresh seed per day of
+    the year, so that the driver's runs keep sampling new cases.  Longer recorded runs: profiles/r01_fuzz_parity_summary.json."""
+    import datetime
+    import json
+    import subprocess
+    import sys
+
+    seed = 1000 + datetime.date.today().timetuple().tm_yday
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts", "fuzz_parity.py")
+    proc = subprocess.run([sys.executable, script, "20", str(seed)], capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
+    summary = json.loads(proc.stdout.strip().splitlines()[-1])
+    assert summary["differences"] == 0 and summary["fuzz_rounds"] > 20
