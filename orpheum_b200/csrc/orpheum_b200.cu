@@ -81,7 +81,7 @@ struct DevBuf {
     int ensure(size_t need)
     {
         if (need > cap) {
-            if (p) cudaFree(p);
+            if (p) cudaFree(p);  // cudaFree waits for the device: work still using the old buffer finishes first
             p = nullptr;
             cap = 0;
             size_t want = need + need / 8 + 256;
@@ -1106,6 +1106,15 @@ static int score_host_pipeline(orph_ctx *ctx, const orph_filter *f, const void *
         }
         ctx->pipe_ready = true;
     }
+    // every early return below leaves copies / kernels of earlier chunks in flight on the three streams, reading the
+    // caller's host buffers: drain the device before handing control back
+    struct DrainOnError {
+        bool armed = true;
+        ~DrainOnError()
+        {
+            if (armed) cudaDeviceSynchronize();
+        }
+    } drain;
     bool input_pinned = false;
     if (!ctx->pool && (allow_pack || n_reads >= (1ULL << 18))) {  // the pool also scans the offsets of large batches
         int n = ctx->host_threads;
@@ -1307,6 +1316,7 @@ static int score_host_pipeline(orph_ctx *ctx, const orph_filter *f, const void *
             for (int k = 0; k < 6; k++) cudaEventDestroy(ct.e[k]);
     }
     CUDA_TRY(cudaMemsetAsync((uint8_t *)ctx->counters.p + offsetof(ScoreCounters, status), 0, sizeof(uint32_t), s));
+    drain.armed = false;  // all three streams were synchronised above
     return status_to_code(counters.status);
 }
 
