@@ -433,9 +433,10 @@ def run_ours(args):
 
             def pass_fastq():
                 got, parts = 0, []
-                for _names, b_flat, b_offs in fastx.read_batches(fq, prefetch=1):
-                    parts.append(gpu.score_reads(graph, b_flat, b_offs, lut, thr, ctx=ctx))
-                    got += len(b_offs) - 1
+                with gpu.ScoringStream(graph, fq, lut, thr, ctx=ctx) as stream:
+                    for batch in stream:
+                        parts.append(batch.results.copy())
+                        got += batch.n_reads
                 return got, parts
 
             pass_fastq()
@@ -447,8 +448,8 @@ def run_ours(args):
             same_fq = got == n_fq and np.concatenate(parts).tobytes() == res_dev[:n_fq].tobytes()
             e2e["from_fastq"] = {"value": n_fq / dtf, "unit": UNIT, "reads": n_fq, "fastq_bytes": fq_bytes, "ms": 1e3 * dtf,
                                  "fastq_GBps": fq_bytes / dtf / 1e9, "identical_to_device_path": bool(same_fq),
-                                 "path": "uncompressed four-line FASTQ on tmpfs -> orph_fastx_* (mmap, parallel parse, one batch "
-                                         "prefetched) -> orph_score_reads (pageable host ASCII, packed on the host) -> records"}
+                                 "path": "uncompressed four-line FASTQ on tmpfs -> orph_stream_* (mapped text parsed and 2-bit packed into "
+                                         "pinned slots in one parallel pass, next batch parsed while this one is copied and scored) -> records"}
         except Exception as exc:  # a measurement extra: never lose the bench line over it (disk full, ...)
             e2e["from_fastq"] = {"error": f"{type(exc).__name__}: {exc}"}
         finally:

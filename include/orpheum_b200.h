@@ -229,6 +229,63 @@ int orph_fastx_next_batch(orph_fastx *fx, uint64_t max_records, uint64_t max_bas
 int orph_fastx_copy_batch(orph_fastx *fx, uint8_t *seq_dst, uint64_t *seq_offsets_dst);
 void orph_fastx_close(orph_fastx *fx);
 
+/* ---- fused host ingest: sequence file -> 2-bit packed batches ------------------------------- */
+/* The same records as orph_fastx_* (screed's semantics, translate.py:370), delivered the way the GPU takes them: the
+ * reads of a batch as ONE 2-bit stream (ORPH_READS_PACKED2, base 0 of the batch at bit 0) with 32-bit base offsets,
+ * the record names, and for every read where its bytes sit in the text.  Strict four-line FASTQ is parsed and packed in a
+ * single parallel pass over the text (the file is mapped; gzip input is inflated block by block); any other layout
+ * (FASTA, wrapped FASTQ, ...) goes through the general parser, same outputs.  Host only: no GPU is touched. */
+typedef struct orph_ingest orph_ingest;
+typedef struct orph_ingest_batch {
+    uint64_t n_reads;              /* 0: end of file */
+    const uint64_t *packed;        /* (total_bases + 31) / 32 words */
+    const uint32_t *offsets32;     /* [n_reads + 1]: read i = bases [offsets32[i], offsets32[i + 1]) of the stream */
+    uint64_t total_bases;
+    uint32_t max_read_len;
+    uint32_t reserved;
+    const uint8_t *names;          /* record names, concatenated */
+    const uint64_t *name_offsets;  /* [n_reads + 1] */
+    const uint8_t *text;           /* read i's bytes as the file has them: text[seq_start[i] .. + seq_len[i]) */
+    const uint64_t *seq_start;     /* [n_reads] */
+    const uint32_t *seq_len;       /* [n_reads] */
+    const uint32_t *flagged;       /* ascending indices of the reads that hold a byte other than upper-case ACGT: */
+    uint64_t n_flagged;            /*   their packed bits are unspecified, score them from their bytes */
+} orph_ingest_batch;
+/* n_threads <= 0: every core of the host.  ORPH_E_INVALID if the file is neither FASTA nor FASTQ. */
+int orph_ingest_open(const char *path, int n_threads, orph_ingest **out);
+/* The next batch of about max_reads reads (batches end at a segment boundary of the text; 0 = 2^20).  The pointers stay
+ * valid until the call after the next one on the same handle. */
+int orph_ingest_next(orph_ingest *ing, uint64_t max_reads, orph_ingest_batch *out);
+void orph_ingest_close(orph_ingest *ing);
+/* The bytes of the reads index[0 .. n_index) of a batch (text / seq_start / seq_len as delivered by orph_ingest_next or
+ * orph_stream_next), concatenated: out_offsets[n_index + 1] always, out_bytes (out_offsets[n_index] bytes) unless NULL. */
+int orph_gather_reads(const uint8_t *text, const uint64_t *seq_start, const uint32_t *seq_len, const uint64_t *index, uint64_t n_index,
+                      uint8_t *out_bytes, uint64_t *out_offsets);
+
+/* ---- scoring stream: file in, records out ------------------------------------------------------------------------ */
+/* orph_ingest feeding the scoring kernels: a background thread parses and packs batch k + 1 into pinned memory while
+ * batch k is copied to the GPU and scored, so a caller looping over orph_stream_next sees one finished batch per call
+ * and never touches the bases.  Replaces the loop `for record in screed.open(reads): score_reads_per_record(...)` of
+ * Translate.score_reads_per_file (translate.py:367-372).  The stream owns a private context on ctx's device: the
+ * caller's ctx stays free for other calls (orph_translate_frames, ...) while the stream runs. */
+typedef struct orph_stream orph_stream;
+typedef struct orph_stream_batch {
+    uint64_t n_reads;                /* 0: end of file */
+    const orph_read_result *results; /* [n_reads] */
+    const uint8_t *names;
+    const uint64_t *name_offsets;    /* [n_reads + 1] */
+    const uint8_t *text;             /* as in orph_ingest_batch */
+    const uint64_t *seq_start;
+    const uint32_t *seq_len;
+    uint64_t n_byte_path;            /* reads that were scored from their bytes (N, lower case, ...) */
+    int status;                      /* ORPH_OK, or ORPH_E_EMPTY_READ / ORPH_E_TOO_LONG if such reads were in the batch */
+} orph_stream_batch;
+int orph_stream_open(orph_ctx *ctx, const orph_filter *f, const char *path, const uint8_t lut[256], double jaccard_threshold,
+                     uint64_t batch_reads, int n_threads, orph_stream **out);
+/* Blocks until the next batch is scored.  The pointers stay valid until the next call on the same stream. */
+int orph_stream_next(orph_stream *st, orph_stream_batch *out);
+void orph_stream_close(orph_stream *st);
+
 /* ---- score CSV straight from the result records -------------------------------------------------- */
 /* The rows of Translate.score_reads_per_record (translate.py:342-365) in the exact text csv.writer produces for
  * them (create_save_summary.py:52-64): `read_id,jaccard,n_kmers,category,frame,filename`, 6 rows per read,

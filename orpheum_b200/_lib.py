@@ -31,6 +31,24 @@ READ_RESULT_DTYPE = np.dtype(
 )
 assert READ_RESULT_DTYPE.itemsize == 32
 
+
+
+class IngestBatch(ctypes.Structure):
+    """struct orph_ingest_batch"""
+    _fields_ = [("n_reads", ctypes.c_uint64), ("packed", ctypes.c_void_p), ("offsets32", ctypes.c_void_p),
+                ("total_bases", ctypes.c_uint64), ("max_read_len", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
+                ("names", ctypes.c_void_p), ("name_offsets", ctypes.c_void_p), ("text", ctypes.c_void_p),
+                ("seq_start", ctypes.c_void_p), ("seq_len", ctypes.c_void_p), ("flagged", ctypes.c_void_p),
+                ("n_flagged", ctypes.c_uint64)]
+
+
+class StreamBatch(ctypes.Structure):
+    """struct orph_stream_batch"""
+    _fields_ = [("n_reads", ctypes.c_uint64), ("results", ctypes.c_void_p), ("names", ctypes.c_void_p),
+                ("name_offsets", ctypes.c_void_p), ("text", ctypes.c_void_p), ("seq_start", ctypes.c_void_p),
+                ("seq_len", ctypes.c_void_p), ("n_byte_path", ctypes.c_uint64), ("status", ctypes.c_int)]
+
+
 # every symbol include/orpheum_b200.h declares: name -> (restype, argtypes)
 _vp, _u8p, _u64p = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p
 _pp = ctypes.POINTER(ctypes.c_void_p)
@@ -72,6 +90,13 @@ PROTOTYPES = {
     "orph_fastx_next_batch": (ctypes.c_int, [_vp, ctypes.c_uint64, ctypes.c_uint64, _u64p, _pp, _pp, _pp, _pp]),
     "orph_fastx_copy_batch": (ctypes.c_int, [_vp, _u8p, _u64p]),
     "orph_fastx_close": (None, [_vp]),
+    "orph_ingest_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, _pp]),
+    "orph_ingest_next": (ctypes.c_int, [_vp, ctypes.c_uint64, ctypes.POINTER(IngestBatch)]),
+    "orph_ingest_close": (None, [_vp]),
+    "orph_gather_reads": (ctypes.c_int, [_vp, _vp, _vp, _u64p, ctypes.c_uint64, _u8p, _u64p]),
+    "orph_stream_open": (ctypes.c_int, [_vp, _vp, ctypes.c_char_p, _u8p, ctypes.c_double, ctypes.c_uint64, ctypes.c_int, _pp]),
+    "orph_stream_next": (ctypes.c_int, [_vp, ctypes.POINTER(StreamBatch)]),
+    "orph_stream_close": (None, [_vp]),
     "orph_csv_write_scores": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, _u8p, _u64p, ctypes.c_uint64, _vp, _vp, ctypes.c_char_p]),
     "orph_format_fasta": (ctypes.c_int, [ctypes.c_int, _u8p, _u64p, ctypes.c_uint64, _vp, _u8p, _u64p, _u8p, _u64p, ctypes.c_int, _u8p,
                                          ctypes.c_uint64, _u64p]),

@@ -174,6 +174,27 @@ extern "C" int orph_fastx_open(const char *path, orph_fastx **out)
     return ORPH_OK;
 }
 
+// internal (ingest.cpp): the general sequential parser from the middle of a file -- at byte `byte_pos` of a plain
+// (mapped) file, or behind the first `skip_records` records of a compressed one
+int orph_fastx_open_general(const char *path, uint64_t byte_pos, uint64_t skip_records, orph_fastx **out)
+{
+    const int rc = orph_fastx_open(path, out);
+    if (rc != ORPH_OK) return rc;
+    orph_fastx *fx = *out;
+    fx->fast_ok = false;
+    if (fx->buf.mapped) {
+        fx->pos = std::min<uint64_t>(byte_pos, fx->end);
+        return ORPH_OK;
+    }
+    while (skip_records > 0) {
+        uint64_t n = 0;
+        const int rc2 = orph_fastx_next_batch(fx, std::min<uint64_t>(skip_records, 1u << 16), 1ull << 40, &n, nullptr, nullptr, nullptr, nullptr);
+        if (rc2 != ORPH_OK || n == 0) break;
+        skip_records -= n;
+    }
+    return ORPH_OK;
+}
+
 extern "C" void orph_fastx_close(orph_fastx *fx)
 {
     if (!fx) return;

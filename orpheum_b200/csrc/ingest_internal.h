@@ -1,0 +1,65 @@
+// Internals of orph_ingest shared between ingest.cpp and the scoring stream in orpheum_b200.cu.
+#pragma once
+#include <zlib.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/orpheum_b200.h"
+#include "fused_ingest.h"
+
+// where the arrays the DMA engine reads come from: plain memory for host-only use, pinned memory under a stream
+struct IngestAlloc {
+    void *(*alloc)(size_t bytes);
+    void (*release)(void *p);
+};
+
+struct IngestSlot {
+    orph_host::FusedBatch b;
+    IngestAlloc alloc{nullptr, nullptr};
+    uint64_t packed_cap = 0, reads_cap = 0, names_cap = 0;
+    const uint8_t *text = nullptr;  // the bytes seq_start points into: the mapped file or own_text
+    uint64_t text_len = 0;
+    uint8_t *own_text = nullptr;    // inflated block (gzip) or the general parser's concatenated sequences
+    uint64_t own_text_cap = 0;
+    IngestSlot() = default;
+    IngestSlot(const IngestSlot &) = delete;
+    IngestSlot &operator=(const IngestSlot &) = delete;
+    IngestSlot(IngestSlot &&o) noexcept { *this = std::move(o); }
+    IngestSlot &operator=(IngestSlot &&o) noexcept
+    {
+        std::swap(b, o.b);
+        std::swap(alloc, o.alloc);
+        std::swap(packed_cap, o.packed_cap);
+        std::swap(reads_cap, o.reads_cap);
+        std::swap(names_cap, o.names_cap);
+        std::swap(text, o.text);
+        std::swap(text_len, o.text_len);
+        std::swap(own_text, o.own_text);
+        std::swap(own_text_cap, o.own_text_cap);
+        return *this;
+    }
+    ~IngestSlot();
+};
+
+struct orph_ingest {
+    std::string path;
+    char kind = 0;                 // '>' FASTA, '@' FASTQ, 0 empty
+    const uint8_t *map = nullptr;  // plain file, mapped
+    uint64_t map_size = 0, pos = 0;
+    gzFile gz = nullptr;           // compressed FASTQ: blocks inflated into the slots
+    bool gz_eof = false;
+    std::vector<uint8_t> carry;    // text of a record cut by the end of the previous block
+    bool general = false;          // the general sequential parser has taken over
+    orph_fastx *fx = nullptr;
+    uint64_t records_done = 0;
+    double bytes_per_record = 0;
+    orph_host::Pool *pool = nullptr;
+    std::vector<IngestSlot> slots;
+    int cur = -1;
+    IngestAlloc alloc{nullptr, nullptr};
+};
+
+int orph_ingest_open_with(const char *path, int n_threads, int n_slots, IngestAlloc alloc, orph_ingest **out);
+// the next batch, in the slot ring's next slot (valid until the ring wraps around)
+int orph_ingest_next_slot(orph_ingest *ing, uint64_t max_reads, IngestSlot **out);

@@ -84,7 +84,10 @@ static int score_host_pipeline(orph_ctx *ctx, const orph_filter *f, const void *
         if (!ctx->pool) return fail(ORPH_E_NOMEM, "out of host memory");
     }
     // chunk boundaries: <= 2^19 reads and <= 2^27 bases each
-    const uint64_t kMaxChunkReads = 1ULL << 19, kMaxChunkBases = 1ULL << 27;
+    static const int chunk_log2 = [] { const char *v = getenv("ORPHEUM_B200_CHUNK_LOG2"); const int n = v ? atoi(v) : 19; return n < 12 ? 12 : n > 24 ? 24 : n; }();
+    static const char *skip_env = getenv("ORPHEUM_B200_AB_SKIP");  // development A/B: "kernels", "d2h", "h2d"
+    static const bool skip_kernels = skip_env && strstr(skip_env, "kernels"), skip_d2h = skip_env && strstr(skip_env, "d2h"), skip_h2d = skip_env && strstr(skip_env, "h2d");
+    const uint64_t kMaxChunkReads = 1ULL << chunk_log2, kMaxChunkBases = 1ULL << (chunk_log2 + 8);
     if (allow_pack) {
         // pinned staging for host-packed chunks: every slot sized now, for the largest chunk this call can form (pinned
         // allocations cost milliseconds and synchronise the device, and nothing is in flight at this point)
@@ -221,7 +224,7 @@ static int score_host_pipeline(orph_ctx *ctx, const orph_filter *f, const void *
             } else {
                 const uint64_t w0 = b0 / 32, w1 = (b1 + 31) / 32;
                 if ((rc = ctx->in_reads2[b].ensure((w1 - w0 + 2) * 8)) != ORPH_OK) return rc;
-                if (w1 > w0) CUDA_TRY(cudaMemcpyAsync(ctx->in_reads2[b].p, (const uint64_t *)reads + w0, (w1 - w0) * 8, cudaMemcpyHostToDevice, ctx->s_in));
+                if (w1 > w0 && !(skip_h2d && c >= 2 * kPipeSlots)) CUDA_TRY(cudaMemcpyAsync(ctx->in_reads2[b].p, (const uint64_t *)reads + w0, (w1 - w0) * 8, cudaMemcpyHostToDevice, ctx->s_in));
                 d_packed = (const uint64_t *)ctx->in_reads2[b].p;
                 pbase0 = w0 * 32;
             }
@@ -232,7 +235,7 @@ static int score_host_pipeline(orph_ctx *ctx, const orph_filter *f, const void *
         CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_in[b], 0));
         if (used[b]) CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_out[b], 0));
         mark(2, s);
-        rc = score_device_impl(ctx, f, d_ascii, b0, d_packed, pbase0, n_ascii, (const uint64_t *)ctx->in_offsets2[b].p, m, max_len, lut,
+        rc = skip_kernels ? ORPH_OK : score_device_impl(ctx, f, d_ascii, b0, d_packed, pbase0, n_ascii, (const uint64_t *)ctx->in_offsets2[b].p, m, max_len, lut,
                                jaccard_threshold, (orph_read_result *)ctx->out_results2[b].p);
         if (rc != ORPH_OK) {
             cudaDeviceSynchronize();
@@ -242,7 +245,7 @@ static int score_host_pipeline(orph_ctx *ctx, const orph_filter *f, const void *
         CUDA_TRY(cudaEventRecord(ctx->ev_kernels[b], s));
         CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->ev_kernels[b], 0));
         mark(4, ctx->s_out);
-        CUDA_TRY(cudaMemcpyAsync(out + lo, ctx->out_results2[b].p, m * sizeof(orph_read_result), cudaMemcpyDeviceToHost, ctx->s_out));
+        if (!skip_d2h) CUDA_TRY(cudaMemcpyAsync(out + lo, ctx->out_results2[b].p, m * sizeof(orph_read_result), cudaMemcpyDeviceToHost, ctx->s_out));
         mark(5, ctx->s_out);
         CUDA_TRY(cudaEventRecord(ctx->ev_out[b], ctx->s_out));
         used[b] = true;

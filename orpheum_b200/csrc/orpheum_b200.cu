@@ -755,6 +755,8 @@ static void apply_l2_window(orph_ctx *ctx, const orph_filter *f)
 {
     if (ctx->l2_window_base == f->buf) return;
     ctx->l2_window_base = f->buf;
+    static const bool no_window = env_flag("ORPHEUM_B200_NO_L2_WINDOW");
+    if (no_window) return;
     if (ctx->l2_persist_max == 0 || ctx->l2_window_max == 0) return;
     size_t want = std::min<size_t>(f->n_bytes, ctx->l2_persist_max);
     cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
@@ -1052,6 +1054,7 @@ extern "C" int orph_score_reads_device(orph_ctx *ctx, const orph_filter *f, cons
 }
 
 #include "ingest_pipeline.inl"
+#include "stream.inl"
 
 extern "C" int orph_translate_frames(orph_ctx *ctx, const uint8_t *reads, const uint64_t *offsets, uint64_t n_reads,
                                      const uint64_t *item_read, const int8_t *item_frame, uint64_t n_items,

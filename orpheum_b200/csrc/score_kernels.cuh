@@ -257,6 +257,18 @@ __global__ void pack_ascii_kernel(const uint8_t *__restrict__ ascii, uint64_t ab
     }
 }
 
+// 32-bit batch-relative offsets (what the host ingest ships) -> the 64-bit absolute offsets the kernels index with
+__global__ void expand_offsets_kernel(const uint32_t *__restrict__ rel, uint64_t base, uint64_t n, uint64_t *__restrict__ out)
+{
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = base + rel[i];
+}
+
+// offsets of a batch of equal-length reads, generated instead of shipped: out[i] = base + i * len
+__global__ void fill_offsets_kernel(uint64_t base, uint64_t len, uint64_t n, uint64_t *__restrict__ out)
+{
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = base + i * len;
+}
+
 // ------------------------------------------------------------------------------------------------
 // prefilter_kernel
 // ------------------------------------------------------------------------------------------------

@@ -1,0 +1,303 @@
+// orph_stream: sequence file in, scored records out (included by orpheum_b200.cu, same translation unit).
+//
+// One background thread per stream runs the whole path: it asks orph_ingest for the next batch (parallel parse + 2-bit
+// pack into pinned memory, fused_ingest.cpp), enqueues that batch's copies and kernels on the stream's private context,
+// and only then waits for the batch before it -- so the host parses batch k + 1 while the GPU scores batch k.  Reads
+// the 2-bit stream cannot represent (N, lower case, ...) are gathered from the text and scored from their bytes in the
+// same enqueue; their records replace the ones the packed pass produced.  The reference's counterpart is the serial
+// loop over screed records in Translate.score_reads_per_file (orpheum/translate.py:367-372).
+#pragma once
+
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <string>
+
+#include "ingest_internal.h"
+
+namespace {
+
+void *pinned_alloc(size_t n)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, n ? n : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void pinned_release(void *p) { cudaFreeHost(p); }
+
+constexpr int kStreamSlots = 4;  // being parsed + on the GPU + finished + held by the caller
+
+}  // namespace
+
+struct orph_stream {
+    orph_ctx *ctx = nullptr;  // private: own CUDA stream and scratch, so the caller's context stays free
+    const orph_filter *f = nullptr;
+    orph_ingest *ing = nullptr;
+    uint8_t lut[256];
+    double thr = 0;
+    uint64_t batch_reads = 0;
+    struct Job {
+        IngestSlot *slot = nullptr;
+        PinnedBuf results, side_ascii, side_offsets, side_results, status_word;
+        cudaEvent_t done = nullptr;
+        uint64_t n = 0, n_side = 0;
+        int status = ORPH_OK;
+    } jobs[kStreamSlots];
+    DevBuf d_packed, d_off32, d_off64, d_results, d_side_ascii, d_side_offsets, d_side_results;
+    std::thread worker;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<int> finished;
+    int outstanding = 0;  // jobs handed to the parser and not yet released by the caller
+    int held = -1;
+    bool eof = false, stop = false;
+    int error = ORPH_OK;
+    std::string error_text;
+};
+
+static int stream_enqueue(orph_stream *st, orph_stream::Job &job)
+{
+    orph_ctx *ctx = st->ctx;
+    cudaStream_t s = ctx->stream;
+    const orph_host::FusedBatch &b = job.slot->b;
+    const uint64_t n = b.n_reads, n_words = (b.total_bases + 31) / 32;
+    int rc;
+    job.n = n;
+    job.n_side = b.flagged.size();
+    if ((rc = st->d_packed.ensure((n_words + 2) * 8)) != ORPH_OK) return rc;
+    if ((rc = st->d_off32.ensure((n + 1) * 4)) != ORPH_OK) return rc;
+    if ((rc = st->d_off64.ensure((n + 1) * 8)) != ORPH_OK) return rc;
+    if ((rc = st->d_results.ensure(n * sizeof(orph_read_result))) != ORPH_OK) return rc;
+    if ((rc = job.results.ensure(n * sizeof(orph_read_result))) != ORPH_OK) return rc;
+    if ((rc = job.status_word.ensure(sizeof(ScoreCounters))) != ORPH_OK) return rc;
+    if (n_words) CUDA_TRY(cudaMemcpyAsync(st->d_packed.p, b.packed, n_words * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(st->d_off32.p, b.off32, (n + 1) * 4, cudaMemcpyHostToDevice, s));
+    expand_offsets_kernel<<<grid_for(n + 1, 256, ctx->sm_count, 8), 256, 0, s>>>((const uint32_t *)st->d_off32.p, 0, n + 1, (uint64_t *)st->d_off64.p);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    const uint32_t max_len = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(b.max_len, ORPH_MAX_READ_LEN));
+    rc = score_device_impl(ctx, st->f, nullptr, 0, (const uint64_t *)st->d_packed.p, 0, 0, (const uint64_t *)st->d_off64.p, n, max_len, st->lut, st->thr,
+                           (orph_read_result *)st->d_results.p);
+    if (rc != ORPH_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(job.results.p, st->d_results.p, n * sizeof(orph_read_result), cudaMemcpyDeviceToHost, s));
+    if (job.n_side) {
+        // the reads the 2-bit stream cannot hold: their bytes, gathered from the text, through the byte-exact kernels
+        const uint64_t m = job.n_side;
+        if ((rc = job.side_offsets.ensure((m + 1) * 8)) != ORPH_OK) return rc;
+        uint64_t *eoff = (uint64_t *)job.side_offsets.p;
+        eoff[0] = 0;
+        uint32_t side_max = 1;
+        for (uint64_t i = 0; i < m; i++) {
+            const uint32_t len = b.seq_len[b.flagged[i]];
+            eoff[i + 1] = eoff[i] + len;
+            side_max = std::max(side_max, len);
+        }
+        const uint64_t total = eoff[m];
+        if ((rc = job.side_ascii.ensure(total + 64)) != ORPH_OK) return rc;
+        if ((rc = job.side_results.ensure(m * sizeof(orph_read_result))) != ORPH_OK) return rc;
+        uint8_t *bytes = (uint8_t *)job.side_ascii.p;
+        const uint8_t *text = job.slot->text;
+        auto gather = [&](uint64_t blk) {
+            const uint64_t i1 = std::min(m, (blk + 1) * 4096);
+            for (uint64_t i = blk * 4096; i < i1; i++) memcpy(bytes + eoff[i], text + b.seq_start[b.flagged[i]], b.seq_len[b.flagged[i]]);
+        };
+        const uint64_t n_blk = (m + 4095) / 4096;
+        if (st->ing->pool && n_blk > 4) st->ing->pool->run(n_blk, gather);
+        else
+            for (uint64_t blk = 0; blk < n_blk; blk++) gather(blk);
+        if ((rc = st->d_side_ascii.ensure(total + 64)) != ORPH_OK) return rc;
+        if ((rc = st->d_side_offsets.ensure((m + 1) * 8)) != ORPH_OK) return rc;
+        if ((rc = st->d_side_results.ensure(m * sizeof(orph_read_result))) != ORPH_OK) return rc;
+        if (total) CUDA_TRY(cudaMemcpyAsync(st->d_side_ascii.p, bytes, total, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(st->d_side_offsets.p, eoff, (m + 1) * 8, cudaMemcpyHostToDevice, s));
+        for (uint64_t lo = 0; lo < m; lo += 1ull << 26) {
+            const uint64_t cnt = std::min<uint64_t>(1ull << 26, m - lo);
+            rc = score_device_impl(ctx, st->f, (const uint8_t *)st->d_side_ascii.p + eoff[lo], eoff[lo], nullptr, 0, eoff[lo + cnt] - eoff[lo],
+                                   (const uint64_t *)st->d_side_offsets.p + lo, cnt, std::min<uint32_t>(side_max, ORPH_MAX_READ_LEN), st->lut, st->thr,
+                                   (orph_read_result *)st->d_side_results.p + lo);
+            if (rc != ORPH_OK) return rc;
+        }
+        CUDA_TRY(cudaMemcpyAsync(job.side_results.p, st->d_side_results.p, m * sizeof(orph_read_result), cudaMemcpyDeviceToHost, s));
+    }
+    // the sticky status of this batch (empty / over-long reads), then clear it for the next one
+    CUDA_TRY(cudaMemcpyAsync(job.status_word.p, ctx->counters.p, sizeof(ScoreCounters), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemsetAsync((uint8_t *)ctx->counters.p + offsetof(ScoreCounters, status), 0, sizeof(uint32_t), s));
+    CUDA_TRY(cudaEventRecord(job.done, s));
+    return ORPH_OK;
+}
+
+static int stream_complete(orph_stream *st, orph_stream::Job &job)
+{
+    CUDA_TRY(cudaEventSynchronize(job.done));
+    if (job.n_side) {
+        orph_read_result *res = (orph_read_result *)job.results.p;
+        const orph_read_result *side = (const orph_read_result *)job.side_results.p;
+        const std::vector<uint32_t> &flagged = job.slot->b.flagged;
+        for (uint64_t i = 0; i < job.n_side; i++) res[flagged[i]] = side[i];
+    }
+    const uint32_t bits = ((const ScoreCounters *)job.status_word.p)->status;
+    job.status = bits & kStatusEmptyRead ? ORPH_E_EMPTY_READ : bits & kStatusTooLong ? ORPH_E_TOO_LONG : ORPH_OK;
+    return ORPH_OK;
+}
+
+static void stream_worker(orph_stream *st)
+{
+    cudaSetDevice(st->ctx->device);
+    int prev = -1;
+    uint64_t k = 0;
+    auto fail_with = [&](int rc) {
+        std::lock_guard<std::mutex> lk(st->mu);
+        st->error = rc;
+        st->error_text = g_err;  // thread-local message of this worker thread
+        st->eof = true;
+        st->cv.notify_all();
+    };
+    auto publish = [&](int j) {
+        std::lock_guard<std::mutex> lk(st->mu);
+        st->finished.push_back(j);
+        st->cv.notify_all();
+    };
+    for (;;) {
+        {
+            std::unique_lock<std::mutex> lk(st->mu);
+            st->cv.wait(lk, [&] { return st->stop || st->outstanding < kStreamSlots; });
+            if (st->stop) break;
+            st->outstanding++;
+        }
+        const int j = (int)(k % kStreamSlots);
+        orph_stream::Job &job = st->jobs[j];
+        int rc = orph_ingest_next_slot(st->ing, st->batch_reads, &job.slot);
+        if (rc == ORPH_OK && job.slot->b.n_reads == 0) {  // end of file
+            if (prev >= 0) {
+                rc = stream_complete(st, st->jobs[prev]);
+                if (rc != ORPH_OK) { fail_with(rc); return; }
+                publish(prev);
+            }
+            std::lock_guard<std::mutex> lk(st->mu);
+            st->outstanding--;
+            st->eof = true;
+            st->cv.notify_all();
+            return;
+        }
+        if (rc == ORPH_OK) rc = stream_enqueue(st, job);
+        if (rc != ORPH_OK) {
+            cudaStreamSynchronize(st->ctx->stream);
+            fail_with(rc);
+            return;
+        }
+        if (prev >= 0) {
+            rc = stream_complete(st, st->jobs[prev]);
+            if (rc != ORPH_OK) { fail_with(rc); return; }
+            publish(prev);
+        }
+        prev = j;
+        k++;
+    }
+    cudaStreamSynchronize(st->ctx->stream);
+}
+
+extern "C" int orph_stream_open(orph_ctx *ctx, const orph_filter *f, const char *path, const uint8_t lut[256], double jaccard_threshold,
+                                uint64_t batch_reads, int n_threads, orph_stream **out)
+{
+    if (!ctx || !f || !path || !lut || !out) return fail(ORPH_E_INVALID, "orph_stream_open: NULL argument");
+    *out = nullptr;
+    if (f->device != ctx->device) return fail(ORPH_E_INVALID, "orph_stream_open: filter lives on device %d, context on %d", f->device, ctx->device);
+    if (std::isnan(jaccard_threshold)) return fail(ORPH_E_INVALID, "orph_stream_open: jaccard_threshold is NaN");
+    DeviceGuard guard(ctx->device);
+    if (n_threads <= 0) {  // the cores this process may run on, shared between the ranks of one node
+        cpu_set_t set;
+        n_threads = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+        const char *lws = getenv("LOCAL_WORLD_SIZE");
+        const int ranks = lws ? atoi(lws) : 1;
+        if (ranks > 1) n_threads /= ranks;
+        n_threads = std::max(1, std::min(n_threads, 64));
+    }
+    orph_ingest *ing = nullptr;
+    int rc = orph_ingest_open_with(path, n_threads, kStreamSlots, IngestAlloc{pinned_alloc, pinned_release}, &ing);
+    if (rc != ORPH_OK) return rc;
+    orph_stream *st = new (std::nothrow) orph_stream();
+    if (!st) {
+        orph_ingest_close(ing);
+        return fail(ORPH_E_NOMEM, "out of host memory");
+    }
+    st->ing = ing;
+    st->f = f;
+    memcpy(st->lut, lut, 256);
+    st->thr = jaccard_threshold;
+    st->batch_reads = batch_reads ? batch_reads : (1u << 20);
+    rc = orph_ctx_create(ctx->device, nullptr, &st->ctx);
+    if (rc == ORPH_OK) {
+        st->ctx->force_exact = ctx->force_exact;
+        st->ctx->disable_task_kernel = ctx->disable_task_kernel;
+        for (auto &job : st->jobs)
+            if (cudaEventCreateWithFlags(&job.done, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) rc = fail(ORPH_E_CUDA, "cudaEventCreate failed");
+    }
+    if (rc != ORPH_OK) {
+        orph_stream_close(st);
+        return rc;
+    }
+    st->worker = std::thread(stream_worker, st);
+    *out = st;
+    return ORPH_OK;
+}
+
+extern "C" int orph_stream_next(orph_stream *st, orph_stream_batch *out)
+{
+    if (!st || !out) return fail(ORPH_E_INVALID, "orph_stream_next: NULL argument");
+    memset(out, 0, sizeof(*out));
+    std::unique_lock<std::mutex> lk(st->mu);
+    if (st->held >= 0) {  // the caller is done with the previous batch: its slot goes back to the parser
+        st->held = -1;
+        st->outstanding--;
+        st->cv.notify_all();
+    }
+    st->cv.wait(lk, [&] { return !st->finished.empty() || st->eof; });
+    if (st->finished.empty()) {
+        if (st->error != ORPH_OK) return fail(st->error, "%s", st->error_text.c_str());
+        return ORPH_OK;  // end of file: n_reads == 0
+    }
+    const int j = st->finished.front();
+    st->finished.pop_front();
+    st->held = j;
+    lk.unlock();
+    const orph_stream::Job &job = st->jobs[j];
+    const orph_host::FusedBatch &b = job.slot->b;
+    out->n_reads = job.n;
+    out->results = (const orph_read_result *)job.results.p;
+    out->names = b.names;
+    out->name_offsets = b.name_off;
+    out->text = job.slot->text;
+    out->seq_start = b.seq_start;
+    out->seq_len = b.seq_len;
+    out->n_byte_path = job.n_side;
+    out->status = job.status;
+    return ORPH_OK;
+}
+
+extern "C" void orph_stream_close(orph_stream *st)
+{
+    if (!st) return;
+    {
+        std::lock_guard<std::mutex> lk(st->mu);
+        st->stop = true;
+        st->cv.notify_all();
+    }
+    if (st->worker.joinable()) st->worker.join();
+    if (st->ctx) {
+        DeviceGuard guard(st->ctx->device);
+        cudaStreamSynchronize(st->ctx->stream);
+        for (DevBuf *b : {&st->d_packed, &st->d_off32, &st->d_off64, &st->d_results, &st->d_side_ascii, &st->d_side_offsets, &st->d_side_results}) b->release();
+        for (auto &job : st->jobs) {
+            for (PinnedBuf *b : {&job.results, &job.side_ascii, &job.side_offsets, &job.side_results, &job.status_word}) b->release();
+            if (job.done) cudaEventDestroy(job.done);
+        }
+        orph_ingest_close(st->ing);  // pinned slot memory: while the device is still current
+        st->ing = nullptr;
+        orph_ctx_destroy(st->ctx);
+    }
+    if (st->ing) orph_ingest_close(st->ing);
+    delete st;
+}

@@ -312,6 +312,87 @@ def score_reads_device(graph, d_reads_ptr, d_offsets_ptr, n_reads, max_read_len,
                                               float(jaccard_threshold), ctypes.c_void_p(d_out_ptr)))
 
 
+class StreamBatch:
+    """One scored batch of a ScoringStream.  ``results`` is a view into the library's pinned memory and, like every other
+    pointer here, only valid until the stream moves on: copy what must outlive the iteration."""
+
+    def __init__(self, raw):
+        self._raw = raw
+        self.n_reads = int(raw.n_reads)
+        self.n_byte_path = int(raw.n_byte_path)
+        self.status = int(raw.status)
+        self.results = np.ctypeslib.as_array(ctypes.cast(raw.results, ctypes.POINTER(ctypes.c_uint8)),
+                                             shape=(self.n_reads * READ_RESULT_DTYPE.itemsize,)).view(READ_RESULT_DTYPE)
+
+    def names(self):
+        """fastx.NameList (owns copies of the name bytes and offsets)."""
+        from .fastx import NameList
+
+        n = self.n_reads
+        offsets = np.ctypeslib.as_array(ctypes.cast(self._raw.name_offsets, ctypes.POINTER(ctypes.c_uint64)), shape=(n + 1,)).copy()
+        return NameList(ctypes.string_at(self._raw.names, int(offsets[-1])) if offsets[-1] else b"", offsets)
+
+    def reads(self, index=None):
+        """(flat uint8 bytes, uint64 offsets) of the reads ``index`` (default: all of them), as the file has them."""
+        index = np.arange(self.n_reads, dtype=np.uint64) if index is None else np.ascontiguousarray(index, dtype=np.uint64)
+        offsets = np.zeros(len(index) + 1, dtype=np.uint64)
+        lib = _lib.load()
+        raw = self._raw
+        check(lib.orph_gather_reads(raw.text, raw.seq_start, raw.seq_len, ptr(index), len(index), None, ptr(offsets)))
+        flat = np.empty(max(int(offsets[-1]), 1), dtype=np.uint8)
+        check(lib.orph_gather_reads(raw.text, raw.seq_start, raw.seq_len, ptr(index), len(index), ptr(flat), ptr(offsets)))
+        return flat[: int(offsets[-1])], offsets
+
+
+class ScoringStream:
+    """``for batch in ScoringStream(graph, path, lut, threshold)``: the file is parsed, 2-bit packed, copied and scored by
+    the native library (orph_stream_*); Python sees one finished StreamBatch per iteration.  Stands in for the loop over
+    ``screed.open(reads)`` in Translate.score_reads_per_file (translate.py:367-372)."""
+
+    def __init__(self, graph, path, lut, jaccard_threshold, batch_reads=1 << 20, n_threads=0, ctx=None):
+        self._lib = _lib.load()
+        self.ctx = ctx or graph.ctx
+        lut = np.ascontiguousarray(lut, dtype=np.uint8)
+        h = ctypes.c_void_p()
+        rc = self._lib.orph_stream_open(self.ctx._h, graph._h, os.fsencode(path), ptr(lut), float(jaccard_threshold), int(batch_reads),
+                                        int(n_threads), ctypes.byref(h))
+        if rc == _lib.ORPH_E_INVALID and "unknown file format" in _lib.last_error():
+            raise ValueError(f"unknown file format for '{path}'")
+        if rc == _lib.ORPH_E_IO:
+            raise OSError(_lib.last_error())
+        check(rc)
+        self._h = h
+        self._graph = graph  # the filter must outlive the stream
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.orph_stream_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __iter__(self):
+        raw = _lib.StreamBatch()
+        while True:
+            rc = self._lib.orph_stream_next(self._h, ctypes.byref(raw))
+            if rc == _lib.ORPH_E_IO:
+                raise OSError(_lib.last_error())
+            check(rc)
+            if raw.n_reads == 0:
+                return
+            yield StreamBatch(raw)
+
+
 def translate_frames(ctx, reads, offsets, item_read, item_frame):
     """Un-encoded peptides of the listed (read index, frame key) pairs, translated on the GPU with the
     reference's codon semantics -> list of str in item order."""
