@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ORPH_ABI_VERSION 1
+#define ORPH_ABI_VERSION 2
 #define ORPH_MAX_TABLES 16
 
 typedef enum orph_status {
@@ -292,10 +292,16 @@ void orph_stream_close(orph_stream *st);
  * jaccard as Python's repr(float) of n_hits / n_kmers or `nan`, n_kmers as an int or `nan`.  name_fields holds
  * the read ids ALREADY rendered as CSV fields (the caller quotes the rare ids that need it), category_text[c]
  * the CSV field of category code c (NULL where the alphabet has none), filename_field likewise.
- * Does not write the header line. */
+ * Does not write the header line.  Blocks of reads are formatted on n_threads host threads (<= 0: every core) and written
+ * at their places in the file in parallel. */
 int orph_csv_write_scores(const char *path, int append, const uint8_t *name_fields, const uint64_t *name_offsets,
                           uint64_t n_reads, const orph_read_result *results, const char *const *category_text,
-                          const char *filename_field);
+                          const char *filename_field, int n_threads);
+/* Helpers of the JSON summary (create_save_summary.py:180-222 groups rows by read id): 64-bit hashes of a batch's read
+ * ids, and whether a set of such hashes is duplicate-free.  all_distinct == 1 proves the ids pairwise different;
+ * 0 means two ids are equal or, very rarely, collide: the caller then compares the ids themselves. */
+int orph_hash_names(const uint8_t *names, const uint64_t *name_offsets, uint64_t n, uint64_t *out_hashes, int n_threads);
+int orph_u64_all_distinct(const uint64_t *values, uint64_t n, int n_threads, int *all_distinct);
 /* The FASTA records Translate emits for one batch (translate.py:244-298), in read order then frame order:
  *   kind 0  coding peptides (the stdout stream): ">{name}__translation_frame:{f}__jaccard:{j}" with every space
  *           replaced by "__", then the peptide;

@@ -97,7 +97,9 @@ PROTOTYPES = {
     "orph_stream_open": (ctypes.c_int, [_vp, _vp, ctypes.c_char_p, _u8p, ctypes.c_double, ctypes.c_uint64, ctypes.c_int, _pp]),
     "orph_stream_next": (ctypes.c_int, [_vp, ctypes.POINTER(StreamBatch)]),
     "orph_stream_close": (None, [_vp]),
-    "orph_csv_write_scores": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, _u8p, _u64p, ctypes.c_uint64, _vp, _vp, ctypes.c_char_p]),
+    "orph_csv_write_scores": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, _u8p, _u64p, ctypes.c_uint64, _vp, _vp, ctypes.c_char_p, ctypes.c_int]),
+    "orph_hash_names": (ctypes.c_int, [_u8p, _u64p, ctypes.c_uint64, _u64p, ctypes.c_int]),
+    "orph_u64_all_distinct": (ctypes.c_int, [_u64p, ctypes.c_uint64, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
     "orph_format_fasta": (ctypes.c_int, [ctypes.c_int, _u8p, _u64p, ctypes.c_uint64, _vp, _u8p, _u64p, _u8p, _u64p, ctypes.c_int, _u8p,
                                          ctypes.c_uint64, _u64p]),
     "orph_format_float_repr": (ctypes.c_int, [ctypes.c_double, ctypes.c_char_p]),

@@ -139,7 +139,7 @@ class ScoreTable:
         records = np.ascontiguousarray(records)
         arr = (ctypes.c_char_p * 6)(*texts)
         _lib.check(lib.orph_csv_write_scores(os.fsencode(path), 1, _lib.ptr(blob), _lib.ptr(offsets), n_fields,
-                                             _lib.ptr(records), arr, self._csv_field(filename).encode()))
+                                             _lib.ptr(records), arr, self._csv_field(filename).encode(), 0))
 
     # -- JSON summary --------------------------------------------------------------------------------------
     def empty_categories(self):

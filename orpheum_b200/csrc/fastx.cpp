@@ -17,6 +17,7 @@
 #include <vector>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <thread>
 
@@ -509,63 +510,116 @@ extern "C" int orph_format_float_repr(double v, char *out32)
 
 extern "C" int orph_csv_write_scores(const char *path, int append, const uint8_t *name_fields, const uint64_t *name_offsets,
                                      uint64_t n_reads, const orph_read_result *results, const char *const *category_text,
-                                     const char *filename_field)
+                                     const char *filename_field, int n_threads)
 {
     if (!path || !category_text || !filename_field || (n_reads && (!name_fields || !name_offsets || !results)))
         return orph_set_error(ORPH_E_INVALID, "orph_csv_write_scores: NULL argument");
-    FILE *f = fopen(path, append ? "ab" : "wb");
-    if (!f) return orph_set_error(ORPH_E_IO, "cannot open '%s' for writing", path);
+    // (no O_APPEND: pwrite would ignore its offset)
+    const int fd = open(path, O_WRONLY | O_CREAT | (append ? 0 : O_TRUNC), 0666);
+    if (fd < 0) return orph_set_error(ORPH_E_IO, "cannot open '%s' for writing", path);
+    struct stat st;
+    uint64_t file_at = 0;
+    if (append && fstat(fd, &st) == 0) file_at = (uint64_t)st.st_size;
+    // everything of a row behind the two numbers, per (category, frame): ",<category>,<frame>,<filename>\n"
     static const char *kFrames[6] = {"1", "2", "3", "-1", "-2", "-3"};
-    std::vector<char> buf;
-    buf.reserve(1 << 22);
-    const size_t fn_len = strlen(filename_field);
-    size_t cat_len[6];
-    for (int c = 0; c < 6; c++) cat_len[c] = category_text[c] ? strlen(category_text[c]) : 0;
-    char num[48];
-    bool ok = true;
-    for (uint64_t r = 0; r < n_reads && ok; r++) {
-        const uint8_t *name = name_fields + name_offsets[r];
-        const size_t name_len = (size_t)(name_offsets[r + 1] - name_offsets[r]);
-        const orph_read_result &res = results[r];
+    std::string tail[6][6];
+    size_t max_tail = 0;
+    for (int c = 0; c < 6; c++)
         for (int fr = 0; fr < 6; fr++) {
-            const unsigned cat = res.category[fr];
-            if (cat > 5 || !category_text[cat]) {
-                fclose(f);
-                return orph_set_error(ORPH_E_INVALID, "orph_csv_write_scores: read %llu frame %d has category %u without a text",
-                                      (unsigned long long)r, fr, cat);
-            }
-            buf.insert(buf.end(), name, name + name_len);
-            buf.push_back(',');
-            const bool scored = cat == ORPH_CAT_CODING || cat == ORPH_CAT_NON_CODING;
-            if (scored) {
-                const size_t n = py_repr_double((double)res.n_hits[fr] / (double)res.n_kmers[fr], num);
-                buf.insert(buf.end(), num, num + n);
-            } else {
-                buf.insert(buf.end(), {'n', 'a', 'n'});
-            }
-            buf.push_back(',');
-            if (scored || cat == ORPH_CAT_LOW_COMPLEXITY_PEPTIDE) {
-                const int n = snprintf(num, sizeof(num), "%u", (unsigned)res.n_kmers[fr]);
-                buf.insert(buf.end(), num, num + n);
-            } else {
-                buf.insert(buf.end(), {'n', 'a', 'n'});
-            }
-            buf.push_back(',');
-            buf.insert(buf.end(), category_text[cat], category_text[cat] + cat_len[cat]);
-            buf.push_back(',');
-            buf.insert(buf.end(), kFrames[fr], kFrames[fr] + strlen(kFrames[fr]));
-            buf.push_back(',');
-            buf.insert(buf.end(), filename_field, filename_field + fn_len);
-            buf.push_back('\n');
+            if (!category_text[c]) continue;
+            tail[c][fr] = std::string(",") + category_text[c] + "," + kFrames[fr] + "," + filename_field + "\n";
+            max_tail = std::max(max_tail, tail[c][fr].size());
         }
-        if (buf.size() >= (1 << 22)) {
-            ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size();
-            buf.clear();
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    n_threads = (int)std::min<uint64_t>((uint64_t)std::min(n_threads, 64), std::max<uint64_t>(1, n_reads / 4096));
+    orph_host::Pool pool(n_threads);
+    constexpr uint64_t kBlock = 8192;
+    const uint64_t n_blocks = (n_reads + kBlock - 1) / kBlock, group = (uint64_t)n_threads * 4;
+    std::vector<std::vector<char>> bufs(std::min(group, std::max<uint64_t>(1, n_blocks)));
+    std::vector<uint64_t> used(bufs.size(), 0), at(bufs.size(), 0);
+    std::atomic<uint64_t> bad_read{~0ull};
+    std::atomic<bool> io_ok{true};
+    for (uint64_t g0 = 0; g0 < n_blocks && io_ok.load() && bad_read.load() == ~0ull; g0 += group) {
+        const uint64_t g1 = std::min(n_blocks, g0 + group);
+        pool.run(g1 - g0, [&](uint64_t k) {
+            const uint64_t r0 = (g0 + k) * kBlock, r1 = std::min(n_reads, r0 + kBlock);
+            std::vector<char> &buf = bufs[k];
+            const uint64_t need = 6 * ((name_offsets[r1] - name_offsets[r0]) + (r1 - r0) * (40 + max_tail));
+            if (buf.size() < need) buf.resize(need);
+            char *o = buf.data();
+            // (n_hits, n_kmers) -> repr(n_hits / n_kmers): the same few quotients come back all the time
+            struct Memo { uint32_t key; uint32_t len; char txt[24]; };
+            static thread_local Memo memo[1024];
+            static thread_local bool memo_ready = false;
+            if (!memo_ready) {
+                for (auto &e : memo) e.key = ~0u;
+                memo_ready = true;
+            }
+            for (uint64_t r = r0; r < r1; r++) {
+                const uint8_t *name = name_fields + name_offsets[r];
+                const size_t name_len = (size_t)(name_offsets[r + 1] - name_offsets[r]);
+                const orph_read_result &res = results[r];
+                for (int fr = 0; fr < 6; fr++) {
+                    const unsigned cat = res.category[fr];
+                    if (cat > 5 || !category_text[cat]) {
+                        uint64_t expect = ~0ull;
+                        bad_read.compare_exchange_strong(expect, r);
+                        used[k] = 0;
+                        return;
+                    }
+                    memcpy(o, name, name_len);
+                    o += name_len;
+                    *o++ = ',';
+                    const bool scored = cat == ORPH_CAT_CODING || cat == ORPH_CAT_NON_CODING;
+                    if (scored) {
+                        const uint32_t key = ((uint32_t)res.n_hits[fr] << 16) | res.n_kmers[fr];
+                        Memo &e = memo[(key * 2654435761u) >> 22];
+                        if (e.key != key) {
+                            e.key = key;
+                            e.len = (uint32_t)py_repr_double((double)res.n_hits[fr] / (double)res.n_kmers[fr], e.txt);
+                        }
+                        memcpy(o, e.txt, e.len);
+                        o += e.len;
+                    } else {
+                        memcpy(o, "nan", 3);
+                        o += 3;
+                    }
+                    *o++ = ',';
+                    if (scored || cat == ORPH_CAT_LOW_COMPLEXITY_PEPTIDE) {
+                        auto res_n = std::to_chars(o, o + 8, (unsigned)res.n_kmers[fr]);
+                        o = res_n.ptr;
+                    } else {
+                        memcpy(o, "nan", 3);
+                        o += 3;
+                    }
+                    const std::string &t = tail[cat][fr];
+                    memcpy(o, t.data(), t.size());
+                    o += t.size();
+                }
+            }
+            used[k] = (uint64_t)(o - buf.data());
+        });
+        if (bad_read.load() != ~0ull) break;
+        for (uint64_t k = 0; k < g1 - g0; k++) {
+            at[k] = file_at;
+            file_at += used[k];
         }
+        pool.run(g1 - g0, [&](uint64_t k) {
+            uint64_t done = 0;
+            while (done < used[k]) {
+                const ssize_t w = pwrite(fd, bufs[k].data() + done, (size_t)(used[k] - done), (off_t)(at[k] + done));
+                if (w <= 0) {
+                    io_ok.store(false);
+                    return;
+                }
+                done += (uint64_t)w;
+            }
+        });
     }
-    if (ok && !buf.empty()) ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size();
-    ok = (fclose(f) == 0) && ok;
-    return ok ? ORPH_OK : orph_set_error(ORPH_E_IO, "write to '%s' failed", path);
+    const bool closed = close(fd) == 0;
+    if (bad_read.load() != ~0ull)
+        return orph_set_error(ORPH_E_INVALID, "orph_csv_write_scores: read %llu has a frame category without a text", (unsigned long long)bad_read.load());
+    return io_ok.load() && closed ? ORPH_OK : orph_set_error(ORPH_E_IO, "write to '%s' failed", path);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -623,5 +677,91 @@ extern "C" int orph_format_fasta(int kind, const uint8_t *names, const uint64_t 
         }
     }
     *out_len = at;
+    return ORPH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Are all read ids different?  The JSON summary groups rows by read id (create_save_summary.py:180-222); when every id
+// occurs once -- the usual case -- the groups are the reads themselves and no per-id bookkeeping is needed.  Ids are
+// compared through 64-bit hashes: "distinct" is certain, "not distinct" may be a hash collision (the caller then takes
+// its exact path).
+// ------------------------------------------------------------------------------------------------
+static inline uint64_t hash_bytes64(const uint8_t *p, size_t len)
+{
+    const uint64_t m = 0xc6a4a7935bd1e995ULL;
+    uint64_t h = 0x9e3779b97f4a7c15ULL ^ (len * m);
+    for (; len >= 8; p += 8, len -= 8) {
+        uint64_t k;
+        memcpy(&k, p, 8);
+        k *= m; k ^= k >> 47; k *= m;
+        h ^= k; h *= m;
+    }
+    uint64_t k = 0;
+    for (size_t i = 0; i < len; i++) k |= (uint64_t)p[i] << (8 * i);
+    h ^= k; h *= m;
+    h ^= h >> 47; h *= m; h ^= h >> 47;
+    return h;
+}
+
+extern "C" int orph_hash_names(const uint8_t *names, const uint64_t *name_offsets, uint64_t n, uint64_t *out_hashes, int n_threads)
+{
+    if (n && (!names || !name_offsets || !out_hashes)) return orph_set_error(ORPH_E_INVALID, "orph_hash_names: NULL argument");
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    n_threads = (int)std::min<uint64_t>((uint64_t)std::min(n_threads, 64), std::max<uint64_t>(1, n / 65536));
+    constexpr uint64_t kBlock = 1 << 15;
+    auto work = [&](uint64_t blk) {
+        const uint64_t r1 = std::min(n, (blk + 1) * kBlock);
+        for (uint64_t r = blk * kBlock; r < r1; r++) out_hashes[r] = hash_bytes64(names + name_offsets[r], (size_t)(name_offsets[r + 1] - name_offsets[r]));
+    };
+    const uint64_t n_blk = (n + kBlock - 1) / kBlock;
+    if (n_threads > 1) {
+        orph_host::Pool pool(n_threads);
+        pool.run(n_blk, work);
+    } else {
+        for (uint64_t b = 0; b < n_blk; b++) work(b);
+    }
+    return ORPH_OK;
+}
+
+extern "C" int orph_u64_all_distinct(const uint64_t *values, uint64_t n, int n_threads, int *all_distinct)
+{
+    if (!all_distinct || (n && !values)) return orph_set_error(ORPH_E_INVALID, "orph_u64_all_distinct: NULL argument");
+    *all_distinct = 1;
+    if (n < 2) return ORPH_OK;
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    n_threads = (int)std::min<uint64_t>((uint64_t)std::min(n_threads, 64), std::max<uint64_t>(1, n / 65536));
+    // partition by the top byte (two parallel passes), then sort every bucket on its own
+    constexpr uint64_t kBlock = 1 << 16;
+    const uint64_t n_blk = (n + kBlock - 1) / kBlock;
+    std::vector<uint64_t> hist(n_blk * 256, 0), tmp(n);
+    orph_host::Pool pool(n_threads);
+    pool.run(n_blk, [&](uint64_t blk) {
+        uint64_t *h = hist.data() + blk * 256;
+        const uint64_t r1 = std::min(n, (blk + 1) * kBlock);
+        for (uint64_t r = blk * kBlock; r < r1; r++) h[values[r] >> 56]++;
+    });
+    uint64_t bucket_start[257], run = 0;
+    for (int b = 0; b < 256; b++) {
+        bucket_start[b] = run;
+        for (uint64_t blk = 0; blk < n_blk; blk++) {
+            const uint64_t c = hist[blk * 256 + b];
+            hist[blk * 256 + b] = run;
+            run += c;
+        }
+    }
+    bucket_start[256] = run;
+    pool.run(n_blk, [&](uint64_t blk) {
+        uint64_t *cur = hist.data() + blk * 256;
+        const uint64_t r1 = std::min(n, (blk + 1) * kBlock);
+        for (uint64_t r = blk * kBlock; r < r1; r++) tmp[cur[values[r] >> 56]++] = values[r];
+    });
+    std::atomic<int> dup{0};
+    pool.run(256, [&](uint64_t b) {
+        uint64_t *a = tmp.data() + bucket_start[b], *e = tmp.data() + bucket_start[b + 1];
+        if (e - a < 2 || dup.load(std::memory_order_relaxed)) return;
+        std::sort(a, e);
+        if (std::adjacent_find(a, e) != e) dup.store(1);
+    });
+    *all_distinct = dup.load() ? 0 : 1;
     return ORPH_OK;
 }

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <sched.h>
 #include <thread>
 #include <vector>
@@ -115,6 +116,83 @@ struct DevBuf {
     }
 };
 
+// Process-wide cache of pinned host buffers.  cudaHostAlloc pins page by page (tens of milliseconds per 100 MB), which
+// would dominate a short scoring stream or the first call of every context; buffers handed back are kept (up to kCap
+// bytes) and given to the next request they fit.
+class PinnedCache {
+public:
+    void *get(size_t need, size_t *got)
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            size_t best = free_.size();
+            for (size_t i = 0; i < free_.size(); i++)
+                if (free_[i].second >= need && free_[i].second <= 2 * need + (1u << 20) && (best == free_.size() || free_[i].second < free_[best].second)) best = i;
+            if (best < free_.size()) {
+                void *p = free_[best].first;
+                *got = free_[best].second;
+                cached_ -= free_[best].second;
+                free_.erase(free_.begin() + (long)best);
+                live_.push_back({p, *got});
+                return p;
+            }
+        }
+        void *p = nullptr;
+        if (cudaHostAlloc(&p, need, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            trim(0);  // give the cached buffers back and try once more
+            if (cudaHostAlloc(&p, need, cudaHostAllocDefault) != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+        }
+        *got = need;
+        std::lock_guard<std::mutex> lk(mu_);
+        live_.push_back({p, need});
+        return p;
+    }
+    void put(void *p)
+    {
+        if (!p) return;
+        size_t size = 0;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            for (size_t i = 0; i < live_.size(); i++)
+                if (live_[i].first == p) {
+                    size = live_[i].second;
+                    live_.erase(live_.begin() + (long)i);
+                    break;
+                }
+            if (size && cached_ + size <= kCap) {
+                free_.push_back({p, size});
+                cached_ += size;
+                return;
+            }
+        }
+        cudaFreeHost(p);
+    }
+    void trim(size_t keep)
+    {
+        std::vector<void *> drop;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            while (cached_ > keep && !free_.empty()) {
+                drop.push_back(free_.back().first);
+                cached_ -= free_.back().second;
+                free_.pop_back();
+            }
+        }
+        for (void *p : drop) cudaFreeHost(p);
+    }
+
+private:
+    static constexpr size_t kCap = 4ull << 30;
+    std::mutex mu_;
+    std::vector<std::pair<void *, size_t>> free_, live_;
+    size_t cached_ = 0;
+};
+static PinnedCache g_pinned;
+
 // pinned host buffer
 struct PinnedBuf {
     void *p = nullptr;
@@ -122,23 +200,35 @@ struct PinnedBuf {
     int ensure(size_t need)
     {
         if (need <= cap) return ORPH_OK;
-        if (p) cudaFreeHost(p);
+        g_pinned.put(p);
         p = nullptr;
         cap = 0;
-        size_t want = need + need / 8 + 256;
-        CUDA_TRY(cudaHostAlloc(&p, want, cudaHostAllocDefault));
-        cap = want;
+        size_t got = 0;
+        p = g_pinned.get(need + need / 8 + 256, &got);
+        if (!p) return fail(ORPH_E_NOMEM, "cudaHostAlloc of %zu bytes failed", need);
+        cap = got;
         return ORPH_OK;
     }
     void release()
     {
-        if (p) cudaFreeHost(p);
+        g_pinned.put(p);
         p = nullptr;
         cap = 0;
     }
 };
 
-constexpr int kPipeSlots = 4;  // chunks in flight in the host-buffer pipeline
+constexpr int kLaneSlots = 3;  // chunks in flight per lane of the host-buffer pipeline (ingest_pipeline.inl)
+
+// staging of one chunk in flight: device buffers, the pinned buffer a host-packed chunk is built in, and the events
+// that order its three stages (H2D -> kernels -> D2H)
+struct PipeSlot {
+    DevBuf in_reads, in_offsets, out_results;
+    PinnedBuf h_stage;
+    cudaEvent_t ev_in = nullptr, ev_kernels = nullptr, ev_out = nullptr;  // ev_out: blocking-sync (the host waits on it to reuse the slot)
+    cudaEvent_t ev_h2d_begin = nullptr, ev_h2d_end = nullptr;             // timed: the H2D rate reported by orph_ctx_ingest_stats
+    uint64_t h2d_bytes = 0;
+    bool used = false;
+};
 
 struct orph_ctx {
     int device = 0;
@@ -159,12 +249,8 @@ struct orph_ctx {
     DevBuf needs_bytes;          // uint8 per read (ASCII input)
     DevBuf packed;               // 2-bit stream built from ASCII input
     DevBuf in_reads, in_offsets, out_results;  // staging for the index build
-    DevBuf in_reads2[kPipeSlots], in_offsets2[kPipeSlots], out_results2[kPipeSlots];  // staging slots of orph_score_reads
-    PinnedBuf h_packed[kPipeSlots];                      // host-packed 2-bit words of a chunk, pinned for the async H2D
-    cudaStream_t s_in = nullptr, s_out = nullptr;        // copy streams of the host-buffer pipeline
-    cudaEvent_t ev_in[kPipeSlots] = {}, ev_kernels[kPipeSlots] = {}, ev_out[kPipeSlots] = {};
-    cudaEvent_t ev_h2d_begin[kPipeSlots] = {}, ev_h2d_end[kPipeSlots] = {};  // timed: calibrate the H2D rate the planner uses
-    uint64_t h2d_bytes[kPipeSlots] = {};
+    PipeSlot lane_slots[2][kLaneSlots];                  // [0] the copy-engine lane, [1] the host-packing lane of orph_score_reads
+    cudaStream_t s_in[2] = {nullptr, nullptr}, s_out = nullptr;  // H2D stream per lane, one D2H stream
     bool pipe_ready = false;
     int host_threads = -1;                               // host packing threads: -1 auto, 0 = never pack on the host
     orph_host::Pool *pool = nullptr;
@@ -189,11 +275,12 @@ static int verify_guards(orph_ctx *ctx)
                               {"task_queue_sorted", &ctx->task_queue_sorted}, {"needs_bytes", &ctx->needs_bytes}, {"packed", &ctx->packed},
                               {"in_reads", &ctx->in_reads}, {"in_offsets", &ctx->in_offsets}, {"out_results", &ctx->out_results}, {"misc", &ctx->misc},
                               {"seen", &ctx->seen}, {"long_scratch", &ctx->long_scratch}};
-    for (int q = 0; q < kPipeSlots; q++) {
-        all.push_back({"in_reads2", &ctx->in_reads2[q]});
-        all.push_back({"in_offsets2", &ctx->in_offsets2[q]});
-        all.push_back({"out_results2", &ctx->out_results2[q]});
-    }
+    for (auto &lane : ctx->lane_slots)
+        for (PipeSlot &q : lane) {
+            all.push_back({"slot.in_reads", &q.in_reads});
+            all.push_back({"slot.in_offsets", &q.in_offsets});
+            all.push_back({"slot.out_results", &q.out_results});
+        }
     for (const Named &n : all)
         if (!n.b->slack_intact()) return fail(ORPH_E_CUDA, "ORPHEUM_B200_GUARD: a kernel wrote past the end of scratch buffer '%s'", n.name);
     return ORPH_OK;
@@ -317,23 +404,20 @@ extern "C" void orph_ctx_destroy(orph_ctx *ctx)
     for (DevBuf *b : {&ctx->counters, &ctx->queue, &ctx->bytes_queue, &ctx->task_queue, &ctx->task_queue_sorted, &ctx->needs_bytes, &ctx->packed, &ctx->in_reads,
                       &ctx->in_offsets, &ctx->out_results, &ctx->misc, &ctx->seen, &ctx->long_scratch})
         b->release();
-    for (int b = 0; b < kPipeSlots; b++) {
-        ctx->in_reads2[b].release();
-        ctx->in_offsets2[b].release();
-        ctx->out_results2[b].release();
-        ctx->h_packed[b].release();
-    }
+    for (auto &lane : ctx->lane_slots)
+        for (PipeSlot &q : lane) {
+            q.in_reads.release();
+            q.in_offsets.release();
+            q.out_results.release();
+            q.h_stage.release();
+            for (cudaEvent_t e : {q.ev_in, q.ev_kernels, q.ev_out, q.ev_h2d_begin, q.ev_h2d_end})
+                if (e) cudaEventDestroy(e);
+        }
     delete ctx->pool;
     if (ctx->pipe_ready) {
-        cudaStreamDestroy(ctx->s_in);
+        cudaStreamDestroy(ctx->s_in[0]);
+        cudaStreamDestroy(ctx->s_in[1]);
         cudaStreamDestroy(ctx->s_out);
-        for (int b = 0; b < kPipeSlots; b++) {
-            cudaEventDestroy(ctx->ev_in[b]);
-            cudaEventDestroy(ctx->ev_kernels[b]);
-            cudaEventDestroy(ctx->ev_out[b]);
-            cudaEventDestroy(ctx->ev_h2d_begin[b]);
-            cudaEventDestroy(ctx->ev_h2d_end[b]);
-        }
     }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -19,14 +19,10 @@ namespace {
 
 void *pinned_alloc(size_t n)
 {
-    void *p = nullptr;
-    if (cudaHostAlloc(&p, n ? n : 1, cudaHostAllocDefault) != cudaSuccess) {
-        cudaGetLastError();
-        return nullptr;
-    }
-    return p;
+    size_t got = 0;
+    return g_pinned.get(n ? n : 1, &got);
 }
-void pinned_release(void *p) { cudaFreeHost(p); }
+void pinned_release(void *p) { g_pinned.put(p); }
 
 constexpr int kStreamSlots = 4;  // being parsed + on the GPU + finished + held by the caller
 
@@ -169,7 +165,10 @@ static void stream_worker(orph_stream *st)
         }
         const int j = (int)(k % kStreamSlots);
         orph_stream::Job &job = st->jobs[j];
+        static const bool trace = getenv("ORPHEUM_B200_TRACE") != nullptr;
+        const auto t0 = std::chrono::steady_clock::now();
         int rc = orph_ingest_next_slot(st->ing, st->batch_reads, &job.slot);
+        const auto t1 = std::chrono::steady_clock::now();
         if (rc == ORPH_OK && job.slot->b.n_reads == 0) {  // end of file
             if (prev >= 0) {
                 rc = stream_complete(st, st->jobs[prev]);
@@ -188,10 +187,17 @@ static void stream_worker(orph_stream *st)
             fail_with(rc);
             return;
         }
+        const auto t2 = std::chrono::steady_clock::now();
         if (prev >= 0) {
             rc = stream_complete(st, st->jobs[prev]);
             if (rc != ORPH_OK) { fail_with(rc); return; }
             publish(prev);
+        }
+        if (trace) {
+            const auto t3 = std::chrono::steady_clock::now();
+            auto ms = [](auto a, auto b) { return 1e3 * std::chrono::duration<double>(b - a).count(); };
+            fprintf(stderr, "[orph trace] stream batch %llu: %llu reads (%llu byte-path), parse+pack %.2f ms, enqueue %.2f ms, wait for the batch before %.2f ms\n",
+                    (unsigned long long)k, (unsigned long long)job.n, (unsigned long long)job.n_side, ms(t0, t1), ms(t1, t2), ms(t2, t3));
         }
         prev = j;
         k++;

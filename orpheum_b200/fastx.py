@@ -112,6 +112,22 @@ class NameList:
     def __eq__(self, other):
         return self.tolist() == (other.tolist() if isinstance(other, NameList) else list(other))
 
+    def take(self, index):
+        """NameList of the names at `index` (numpy gather on the blob, no python strings)."""
+        index = np.asarray(index, dtype=np.int64)
+        offs = np.asarray(self.offsets, dtype=np.int64)
+        starts = offs[index]
+        lens = offs[index + 1] - starts
+        new_off = np.zeros(len(index) + 1, dtype=np.int64)
+        np.cumsum(lens, out=new_off[1:])
+        total = int(new_off[-1])
+        if total:
+            src = np.repeat(starts - new_off[:-1], lens) + np.arange(total, dtype=np.int64)
+            blob = np.frombuffer(self.blob, dtype=np.uint8)[src].tobytes()
+        else:
+            blob = b""
+        return NameList(blob, new_off.astype(np.uint64))
+
     def tolist(self):
         if self._list is None:
             offs = self.offsets.tolist()

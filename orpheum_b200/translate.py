@@ -15,7 +15,7 @@ import numpy as np
 from . import _lib, constants_index, constants_translate, fastx
 from .constants_translate import FRAMES, SingleReadScore, category_text
 from .create_save_summary import CreateSaveSummary
-from .gpu import concat_reads, format_fasta, score_reads, translate_frames, translate_frames_raw
+from .gpu import ScoringStream, concat_reads, format_fasta, score_reads, translate_frames, translate_frames_raw
 from .index import maybe_make_peptide_bloom_filter, maybe_save_peptide_bloom_filter
 from .sequence_encodings import encode_lut, encode_peptide
 from .translate_single_seq import TranslateSingleSeq  # noqa: F401  (re-exported: part of the reference's surface)
@@ -277,13 +277,40 @@ class Translate:
         self.maybe_open_fastas()
         try:
             for reads in self.reads:
-                for names, flat, offsets in fastx.read_batches(reads, prefetch=1):  # the next batch is parsed meanwhile
-                    results = score_reads(self.peptide_bloom_filter, flat, offsets, self._lut, self.jaccard_threshold)
-                    self._emit_batch(names, flat, offsets, results)
-                    table.append(names, results, reads)
+                if fastx._is_bz2(reads):  # bzip2 goes through the python reader
+                    for names, flat, offsets in fastx.read_batches(reads, prefetch=1):
+                        results = score_reads(self.peptide_bloom_filter, flat, offsets, self._lut, self.jaccard_threshold)
+                        self._emit_batch(names, flat, offsets, results)
+                        table.append(names, results, reads)
+                    continue
+                # file in, records out: parsed, packed, copied and scored by the native stream (orph_stream_*), the next
+                # batch on its way while this one is expanded into the outputs
+                with ScoringStream(self.peptide_bloom_filter, reads, self._lut, self.jaccard_threshold) as stream:
+                    for batch in stream:
+                        _lib.check(batch.status)  # an empty read: ZeroDivisionError, as in the reference (translate.py:83)
+                        results = batch.results.copy()
+                        names = batch.names()
+                        self._emit_stream_batch(batch, names, results)
+                        table.append(names, results, reads)
         finally:
             self.maybe_close_fastas()
         return table
+
+    def _emit_stream_batch(self, batch, names, results):
+        """Side effects of one stream batch: only the reads that emit something (a coding frame; a low-complexity
+        peptide or a non-coding frame when those files were asked for) are gathered from the text."""
+        cat = results["category"]
+        handles = self.file_handles
+        want = cat == _lib.CAT_CODING
+        if handles["low_complexity_peptide"] is not None:
+            want = want | (cat == _lib.CAT_LOW_COMPLEXITY_PEPTIDE)
+        if handles["noncoding_nucleotide"] is not None:
+            want = want | (cat == _lib.CAT_NON_CODING)
+        index = np.nonzero(want.any(axis=1))[0]
+        if len(index) == 0:
+            return
+        flat, offsets = batch.reads(index)
+        self._emit_batch(names.take(index), flat, offsets, results[index])
 
     def set_coding_scores_all_files(self):
         self.maybe_open_fastas()

@@ -33,7 +33,7 @@ def test_header_and_binding_agree(lib):
 
 
 def test_abi_version_and_struct_size(lib):
-    assert lib.orph_abi_version() == 1
+    assert lib.orph_abi_version() == 2
     assert _lib.READ_RESULT_DTYPE.itemsize == 32
     assert _lib.READ_RESULT_DTYPE.fields["category"][1] == 24
     assert _lib.READ_RESULT_DTYPE.fields["best_frame"][1] == 30

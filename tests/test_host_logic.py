@@ -515,3 +515,41 @@ def test_native_fasta_formatter_against_python(tmp_path):
         for kind in (0, 1, 2) + ((3,) if with_lcp else ()):
             got = gpu.format_fasta(kind, name_blob, name_offsets, rec, flat, offsets, pep_blob, pep_offsets, with_lcp)
             assert got.decode("utf-8") == "".join(want[kind]), (kind, with_lcp)
+
+
+def test_native_csv_writer_many_blocks_and_threads(tmp_path):
+    """orph_csv_write_scores formats blocks of reads on several threads and writes them at their places in the file: a
+    table of many blocks, appended in two calls, against csv.writer over the reference's rows."""
+    import csv as pycsv
+
+    from orpheum_b200 import _lib, build
+    from orpheum_b200.columnar import ScoreTable
+    from orpheum_b200.constants_translate import FRAMES, category_text
+
+    build.build()
+    rng = np.random.default_rng(99)
+    n = 70_000
+    rec = np.zeros(n, dtype=_lib.READ_RESULT_DTYPE)
+    cat = rng.choice(6, size=(n, 6), p=[.4, .1, .1, .2, .2, 0])
+    cat[rng.random(n) < 0.1] = 5
+    nk = rng.integers(1, 300, size=(n, 6))
+    nh = np.minimum((rng.random((n, 6)) * (nk + 1)).astype(np.int64), nk)
+    rec["category"] = cat
+    rec["n_kmers"] = np.where((cat >= 2) & (cat <= 4), nk, 0)
+    rec["n_hits"] = np.where((cat == 3) | (cat == 4), nh, 0)
+    names = [f"read{i}/{'x' * (i % 40)}" for i in range(n)]
+    table = ScoreTable("protein")
+    half = n // 2
+    table.append(names[:half], rec[:half], "a.fq")
+    table.append(names[half:], rec[half:], "b,with comma.fq")
+    table.write_csv(str(tmp_path / "native.csv"))
+    with open(tmp_path / "python.csv", "w", newline="") as f:
+        w = pycsv.writer(f, lineterminator="\n")
+        w.writerow(["read_id", "jaccard_in_peptide_db", "n_kmers", "category", "translation_frame", "filename"])
+        for i in range(n):
+            for fr in range(6):
+                c = int(cat[i, fr])
+                jac = int(rec["n_hits"][i, fr]) / int(rec["n_kmers"][i, fr]) if c in (3, 4) else np.nan
+                w.writerow([names[i], jac, int(rec["n_kmers"][i, fr]) if c in (2, 3, 4) else np.nan, category_text(c, "protein"), FRAMES[fr],
+                            "a.fq" if i < half else "b,with comma.fq"])
+    assert (tmp_path / "native.csv").read_bytes() == (tmp_path / "python.csv").read_bytes()

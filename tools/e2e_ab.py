@@ -15,16 +15,8 @@ CACHE = "/dev/shm/orph_ab"
 CONFIGS = [
     ("default", {}),
     ("no_l2_window", {"ORPHEUM_B200_NO_L2_WINDOW": "1"}),
-    ("chunk_2^20", {"ORPHEUM_B200_CHUNK_LOG2": "20"}),
-    ("chunk_2^21", {"ORPHEUM_B200_CHUNK_LOG2": "21"}),
-    ("chunk_2^22", {"ORPHEUM_B200_CHUNK_LOG2": "22"}),
-    ("chunk_2^21_no_window", {"ORPHEUM_B200_CHUNK_LOG2": "21", "ORPHEUM_B200_NO_L2_WINDOW": "1"}),
-    ("skip_kernels", {"ORPHEUM_B200_AB_SKIP": "kernels"}),
-    ("skip_d2h", {"ORPHEUM_B200_AB_SKIP": "d2h"}),
-    ("skip_h2d", {"ORPHEUM_B200_AB_SKIP": "h2d"}),
-    ("skip_kernels_d2h", {"ORPHEUM_B200_AB_SKIP": "kernels,d2h"}),
-    ("skip_kernels_h2d", {"ORPHEUM_B200_AB_SKIP": "kernels,h2d"}),
-    ("skip_h2d_d2h", {"ORPHEUM_B200_AB_SKIP": "h2d,d2h"}),
+    ("plain_chunk_2^20", {"ORPHEUM_B200_CHUNK_LOG2": "20"}),
+    ("plain_chunk_2^22", {"ORPHEUM_B200_CHUNK_LOG2": "22"}),
 ]
 
 
