@@ -431,21 +431,23 @@ def run_ours(args):
                     fh.write(b"".join(b"@read%d 1:N:0\n%s\n+\n%s\n" % (i, rows[i].tobytes(), qual) for i in range(lo, min(n_fq, lo + 200_000))))
             fq_bytes = os.path.getsize(fq)
 
+            fq_out = np.zeros(n_fq, dtype=_lib.READ_RESULT_DTYPE)  # the caller's result array (pages touched before the clock starts)
+
             def pass_fastq():
-                got, parts = 0, []
+                got = 0
                 with gpu.ScoringStream(graph, fq, lut, thr, ctx=ctx) as stream:
                     for batch in stream:
-                        parts.append(batch.results.copy())
+                        fq_out[got:got + batch.n_reads] = batch.results
                         got += batch.n_reads
-                return got, parts
+                return got
 
             pass_fastq()
             reps = 3
             t0 = time.perf_counter()
             for _ in range(reps):
-                got, parts = pass_fastq()
+                got = pass_fastq()
             dtf = (time.perf_counter() - t0) / reps
-            same_fq = got == n_fq and np.concatenate(parts).tobytes() == res_dev[:n_fq].tobytes()
+            same_fq = got == n_fq and fq_out.tobytes() == res_dev[:n_fq].tobytes()
             e2e["from_fastq"] = {"value": n_fq / dtf, "unit": UNIT, "reads": n_fq, "fastq_bytes": fq_bytes, "ms": 1e3 * dtf,
                                  "fastq_GBps": fq_bytes / dtf / 1e9, "identical_to_device_path": bool(same_fq),
                                  "path": "uncompressed four-line FASTQ on tmpfs -> orph_stream_* (mapped text parsed and 2-bit packed into "

@@ -58,7 +58,9 @@ struct PipeCall {
     double thr;
     orph_read_result *out;
     std::vector<uint64_t> *exceptions;
-    std::mutex claim_mu, enqueue_mu;
+    std::mutex claim_mu, stats_mu;
+    orph_host::Pool *scan_pool = nullptr;  // free for the front lane's offset scans (no packing lane in this call)
+    bool share_h2d = false;                // both lanes are running
     uint64_t front = 0, back = 0;  // reads [front, back) are unclaimed
     int n_front_claims = 0;
     int error = ORPH_OK;
@@ -66,7 +68,7 @@ struct PipeCall {
     bool trace = false;
     std::chrono::steady_clock::time_point t_call;
     std::vector<ChunkTrace> traces;
-    uint64_t max_chunk_reads[2], max_chunk_bases[2], min_chunk_reads = 1u << 15;
+    uint64_t max_chunk_reads[2], max_chunk_bases[2], min_chunk_reads = 1u << 16;
 
     void set_error(int rc)
     {
@@ -84,7 +86,7 @@ struct PipeCall {
         const uint64_t remaining = back - front;
         // sizes shrink as the lanes approach each other (and ramp up at the very start of lane 0), so that the pipeline
         // fills quickly and whatever finishes last is small
-        uint64_t sz = std::min<uint64_t>(max_chunk_reads[lane], std::max<uint64_t>(min_chunk_reads, remaining / 4));
+        uint64_t sz = std::min<uint64_t>(max_chunk_reads[lane], std::max<uint64_t>(min_chunk_reads, remaining / 3));
         if (lane == 0 && n_front_claims < 3) sz = std::min<uint64_t>(sz, std::max<uint64_t>(min_chunk_reads, max_chunk_reads[0] >> (3 - n_front_claims)));
         sz = std::max<uint64_t>(1, std::min(sz, remaining));
         if (remaining - sz < min_chunk_reads / 2) sz = remaining;  // no crumbs
@@ -115,17 +117,32 @@ struct PipeCall {
 
 }  // namespace
 
+// Host wait for an event by polling: a blocking-sync wait costs ~0.5 ms of wake-up latency on these hosts (measured in the
+// per-chunk timelines: every chunk that really had to wait for its slot was enqueued that much after the slot was free),
+// which is a third of a chunk's copy time.  Yields the core once the wait gets long.
+static cudaError_t wait_event_polling(cudaEvent_t e)
+{
+    for (uint32_t spins = 0;; spins++) {
+        const cudaError_t rc = cudaEventQuery(e);
+        if (rc != cudaErrorNotReady) return rc;
+        if (spins > 2000) sched_yield();
+    }
+}
+
 static int pipe_setup(orph_ctx *ctx)
 {
     if (ctx->pipe_ready) return ORPH_OK;
+    // ONE H2D stream for both lanes: copies leave in the order the lanes submit them.  With a stream per lane the copy
+    // engine served the stream that always had a copy queued and starved the other until the first ran dry.
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_in[0], cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_in[1], cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    ctx->s_in[1] = ctx->s_in[0];
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_out[0], cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_out[1], cudaStreamNonBlocking));
     for (auto &lane : ctx->lane_slots)
         for (PipeSlot &q : lane) {
             CUDA_TRY(cudaEventCreateWithFlags(&q.ev_in, cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&q.ev_kernels, cudaEventDisableTiming));
-            CUDA_TRY(cudaEventCreateWithFlags(&q.ev_out, cudaEventDisableTiming | cudaEventBlockingSync));
+            CUDA_TRY(cudaEventCreateWithFlags(&q.ev_out, cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreate(&q.ev_h2d_begin));
             CUDA_TRY(cudaEventCreate(&q.ev_h2d_end));
         }
@@ -139,7 +156,10 @@ static int pipe_enqueue_chunk(PipeCall &pc, int lane, PipeSlot &q, uint64_t lo, 
                               double host_pack_s)
 {
     orph_ctx *ctx = pc.ctx;
-    cudaStream_t s = ctx->stream, s_in = ctx->s_in[lane];
+    // lane 1 launches on its own context: an in-order kernel stream shared by the lanes would make the chunks of one
+    // lane wait for the copies of the other
+    orph_ctx *kctx = lane == 1 && ctx->lane_ctx ? ctx->lane_ctx : ctx;
+    cudaStream_t s = kctx->stream, s_in = ctx->s_in[lane], s_out = ctx->s_out[lane];
     const uint64_t *offsets = pc.offsets;
     const uint64_t m = hi - lo, b0 = offsets[lo], b1 = offsets[hi];
     int rc;
@@ -200,31 +220,31 @@ static int pipe_enqueue_chunk(PipeCall &pc, int lane, PipeSlot &q, uint64_t lo, 
     mark(1, s_in);
     CUDA_TRY(cudaEventRecord(q.ev_h2d_end, s_in));
     CUDA_TRY(cudaEventRecord(q.ev_in, s_in));
-    // ---- kernels and D2H: one chunk at a time on the kernel stream (the scratch of score_device_impl is per context)
+    // ---- kernels and D2H: one chunk at a time on the lane's kernel stream (the scratch of score_device_impl is per context)
     {
-        std::lock_guard<std::mutex> lk(pc.enqueue_mu);
         CUDA_TRY(cudaStreamWaitEvent(s, q.ev_in, 0));
         mark(2, s);
         if (fixed_len) {
             fill_offsets_kernel<<<grid_for(m + 1, 256, ctx->sm_count, 4), 256, 0, s>>>(b0, fixed_len, m + 1, (uint64_t *)q.in_offsets.p);
-            ctx->launches++;
+            kctx->launches++;
         } else if (d_rel) {
             expand_offsets_kernel<<<grid_for(m + 1, 256, ctx->sm_count, 4), 256, 0, s>>>(d_rel, b0, m + 1, (uint64_t *)q.in_offsets.p);
-            ctx->launches++;
+            kctx->launches++;
         }
         CUDA_TRY(cudaGetLastError());
         if (!skip_kernels) {
-            rc = score_device_impl(ctx, pc.f, d_ascii, b0, d_packed, pbase0, n_ascii, (const uint64_t *)q.in_offsets.p, m, max_len, pc.lut, pc.thr,
+            rc = score_device_impl(kctx, pc.f, d_ascii, b0, d_packed, pbase0, n_ascii, (const uint64_t *)q.in_offsets.p, m, max_len, pc.lut, pc.thr,
                                    (orph_read_result *)q.out_results.p);
             if (rc != ORPH_OK) return rc;
         }
         mark(3, s);
         CUDA_TRY(cudaEventRecord(q.ev_kernels, s));
-        CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, q.ev_kernels, 0));
-        mark(4, ctx->s_out);
-        if (!skip_d2h) CUDA_TRY(cudaMemcpyAsync(pc.out + lo, q.out_results.p, m * sizeof(orph_read_result), cudaMemcpyDeviceToHost, ctx->s_out));
-        mark(5, ctx->s_out);
-        CUDA_TRY(cudaEventRecord(q.ev_out, ctx->s_out));
+        CUDA_TRY(cudaStreamWaitEvent(s_out, q.ev_kernels, 0));
+        mark(4, s_out);
+        if (!skip_d2h) CUDA_TRY(cudaMemcpyAsync(pc.out + lo, q.out_results.p, m * sizeof(orph_read_result), cudaMemcpyDeviceToHost, s_out));
+        mark(5, s_out);
+        CUDA_TRY(cudaEventRecord(q.ev_out, s_out));
+        std::lock_guard<std::mutex> lk(pc.stats_mu);
         if (packed_here) ctx->chunks_packed_on_host++;
         else if (pc.reads_format == ORPH_READS_ASCII) ctx->chunks_sent_ascii++;
         if (pc.trace) pc.traces.push_back(tr);
@@ -235,10 +255,27 @@ static int pipe_enqueue_chunk(PipeCall &pc, int lane, PipeSlot &q, uint64_t lo, 
 
 // Validates a claimed chunk: the longest read (clamped to what the kernels are told), the common length when every
 // read has the same one (0 otherwise), monotonic offsets.
-static int pipe_scan_chunk(PipeCall &pc, uint64_t lo, uint64_t hi, uint32_t *max_len, uint64_t *fixed_len)
+static int pipe_scan_chunk(PipeCall &pc, uint64_t lo, uint64_t hi, uint32_t *max_len, uint64_t *fixed_len, orph_host::Pool *pool = nullptr)
 {
     uint64_t longest, shortest;
-    scan_read_lengths(pc.offsets + lo, hi - lo, &longest, &shortest);
+    constexpr uint64_t kBlock = 1u << 15;
+    if (pool && hi - lo >= 8 * kBlock) {
+        // one core reads offsets at ~10 GB/s, a 2-bit chunk of 2 M reads crosses PCIe in 1.4 ms: the scan is spread over the pool
+        const uint64_t n_blk = (hi - lo + kBlock - 1) / kBlock;
+        std::vector<uint64_t> part(2 * n_blk);
+        pool->run(n_blk, [&](uint64_t b) {
+            const uint64_t a = lo + b * kBlock;
+            scan_read_lengths(pc.offsets + a, std::min(hi, a + kBlock) - a, &part[2 * b], &part[2 * b + 1]);
+        });
+        longest = 0;
+        shortest = ~0ull;
+        for (uint64_t b = 0; b < n_blk; b++) {
+            longest = std::max(longest, part[2 * b]);
+            shortest = std::min(shortest, part[2 * b + 1]);
+        }
+    } else {
+        scan_read_lengths(pc.offsets + lo, hi - lo, &longest, &shortest);
+    }
     if (longest >= (1ULL << 63)) {  // a decreasing pair wraps around
         uint64_t at = lo;
         while (at < hi && pc.offsets[at + 1] >= pc.offsets[at]) at++;
@@ -256,14 +293,23 @@ static void pipe_front_lane(PipeCall &pc)
     uint64_t lo, hi;
     int c = 0;
     while (pc.claim(0, &lo, &hi)) {
-        PipeSlot &q = ctx->lane_slots[0][c++ % kLaneSlots];
-        if (q.used && cudaEventSynchronize(q.ev_out) != cudaSuccess) {  // the slot's previous chunk has left the device
-            pc.set_error(fail(ORPH_E_CUDA, "cudaEventSynchronize: %s", cudaGetErrorString(cudaGetLastError())));
+        PipeSlot &q = ctx->lane_slots[0][c % kFrontSlots];
+        if (q.used && wait_event_polling(q.ev_out) != cudaSuccess) {  // the slot's previous chunk has left the device
+            pc.set_error(fail(ORPH_E_CUDA, "cudaEventQuery: %s", cudaGetErrorString(cudaGetLastError())));
             return;
         }
-        uint32_t max_len;
-        uint64_t fixed_len;
-        int rc = pipe_scan_chunk(pc, lo, hi, &max_len, &fixed_len);
+        if (pc.share_h2d && c >= 2) {
+            // the packing lane's copies queue behind this lane's in the shared H2D stream: at most two ASCII chunks there
+            PipeSlot &q2 = ctx->lane_slots[0][(c - 2) % kFrontSlots];
+            if (q2.used && wait_event_polling(q2.ev_in) != cudaSuccess) {
+                pc.set_error(fail(ORPH_E_CUDA, "cudaEventQuery: %s", cudaGetErrorString(cudaGetLastError())));
+                return;
+            }
+        }
+        c++;
+        uint32_t max_len = 0;
+        uint64_t fixed_len = 0;
+        int rc = pipe_scan_chunk(pc, lo, hi, &max_len, &fixed_len, pc.scan_pool);
         if (rc == ORPH_OK) rc = pipe_enqueue_chunk(pc, 0, q, lo, hi, max_len, fixed_len, false, 0.0);
         if (rc != ORPH_OK) {
             pc.set_error(rc);
@@ -283,12 +329,12 @@ static void pipe_back_lane(PipeCall &pc)
     int c = 0, ascii_streak = 0;
     while (pc.claim(1, &lo, &hi)) {
         PipeSlot &q = ctx->lane_slots[1][c++ % kLaneSlots];
-        if (q.used && cudaEventSynchronize(q.ev_out) != cudaSuccess) {
-            pc.set_error(fail(ORPH_E_CUDA, "cudaEventSynchronize: %s", cudaGetErrorString(cudaGetLastError())));
+        if (q.used && wait_event_polling(q.ev_out) != cudaSuccess) {
+            pc.set_error(fail(ORPH_E_CUDA, "cudaEventQuery: %s", cudaGetErrorString(cudaGetLastError())));
             return;
         }
-        uint32_t max_len;
-        uint64_t fixed_len;
+        uint32_t max_len = 0;
+        uint64_t fixed_len = 0;
         int rc = pipe_scan_chunk(pc, lo, hi, &max_len, &fixed_len);
         if (rc != ORPH_OK) {
             pc.set_error(rc);
@@ -351,7 +397,8 @@ static int score_host_pipeline(orph_ctx *ctx, const orph_filter *f, const void *
             if (armed) cudaDeviceSynchronize();
         }
     } drain;
-    if (allow_pack && !ctx->pool) {
+    const bool want_pool = allow_pack || (ctx->host_threads != 0 && n_reads >= (1u << 20));
+    if (want_pool && !ctx->pool) {
         int n = ctx->host_threads;
         if (n <= 0) {  // auto: the cores this process may run on, shared between the ranks of one node
             cpu_set_t set;
@@ -370,8 +417,16 @@ static int score_host_pipeline(orph_ctx *ctx, const orph_filter *f, const void *
         if (cudaPointerGetAttributes(&attr, reads) == cudaSuccess) input_pinned = attr.type == cudaMemoryTypeHost;
         else cudaGetLastError();
     }
+    if (allow_pack && !ctx->lane_ctx) {
+        if ((rc = orph_ctx_create(ctx->device, nullptr, &ctx->lane_ctx)) != ORPH_OK) return rc;
+    }
+    if (ctx->lane_ctx) {
+        ctx->lane_ctx->force_exact = ctx->force_exact;
+        ctx->lane_ctx->disable_task_kernel = ctx->disable_task_kernel;
+    }
     PipeCall pc;
     pc.ctx = ctx;
+    pc.scan_pool = allow_pack ? nullptr : ctx->pool;
     pc.f = f;
     pc.reads = (const uint8_t *)reads;
     pc.reads_format = reads_format;
@@ -392,10 +447,12 @@ static int score_host_pipeline(orph_ctx *ctx, const orph_filter *f, const void *
     pc.max_chunk_bases[0] = 1ULL << (log2_plain + 8);
     pc.max_chunk_reads[1] = 1ULL << 19;
     pc.max_chunk_bases[1] = 1ULL << 27;
+    pc.min_chunk_reads = reads_format == ORPH_READS_ASCII ? 1u << 16 : 1u << 17;  // a chunk costs ~50 us of launches and copy set-up
     // a pageable ASCII buffer cannot be shipped asynchronously: the packing lane takes all of it (the CPU reads it faster
     // than a staged copy would)
     const bool lane0 = !(allow_pack && !input_pinned);
     const bool lane1 = allow_pack;
+    pc.share_h2d = lane0 && lane1;
     std::thread packer;
     if (lane1) packer = std::thread(pipe_back_lane, std::ref(pc));
     if (lane0) pipe_front_lane(pc);
@@ -407,12 +464,20 @@ static int score_host_pipeline(orph_ctx *ctx, const orph_filter *f, const void *
             for (PipeSlot &q : lane) q.used = false;
         return fail(pc.error, "%s", pc.error_text);
     }
-    ScoreCounters counters;
+    ScoreCounters counters, counters1;
+    counters1.status = 0;
     CUDA_TRY(cudaMemcpyAsync(&counters, ctx->counters.p, sizeof(counters), cudaMemcpyDeviceToHost, s));
+    if (lane1) {
+        cudaStream_t s1 = ctx->lane_ctx->stream;
+        CUDA_TRY(cudaMemcpyAsync(&counters1, ctx->lane_ctx->counters.p, sizeof(counters1), cudaMemcpyDeviceToHost, s1));
+        CUDA_TRY(cudaMemsetAsync((uint8_t *)ctx->lane_ctx->counters.p + offsetof(ScoreCounters, status), 0, sizeof(uint32_t), s1));
+        CUDA_TRY(cudaStreamSynchronize(s1));
+        ctx->launches += ctx->lane_ctx->launches;
+        ctx->lane_ctx->launches = 0;
+    }
     CUDA_TRY(cudaStreamSynchronize(s));
-    CUDA_TRY(cudaStreamSynchronize(ctx->s_out));
-    CUDA_TRY(cudaStreamSynchronize(ctx->s_in[0]));
-    CUDA_TRY(cudaStreamSynchronize(ctx->s_in[1]));
+    for (cudaStream_t st : {ctx->s_out[0], ctx->s_out[1], ctx->s_in[0]}) CUDA_TRY(cudaStreamSynchronize(st));
+    counters.status |= counters1.status;
     for (auto &lane : ctx->lane_slots)
         for (PipeSlot &q : lane) q.used = false;  // everything has left the device: the next call starts with free slots
     if (pc.trace && !pc.traces.empty()) {

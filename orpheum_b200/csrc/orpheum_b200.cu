@@ -217,7 +217,9 @@ struct PinnedBuf {
     }
 };
 
-constexpr int kLaneSlots = 3;  // chunks in flight per lane of the host-buffer pipeline (ingest_pipeline.inl)
+constexpr int kLaneSlots = 6;   // chunks in flight on the host-packing lane of the host-buffer pipeline (ingest_pipeline.inl):
+                                // its small copies wait behind the other lane's large ones
+constexpr int kFrontSlots = 4;  // chunks in flight on the copy-engine lane
 
 // staging of one chunk in flight: device buffers, the pinned buffer a host-packed chunk is built in, and the events
 // that order its three stages (H2D -> kernels -> D2H)
@@ -238,6 +240,7 @@ struct orph_ctx {
     int max_smem_optin = 0;
     size_t l2_persist_max = 0, l2_window_max = 0;
     const void *l2_window_base = nullptr;  // filter buffer the access-policy window currently covers
+    uint64_t l2_window_bytes = 0;
     bool force_exact = false;
     bool disable_task_kernel = false;  // test hook: route every read through the warp-per-read kernel
     uint64_t launches = 0;
@@ -250,7 +253,9 @@ struct orph_ctx {
     DevBuf packed;               // 2-bit stream built from ASCII input
     DevBuf in_reads, in_offsets, out_results;  // staging for the index build
     PipeSlot lane_slots[2][kLaneSlots];                  // [0] the copy-engine lane, [1] the host-packing lane of orph_score_reads
-    cudaStream_t s_in[2] = {nullptr, nullptr}, s_out = nullptr;  // H2D stream per lane, one D2H stream
+    cudaStream_t s_in[2] = {nullptr, nullptr}, s_out[2] = {nullptr, nullptr};  // H2D and D2H stream per lane
+    orph_ctx *lane_ctx = nullptr;  // private context (kernel stream + scratch) of the host-packing lane, so that neither
+                                   // lane's kernels queue behind the other lane's copies
     bool pipe_ready = false;
     int host_threads = -1;                               // host packing threads: -1 auto, 0 = never pack on the host
     orph_host::Pool *pool = nullptr;
@@ -283,6 +288,7 @@ static int verify_guards(orph_ctx *ctx)
         }
     for (const Named &n : all)
         if (!n.b->slack_intact()) return fail(ORPH_E_CUDA, "ORPHEUM_B200_GUARD: a kernel wrote past the end of scratch buffer '%s'", n.name);
+    if (ctx->lane_ctx) return verify_guards(ctx->lane_ctx);
     return ORPH_OK;
 }
 
@@ -370,6 +376,15 @@ extern "C" int orph_ctx_create(int device, void *stream, orph_ctx **out)
     ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     ctx->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
     ctx->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+    {
+        static std::mutex mu;
+        static bool carved[64] = {false};
+        std::lock_guard<std::mutex> lk(mu);
+        if (device < 64 && !carved[device] && ctx->l2_persist_max && !env_flag("ORPHEUM_B200_NO_L2_WINDOW")) {
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ctx->l2_persist_max) != cudaSuccess) cudaGetLastError();
+            carved[device] = true;
+        }
+    }
     if (stream) {
         ctx->stream = (cudaStream_t)stream;
     } else {
@@ -414,11 +429,9 @@ extern "C" void orph_ctx_destroy(orph_ctx *ctx)
                 if (e) cudaEventDestroy(e);
         }
     delete ctx->pool;
-    if (ctx->pipe_ready) {
-        cudaStreamDestroy(ctx->s_in[0]);
-        cudaStreamDestroy(ctx->s_in[1]);
-        cudaStreamDestroy(ctx->s_out);
-    }
+    if (ctx->lane_ctx) orph_ctx_destroy(ctx->lane_ctx);
+    for (cudaStream_t st : {ctx->s_in[0], ctx->s_out[0], ctx->s_out[1]})  // s_in[1] is s_in[0]
+        if (st) cudaStreamDestroy(st);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -837,13 +850,15 @@ static uint32_t next_pow2(uint32_t x)
 // window on the context's stream over the single contiguous filter allocation.
 static void apply_l2_window(orph_ctx *ctx, const orph_filter *f)
 {
-    if (ctx->l2_window_base == f->buf) return;
+    if (ctx->l2_window_base == f->buf && ctx->l2_window_bytes == f->n_bytes) return;
     ctx->l2_window_base = f->buf;
+    ctx->l2_window_bytes = f->n_bytes;
     static const bool no_window = env_flag("ORPHEUM_B200_NO_L2_WINDOW");
     if (no_window) return;
     if (ctx->l2_persist_max == 0 || ctx->l2_window_max == 0) return;
+    // the persisting carve-out is a DEVICE-wide limit: it was set once, to the device's maximum, when the first context of
+    // the device was created; contexts only describe their own filter's window on their own stream
     size_t want = std::min<size_t>(f->n_bytes, ctx->l2_persist_max);
-    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
     cudaStreamAttrValue attr;
     memset(&attr, 0, sizeof(attr));
     attr.accessPolicyWindow.base_ptr = f->buf;

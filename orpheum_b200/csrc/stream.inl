@@ -26,15 +26,12 @@ void pinned_release(void *p) { g_pinned.put(p); }
 
 constexpr int kStreamSlots = 4;  // being parsed + on the GPU + finished + held by the caller
 
-}  // namespace
-
-struct orph_stream {
+// Everything of a stream that is expensive to set up and independent of the file: the private context (CUDA stream,
+// kernel scratch, L2 window), the device staging and the pinned result buffers.  Closed streams hand theirs to a
+// process-wide free list (two per device are kept), so opening a stream per file costs no allocation after the first.
+struct StreamRes {
+    int device = 0;
     orph_ctx *ctx = nullptr;  // private: own CUDA stream and scratch, so the caller's context stays free
-    const orph_filter *f = nullptr;
-    orph_ingest *ing = nullptr;
-    uint8_t lut[256];
-    double thr = 0;
-    uint64_t batch_reads = 0;
     struct Job {
         IngestSlot *slot = nullptr;
         PinnedBuf results, side_ascii, side_offsets, side_results, status_word;
@@ -43,6 +40,80 @@ struct orph_stream {
         int status = ORPH_OK;
     } jobs[kStreamSlots];
     DevBuf d_packed, d_off32, d_off64, d_results, d_side_ascii, d_side_offsets, d_side_results;
+};
+
+std::mutex g_stream_res_mu;
+std::vector<StreamRes *> g_stream_res_free;
+
+void stream_res_destroy(StreamRes *r)
+{
+    if (!r) return;
+    DeviceGuard guard(r->device);
+    if (r->ctx) cudaStreamSynchronize(r->ctx->stream);
+    for (DevBuf *b : {&r->d_packed, &r->d_off32, &r->d_off64, &r->d_results, &r->d_side_ascii, &r->d_side_offsets, &r->d_side_results}) b->release();
+    for (auto &job : r->jobs) {
+        for (PinnedBuf *b : {&job.results, &job.side_ascii, &job.side_offsets, &job.side_results, &job.status_word}) b->release();
+        if (job.done) cudaEventDestroy(job.done);
+    }
+    if (r->ctx) orph_ctx_destroy(r->ctx);
+    delete r;
+}
+
+int stream_res_acquire(int device, StreamRes **out)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_stream_res_mu);
+        for (size_t i = 0; i < g_stream_res_free.size(); i++)
+            if (g_stream_res_free[i]->device == device) {
+                *out = g_stream_res_free[i];
+                g_stream_res_free.erase(g_stream_res_free.begin() + (long)i);
+                return ORPH_OK;
+            }
+    }
+    StreamRes *r = new (std::nothrow) StreamRes();
+    if (!r) return fail(ORPH_E_NOMEM, "out of host memory");
+    r->device = device;
+    int rc = orph_ctx_create(device, nullptr, &r->ctx);
+    if (rc == ORPH_OK)
+        for (auto &job : r->jobs)
+            if (cudaEventCreateWithFlags(&job.done, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) rc = fail(ORPH_E_CUDA, "cudaEventCreate failed");
+    if (rc != ORPH_OK) {
+        stream_res_destroy(r);
+        return rc;
+    }
+    *out = r;
+    return ORPH_OK;
+}
+
+void stream_res_release(StreamRes *r)
+{
+    if (!r) return;
+    {
+        DeviceGuard guard(r->device);
+        cudaStreamSynchronize(r->ctx->stream);
+    }
+    for (auto &job : r->jobs) job.slot = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_stream_res_mu);
+        int same = 0;
+        for (StreamRes *o : g_stream_res_free) same += o->device == r->device;
+        if (same < 2) {
+            g_stream_res_free.push_back(r);
+            return;
+        }
+    }
+    stream_res_destroy(r);
+}
+
+}  // namespace
+
+struct orph_stream {
+    StreamRes *r = nullptr;
+    const orph_filter *f = nullptr;
+    orph_ingest *ing = nullptr;
+    uint8_t lut[256];
+    double thr = 0;
+    uint64_t batch_reads = 0;
     std::thread worker;
     std::mutex mu;
     std::condition_variable cv;
@@ -54,31 +125,39 @@ struct orph_stream {
     std::string error_text;
 };
 
-static int stream_enqueue(orph_stream *st, orph_stream::Job &job)
+static int stream_enqueue(orph_stream *st, StreamRes::Job &job)
 {
-    orph_ctx *ctx = st->ctx;
+    orph_ctx *ctx = st->r->ctx;
     cudaStream_t s = ctx->stream;
     const orph_host::FusedBatch &b = job.slot->b;
     const uint64_t n = b.n_reads, n_words = (b.total_bases + 31) / 32;
     int rc;
     job.n = n;
     job.n_side = b.flagged.size();
-    if ((rc = st->d_packed.ensure((n_words + 2) * 8)) != ORPH_OK) return rc;
-    if ((rc = st->d_off32.ensure((n + 1) * 4)) != ORPH_OK) return rc;
-    if ((rc = st->d_off64.ensure((n + 1) * 8)) != ORPH_OK) return rc;
-    if ((rc = st->d_results.ensure(n * sizeof(orph_read_result))) != ORPH_OK) return rc;
+    static const bool trace = getenv("ORPHEUM_B200_TRACE") != nullptr;
+    const auto t_a = std::chrono::steady_clock::now();
+    if ((rc = st->r->d_packed.ensure((n_words + 2) * 8)) != ORPH_OK) return rc;
+    if ((rc = st->r->d_off32.ensure((n + 1) * 4)) != ORPH_OK) return rc;
+    if ((rc = st->r->d_off64.ensure((n + 1) * 8)) != ORPH_OK) return rc;
+    if ((rc = st->r->d_results.ensure(n * sizeof(orph_read_result))) != ORPH_OK) return rc;
     if ((rc = job.results.ensure(n * sizeof(orph_read_result))) != ORPH_OK) return rc;
     if ((rc = job.status_word.ensure(sizeof(ScoreCounters))) != ORPH_OK) return rc;
-    if (n_words) CUDA_TRY(cudaMemcpyAsync(st->d_packed.p, b.packed, n_words * 8, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(st->d_off32.p, b.off32, (n + 1) * 4, cudaMemcpyHostToDevice, s));
-    expand_offsets_kernel<<<grid_for(n + 1, 256, ctx->sm_count, 8), 256, 0, s>>>((const uint32_t *)st->d_off32.p, 0, n + 1, (uint64_t *)st->d_off64.p);
+    const auto t_b = std::chrono::steady_clock::now();
+    if (n_words) CUDA_TRY(cudaMemcpyAsync(st->r->d_packed.p, b.packed, n_words * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(st->r->d_off32.p, b.off32, (n + 1) * 4, cudaMemcpyHostToDevice, s));
+    expand_offsets_kernel<<<grid_for(n + 1, 256, ctx->sm_count, 8), 256, 0, s>>>((const uint32_t *)st->r->d_off32.p, 0, n + 1, (uint64_t *)st->r->d_off64.p);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     const uint32_t max_len = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(b.max_len, ORPH_MAX_READ_LEN));
-    rc = score_device_impl(ctx, st->f, nullptr, 0, (const uint64_t *)st->d_packed.p, 0, 0, (const uint64_t *)st->d_off64.p, n, max_len, st->lut, st->thr,
-                           (orph_read_result *)st->d_results.p);
+    rc = score_device_impl(ctx, st->f, nullptr, 0, (const uint64_t *)st->r->d_packed.p, 0, 0, (const uint64_t *)st->r->d_off64.p, n, max_len, st->lut, st->thr,
+                           (orph_read_result *)st->r->d_results.p);
     if (rc != ORPH_OK) return rc;
-    CUDA_TRY(cudaMemcpyAsync(job.results.p, st->d_results.p, n * sizeof(orph_read_result), cudaMemcpyDeviceToHost, s));
+    if (trace) {
+        const auto t_c = std::chrono::steady_clock::now();
+        auto ms = [](auto a, auto b) { return 1e3 * std::chrono::duration<double>(b - a).count(); };
+        fprintf(stderr, "[orph trace] stream enqueue: buffers %.2f ms, copies + kernel launches %.2f ms\n", ms(t_a, t_b), ms(t_b, t_c));
+    }
+    CUDA_TRY(cudaMemcpyAsync(job.results.p, st->r->d_results.p, n * sizeof(orph_read_result), cudaMemcpyDeviceToHost, s));
     if (job.n_side) {
         // the reads the 2-bit stream cannot hold: their bytes, gathered from the text, through the byte-exact kernels
         const uint64_t m = job.n_side;
@@ -104,19 +183,19 @@ static int stream_enqueue(orph_stream *st, orph_stream::Job &job)
         if (st->ing->pool && n_blk > 4) st->ing->pool->run(n_blk, gather);
         else
             for (uint64_t blk = 0; blk < n_blk; blk++) gather(blk);
-        if ((rc = st->d_side_ascii.ensure(total + 64)) != ORPH_OK) return rc;
-        if ((rc = st->d_side_offsets.ensure((m + 1) * 8)) != ORPH_OK) return rc;
-        if ((rc = st->d_side_results.ensure(m * sizeof(orph_read_result))) != ORPH_OK) return rc;
-        if (total) CUDA_TRY(cudaMemcpyAsync(st->d_side_ascii.p, bytes, total, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(st->d_side_offsets.p, eoff, (m + 1) * 8, cudaMemcpyHostToDevice, s));
+        if ((rc = st->r->d_side_ascii.ensure(total + 64)) != ORPH_OK) return rc;
+        if ((rc = st->r->d_side_offsets.ensure((m + 1) * 8)) != ORPH_OK) return rc;
+        if ((rc = st->r->d_side_results.ensure(m * sizeof(orph_read_result))) != ORPH_OK) return rc;
+        if (total) CUDA_TRY(cudaMemcpyAsync(st->r->d_side_ascii.p, bytes, total, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(st->r->d_side_offsets.p, eoff, (m + 1) * 8, cudaMemcpyHostToDevice, s));
         for (uint64_t lo = 0; lo < m; lo += 1ull << 26) {
             const uint64_t cnt = std::min<uint64_t>(1ull << 26, m - lo);
-            rc = score_device_impl(ctx, st->f, (const uint8_t *)st->d_side_ascii.p + eoff[lo], eoff[lo], nullptr, 0, eoff[lo + cnt] - eoff[lo],
-                                   (const uint64_t *)st->d_side_offsets.p + lo, cnt, std::min<uint32_t>(side_max, ORPH_MAX_READ_LEN), st->lut, st->thr,
-                                   (orph_read_result *)st->d_side_results.p + lo);
+            rc = score_device_impl(ctx, st->f, (const uint8_t *)st->r->d_side_ascii.p + eoff[lo], eoff[lo], nullptr, 0, eoff[lo + cnt] - eoff[lo],
+                                   (const uint64_t *)st->r->d_side_offsets.p + lo, cnt, std::min<uint32_t>(side_max, ORPH_MAX_READ_LEN), st->lut, st->thr,
+                                   (orph_read_result *)st->r->d_side_results.p + lo);
             if (rc != ORPH_OK) return rc;
         }
-        CUDA_TRY(cudaMemcpyAsync(job.side_results.p, st->d_side_results.p, m * sizeof(orph_read_result), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(job.side_results.p, st->r->d_side_results.p, m * sizeof(orph_read_result), cudaMemcpyDeviceToHost, s));
     }
     // the sticky status of this batch (empty / over-long reads), then clear it for the next one
     CUDA_TRY(cudaMemcpyAsync(job.status_word.p, ctx->counters.p, sizeof(ScoreCounters), cudaMemcpyDeviceToHost, s));
@@ -125,7 +204,7 @@ static int stream_enqueue(orph_stream *st, orph_stream::Job &job)
     return ORPH_OK;
 }
 
-static int stream_complete(orph_stream *st, orph_stream::Job &job)
+static int stream_complete(orph_stream *st, StreamRes::Job &job)
 {
     CUDA_TRY(cudaEventSynchronize(job.done));
     if (job.n_side) {
@@ -141,7 +220,7 @@ static int stream_complete(orph_stream *st, orph_stream::Job &job)
 
 static void stream_worker(orph_stream *st)
 {
-    cudaSetDevice(st->ctx->device);
+    cudaSetDevice(st->r->ctx->device);
     int prev = -1;
     uint64_t k = 0;
     auto fail_with = [&](int rc) {
@@ -164,14 +243,14 @@ static void stream_worker(orph_stream *st)
             st->outstanding++;
         }
         const int j = (int)(k % kStreamSlots);
-        orph_stream::Job &job = st->jobs[j];
+        StreamRes::Job &job = st->r->jobs[j];
         static const bool trace = getenv("ORPHEUM_B200_TRACE") != nullptr;
         const auto t0 = std::chrono::steady_clock::now();
         int rc = orph_ingest_next_slot(st->ing, st->batch_reads, &job.slot);
         const auto t1 = std::chrono::steady_clock::now();
         if (rc == ORPH_OK && job.slot->b.n_reads == 0) {  // end of file
             if (prev >= 0) {
-                rc = stream_complete(st, st->jobs[prev]);
+                rc = stream_complete(st, st->r->jobs[prev]);
                 if (rc != ORPH_OK) { fail_with(rc); return; }
                 publish(prev);
             }
@@ -183,13 +262,13 @@ static void stream_worker(orph_stream *st)
         }
         if (rc == ORPH_OK) rc = stream_enqueue(st, job);
         if (rc != ORPH_OK) {
-            cudaStreamSynchronize(st->ctx->stream);
+            cudaStreamSynchronize(st->r->ctx->stream);
             fail_with(rc);
             return;
         }
         const auto t2 = std::chrono::steady_clock::now();
         if (prev >= 0) {
-            rc = stream_complete(st, st->jobs[prev]);
+            rc = stream_complete(st, st->r->jobs[prev]);
             if (rc != ORPH_OK) { fail_with(rc); return; }
             publish(prev);
         }
@@ -202,7 +281,7 @@ static void stream_worker(orph_stream *st)
         prev = j;
         k++;
     }
-    cudaStreamSynchronize(st->ctx->stream);
+    cudaStreamSynchronize(st->r->ctx->stream);
 }
 
 extern "C" int orph_stream_open(orph_ctx *ctx, const orph_filter *f, const char *path, const uint8_t lut[256], double jaccard_threshold,
@@ -234,12 +313,10 @@ extern "C" int orph_stream_open(orph_ctx *ctx, const orph_filter *f, const char 
     memcpy(st->lut, lut, 256);
     st->thr = jaccard_threshold;
     st->batch_reads = batch_reads ? batch_reads : (1u << 20);
-    rc = orph_ctx_create(ctx->device, nullptr, &st->ctx);
+    rc = stream_res_acquire(ctx->device, &st->r);
     if (rc == ORPH_OK) {
-        st->ctx->force_exact = ctx->force_exact;
-        st->ctx->disable_task_kernel = ctx->disable_task_kernel;
-        for (auto &job : st->jobs)
-            if (cudaEventCreateWithFlags(&job.done, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) rc = fail(ORPH_E_CUDA, "cudaEventCreate failed");
+        st->r->ctx->force_exact = ctx->force_exact;
+        st->r->ctx->disable_task_kernel = ctx->disable_task_kernel;
     }
     if (rc != ORPH_OK) {
         orph_stream_close(st);
@@ -269,7 +346,7 @@ extern "C" int orph_stream_next(orph_stream *st, orph_stream_batch *out)
     st->finished.pop_front();
     st->held = j;
     lk.unlock();
-    const orph_stream::Job &job = st->jobs[j];
+    const StreamRes::Job &job = st->r->jobs[j];
     const orph_host::FusedBatch &b = job.slot->b;
     out->n_reads = job.n;
     out->results = (const orph_read_result *)job.results.p;
@@ -292,17 +369,12 @@ extern "C" void orph_stream_close(orph_stream *st)
         st->cv.notify_all();
     }
     if (st->worker.joinable()) st->worker.join();
-    if (st->ctx) {
-        DeviceGuard guard(st->ctx->device);
-        cudaStreamSynchronize(st->ctx->stream);
-        for (DevBuf *b : {&st->d_packed, &st->d_off32, &st->d_off64, &st->d_results, &st->d_side_ascii, &st->d_side_offsets, &st->d_side_results}) b->release();
-        for (auto &job : st->jobs) {
-            for (PinnedBuf *b : {&job.results, &job.side_ascii, &job.side_offsets, &job.side_results, &job.status_word}) b->release();
-            if (job.done) cudaEventDestroy(job.done);
-        }
+    if (st->r) {
+        DeviceGuard guard(st->r->device);
+        cudaStreamSynchronize(st->r->ctx->stream);
         orph_ingest_close(st->ing);  // pinned slot memory: while the device is still current
         st->ing = nullptr;
-        orph_ctx_destroy(st->ctx);
+        stream_res_release(st->r);
     }
     if (st->ing) orph_ingest_close(st->ing);
     delete st;

@@ -445,6 +445,52 @@ def test_table_larger_than_2_31_bits(gpu, enc, orc):
     np.testing.assert_array_equal(gg.get_many(hashes), np.array([go.get(int(h)) for h in hashes], dtype=np.uint8))
 
 
+def test_table_larger_than_2_32_bits(gpu, enc, orc):
+    """SURVEY App. B lists tablesize 4e9: one table of more than 2^32 bits (550 MB) -- bins no longer fit 32 bits, byte offsets
+    pass 2^29 -- built on the GPU, queried hash by hash and probed by every scoring kernel tier."""
+    from orpheum_b200 import synth
+
+    residues, poffs = synth.make_proteome(n_proteins=400, seed=23)
+    tablesize = 4_400_000_000
+    gg = gpu.GpuNodegraph(7, tablesize, 1)
+    assert gg.hashsizes()[0] > 2**32
+    gg.add_peptides(residues, poffs, enc.encode_lut("protein"))
+    go = orc.Nodegraph(7, tablesize, 1)
+    assert go.hashsizes()[0] == gg.hashsizes()[0]
+    go.add_peptides(residues, poffs, orc.encode_lut("protein"))
+    assert gg.n_occupied(0) == go.n_occupied(0)
+    flat, offsets = synth.make_reads_mixed(6000, residues, poffs, ksize=7, seed=24, min_len=30, max_len=900)
+    ora, _ = orc.score_reads(go, flat, offsets, orc.encode_lut("protein"), 0.5, n_threads=0)
+    res = gpu.score_reads(gg, flat, offsets, enc.encode_lut("protein"), 0.5)
+    assert_same_as_oracle(res, ora, "2^32")
+    assert int((res["category"] == 3).sum()) > 500
+    rng = np.random.default_rng(6)
+    hashes = rng.integers(0, 2**64, 5000, dtype=np.uint64)
+    np.testing.assert_array_equal(gg.get_many(hashes), np.array([go.get(int(h)) for h in hashes], dtype=np.uint8))
+
+
+def test_scoring_against_hbm_resident_filter(gpu, enc, orc):
+    """BASELINE cfg4's filter geometry (tablesize 1e9 x 4 = 500 MB, four times the L2): 1e5 reads scored on the GPU against
+    the oracle -- the probes of every table go to HBM, the persisting-L2 window covers only part of the buffer."""
+    from orpheum_b200 import _lib, synth
+
+    residues, poffs = synth.make_proteome(n_proteins=4000, seed=25)
+    lut, olut = enc.encode_lut("protein"), orc.encode_lut("protein")
+    gg = gpu.GpuNodegraph(7, int(1e9), 4)
+    gg.add_peptides(residues, poffs, lut)
+    go = orc.Nodegraph(7, int(1e9), 4)
+    go.add_peptides(residues, poffs, olut)
+    assert [gg.n_occupied(i) for i in range(4)] == [go.n_occupied(i) for i in range(4)]
+    flat, offsets = synth.concat_fixed(synth.make_reads_fixed(100_000, residues, poffs, length=150, seed=26))
+    ora, _ = orc.score_reads(go, flat, offsets, olut, 0.5, n_threads=0)
+    res = gpu.score_reads(gg, flat, offsets, lut, 0.5)
+    assert_same_as_oracle(res, ora, "hbm-resident filter")
+    packed, needs = gpu.pack_reads(flat, offsets)
+    assert not needs.any()
+    res2 = gpu.score_reads(gg, packed, offsets, lut, 0.5, reads_format=_lib.READS_PACKED2)
+    assert res2.tobytes() == res.tobytes()
+
+
 def _orf_read(rng, residues, poffs, n_codons, subst=0.0):
     """A read with one long open frame: back-translated proteome residues (one fixed codon per amino acid)."""
     codon = {"A": "GCT", "R": "CGT", "N": "AAC", "D": "GAC", "C": "TGC", "Q": "CAG", "E": "GAA", "G": "GGT", "H": "CAC",
@@ -839,15 +885,17 @@ def test_context_and_filter_lifecycle_churn(gpu, enc, orc):
 def test_randomised_differential_smoke():
     """A short run of tests/scripts/fuzz_parity.py (random alphabets, k, geometries, read-length tiers, dirty bytes, input
     formats, kernel routes; GPU records, filter tables and emitted peptides against the oracle) with a fresh seed per day of
-    the year, so that the driver's runs keep sampling new cases.  Longer recorded runs: profiles/r01_fuzz_parity_summary.json."""
+    the year, so that the driver's runs keep sampling new cases.  The seed is printed and is part of every failure message;
+    ORPHEUM_B200_FUZZ_SEED=<seed> re-runs exactly that case list.  Longer recorded runs: profiles/r01_fuzz_parity_summary.json."""
     import datetime
     import json
     import subprocess
     import sys
 
-    seed = 1000 + datetime.date.today().timetuple().tm_yday
+    seed = int(os.environ.get("ORPHEUM_B200_FUZZ_SEED", 1000 + datetime.date.today().timetuple().tm_yday))
+    print(f"fuzz seed {seed} (re-run with ORPHEUM_B200_FUZZ_SEED={seed})")
     script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts", "fuzz_parity.py")
     proc = subprocess.run([sys.executable, script, "20", str(seed)], capture_output=True, text=True, timeout=600)
-    assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
+    assert proc.returncode == 0, f"fuzz seed {seed} (ORPHEUM_B200_FUZZ_SEED={seed} reproduces it)\n" + proc.stdout[-3000:] + proc.stderr[-3000:]
     summary = json.loads(proc.stdout.strip().splitlines()[-1])
-    assert summary["differences"] == 0 and summary["fuzz_rounds"] > 20
+    assert summary["differences"] == 0 and summary["fuzz_rounds"] > 20, f"fuzz seed {seed}: {summary}"

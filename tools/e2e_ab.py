@@ -15,8 +15,7 @@ CACHE = "/dev/shm/orph_ab"
 CONFIGS = [
     ("default", {}),
     ("no_l2_window", {"ORPHEUM_B200_NO_L2_WINDOW": "1"}),
-    ("plain_chunk_2^20", {"ORPHEUM_B200_CHUNK_LOG2": "20"}),
-    ("plain_chunk_2^22", {"ORPHEUM_B200_CHUNK_LOG2": "22"}),
+    ("host_threads_4", {"ORPH_AB_HOST_THREADS": "4"}),
 ]
 
 
@@ -55,6 +54,8 @@ def run(routes):
     h_off = pin(offsets.view(np.int64))
     h_out = torch.empty(n * 32, dtype=torch.uint8).pin_memory()
     lib = _lib.load()
+    if os.environ.get("ORPH_AB_HOST_THREADS"):
+        ctx.set_host_threads(int(os.environ["ORPH_AB_HOST_THREADS"]))
     res = {}
     for route in routes:
         buf, fmt = (pin(ld("packed").view(np.int64)), _lib.READS_PACKED2) if route == "packed" else (pin(ld("flat")), _lib.READS_ASCII)
