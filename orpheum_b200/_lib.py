@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "liborpheum_b200.so")
+LIB_PATH = os.environ.get("ORPHEUM_B200_LIB") or os.path.join(_HERE, "csrc", "liborpheum_b200.so")  # (override: kernel A/B builds)
 
 ORPH_OK = 0
 ORPH_E_INVALID, ORPH_E_CUDA, ORPH_E_NOMEM, ORPH_E_TOO_LONG, ORPH_E_EMPTY_READ, ORPH_E_IO = -1, -2, -3, -4, -5, -6

@@ -32,15 +32,15 @@ def is_stale():
     return any(os.path.exists(d) and os.path.getmtime(d) > built for d in deps)
 
 
-def build(force=False, verbose=False, extra_flags=()):
-    """Compile csrc/*.cu into csrc/liborpheum_b200.so."""
-    if not force and not is_stale():
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    """Compile csrc/*.cu into csrc/liborpheum_b200.so (or `out`: a development variant built with extra -D flags)."""
+    if out is None and not force and not is_stale():
         return LIB_PATH
-    cmd = [nvcc(), *NVCC_FLAGS, *extra_flags, "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lz"]
+    cmd = [nvcc(), *NVCC_FLAGS, *extra_flags, "-o", out or LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lz"]
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)
-    return LIB_PATH
+    return out or LIB_PATH
 
 
 if __name__ == "__main__":

@@ -259,7 +259,7 @@ static int pipe_scan_chunk(PipeCall &pc, uint64_t lo, uint64_t hi, uint32_t *max
 {
     uint64_t longest, shortest;
     constexpr uint64_t kBlock = 1u << 15;
-    if (pool && hi - lo >= 8 * kBlock) {
+    if (pool && hi - lo >= 4 * kBlock) {
         // one core reads offsets at ~10 GB/s, a 2-bit chunk of 2 M reads crosses PCIe in 1.4 ms: the scan is spread over the pool
         const uint64_t n_blk = (hi - lo + kBlock - 1) / kBlock;
         std::vector<uint64_t> part(2 * n_blk);
@@ -335,7 +335,7 @@ static void pipe_back_lane(PipeCall &pc)
         }
         uint32_t max_len = 0;
         uint64_t fixed_len = 0;
-        int rc = pipe_scan_chunk(pc, lo, hi, &max_len, &fixed_len);
+        int rc = pipe_scan_chunk(pc, lo, hi, &max_len, &fixed_len, ctx->pool);  // this lane owns the pool
         if (rc != ORPH_OK) {
             pc.set_error(rc);
             return;

@@ -376,15 +376,6 @@ extern "C" int orph_ctx_create(int device, void *stream, orph_ctx **out)
     ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     ctx->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
     ctx->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
-    {
-        static std::mutex mu;
-        static bool carved[64] = {false};
-        std::lock_guard<std::mutex> lk(mu);
-        if (device < 64 && !carved[device] && ctx->l2_persist_max && !env_flag("ORPHEUM_B200_NO_L2_WINDOW")) {
-            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ctx->l2_persist_max) != cudaSuccess) cudaGetLastError();
-            carved[device] = true;
-        }
-    }
     if (stream) {
         ctx->stream = (cudaStream_t)stream;
     } else {
@@ -856,9 +847,22 @@ static void apply_l2_window(orph_ctx *ctx, const orph_filter *f)
     static const bool no_window = env_flag("ORPHEUM_B200_NO_L2_WINDOW");
     if (no_window) return;
     if (ctx->l2_persist_max == 0 || ctx->l2_window_max == 0) return;
-    // the persisting carve-out is a DEVICE-wide limit: it was set once, to the device's maximum, when the first context of
-    // the device was created; contexts only describe their own filter's window on their own stream
+    // The persisting carve-out is a DEVICE-wide limit shared by every context of the process: it only ever grows, to the
+    // largest filter seen on the device (capped by the hardware), so two contexts with different filters do not shrink it
+    // under each other.  Not simply the maximum: the carve-out is taken from the L2 the streaming kernels use (measured,
+    // profiles/r02_kernel_ab_stage_split_carve.log: finalize_best 0.13 -> 0.24 ms per 10 M reads with the maximum carved
+    // out for a 50 MB filter).
     size_t want = std::min<size_t>(f->n_bytes, ctx->l2_persist_max);
+    {
+        static std::mutex mu;
+        static size_t carved[64] = {0};
+        std::lock_guard<std::mutex> lk(mu);
+        const int d = ctx->device < 64 ? ctx->device : 63;
+        if (want > carved[d]) {
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) cudaGetLastError();
+            carved[d] = want;
+        }
+    }
     cudaStreamAttrValue attr;
     memset(&attr, 0, sizeof(attr));
     attr.accessPolicyWindow.base_ptr = f->buf;
@@ -1267,8 +1271,7 @@ extern "C" int orph_bench_gather_peak(orph_ctx *ctx, uint64_t footprint_bytes, u
     CUDA_TRY(cudaMalloc((void **)&sink, 4));
     CUDA_TRY(cudaMemsetAsync(buf, 1, footprint_bytes, s));
     if (persist_l2 && ctx->l2_persist_max && ctx->l2_window_max) {
-        size_t want = std::min<size_t>(footprint_bytes, ctx->l2_persist_max);
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+        size_t want = std::min<size_t>(footprint_bytes, ctx->l2_persist_max);  // (the device-wide carve-out stays as orph_ctx_create set it)
         cudaStreamAttrValue attr;
         memset(&attr, 0, sizeof(attr));
         attr.accessPolicyWindow.base_ptr = buf;

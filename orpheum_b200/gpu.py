@@ -324,6 +324,14 @@ class StreamBatch:
         self.results = np.ctypeslib.as_array(ctypes.cast(raw.results, ctypes.POINTER(ctypes.c_uint8)),
                                              shape=(self.n_reads * READ_RESULT_DTYPE.itemsize,)).view(READ_RESULT_DTYPE)
 
+    def copy_results_into(self, out, at=0):
+        """Copies this batch's records to ``out[at : at + n_reads]`` (a READ_RESULT_DTYPE array) as one memmove -- numpy's
+        element-wise structured assignment is ten times slower than the bytes take to move."""
+        if out.dtype != READ_RESULT_DTYPE or not out.flags["C_CONTIGUOUS"] or at < 0 or at + self.n_reads > len(out):
+            raise ValueError("copy_results_into: out must be a contiguous READ_RESULT_DTYPE array with room for the batch")
+        ctypes.memmove(out.ctypes.data + at * READ_RESULT_DTYPE.itemsize, self._raw.results, self.n_reads * READ_RESULT_DTYPE.itemsize)
+        return at + self.n_reads
+
     def names(self):
         """fastx.NameList (owns copies of the name bytes and offsets)."""
         from .fastx import NameList

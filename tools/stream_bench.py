@@ -49,8 +49,7 @@ for threads in thread_list:
             at = 0
             with gpu.ScoringStream(g, fq, lut, 0.5, batch_reads=batch_reads, n_threads=threads) as st:
                 for batch in st:
-                    got[at:at + batch.n_reads] = batch.results
-                    at += batch.n_reads
+                    at = batch.copy_results_into(got, at)
             best = min(best, time.perf_counter() - t0)
         same = at == n and got.tobytes() == want.tobytes()
         print(f"stream, {threads} threads, batches of {batch_reads}: {n / best / 1e6:.1f} M reads/s, {size / best / 1e9:.2f} GB/s of text, identical {same}", flush=True)
