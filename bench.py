@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fastq", action="store_true", help="skip the FASTQ-file end-to-end leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg3 / cfg4 / cfg5 legs")
     ap.add_argument("--ref-sample", type=int, default=3000, help="--impl reference: reads per host process per step (unmodified reference)")
     ap.add_argument("--reference-port", action="store_true", help="--impl reference: time the C oracle port even when oracle/_ref is staged")
     return ap.parse_args()
@@ -77,6 +78,23 @@ def default_ksize(alphabet):
 
 def default_threshold(alphabet):
     return 0.8 if alphabet in ("hp", "hydrophobic-polar") else 0.5  # translate.py:31-37
+
+
+class _LimitedReader:
+    """File-like view of the first `limit` bytes up to the last complete four-line record in them."""
+
+    def __init__(self, fh, limit):
+        data = fh.read(limit)
+        lines = data.split(b"\n")
+        keep = (len(lines) - 1) // 4 * 4
+        self._buf = b"\n".join(lines[:keep]) + (b"\n" if keep else b"")
+        self._at = 0
+
+    def read(self, n=-1):
+        n = len(self._buf) - self._at if n is None or n < 0 else n
+        out = self._buf[self._at:self._at + n]
+        self._at += len(out)
+        return out
 
 
 class ClockSampler:
@@ -197,18 +215,17 @@ def _reference_worker(conn, ng_path, fq_path, csv_path, alphabet, ksize):
             conn.send("done")
 
 
-def run_reference_unmodified(args):
-    """CPU arm, kind "reference": orpheum's own `translate` CLI (orpheum/translate.py:385-602, unmodified, staged in
-    oracle/_ref by build()) on every host core -- the reference is single-threaded, so one process per core, each on its
-    own FASTQ slice of the same synthetic workload against the same Bloom filter (.nodegraph written by the oracle)."""
+def time_reference_unmodified(args, cores, per_worker, steps, warmup):
+    """orpheum's own `translate` CLI (orpheum/translate.py:385-602, unmodified, staged in oracle/_ref by build()) on `cores`
+    host cores -- the reference is single-threaded, so one process per core, each on its own FASTQ slice of the same
+    synthetic workload against the same Bloom filter (.nodegraph written by the oracle).  -> (reads/s, seconds, CSV of
+    worker 0 identical to the oracle's scores)."""
     import multiprocessing as mp
     import shutil
     import tempfile
 
     from oracle import oracle as orc
 
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
-    per_worker = args.ref_sample
     total = per_worker * cores
     residues, poffs, flat, offsets = make_inputs(argparse.Namespace(**{**vars(args), "reads": total}), 0)
     g = oracle_filter(args, residues, poffs)
@@ -238,10 +255,10 @@ def run_reference_unmodified(args):
             for _, conn in workers:
                 assert conn.recv() == "done"
 
-        for _ in range(args.warmup):
+        for _ in range(warmup):
             step()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             step()
         dt = time.perf_counter() - t0
         for proc, conn in workers:
@@ -263,7 +280,15 @@ def run_reference_unmodified(args):
                       and np.array_equal(np.isnan(jac), ~has_j) and (jac[has_j] == want_j[has_j]).all())
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
-    value = args.steps * total / dt
+    return steps * total / dt, dt, agrees
+
+
+def run_reference_unmodified(args):
+    """CPU arm, kind "reference": the unmodified reference on every host core (time_reference_unmodified)."""
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    per_worker = args.ref_sample
+    total = per_worker * cores
+    value, dt, agrees = time_reference_unmodified(args, cores, per_worker, args.steps, args.warmup)
     sample = (f"{per_worker} reads per process per step x {cores} single-threaded processes (the same synthetic workload), unmodified "
               f"orpheum/translate.py CLI in-process with --csv, khmer/sourmash calls native (oracle/refnative)")
     print(json.dumps({
@@ -309,6 +334,90 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def check_prefix_against_oracle(res, ora):
+    scored = ora["n_kmers"] >= 0
+    return bool((res["category"].astype(np.int64) == ora["category"]).all() and (res["n_kmers"][scored] == ora["n_kmers"][scored]).all()
+                and (res["n_hits"][scored] == ora["n_hits"][scored]).all())
+
+
+def config_leg(name, ctx, stream, dev, alphabet, workload, n_reads, tablesize, n_tables, proteins, steps, warmup, n_check=50_000):
+    """One of BASELINE.json's other configs on ONE GPU, reads resident in HBM: the same kernel-level measurement as the
+    headline (CUDA events on the launch stream around `steps` passes), a prefix checked against the oracle, and the
+    random-gather ceiling measured for THIS filter's footprint."""
+    import torch
+
+    from oracle import oracle as orc
+    from orpheum_b200 import _lib, gpu, sequence_encodings as enc, synth
+
+    ksize = default_ksize(alphabet)
+    thr = default_threshold(alphabet)
+    lut, olut = enc.encode_lut(alphabet), orc.encode_lut(alphabet)
+    residues, poffs = synth.make_proteome(n_proteins=proteins, seed=1001)
+    if workload == "mixed":
+        flat, offsets = synth.make_reads_mixed(n_reads, residues, poffs, ksize=ksize, seed=5005)
+    else:
+        flat, offsets = synth.concat_fixed(synth.make_reads_fixed(n_reads, residues, poffs, length=READ_LEN, seed=2002))
+    graph = gpu.GpuNodegraph(ksize, int(tablesize), n_tables, ctx=ctx)
+    graph.add_peptides(residues, poffs, lut, count_unique=False)
+    packed, needs = gpu.pack_reads(flat, offsets)
+    if needs.any():
+        d_reads, fmt = torch.from_numpy(flat).to(dev), _lib.READS_ASCII
+    else:
+        d_reads, fmt = torch.from_numpy(packed.view(np.int64)).to(dev), _lib.READS_PACKED2
+    d_offsets = torch.from_numpy(offsets.view(np.int64)).to(dev)
+    d_out = torch.zeros(n_reads * 32, dtype=torch.uint8, device=dev)
+    max_len = int(np.diff(offsets.astype(np.int64)).max())
+
+    def step():
+        gpu.score_reads_device(graph, d_reads.data_ptr(), d_offsets.data_ptr(), n_reads, max_len, lut, thr, d_out.data_ptr(), reads_format=fmt, ctx=ctx)
+
+    with torch.cuda.stream(stream):
+        for _ in range(warmup):
+            step()
+        ctx.check()
+        torch.cuda.synchronize()
+        ctx.set_kernel_timing(True)
+        ctx.kernel_times()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        ktimes = ctx.kernel_times()
+        ctx.set_kernel_timing(False)
+        ctx.check()
+    res = d_out.cpu().numpy().view(_lib.READ_RESULT_DTYPE)
+    n_check = min(n_check, n_reads)
+    g_cpu = orc.Nodegraph(ksize, int(tablesize), n_tables)
+    g_cpu.add_peptides(residues, poffs, olut)
+    ora, _ = orc.score_reads(g_cpu, flat, offsets[: n_check + 1], olut, thr, n_threads=orc.max_threads())
+    parity = check_prefix_against_oracle(res[:n_check], ora)
+    if not parity:
+        raise SystemExit(f"bench: leg {name}: GPU results differ from the oracle on the checked prefix")
+    pmin = float(ora["probes_min"].sum()) / n_check
+    _, fbytes, _ = graph.device_buffer()
+    peak = max(ctx.gather_peak(fbytes, 512, False), ctx.gather_peak(fbytes, 512, True))
+    dominant = max(ktimes, key=lambda k: ktimes[k][0])
+    dom_ms = ktimes[dominant][0] / steps  # all launches of the kernel in one step (mixed lengths: one per length tier)
+    # the kernels that probe the filter (thread-per-frame, warp-per-read, byte-exact, block-per-read), per step
+    probing_ms = sum(ktimes[k][0] for k in ("score_tasks", "score_frames", "score_bytes", "score_long") if k in ktimes) / steps
+    probe_rate = n_reads * pmin / (probing_ms * 1e-3)
+    out = {"workload": f"{n_reads} {'mixed 50-300 nt (cfg5 recipe)' if workload == 'mixed' else '150-nt'} reads vs {proteins}-protein proteome, {alphabet} k={ksize}, "
+                       f"tablesize {int(tablesize):.0e} x {n_tables} ({fbytes / 1e6:.0f} MB filter)",
+           "value": n_reads / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "reads": n_reads,
+           "input_format": "ascii (reads with N cannot be 2-bit packed)" if fmt == _lib.READS_ASCII else "packed2",
+           "dominant_kernel": dominant + "_kernel", "dominant_kernel_ms_per_step": dom_ms, "probing_kernels_ms_per_step": probing_ms,
+           "kernel_ms_per_step": {k: v[0] / steps for k, v in ktimes.items() if v[0] > 0},
+           "probes_min_per_read": pmin, "probe_sectors_per_s": probe_rate, "gather_peak_sectors_per_s": peak,
+           "gather_frac": probe_rate / peak, "byte_path_reads": int((res["flags"] & _lib.FLAG_BYTE_PATH != 0).sum()),
+           "parity_checked_vs_oracle": parity, "parity_reads_checked": n_check}
+    del graph, d_reads, d_offsets, d_out
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_ours(args):
@@ -422,6 +531,17 @@ def run_ours(args):
             rate, ora = time_oracle(args, g_cpu, flat, offsets, n_chk, threads)
             cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"first {n_chk} reads of the same workload, C oracle (oracle/orpheum_oracle.c), {threads} threads"}
+            from oracle import stage_reference
+
+            if stage_reference.staged() and args.workload == "r150":
+                # BASELINE.md 2's CPU-1 figure: the unmodified reference CLI on ONE core (the all-core figure is the
+                # `--impl reference` arm's line)
+                try:
+                    v1, _, ok1 = time_reference_unmodified(args, 1, 3000, 2, 1)
+                    cpu["unmodified_reference_one_core"] = {"value": v1, "unit": UNIT, "cores": 1, "kind": "reference", "csv_matches_oracle": ok1,
+                                                            "sample": "3000 reads per step, 2 steps, orpheum/translate.py CLI in-process (oracle/_ref)"}
+                except Exception as exc:
+                    cpu["unmodified_reference_one_core"] = {"error": f"{type(exc).__name__}: {exc}"}
         else:
             n_chk = min(50_000, args.reads)
             _, ora = time_oracle(args, g_cpu, flat, offsets, n_chk, orc.max_threads())
@@ -518,50 +638,98 @@ def run_ours(args):
                                    "h2d_bytes_per_step": int(packed.nbytes + offsets.nbytes),
                                    "identical_to_device_path": bool(h_out.numpy().view(_lib.READ_RESULT_DTYPE).tobytes() == res_dev.tobytes())}
 
-    # ---- from a FASTQ file: parse (native parallel parser, next batch prefetched) -> orph_score_reads -> records ----
-    if e2e is not None and rank == 0 and world == 1 and args.workload == "r150" and not args.no_fastq:
+    # ---- from a FASTQ file: orph_stream_* (parallel parse + 2-bit pack into pinned slots -> H2D -> kernels -> records) ----
+    # every rank streams its own file (its shard of the reads) at the same time; value = all reads / slowest rank
+    if e2e is not None and args.workload == "r150" and not args.no_fastq:
         import shutil
         import tempfile
 
-        from orpheum_b200 import fastx
-
-        n_fq = min(args.reads, 4_000_000)
-        need_bytes = n_fq * (2 * READ_LEN + 40)
-        shm_ok = os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 2 * need_bytes
+        n_fq = min(args.reads, 4_000_000 if world == 1 else 2_000_000)
+        need_bytes = n_fq * (2 * READ_LEN + 40) * (world if rank == 0 else 1)
+        shm_ok = os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 2 * need_bytes * max(1, world)
         tmpdir = tempfile.mkdtemp(prefix="orph_bench_", dir="/dev/shm" if shm_ok else None)
+        fq_leg = None
+        fq_out = np.zeros(n_fq, dtype=_lib.READ_RESULT_DTYPE)  # the caller's result array (pages touched before the clock starts)
+        problems = []
+
+        def pass_fastq(path):
+            # never raises: every rank must reach the barriers around the timed passes
+            got = 0
+            try:
+                with gpu.ScoringStream(graph, path, lut, thr, ctx=ctx) as stream_:
+                    for batch in stream_:
+                        got = batch.copy_results_into(fq_out, got)
+            except Exception as exc:
+                problems.append(f"{type(exc).__name__}: {exc}")
+                return -1
+            return got
+
         try:
             fq = os.path.join(tmpdir, "reads.fq")
-            qual = b"I" * READ_LEN
-            rows = flat[: n_fq * READ_LEN].reshape(n_fq, READ_LEN)
-            with open(fq, "wb") as fh:
-                for lo in range(0, n_fq, 200_000):
-                    fh.write(b"".join(b"@read%d 1:N:0\n%s\n+\n%s\n" % (i, rows[i].tobytes(), qual) for i in range(lo, min(n_fq, lo + 200_000))))
-            fq_bytes = os.path.getsize(fq)
-
-            fq_out = np.zeros(n_fq, dtype=_lib.READ_RESULT_DTYPE)  # the caller's result array (pages touched before the clock starts)
-
-            def pass_fastq():
-                got = 0
-                with gpu.ScoringStream(graph, fq, lut, thr, ctx=ctx) as stream:
-                    for batch in stream:
-                        got = batch.copy_results_into(fq_out, got)
-                return got
-
-            pass_fastq()
+            fq_bytes = 0
+            try:
+                qual = b"I" * READ_LEN
+                rows = flat[: n_fq * READ_LEN].reshape(n_fq, READ_LEN)
+                with open(fq, "wb") as fh:
+                    for lo in range(0, n_fq, 200_000):
+                        fh.write(b"".join(b"@read%d 1:N:0\n%s\n+\n%s\n" % (i, rows[i].tobytes(), qual) for i in range(lo, min(n_fq, lo + 200_000))))
+                fq_bytes = os.path.getsize(fq)
+            except Exception as exc:
+                problems.append(f"{type(exc).__name__}: {exc}")
+            pass_fastq(fq)
             reps = 3
+            barrier()
             t0 = time.perf_counter()
             for _ in range(reps):
-                got = pass_fastq()
+                got = pass_fastq(fq)
+            barrier()
             dtf = (time.perf_counter() - t0) / reps
             same_fq = got == n_fq and fq_out.tobytes() == res_dev[:n_fq].tobytes()
-            e2e["from_fastq"] = {"value": n_fq / dtf, "unit": UNIT, "reads": n_fq, "fastq_bytes": fq_bytes, "ms": 1e3 * dtf,
-                                 "fastq_GBps": fq_bytes / dtf / 1e9, "identical_to_device_path": bool(same_fq),
-                                 "path": "uncompressed four-line FASTQ on tmpfs -> orph_stream_* (mapped text parsed and 2-bit packed into "
-                                         "pinned slots in one parallel pass, next batch parsed while this one is copied and scored) -> records"}
+            if world > 1:
+                t = torch.tensor([dtf, 0.0 if same_fq else 1.0, float(len(problems))], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dtf, same_fq = float(t[0].item()), bool(t[1].item() == 0.0)
+                if t[2].item() > 0 and not problems:
+                    problems.append("another rank failed")
+            if problems:
+                raise RuntimeError("; ".join(problems))
+            fq_leg = {"value": world * n_fq / dtf, "unit": UNIT, "reads_per_gpu": n_fq, "fastq_bytes_per_gpu": fq_bytes, "ms": 1e3 * dtf,
+                      "fastq_GBps": world * fq_bytes / dtf / 1e9, "identical_to_device_path": bool(same_fq),
+                      "path": "uncompressed four-line FASTQ on tmpfs (one file per rank) -> orph_stream_* (mapped text parsed and 2-bit packed "
+                              "into pinned slots in one parallel pass, next batch parsed while this one is copied and scored) -> records "
+                              "copied into the caller's array; includes opening and closing the stream"}
+            if world == 1:
+                # the same reads as gzip (screed reads .gz transparently, translate.py:370): one member, zlib level 1
+                import gzip
+
+                n_gz = min(n_fq, 1_000_000)
+                gz_path = os.path.join(tmpdir, "reads.fq.gz")
+                with open(fq, "rb") as fh, gzip.open(gz_path, "wb", compresslevel=1) as gzf:
+                    shutil.copyfileobj(_LimitedReader(fh, n_gz * (fq_bytes // n_fq + 2)), gzf, 1 << 24)
+                got = pass_fastq(gz_path)
+                t0 = time.perf_counter()
+                got = pass_fastq(gz_path)
+                dtg = time.perf_counter() - t0
+                fq_leg["gzip"] = {"value": got / dtg, "unit": UNIT, "reads": got, "gz_bytes": os.path.getsize(gz_path), "ms": 1e3 * dtg,
+                                  "identical_to_device_path": bool(fq_out[:got].tobytes() == res_dev[:got].tobytes())}
         except Exception as exc:  # a measurement extra: never lose the bench line over it (disk full, ...)
-            e2e["from_fastq"] = {"error": f"{type(exc).__name__}: {exc}"}
+            fq_leg = {"error": f"{type(exc).__name__}: {exc}"}
         finally:
             shutil.rmtree(tmpdir, ignore_errors=True)
+        e2e["from_fastq"] = fq_leg
+
+    # ---- cfg5 output parity over the ranks (BASELINE configs[4]): records gathered in read order, CSV / parquet / JSON ----
+    output_parity = None
+    if world > 1:
+        import importlib.util
+
+        spec = importlib.util.spec_from_file_location("orph_mgpu_parity", os.path.join(ROOT, "tests", "scripts", "multi_gpu_output_parity.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        try:
+            output_parity = mod.check(50_000, rank, world, local, ctx)
+        except Exception as exc:
+            output_parity = {"error": f"{type(exc).__name__}: {exc}"}
 
     # ---- measured random-gather ceiling for this filter footprint ----
     gather = None
@@ -585,31 +753,54 @@ def run_ours(args):
         peak_gbs, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     dominant = max(ktimes, key=lambda name: ktimes[name][0])
     sf_ms, sf_n = ktimes[dominant]
-    sf_ms_per_launch = sf_ms / max(1, sf_n)
-    # algorithmic bytes of one score_frames launch: stream bytes of every read + 32 B per required probe
+    sf_ms_per_launch = sf_ms / args.steps  # the kernel's launches of one step (one, unless the batch has two length tiers)
+    # The dominant kernel is bound by the random 32-byte-sector gather rate of the Bloom probes (L1TEX tag stage / L2), not by
+    # the HBM stream: SURVEY 8(d)'s per-unit figure is P_min probes per read (counted exactly by the oracle) x 32 B, the roof is
+    # the gather ceiling measured on this GPU for this filter's footprint (orph_bench_gather_peak), both in GB/s of sectors.
     stream_bytes = ((packed.nbytes if fmt == _lib.READS_PACKED2 else flat.nbytes) / args.reads) + 4 + 32
-    algo_bytes = args.reads * (stream_bytes + 32.0 * pmin_mean)
-    achieved = algo_bytes / (sf_ms_per_launch * 1e-3) / 1e9
-    roofline = {
-        "kernel": dominant + "_kernel", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-        "frac": achieved / peak_gbs,
-        "note": "achieved counts 32 B per required Bloom probe; the probes are served by the L2-resident filter, not HBM, so frac can "
-                "exceed 1 -- gather_frac (required probe sectors/s over the measured random-gather ceiling) grades the kernel",
-        # DRAM bytes of this kernel per launch: 115.8 B/read measured by `ncu --set full` on a 2 M-read launch of the
-        # same workload (profiles/r01_ncu_full_final_score_tasks.csv: dram read 187.4 MB + write 44.2 MB), scaled by reads.
-        # Far below the algorithmic bytes because the probes are served by the L2-resident filter.
-        "traffic": (115.8 * args.reads) if (args.workload == "r150" and dominant == "score_tasks" and args.alphabet == "protein") else None,
-        "peak_source": peak_src,
-        "ms_per_launch": sf_ms_per_launch, "share_of_step": sf_ms_per_launch / ms_per_step,
-        "algorithmic_bytes_per_read": stream_bytes + 32.0 * pmin_mean,
-        "probes_min_per_read": pmin_mean, "probes_max_per_read": pmax_mean,
-        "probe_sectors_per_s": args.reads * pmin_mean / (sf_ms_per_launch * 1e-3),
-        "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items()},
-    }
+    probe_rate = args.reads * pmin_mean / (sf_ms_per_launch * 1e-3)
+    roofline = {"kernel": dominant + "_kernel", "ms_per_launch": sf_ms_per_launch, "share_of_step": sf_ms_per_launch / ms_per_step,
+                "probes_min_per_read": pmin_mean, "probes_max_per_read": pmax_mean, "probe_sectors_per_s": probe_rate,
+                "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items()}}
     if gather and "sectors_per_s_plain" in gather:
         best = max(gather["sectors_per_s_plain"], gather["sectors_per_s_l2_persist"])
-        roofline["gather_peak_sectors_per_s"] = best
-        roofline["gather_frac"] = roofline["probe_sectors_per_s"] / best
+        roofline.update({"bound": "l2-gather", "achieved": probe_rate * 32 / 1e9, "peak": best * 32 / 1e9, "unit": "GB/s",
+                         "frac": probe_rate / best, "gather_frac": probe_rate / best, "gather_peak_sectors_per_s": best,
+                         "peak_source": f"measured in this run: orph_bench_gather_peak over the filter's {gather['footprint_bytes']} bytes "
+                                        "(random 32-byte sector loads, 512 per thread); not in MEASURED_PEAKS.json, cross-check: "
+                                        "148 SMs x 1 sector/clk x SM clock",
+                         "algorithmic_bytes_per_read": 32.0 * pmin_mean,
+                         "note": "achieved = P_min required probes per read x 32-byte sectors / dominant kernel time"})
+    else:
+        roofline.update({"bound": "l2-gather", "achieved": probe_rate * 32 / 1e9, "peak": None, "unit": "GB/s", "frac": None})
+    # secondary: the same kernel time against the HBM roof (74 B/read of stream + 32 B per required probe): exceeds 1 when the
+    # filter is L2-resident, because the probes never reach HBM
+    algo_bytes = args.reads * (stream_bytes + 32.0 * pmin_mean)
+    roofline["hbm_stream"] = {"bound": "hbm", "achieved": algo_bytes / (sf_ms_per_launch * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                              "frac": algo_bytes / (sf_ms_per_launch * 1e-3) / 1e9 / peak_gbs, "peak_source": peak_src,
+                              "stream_bytes_per_read": stream_bytes}
+    # DRAM bytes of the dominant kernel per launch are NOT measured by this run (that needs ncu): the figure below is the
+    # committed `ncu --set full` capture of the same kernel and workload on 2 M reads, scaled to this launch's reads
+    if args.workload == "r150" and dominant == "score_tasks" and args.alphabet == "protein":
+        roofline["traffic"] = 115.8 * args.reads
+        roofline["traffic_source"] = ("ncu --set full, profiles/r01_ncu_full_final_score_tasks.csv: dram__bytes_read.sum 187.4 MB + "
+                                      "dram__bytes_write.sum 44.2 MB per 2 M-read launch = 115.8 B/read (kernel unchanged since), scaled by reads")
+    else:
+        roofline["traffic"] = None
+    configs = None
+    if not args.no_configs and args.workload == "r150" and args.alphabet == "protein":
+        # the other BASELINE.json configs, on this rank's GPU (the other ranks have left): kernel-level, parity-checked
+        configs = {}
+        for name, kw in (("cfg3_dayhoff", dict(alphabet="dayhoff", workload="r150", n_reads=2_000_000, tablesize=1e8)),
+                         ("cfg3_hp", dict(alphabet="hp", workload="r150", n_reads=2_000_000, tablesize=1e8)),
+                         ("cfg5_mixed", dict(alphabet="protein", workload="mixed", n_reads=1_000_000, tablesize=1e8)),
+                         ("cfg4_hbm_filter", dict(alphabet="protein", workload="r150", n_reads=2_000_000, tablesize=1e9))):
+            try:
+                configs[name] = config_leg(name, ctx, stream, dev, n_tables=args.n_tables, proteins=args.proteins, steps=5, warmup=2, **kw)
+            except SystemExit:
+                raise
+            except Exception as exc:
+                configs[name] = {"error": f"{type(exc).__name__}: {exc}"}
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
@@ -618,7 +809,7 @@ def run_ours(args):
                    "filter_fill_table0": fill, "l2_flush": "inputs (375 MB packed + 80 MB offsets + 320 MB results per step) exceed the 126 MB L2",
                    "parallelism": f"reads sharded over {world} GPU(s), filter replicated (NCCL broadcast), no steady-state collectives"},
         "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-        "gather_peak": gather, "parity_checked_vs_oracle": parity,
+        "gather_peak": gather, "parity_checked_vs_oracle": parity, "configs": configs, "output_parity": output_parity,
         "setup_s": {"generate_inputs": t_gen, "bloom_build_gpu": t_build},
     }
     print(json.dumps(out))

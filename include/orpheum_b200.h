@@ -40,7 +40,7 @@ typedef enum orph_status {
     ORPH_E_INVALID = -1,    /* bad argument */
     ORPH_E_CUDA = -2,       /* CUDA runtime failure (message has the CUDA error string) */
     ORPH_E_NOMEM = -3,      /* host or device allocation failed */
-    ORPH_E_TOO_LONG = -4,   /* a read is longer than ORPH_MAX_READ_LEN */
+    ORPH_E_TOO_LONG = -4,   /* a read longer than ORPH_MAX_READ_LEN has a stop-free frame (or a read exceeds the declared bound) */
     ORPH_E_EMPTY_READ = -5, /* a zero-length read: the reference raises ZeroDivisionError (translate.py:83) */
     ORPH_E_IO = -6
 } orph_status;
@@ -84,8 +84,12 @@ typedef enum orph_reads_format {
                               through an ASCII batch (orph_pack_reads reports which). */
 } orph_reads_format;
 
-#define ORPH_MAX_READ_LEN 196607u /* longest read scored (over-long -> ORPH_E_TOO_LONG): a frame of 65535 residues is the
-                                     most whose distinct k-mer count fits the record's 16-bit fields */
+#define ORPH_MAX_READ_LEN 196607u /* longest read whose frames can be SCORED: a frame of 65535 residues is the most whose
+                                     distinct k-mer count fits the record's 16-bit fields.  Longer reads (contigs, transcripts;
+                                     the reference has no limit, translate.py:323-331) are still classified exactly whenever
+                                     none of their frames needs scoring -- the read is low-complexity or every frame holds a
+                                     stop codon, i.e. practically always.  Only a longer read with a stop-free frame gives
+                                     ORPH_E_TOO_LONG; its record is ORPH_CAT_INVALID, every other read's record is filled. */
 
 typedef struct orph_ctx orph_ctx;
 typedef struct orph_filter orph_filter;
@@ -282,6 +286,14 @@ typedef struct orph_stream_batch {
 } orph_stream_batch;
 int orph_stream_open(orph_ctx *ctx, const orph_filter *f, const char *path, const uint8_t lut[256], double jaccard_threshold,
                      uint64_t batch_reads, int n_threads, orph_stream **out);
+/* The same stream over several GPUs of the box (or several private contexts of one GPU): ONE parser feeds n_lanes device
+ * lanes, batch k is copied to and scored on lane k % n_lanes, and orph_stream_next still delivers the batches in file order.
+ * filters[i] must be a replica of filters[0] living on ctxs[i]'s device (orph_filter_replicate).  This is what replaces the
+ * reference's serial loop over files and reads (translate.py:367-379) on a multi-GPU box; the parser, not a GPU, is the
+ * limiting stage, so lanes beyond the first only add head-room. */
+int orph_stream_open_multi(orph_ctx *const *ctxs, const orph_filter *const *filters, int n_lanes, const char *path,
+                           const uint8_t lut[256], double jaccard_threshold, uint64_t batch_reads, int n_threads,
+                           orph_stream **out);
 /* Blocks until the next batch is scored.  The pointers stay valid until the next call on the same stream. */
 int orph_stream_next(orph_stream *st, orph_stream_batch *out);
 void orph_stream_close(orph_stream *st);

@@ -59,7 +59,12 @@ score_long_kernel(const ScoreParams P, const void *__restrict__ src, const uint6
         if (item >= n_long) break;
         const uint64_t r = list_back[list_capacity - 1 - item];  // long reads are queued from the back of the byte queue
         const uint64_t o0 = offsets[r];
-        const uint32_t L = (uint32_t)(offsets[r + 1] - o0);  // kBytesMaxLen < L <= P.max_len (prefilter_kernel)
+        const uint32_t L = (uint32_t)(offsets[r + 1] - o0);  // kBytesMaxLen < L (prefilter_kernel)
+        // A read beyond ORPH_MAX_READ_LEN (the reference has no limit, translate.py:323-331) is classified exactly as long as
+        // no frame of it needs scoring: every frame with a stop codon, or the whole read low-complexity -- which is what a
+        // contig or a transcript of that length looks like.  A stop-free frame of more than 65535 residues cannot be
+        // represented in the record's 16-bit counts: ORPH_E_TOO_LONG, the read's record stays ORPH_CAT_INVALID.
+        const bool over_long = L > P.max_len;
         // compute_fastp_complexity (translate.py:79-84) and the stop codons of all six frames in one pass
         {
             uint32_t ndiff = 0, stops = 0;
@@ -97,6 +102,11 @@ score_long_kernel(const ScoreParams P, const void *__restrict__ src, const uint6
                 const uint32_t plen = (L - phase) / 3;
                 if ((stops >> f) & 1u) { cat[f] = ORPH_CAT_STOP_CODONS; continue; }
                 if (plen <= k) { cat[f] = ORPH_CAT_TOO_SHORT_PEPTIDE; continue; }
+                if (over_long) {
+                    cat[f] = ORPH_CAT_INVALID;
+                    if (threadIdx.x == 0) atomicOr(&counters->status, kStatusTooLong);
+                    continue;
+                }
                 open |= 1u << f;
                 const uint32_t n = plen - k + 1;
                 uint32_t mask = 1023;
@@ -161,6 +171,15 @@ score_long_kernel(const ScoreParams P, const void *__restrict__ src, const uint6
                 best.offer(nh[f], nk[f], cat[f], frame_key(f));
             }
             flags |= (uint8_t)open;
+            if (over_long && open == 0) {
+                bool invalid = false;
+#pragma unroll
+                for (int f = 0; f < 6; f++) invalid |= cat[f] == ORPH_CAT_INVALID;
+                if (invalid) {  // the record of a read that could not be scored carries no partial answer
+#pragma unroll
+                    for (int f = 0; f < 6; f++) cat[f] = ORPH_CAT_INVALID;
+                }
+            }
         }
         if (threadIdx.x == 0) {
             orph_read_result rec;

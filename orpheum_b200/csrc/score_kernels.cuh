@@ -315,9 +315,10 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
             rec.flags = 0;
             if (L == 0) {
                 atomicOr(&counters->status, kStatusEmptyRead);
-            } else if (L > max_len) {
-                atomicOr(&counters->status, kStatusTooLong);
+            } else if (L > max_len && (max_len < ORPH_MAX_READ_LEN || L > 0xFFFFFFF0ull)) {
+                atomicOr(&counters->status, kStatusTooLong);  // longer than the caller declared
             } else if (L > bytes_max_len) {
+                // (beyond ORPH_MAX_READ_LEN too: score_long_kernel classifies such a read from its stop codons alone)
                 to_long = true;
                 rec.flags = ORPH_FLAG_BYTE_PATH;
             } else if ((needs_bytes && needs_bytes[r]) || L > fast_max_len) {

@@ -108,8 +108,9 @@ void stream_res_release(StreamRes *r)
 }  // namespace
 
 struct orph_stream {
-    StreamRes *r = nullptr;
-    const orph_filter *f = nullptr;
+    // one entry per device lane (the same device may appear twice: two private contexts); batch k runs on lane k % n
+    std::vector<StreamRes *> rs;
+    std::vector<const orph_filter *> fs;
     orph_ingest *ing = nullptr;
     uint8_t lut[256];
     double thr = 0;
@@ -117,47 +118,48 @@ struct orph_stream {
     std::thread worker;
     std::mutex mu;
     std::condition_variable cv;
-    std::deque<int> finished;
-    int outstanding = 0;  // jobs handed to the parser and not yet released by the caller
-    int held = -1;
+    std::deque<uint64_t> finished;  // batch numbers, in file order
+    int outstanding = 0;  // batches handed to the parser and not yet released by the caller
+    int max_outstanding = kStreamSlots;
+    bool holding = false;
+    uint64_t held = 0;
     bool eof = false, stop = false;
     int error = ORPH_OK;
     std::string error_text;
+    size_t lanes() const { return rs.size(); }
+    StreamRes *res_of(uint64_t k) const { return rs[k % rs.size()]; }
+    StreamRes::Job &job_of(uint64_t k) const { return rs[k % rs.size()]->jobs[(k / rs.size()) % kStreamSlots]; }
 };
 
-static int stream_enqueue(orph_stream *st, StreamRes::Job &job)
+static int stream_enqueue(orph_stream *st, uint64_t k)
 {
-    orph_ctx *ctx = st->r->ctx;
+    StreamRes *r = st->res_of(k);
+    StreamRes::Job &job = st->job_of(k);
+    const orph_filter *f = st->fs[k % st->lanes()];
+    orph_ctx *ctx = r->ctx;
+    DeviceGuard guard(r->device);
     cudaStream_t s = ctx->stream;
     const orph_host::FusedBatch &b = job.slot->b;
     const uint64_t n = b.n_reads, n_words = (b.total_bases + 31) / 32;
     int rc;
     job.n = n;
     job.n_side = b.flagged.size();
-    static const bool trace = getenv("ORPHEUM_B200_TRACE") != nullptr;
-    const auto t_a = std::chrono::steady_clock::now();
-    if ((rc = st->r->d_packed.ensure((n_words + 2) * 8)) != ORPH_OK) return rc;
-    if ((rc = st->r->d_off32.ensure((n + 1) * 4)) != ORPH_OK) return rc;
-    if ((rc = st->r->d_off64.ensure((n + 1) * 8)) != ORPH_OK) return rc;
-    if ((rc = st->r->d_results.ensure(n * sizeof(orph_read_result))) != ORPH_OK) return rc;
+    if ((rc = r->d_packed.ensure((n_words + 2) * 8)) != ORPH_OK) return rc;
+    if ((rc = r->d_off32.ensure((n + 1) * 4)) != ORPH_OK) return rc;
+    if ((rc = r->d_off64.ensure((n + 1) * 8)) != ORPH_OK) return rc;
+    if ((rc = r->d_results.ensure(n * sizeof(orph_read_result))) != ORPH_OK) return rc;
     if ((rc = job.results.ensure(n * sizeof(orph_read_result))) != ORPH_OK) return rc;
     if ((rc = job.status_word.ensure(sizeof(ScoreCounters))) != ORPH_OK) return rc;
-    const auto t_b = std::chrono::steady_clock::now();
-    if (n_words) CUDA_TRY(cudaMemcpyAsync(st->r->d_packed.p, b.packed, n_words * 8, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(st->r->d_off32.p, b.off32, (n + 1) * 4, cudaMemcpyHostToDevice, s));
-    expand_offsets_kernel<<<grid_for(n + 1, 256, ctx->sm_count, 8), 256, 0, s>>>((const uint32_t *)st->r->d_off32.p, 0, n + 1, (uint64_t *)st->r->d_off64.p);
+    if (n_words) CUDA_TRY(cudaMemcpyAsync(r->d_packed.p, b.packed, n_words * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(r->d_off32.p, b.off32, (n + 1) * 4, cudaMemcpyHostToDevice, s));
+    expand_offsets_kernel<<<grid_for(n + 1, 256, ctx->sm_count, 8), 256, 0, s>>>((const uint32_t *)r->d_off32.p, 0, n + 1, (uint64_t *)r->d_off64.p);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     const uint32_t max_len = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(b.max_len, ORPH_MAX_READ_LEN));
-    rc = score_device_impl(ctx, st->f, nullptr, 0, (const uint64_t *)st->r->d_packed.p, 0, 0, (const uint64_t *)st->r->d_off64.p, n, max_len, st->lut, st->thr,
-                           (orph_read_result *)st->r->d_results.p);
+    rc = score_device_impl(ctx, f, nullptr, 0, (const uint64_t *)r->d_packed.p, 0, 0, (const uint64_t *)r->d_off64.p, n, max_len, st->lut, st->thr,
+                           (orph_read_result *)r->d_results.p);
     if (rc != ORPH_OK) return rc;
-    if (trace) {
-        const auto t_c = std::chrono::steady_clock::now();
-        auto ms = [](auto a, auto b) { return 1e3 * std::chrono::duration<double>(b - a).count(); };
-        fprintf(stderr, "[orph trace] stream enqueue: buffers %.2f ms, copies + kernel launches %.2f ms\n", ms(t_a, t_b), ms(t_b, t_c));
-    }
-    CUDA_TRY(cudaMemcpyAsync(job.results.p, st->r->d_results.p, n * sizeof(orph_read_result), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(job.results.p, r->d_results.p, n * sizeof(orph_read_result), cudaMemcpyDeviceToHost, s));
     if (job.n_side) {
         // the reads the 2-bit stream cannot hold: their bytes, gathered from the text, through the byte-exact kernels
         const uint64_t m = job.n_side;
@@ -183,19 +185,19 @@ static int stream_enqueue(orph_stream *st, StreamRes::Job &job)
         if (st->ing->pool && n_blk > 4) st->ing->pool->run(n_blk, gather);
         else
             for (uint64_t blk = 0; blk < n_blk; blk++) gather(blk);
-        if ((rc = st->r->d_side_ascii.ensure(total + 64)) != ORPH_OK) return rc;
-        if ((rc = st->r->d_side_offsets.ensure((m + 1) * 8)) != ORPH_OK) return rc;
-        if ((rc = st->r->d_side_results.ensure(m * sizeof(orph_read_result))) != ORPH_OK) return rc;
-        if (total) CUDA_TRY(cudaMemcpyAsync(st->r->d_side_ascii.p, bytes, total, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(st->r->d_side_offsets.p, eoff, (m + 1) * 8, cudaMemcpyHostToDevice, s));
+        if ((rc = r->d_side_ascii.ensure(total + 64)) != ORPH_OK) return rc;
+        if ((rc = r->d_side_offsets.ensure((m + 1) * 8)) != ORPH_OK) return rc;
+        if ((rc = r->d_side_results.ensure(m * sizeof(orph_read_result))) != ORPH_OK) return rc;
+        if (total) CUDA_TRY(cudaMemcpyAsync(r->d_side_ascii.p, bytes, total, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(r->d_side_offsets.p, eoff, (m + 1) * 8, cudaMemcpyHostToDevice, s));
         for (uint64_t lo = 0; lo < m; lo += 1ull << 26) {
             const uint64_t cnt = std::min<uint64_t>(1ull << 26, m - lo);
-            rc = score_device_impl(ctx, st->f, (const uint8_t *)st->r->d_side_ascii.p + eoff[lo], eoff[lo], nullptr, 0, eoff[lo + cnt] - eoff[lo],
-                                   (const uint64_t *)st->r->d_side_offsets.p + lo, cnt, std::min<uint32_t>(side_max, ORPH_MAX_READ_LEN), st->lut, st->thr,
-                                   (orph_read_result *)st->r->d_side_results.p + lo);
+            rc = score_device_impl(ctx, f, (const uint8_t *)r->d_side_ascii.p + eoff[lo], eoff[lo], nullptr, 0, eoff[lo + cnt] - eoff[lo],
+                                   (const uint64_t *)r->d_side_offsets.p + lo, cnt, std::min<uint32_t>(side_max, ORPH_MAX_READ_LEN), st->lut, st->thr,
+                                   (orph_read_result *)r->d_side_results.p + lo);
             if (rc != ORPH_OK) return rc;
         }
-        CUDA_TRY(cudaMemcpyAsync(job.side_results.p, st->r->d_side_results.p, m * sizeof(orph_read_result), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(job.side_results.p, r->d_side_results.p, m * sizeof(orph_read_result), cudaMemcpyDeviceToHost, s));
     }
     // the sticky status of this batch (empty / over-long reads), then clear it for the next one
     CUDA_TRY(cudaMemcpyAsync(job.status_word.p, ctx->counters.p, sizeof(ScoreCounters), cudaMemcpyDeviceToHost, s));
@@ -204,8 +206,10 @@ static int stream_enqueue(orph_stream *st, StreamRes::Job &job)
     return ORPH_OK;
 }
 
-static int stream_complete(orph_stream *st, StreamRes::Job &job)
+static int stream_complete(orph_stream *st, uint64_t k)
 {
+    StreamRes::Job &job = st->job_of(k);
+    DeviceGuard guard(st->res_of(k)->device);
     CUDA_TRY(cudaEventSynchronize(job.done));
     if (job.n_side) {
         orph_read_result *res = (orph_read_result *)job.results.p;
@@ -220,78 +224,86 @@ static int stream_complete(orph_stream *st, StreamRes::Job &job)
 
 static void stream_worker(orph_stream *st)
 {
-    cudaSetDevice(st->r->ctx->device);
-    int prev = -1;
-    uint64_t k = 0;
+    const uint64_t lanes = st->lanes();
+    uint64_t k = 0, completed = 0;  // batches [completed, k) are on the GPUs
+    static const bool trace = getenv("ORPHEUM_B200_TRACE") != nullptr;
     auto fail_with = [&](int rc) {
+        for (StreamRes *r : st->rs) {
+            DeviceGuard guard(r->device);
+            cudaStreamSynchronize(r->ctx->stream);
+        }
         std::lock_guard<std::mutex> lk(st->mu);
         st->error = rc;
         st->error_text = g_err;  // thread-local message of this worker thread
         st->eof = true;
         st->cv.notify_all();
     };
-    auto publish = [&](int j) {
-        std::lock_guard<std::mutex> lk(st->mu);
-        st->finished.push_back(j);
-        st->cv.notify_all();
+    auto complete_next = [&]() -> int {
+        const int rc = stream_complete(st, completed);
+        if (rc != ORPH_OK) return rc;
+        {
+            std::lock_guard<std::mutex> lk(st->mu);
+            st->finished.push_back(completed);
+            st->cv.notify_all();
+        }
+        completed++;
+        return ORPH_OK;
     };
     for (;;) {
         {
             std::unique_lock<std::mutex> lk(st->mu);
-            st->cv.wait(lk, [&] { return st->stop || st->outstanding < kStreamSlots; });
+            st->cv.wait(lk, [&] { return st->stop || st->outstanding < st->max_outstanding; });
             if (st->stop) break;
             st->outstanding++;
         }
-        const int j = (int)(k % kStreamSlots);
-        StreamRes::Job &job = st->r->jobs[j];
-        static const bool trace = getenv("ORPHEUM_B200_TRACE") != nullptr;
+        StreamRes::Job &job = st->job_of(k);
         const auto t0 = std::chrono::steady_clock::now();
         int rc = orph_ingest_next_slot(st->ing, st->batch_reads, &job.slot);
         const auto t1 = std::chrono::steady_clock::now();
-        if (rc == ORPH_OK && job.slot->b.n_reads == 0) {  // end of file
-            if (prev >= 0) {
-                rc = stream_complete(st, st->r->jobs[prev]);
-                if (rc != ORPH_OK) { fail_with(rc); return; }
-                publish(prev);
-            }
+        if (rc == ORPH_OK && job.slot->b.n_reads == 0) {  // end of file: drain what is on the GPUs, in order
+            while (rc == ORPH_OK && completed < k) rc = complete_next();
+            if (rc != ORPH_OK) { fail_with(rc); return; }
             std::lock_guard<std::mutex> lk(st->mu);
             st->outstanding--;
             st->eof = true;
             st->cv.notify_all();
             return;
         }
-        if (rc == ORPH_OK) rc = stream_enqueue(st, job);
-        if (rc != ORPH_OK) {
-            cudaStreamSynchronize(st->r->ctx->stream);
-            fail_with(rc);
-            return;
-        }
+        if (rc == ORPH_OK) rc = stream_enqueue(st, k);
+        if (rc != ORPH_OK) { fail_with(rc); return; }
         const auto t2 = std::chrono::steady_clock::now();
-        if (prev >= 0) {
-            rc = stream_complete(st, st->r->jobs[prev]);
+        k++;
+        // keep one batch per lane on the GPUs: the parser works on the next one while they run
+        while (k - completed > lanes) {
+            rc = complete_next();
             if (rc != ORPH_OK) { fail_with(rc); return; }
-            publish(prev);
         }
         if (trace) {
             const auto t3 = std::chrono::steady_clock::now();
             auto ms = [](auto a, auto b) { return 1e3 * std::chrono::duration<double>(b - a).count(); };
-            fprintf(stderr, "[orph trace] stream batch %llu: %llu reads (%llu byte-path), parse+pack %.2f ms, enqueue %.2f ms, wait for the batch before %.2f ms\n",
-                    (unsigned long long)k, (unsigned long long)job.n, (unsigned long long)job.n_side, ms(t0, t1), ms(t1, t2), ms(t2, t3));
+            fprintf(stderr, "[orph trace] stream batch %llu (lane %llu): %llu reads (%llu byte-path), parse+pack %.2f ms, enqueue %.2f ms, wait for the batch before %.2f ms\n",
+                    (unsigned long long)(k - 1), (unsigned long long)((k - 1) % lanes), (unsigned long long)job.n, (unsigned long long)job.n_side, ms(t0, t1), ms(t1, t2), ms(t2, t3));
         }
-        prev = j;
-        k++;
     }
-    cudaStreamSynchronize(st->r->ctx->stream);
+    for (StreamRes *r : st->rs) {
+        DeviceGuard guard(r->device);
+        cudaStreamSynchronize(r->ctx->stream);
+    }
 }
 
-extern "C" int orph_stream_open(orph_ctx *ctx, const orph_filter *f, const char *path, const uint8_t lut[256], double jaccard_threshold,
-                                uint64_t batch_reads, int n_threads, orph_stream **out)
+extern "C" int orph_stream_open_multi(orph_ctx *const *ctxs, const orph_filter *const *filters, int n_lanes, const char *path, const uint8_t lut[256],
+                                      double jaccard_threshold, uint64_t batch_reads, int n_threads, orph_stream **out)
 {
-    if (!ctx || !f || !path || !lut || !out) return fail(ORPH_E_INVALID, "orph_stream_open: NULL argument");
+    if (!ctxs || !filters || !path || !lut || !out || n_lanes < 1 || n_lanes > 64) return fail(ORPH_E_INVALID, "orph_stream_open: bad argument");
     *out = nullptr;
-    if (f->device != ctx->device) return fail(ORPH_E_INVALID, "orph_stream_open: filter lives on device %d, context on %d", f->device, ctx->device);
+    for (int i = 0; i < n_lanes; i++) {
+        if (!ctxs[i] || !filters[i]) return fail(ORPH_E_INVALID, "orph_stream_open: NULL context / filter");
+        if (filters[i]->device != ctxs[i]->device)
+            return fail(ORPH_E_INVALID, "orph_stream_open: filter lives on device %d, context on %d", filters[i]->device, ctxs[i]->device);
+        if (filters[i]->ksize != filters[0]->ksize || filters[i]->n_tables != filters[0]->n_tables || filters[i]->n_bytes != filters[0]->n_bytes)
+            return fail(ORPH_E_INVALID, "orph_stream_open: the filters of the lanes are not replicas of one another");
+    }
     if (std::isnan(jaccard_threshold)) return fail(ORPH_E_INVALID, "orph_stream_open: jaccard_threshold is NaN");
-    DeviceGuard guard(ctx->device);
     if (n_threads <= 0) {  // the cores this process may run on, shared between the ranks of one node
         cpu_set_t set;
         n_threads = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
@@ -301,7 +313,12 @@ extern "C" int orph_stream_open(orph_ctx *ctx, const orph_filter *f, const char 
         n_threads = std::max(1, std::min(n_threads, 64));
     }
     orph_ingest *ing = nullptr;
-    int rc = orph_ingest_open_with(path, n_threads, kStreamSlots, IngestAlloc{pinned_alloc, pinned_release}, &ing);
+    // slots of the parser ring: one per lane on the GPUs + being parsed + finished + held by the caller
+    int rc;
+    {
+        DeviceGuard guard(ctxs[0]->device);  // pinned allocations
+        rc = orph_ingest_open_with(path, n_threads, n_lanes + 3, IngestAlloc{pinned_alloc, pinned_release}, &ing);
+    }
     if (rc != ORPH_OK) return rc;
     orph_stream *st = new (std::nothrow) orph_stream();
     if (!st) {
@@ -309,14 +326,19 @@ extern "C" int orph_stream_open(orph_ctx *ctx, const orph_filter *f, const char 
         return fail(ORPH_E_NOMEM, "out of host memory");
     }
     st->ing = ing;
-    st->f = f;
+    st->max_outstanding = n_lanes + 3;
     memcpy(st->lut, lut, 256);
     st->thr = jaccard_threshold;
     st->batch_reads = batch_reads ? batch_reads : (1u << 20);
-    rc = stream_res_acquire(ctx->device, &st->r);
-    if (rc == ORPH_OK) {
-        st->r->ctx->force_exact = ctx->force_exact;
-        st->r->ctx->disable_task_kernel = ctx->disable_task_kernel;
+    for (int i = 0; i < n_lanes && rc == ORPH_OK; i++) {
+        StreamRes *r = nullptr;
+        DeviceGuard guard(ctxs[i]->device);
+        rc = stream_res_acquire(ctxs[i]->device, &r);
+        if (rc != ORPH_OK) break;
+        r->ctx->force_exact = ctxs[i]->force_exact;
+        r->ctx->disable_task_kernel = ctxs[i]->disable_task_kernel;
+        st->rs.push_back(r);
+        st->fs.push_back(filters[i]);
     }
     if (rc != ORPH_OK) {
         orph_stream_close(st);
@@ -327,13 +349,20 @@ extern "C" int orph_stream_open(orph_ctx *ctx, const orph_filter *f, const char 
     return ORPH_OK;
 }
 
+extern "C" int orph_stream_open(orph_ctx *ctx, const orph_filter *f, const char *path, const uint8_t lut[256], double jaccard_threshold,
+                                uint64_t batch_reads, int n_threads, orph_stream **out)
+{
+    if (!ctx || !f) return fail(ORPH_E_INVALID, "orph_stream_open: NULL argument");
+    return orph_stream_open_multi(&ctx, &f, 1, path, lut, jaccard_threshold, batch_reads, n_threads, out);
+}
+
 extern "C" int orph_stream_next(orph_stream *st, orph_stream_batch *out)
 {
     if (!st || !out) return fail(ORPH_E_INVALID, "orph_stream_next: NULL argument");
     memset(out, 0, sizeof(*out));
     std::unique_lock<std::mutex> lk(st->mu);
-    if (st->held >= 0) {  // the caller is done with the previous batch: its slot goes back to the parser
-        st->held = -1;
+    if (st->holding) {  // the caller is done with the previous batch: its slot goes back to the parser
+        st->holding = false;
         st->outstanding--;
         st->cv.notify_all();
     }
@@ -342,11 +371,12 @@ extern "C" int orph_stream_next(orph_stream *st, orph_stream_batch *out)
         if (st->error != ORPH_OK) return fail(st->error, "%s", st->error_text.c_str());
         return ORPH_OK;  // end of file: n_reads == 0
     }
-    const int j = st->finished.front();
+    const uint64_t k = st->finished.front();
     st->finished.pop_front();
-    st->held = j;
+    st->holding = true;
+    st->held = k;
     lk.unlock();
-    const StreamRes::Job &job = st->r->jobs[j];
+    const StreamRes::Job &job = st->job_of(k);
     const orph_host::FusedBatch &b = job.slot->b;
     out->n_reads = job.n;
     out->results = (const orph_read_result *)job.results.p;
@@ -369,13 +399,15 @@ extern "C" void orph_stream_close(orph_stream *st)
         st->cv.notify_all();
     }
     if (st->worker.joinable()) st->worker.join();
-    if (st->r) {
-        DeviceGuard guard(st->r->device);
-        cudaStreamSynchronize(st->r->ctx->stream);
-        orph_ingest_close(st->ing);  // pinned slot memory: while the device is still current
-        st->ing = nullptr;
-        stream_res_release(st->r);
+    for (StreamRes *r : st->rs) {
+        DeviceGuard guard(r->device);
+        cudaStreamSynchronize(r->ctx->stream);
     }
-    if (st->ing) orph_ingest_close(st->ing);
+    if (st->ing) {
+        DeviceGuard guard(st->rs.empty() ? 0 : st->rs[0]->device);
+        orph_ingest_close(st->ing);  // pinned slot memory: while a device is current
+        st->ing = nullptr;
+    }
+    for (StreamRes *r : st->rs) stream_res_release(r);
     delete st;
 }

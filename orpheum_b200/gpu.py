@@ -357,13 +357,19 @@ class ScoringStream:
     the native library (orph_stream_*); Python sees one finished StreamBatch per iteration.  Stands in for the loop over
     ``screed.open(reads)`` in Translate.score_reads_per_file (translate.py:367-372)."""
 
-    def __init__(self, graph, path, lut, jaccard_threshold, batch_reads=1 << 20, n_threads=0, ctx=None):
+    def __init__(self, graph, path, lut, jaccard_threshold, batch_reads=1 << 20, n_threads=0, ctx=None, replicas=None):
+        """``replicas``: extra (Context, GpuNodegraph) lanes -- replicas of ``graph`` on other GPUs (``graph.replicate``) or
+        on further contexts of the same GPU; batch k is scored on lane k % n_lanes, batches still arrive in file order."""
         self._lib = _lib.load()
         self.ctx = ctx or graph.ctx
         lut = np.ascontiguousarray(lut, dtype=np.uint8)
         h = ctypes.c_void_p()
-        rc = self._lib.orph_stream_open(self.ctx._h, graph._h, os.fsencode(path), ptr(lut), float(jaccard_threshold), int(batch_reads),
-                                        int(n_threads), ctypes.byref(h))
+        lanes = [(self.ctx, graph)] + list(replicas or [])
+        ctxs = (ctypes.c_void_p * len(lanes))(*[c._h for c, _ in lanes])
+        filters = (ctypes.c_void_p * len(lanes))(*[g._h for _, g in lanes])
+        self._lanes = lanes  # contexts and filters must outlive the stream
+        rc = self._lib.orph_stream_open_multi(ctxs, filters, len(lanes), os.fsencode(path), ptr(lut), float(jaccard_threshold), int(batch_reads),
+                                              int(n_threads), ctypes.byref(h))
         if rc == _lib.ORPH_E_INVALID and "unknown file format" in _lib.last_error():
             raise ValueError(f"unknown file format for '{path}'")
         if rc == _lib.ORPH_E_IO:
@@ -399,6 +405,29 @@ class ScoringStream:
             if raw.n_reads == 0:
                 return
             yield StreamBatch(raw)
+
+
+def device_count():
+    """GPUs visible to this process (no CUDA context is created)."""
+    try:
+        import torch
+
+        return int(torch.cuda.device_count())
+    except Exception:
+        return 1
+
+
+def replica_lanes(graph, n_lanes, devices=None):
+    """(Context, GpuNodegraph) lanes for ScoringStream(replicas=...): the filter replicated over NVLink onto the other GPUs
+    of the box (``devices``: explicit device indices, repeats allowed -- two contexts on one GPU)."""
+    if devices is None:
+        n_dev = max(1, device_count())
+        devices = [(graph.ctx.device + i) % n_dev for i in range(1, n_lanes)]
+    lanes = []
+    for d in devices:
+        ctx = Context(int(d))
+        lanes.append((ctx, graph.replicate(ctx)))
+    return lanes
 
 
 def translate_frames(ctx, reads, offsets, item_read, item_frame):

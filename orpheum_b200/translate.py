@@ -7,6 +7,7 @@ six-frame translation, alphabet re-encoding, distinct k-mers, MurmurHash, Bloom 
 and only expands the integer results into the reference's rows and FASTA writes here.  There is no
 host implementation of the scoring; without the CUDA library and a B200 the calls raise.
 """
+import os
 import sys
 
 import click
@@ -285,8 +286,13 @@ class Translate:
                     continue
                 # file in, records out: parsed, packed, copied and scored by the native stream (orph_stream_*), the next
                 # batch on its way while this one is expanded into the outputs
-                with ScoringStream(self.peptide_bloom_filter, reads, self._lut, self.jaccard_threshold) as stream:
+                with ScoringStream(self.peptide_bloom_filter, reads, self._lut, self.jaccard_threshold, replicas=self._replica_lanes()) as stream:
                     for batch in stream:
+                        if batch.status == _lib.ORPH_E_TOO_LONG:
+                            bad = np.nonzero((batch.results["category"] == _lib.CAT_INVALID).all(axis=1))[0]
+                            name = batch.names().tolist()[int(bad[0])] if len(bad) else "?"
+                            raise ValueError(f"{reads}: read '{name}' is longer than {_lib.MAX_READ_LEN} nt and has a translation frame without a "
+                                             "stop codon; such a frame (more than 65535 residues) cannot be scored")
                         _lib.check(batch.status)  # an empty read: ZeroDivisionError, as in the reference (translate.py:83)
                         results = batch.results.copy()
                         names = batch.names()
@@ -295,6 +301,32 @@ class Translate:
         finally:
             self.maybe_close_fastas()
         return table
+
+    def _replica_lanes(self):
+        """Every GPU of the box takes part in scoring (the reference walks its files and reads serially,
+        translate.py:367-379): the filter is replicated once over NVLink and batches are dealt round-robin to the devices
+        by one native parser (orph_stream_open_multi); the outputs do not depend on the number of lanes.
+        ORPHEUM_B200_DEVICES="0,1,..." names the lanes explicitly (repeats allowed); otherwise one lane per 512 MB of
+        input, up to the visible GPUs -- a small input is not worth a CUDA context per GPU."""
+        if getattr(self, "_lanes", None) is not None:
+            return self._lanes
+        from .gpu import device_count, replica_lanes
+
+        graph = self.peptide_bloom_filter
+        spec = os.environ.get("ORPHEUM_B200_DEVICES")
+        if spec:
+            devices = [int(d) for d in spec.split(",") if d.strip() != ""]
+            self._lanes = replica_lanes(graph, len(devices), devices=devices[1:]) if len(devices) > 1 else []
+            return self._lanes
+        total = 0
+        for path in self.reads:
+            try:
+                total += os.path.getsize(path)
+            except OSError:
+                pass
+        n = max(1, min(device_count(), total // (512 << 20)))
+        self._lanes = replica_lanes(graph, n) if n > 1 else []
+        return self._lanes
 
     def _emit_stream_batch(self, batch, names, results):
         """Side effects of one stream batch: only the reads that emit something (a coding frame; a low-complexity

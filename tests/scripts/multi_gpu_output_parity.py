@@ -18,9 +18,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 
 
-def main():
+def check(n_reads, rank, world, local, ctx=None):
+    """Runs the comparison inside an initialised process group (or a single process); every rank calls it, rank 0 gets the
+    report (the others None).  bench.py calls it at N > 1 (`output_parity`)."""
     import torch
-    import torch.distributed as dist
 
     from oracle import oracle as orc
     from orpheum_b200 import _lib, gpu, parallel, sequence_encodings as enc, synth
@@ -28,13 +29,7 @@ def main():
     from orpheum_b200.constants_translate import FRAMES, category_text
     from orpheum_b200.create_save_summary import CreateSaveSummary
 
-    n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
-    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
-    ctx = gpu.Context(local)
+    ctx = ctx or gpu.Context(local)
     alphabet, ksize, thr = "protein", 7, 0.5
     lut = enc.encode_lut(alphabet)
     residues, poffs = synth.make_proteome(n_proteins=20000, seed=1001)
@@ -48,10 +43,11 @@ def main():
     lo, hi, view = parallel.shard_reads(offsets, rank, world)
     mine = gpu.score_reads(graph, flat, view, lut, thr, ctx=ctx)
     full = parallel.gather_records(mine, dst=0, device=f"cuda:{local}") if world > 1 else mine
-    ok = True
-    if rank == 0:
-        names = [f"read{i} mixed/{i % 7}" + (', "quoted"' if i % 1000 == 3 else "") for i in range(n_reads)]
-        tmp = tempfile.mkdtemp(prefix="orph_mgpu_")
+    if rank != 0:
+        return None
+    names = [f"read{i} mixed/{i % 7}" + (', "quoted"' if i % 1000 == 3 else "") for i in range(n_reads)]
+    tmp = tempfile.mkdtemp(prefix="orph_mgpu_")
+    try:
         table = ScoreTable(alphabet)
         table.append(names, full, "reads.fq")
         table.write_csv(os.path.join(tmp, "gpu.csv"))
@@ -82,11 +78,32 @@ def main():
         single = gpu.score_reads(graph, flat, offsets, lut, thr, ctx=ctx)
         same_as_single = single.tobytes() == full.tobytes()
         cats = np.bincount(full["category"].reshape(-1), minlength=6).tolist()
-        ok = csv_same and pq_same and json_same and same_as_single
-        print(json.dumps({"n_gpus": world, "n_reads": n_reads, "csv_identical": csv_same, "parquet_identical": bool(pq_same),
-                          "json_summary_identical": json_same, "records_identical_to_single_gpu": same_as_single,
-                          "csv_bytes": os.path.getsize(os.path.join(tmp, "gpu.csv")), "frames_per_category_code": cats,
-                          "byte_path_reads": int((full["flags"] & _lib.FLAG_BYTE_PATH != 0).sum())}))
+        csv_bytes = os.path.getsize(os.path.join(tmp, "gpu.csv"))
+    finally:
+        import shutil
+
+        shutil.rmtree(tmp, ignore_errors=True)
+    return {"n_gpus": world, "n_reads": n_reads, "csv_identical": csv_same, "parquet_identical": bool(pq_same),
+            "json_summary_identical": json_same, "records_identical_to_single_gpu": same_as_single, "csv_bytes": csv_bytes,
+            "frames_per_category_code": cats, "byte_path_reads": int((full["flags"] & _lib.FLAG_BYTE_PATH != 0).sum()),
+            "compared_with": "row-list CreateSaveSummary writers fed with oracle scores of the same reads"}
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    report = check(n_reads, rank, world, local)
+    ok = True
+    if rank == 0:
+        print(json.dumps(report))
+        ok = all(report[k] for k in ("csv_identical", "parquet_identical", "json_summary_identical", "records_identical_to_single_gpu"))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -195,3 +195,34 @@ def test_columnar_outputs_equal_row_list_outputs(workdir, monkeypatch, tmp_path)
 
     a, b = pq.read_table(str(tmp_path / "c.parquet")), pq.read_table(str(tmp_path / "r.parquet"))
     assert a.schema.equals(b.schema) and a.to_pandas().equals(b.to_pandas())
+
+
+def test_translate_cli_on_several_lanes_writes_the_same_files(workdir, golden_dir, monkeypatch):
+    """The product multi-GPU path (Translate._replica_lanes -> orph_stream_open_multi): ORPHEUM_B200_DEVICES="0,0,0" runs
+    three lanes (three private contexts, the filter replicated twice) on the one GPU of the test box; stdout, CSV, JSON summary
+    and the FASTA files must be byte-identical to the single-lane run (which is pinned to the reference's golden outputs)."""
+    from orpheum_b200 import build, translate
+
+    build.build()
+    run = next(m for m in manifest(golden_dir) if m["tag"] == "synth_protein7")
+    monkeypatch.chdir(workdir)
+    outputs = {}
+    for label, devices in (("one", "0"), ("three", "0,0,0")):
+        monkeypatch.setenv("ORPHEUM_B200_DEVICES", devices)
+        argv = [a.replace("ref_cli/synth_protein7", f"ours/lanes_{label}") for a in run["argv"]]
+        result = CliRunner().invoke(translate.cli, argv)
+        assert result.exit_code == 0, result.exception
+        files = {ext: open(os.path.join("ours", f"lanes_{label}" + ext), "rb").read()
+                 for ext in (".csv", ".json", ".coding_nt.fa", ".noncoding_nt.fa", ".lowcplx_nt.fa", ".lowcplx_pep.fa")}
+        outputs[label] = (result.output, files)
+    assert outputs["one"][0] == outputs["three"][0] and len(outputs["one"][0]) > 0
+    for ext, blob in outputs["one"][1].items():
+        other = outputs["three"][1][ext]
+        if ext == ".json":  # the summary names its own output-independent inputs only
+            assert json.loads(blob) == json.loads(other)
+        else:
+            assert blob == other, ext
+    assert outputs["three"][1][".csv"] == open(os.path.join("ref_cli", "synth_protein7.csv"), "rb").read()
+    saved = os.path.splitext(run["peptides"])[0] + f".alphabet-{run['alphabet']}_ksize-{run['ksize']}.bloomfilter.nodegraph"
+    if os.path.exists(saved):
+        os.remove(saved)

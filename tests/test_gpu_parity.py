@@ -469,6 +469,62 @@ def test_table_larger_than_2_32_bits(gpu, enc, orc):
     np.testing.assert_array_equal(gg.get_many(hashes), np.array([go.get(int(h)) for h in hashes], dtype=np.uint8))
 
 
+@pytest.mark.parametrize("reads_format", ["ascii", "packed"])
+def test_reads_beyond_the_scoring_limit_are_classified_from_their_stop_codons(gpu, enc, orc, reads_format):
+    """The reference has no read-length limit (translate.py:323-331).  Reads beyond ORPH_MAX_READ_LEN -- contigs, long
+    transcripts -- are classified exactly when no frame needs scoring (stop codons in every frame, or a low-complexity
+    read); only a longer read with a stop-free frame is refused, by name, with every other record filled in."""
+    from orpheum_b200 import _lib, synth
+
+    residues, poffs = synth.make_proteome(n_proteins=300, seed=31)
+    lut, olut = enc.encode_lut("protein"), orc.encode_lut("protein")
+    gg = gpu.GpuNodegraph(7, 1e6, 4)
+    gg.add_peptides(residues, poffs, lut)
+    go = orc.Nodegraph(7, int(1e6), 4)
+    go.add_peptides(residues, poffs, olut)
+    rng = np.random.default_rng(32)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    random_read = lambda n: acgt[rng.integers(0, 4, n)].tobytes().decode()
+    low = list("A" * 250_000)
+    for p in rng.integers(0, len(low), 2000):
+        low[int(p)] = "C"
+    reads = [random_read(150), random_read(_lib.MAX_READ_LEN + 1), random_read(300_000), "".join(low), random_read(7000),
+             random_read(1_000_003), random_read(151)]
+    if reads_format == "ascii":
+        with_n = list(random_read(220_000))
+        for p in rng.integers(0, len(with_n), 50):
+            with_n[int(p)] = "N"
+        reads += ["".join(with_n), random_read(200_000).lower()]
+    flat = np.frombuffer("".join(reads).encode(), dtype=np.uint8)
+    offsets = np.zeros(len(reads) + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum([len(r) for r in reads])
+    ora, _ = orc.score_reads(go, flat, offsets, olut, 0.5, n_threads=0)
+    if reads_format == "ascii":
+        res = gpu.score_reads(gg, flat, offsets, lut, 0.5)
+    else:
+        packed, needs = gpu.pack_reads(flat, offsets)
+        assert not needs.any()
+        res = gpu.score_reads(gg, packed, offsets, lut, 0.5, reads_format=_lib.READS_PACKED2)
+    assert_same_as_oracle(res, ora, "over-long reads")
+    assert (res["category"][3] == _lib.CAT_LOW_COMPLEXITY_NUCLEOTIDE).all() and (res["category"][2] == _lib.CAT_STOP_CODONS).all()
+    # a stop-free frame of more than 65535 residues: refused, the other records are still there
+    orf = "GCTGAA" * 40_000  # 240 kb, frame 1 = (AE)^40000
+    reads2 = [random_read(150), orf, random_read(210_000)]
+    flat2 = np.frombuffer("".join(reads2).encode(), dtype=np.uint8)
+    offs2 = np.zeros(4, dtype=np.uint64)
+    offs2[1:] = np.cumsum([len(r) for r in reads2])
+    out = np.zeros(3, dtype=_lib.READ_RESULT_DTYPE)
+    if reads_format == "ascii":
+        buf, fmt = flat2, _lib.READS_ASCII
+    else:
+        buf, fmt = gpu.pack_reads(flat2, offs2)[0], _lib.READS_PACKED2
+    rc = _lib.load().orph_score_reads(gg.ctx._h, gg._h, buf.ctypes.data, fmt, offs2.ctypes.data, 3, lut.ctypes.data, 0.5, out.ctypes.data)
+    assert rc == _lib.ORPH_E_TOO_LONG
+    assert (out["category"][1] == _lib.CAT_INVALID).all()
+    ora2, _ = orc.score_reads(go, flat2, offs2, olut, 0.5, n_threads=0)
+    assert_same_as_oracle(out[[0, 2]], ora2[[0, 2]], "records next to a refused read")
+
+
 def test_scoring_against_hbm_resident_filter(gpu, enc, orc):
     """BASELINE cfg4's filter geometry (tablesize 1e9 x 4 = 500 MB, four times the L2): 1e5 reads scored on the GPU against
     the oracle -- the probes of every table go to HBM, the persisting-L2 window covers only part of the buffer."""
@@ -626,7 +682,7 @@ def test_host_packing_ingest_paths(gpu, enc, orc):
     every route must give the records of the plain ASCII path (host_threads = 0) and of the oracle."""
     import torch
 
-    from orpheum_b200 import synth
+    from orpheum_b200 import _lib, synth
 
     residues, poffs = synth.make_proteome(n_proteins=2000, seed=41)
     lut, olut = enc.encode_lut("protein"), orc.encode_lut("protein")
@@ -660,15 +716,16 @@ def test_host_packing_ingest_paths(gpu, enc, orc):
         ctx.set_host_threads(-1)
         a, b = 12_345, 2_222_222
         assert gpu.score_reads(gg, flat, offsets[a:b + 1], lut, 0.5).tobytes() == want[a:b].tobytes()
-        # an empty read / an over-long read inside a large host-packed batch: same errors as on the small-batch route
+        # an empty read / an over-long read inside a large host-packed batch: same behaviour as on the small-batch route
         cut = 1_000_000
         offs_empty = np.concatenate([offsets[:cut + 1], offsets[cut:cut + 200_001]])  # read `cut` has length 0
         with pytest.raises(ZeroDivisionError):
             gpu.score_reads(gg, flat, offs_empty, lut, 0.5)
         offs_long = np.concatenate([offsets[:cut], offsets[cut + 2000:cut + 100_000]])  # one read of ~350 k bases
         assert int(np.diff(offs_long.astype(np.int64)).max()) > 196_607
-        with pytest.raises(ValueError):
-            gpu.score_reads(gg, flat, offs_long, lut, 0.5)
+        got_long = gpu.score_reads(gg, flat, offs_long, lut, 0.5)  # beyond ORPH_MAX_READ_LEN, stop codons in every frame: classified
+        assert (got_long["category"][cut - 1] == _lib.CAT_STOP_CODONS).all() and got_long[:cut - 1].tobytes() == want[:cut - 1].tobytes()
+        assert got_long[cut:].tobytes() == want[cut + 2000:cut + 99_999].tobytes()
         assert gpu.score_reads(gg, flat, offsets[:cut + 1], lut, 0.5).tobytes() == want[:cut].tobytes()  # the context recovers
         # mostly unpackable input: soft-masked everything
         low = np.frombuffer(flat.tobytes().lower(), dtype=np.uint8)

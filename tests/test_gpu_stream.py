@@ -173,3 +173,29 @@ def test_stream_early_close_and_reads_accessor(env, tmp_path):
     want = gpu.score_reads(env["graph"], flat, offsets, env["lut"], 0.5)
     na, nb = sum(len(x) for x in ra), sum(len(x) for x in rb)
     assert np.concatenate(ra).tobytes() == want[:na].tobytes() and np.concatenate(rb).tobytes() == want[:nb].tobytes()
+
+
+@pytest.mark.parametrize("n_lanes", [2, 3])
+def test_multi_lane_stream_delivers_the_same_batches_in_file_order(env, tmp_path, n_lanes):
+    """orph_stream_open_multi: one parser dealing batches round-robin to several device lanes (here: further private contexts
+    on the one GPU of the test box, the filter replicated with orph_filter_replicate) must deliver exactly the single-lane
+    stream -- same records, same names, same order -- including byte-path reads and a short last batch."""
+    gpu = env["gpu"]
+    n = 150_000
+    flat, offsets = mixed_reads(env, n, seed=17)
+    path = str(tmp_path / "reads.fq")
+    write_fastq(path, flat, offsets)
+    names1, res1, bp1 = stream_all(env, path, batch_reads=8192)
+    lanes = gpu.replica_lanes(env["graph"], n_lanes, devices=[0] * (n_lanes - 1))
+    for _, g in lanes:
+        assert [g.n_occupied(i) for i in range(4)] == [env["graph"].n_occupied(i) for i in range(4)]
+    names2, res2, bp2 = stream_all(env, path, batch_reads=8192, replicas=lanes)
+    assert len(res2) == n and names2 == names1 and bp2 == bp1 > 0
+    assert res2.tobytes() == res1.tobytes()
+    want = gpu.score_reads(env["graph"], flat, offsets, env["lut"], 0.5)
+    assert res2.tobytes() == want.tobytes()
+    # a caller that abandons the stream half way: close() must drain every lane
+    with gpu.ScoringStream(env["graph"], path, env["lut"], 0.5, batch_reads=8192, replicas=lanes) as st:
+        for i, batch in enumerate(st):
+            if i == 3:
+                break

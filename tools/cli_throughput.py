@@ -49,6 +49,15 @@ def main():
         result = CliRunner().invoke(translate.cli, argv)
         dt = time.perf_counter() - t
         assert result.exit_code == 0, result.exception
+    if "--profile" in sys.argv:
+        import cProfile
+        import pstats
+
+        prof = cProfile.Profile()
+        prof.enable()
+        result = CliRunner().invoke(translate.cli, argv)
+        prof.disable()
+        pstats.Stats(prof, stream=sys.stderr).sort_stats("cumulative").print_stats(45)
     summary = json.load(open(js))
     print(json.dumps({"n_reads": n_reads, "input": os.path.basename(fq), "input_bytes": size, "seconds": dt,
                       "reads_per_s": n_reads / dt, "csv_bytes": os.path.getsize(csv),
