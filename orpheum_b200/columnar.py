@@ -145,8 +145,46 @@ class ScoreTable:
     def empty_categories(self):
         return empty_categories(self.alphabet)
 
+    def _ids_all_distinct(self):
+        """True when every read id of the table is provably different from every other one: 64-bit hashes of the ids (taken
+        from the parser's name blobs, natively, no python strings) are pairwise distinct.  False = unknown (a repeated id,
+        a rare hash collision, or names held as python lists): the caller compares the ids themselves."""
+        import ctypes
+
+        lib = _lib.load()
+        hashes = []
+        for names in self._names:
+            blob, offsets = getattr(names, "blob", None), getattr(names, "offsets", None)
+            if blob is None or offsets is None:
+                return False
+            raw = np.frombuffer(blob, dtype=np.uint8) if len(blob) else np.zeros(1, dtype=np.uint8)
+            offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+            out = np.empty(len(names), dtype=np.uint64)
+            _lib.check(lib.orph_hash_names(_lib.ptr(raw), _lib.ptr(offs), len(names), _lib.ptr(out), 0))
+            hashes.append(out)
+        allh = np.concatenate(hashes) if len(hashes) > 1 else hashes[0]
+        flag = ctypes.c_int(0)
+        _lib.check(lib.orph_u64_all_distinct(_lib.ptr(allh), len(allh), 0, ctypes.byref(flag)))
+        return bool(flag.value)
+
+    def _summary_from_records(self, filenames, peptide_bloom_filter_filename, peptide_ksize, jaccard_threshold):
+        """The summary of a table whose read ids are all different (the usual case), straight from the record arrays: no
+        per-row python objects, no 6-rows-per-read expansion of anything but the jaccard column."""
+        rec = np.concatenate(self._records) if len(self._records) > 1 else self._records[0]
+        cat = rec["category"]                                     # [n, 6] uint8
+        bits = np.bitwise_or.reduce(np.left_shift(np.uint8(1), cat), axis=1)  # categories present per read, one bit each
+        present = (bits[:, None] >> np.arange(6, dtype=np.uint8)) & 1 != 0
+        per_read = (cat == _lib.CAT_CODING).sum(axis=1)
+        scored = ((cat == _lib.CAT_CODING) | (cat == _lib.CAT_NON_CODING)).reshape(-1)
+        jaccard = np.full(scored.shape, np.nan)
+        np.divide(rec["n_hits"].reshape(-1), rec["n_kmers"].reshape(-1), out=jaccard, where=scored)  # translate.py:204
+        return summarize(self.alphabet, (present, None, per_read[per_read > 0], (jaccard, scored)), filenames, peptide_bloom_filter_filename,
+                         peptide_ksize, jaccard_threshold)
+
     def summary(self, filenames, peptide_bloom_filter_filename, peptide_ksize, jaccard_threshold):
         """The dict ``CreateSaveSummary.maybe_write_json_summary`` dumps (create_save_summary.py:91-240)."""
+        if self._names and self._ids_all_distinct():
+            return self._summary_from_records(filenames, peptide_bloom_filter_filename, peptide_ksize, jaccard_threshold)
         c = self._columns()
         if c is None:
             return summarize(self.alphabet, None, filenames, peptide_bloom_filter_filename, peptide_ksize, jaccard_threshold)
@@ -190,7 +228,23 @@ def jaccard_info(jaccard):
     """count / mean / std / min / quartiles / max of the non-NaN jaccards.  Mean and std keep numpy's nan-functions (the
     summation order over the full column is part of the value, to the last bit); the order statistics are taken once
     from the compacted column instead of five separate NaN-stripping passes -- same elements, same linear
-    interpolation, same values."""
+    interpolation, same values.  A (column, validity mask) pair takes the same arithmetic without numpy's temporaries."""
+    if isinstance(jaccard, tuple):
+        jaccard, ok = jaccard
+        valid = jaccard[ok]
+        if valid.size:
+            # np.nanmean / np.nanstd, step by step (numpy/lib/_nanfunctions_impl.py): NaN -> 0, pairwise sum over the FULL
+            # column, divide by the count; deviations with the NaN positions reset to 0, squared, summed, divided
+            arr = np.where(ok, jaccard, 0.0)
+            cnt = int(ok.sum())
+            mean = np.sum(arr) / cnt
+            np.subtract(arr, mean, out=arr)
+            arr[~ok] = 0.0
+            np.multiply(arr, arr, out=arr)
+            std = np.sqrt(np.sum(arr) / cnt)
+            q25, q50, q75 = np.percentile(valid, [25, 50, 75])
+            return {"count": int(valid.size), "mean": mean, "std": std, "min": valid.min(), "25%": q25, "50%": q50, "75%": q75,
+                    "max": valid.max()}
     valid = jaccard[~np.isnan(jaccard)]
     if valid.size == 0:
         nan = float("nan")
@@ -219,8 +273,11 @@ def summarize(alphabet, rows, filenames, peptide_bloom_filter_filename, peptide_
         }
     group, codes, coding_ids, jaccard = rows
     # one category per group of rows: Coding > too-short peptide > too-short read > the only category > Non-coding
-    present = np.zeros((int(group[-1]) + 1, 6), dtype=bool)
-    present[group, codes] = True
+    if codes is None:
+        present = group  # the fast form: already the [n_groups, 6] presence matrix
+    else:
+        present = np.zeros((int(group[-1]) + 1, 6), dtype=bool)
+        present[group, codes] = True
     coding = present[:, _lib.CAT_CODING]
     short_pep = ~coding & present[:, _lib.CAT_TOO_SHORT_PEPTIDE]
     short_read = ~coding & ~short_pep & present[:, _lib.CAT_LOW_COMPLEXITY_NUCLEOTIDE]

@@ -11,6 +11,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -22,6 +23,8 @@ extern int orph_set_error(int code, const char *fmt, ...);  // orpheum_b200.cu
 int orph_fastx_open_general(const char *path, uint64_t byte_pos, uint64_t skip_records, orph_fastx **out);  // fastx.cpp
 
 using namespace orph_host;
+
+static uint64_t bgzf_block_size(const uint8_t *z, uint64_t zsize, uint64_t at);
 
 namespace {
 
@@ -135,6 +138,21 @@ int orph_ingest_open_with(const char *path, int n_threads, int n_slots, IngestAl
     if (first == '@' && compressed) {
         ing->gz = gz;  // fused parser over inflated blocks
         gz = nullptr;
+        // blocked gzip?  then the members are inflated in parallel straight from the mapped file
+        const int zfd = regular ? open(path, O_RDONLY) : -1;
+        if (zfd >= 0) {
+            void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, zfd, 0);
+            close(zfd);
+            if (m != MAP_FAILED) {
+                if (bgzf_block_size(static_cast<const uint8_t *>(m), (uint64_t)st.st_size, 0) > 0) {
+                    ing->zmap = static_cast<const uint8_t *>(m);
+                    ing->zsize = (uint64_t)st.st_size;
+                    madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+                } else {
+                    munmap(m, (size_t)st.st_size);
+                }
+            }
+        }
     }
     if (gz) gzclose(gz);
     if (ing->map || ing->gz) {
@@ -156,6 +174,7 @@ extern "C" void orph_ingest_close(orph_ingest *ing)
 {
     if (!ing) return;
     if (ing->map) munmap(const_cast<uint8_t *>(ing->map), ing->map_size);
+    if (ing->zmap) munmap(const_cast<uint8_t *>(ing->zmap), ing->zsize);
     if (ing->gz) gzclose(ing->gz);
     if (ing->fx) orph_fastx_close(ing->fx);
     ing->slots.clear();
@@ -209,6 +228,104 @@ static int next_general(orph_ingest *ing, IngestSlot &s, uint64_t max_reads)
     return ORPH_OK;
 }
 
+// BGZF: gzip members of at most 64 KiB, each with an extra field "BC" holding (member size - 1) [SAM spec 4.1].  Returns the
+// size of the member that starts at `at`, 0 if there is no well-formed BGZF member header there.
+static uint64_t bgzf_block_size(const uint8_t *z, uint64_t zsize, uint64_t at)
+{
+    if (at + 18 > zsize) return 0;
+    const uint8_t *h = z + at;
+    if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return 0;
+    const uint32_t xlen = h[10] | (h[11] << 8);
+    if (at + 12 + xlen > zsize) return 0;
+    for (uint32_t x = 0; x + 4 <= xlen;) {
+        const uint8_t *f = h + 12 + x;
+        const uint32_t slen = f[2] | (f[3] << 8);
+        if (f[0] == 'B' && f[1] == 'C' && slen == 2 && x + 6 <= xlen) {
+            const uint64_t bsize = (uint64_t)(f[4] | (f[5] << 8)) + 1;
+            if (bsize < 12 + xlen + 8 || at + bsize > zsize || (h[3] & ~4)) return 0;  // no name / comment / hcrc fields in BGZF
+            return bsize;
+        }
+        x += 4 + slen;
+    }
+    return 0;
+}
+
+// BGZF: the members that follow zpos, about `want` bytes of text, inflated in parallel behind the carried-over tail.
+// false: a member is damaged (error set) -- or *not_bgzf: the file stops being BGZF here (the caller falls back).
+static bool fill_bgzf_text(orph_ingest *ing, IngestSlot &s, uint64_t want, bool *not_bgzf)
+{
+    struct Member { uint64_t in, in_len, out, out_len; uint32_t crc; };
+    std::vector<Member> members;
+    uint64_t at = ing->zpos, out_total = 0;
+    *not_bgzf = false;
+    while (at < ing->zsize && out_total < want) {
+        const uint64_t bsize = bgzf_block_size(ing->zmap, ing->zsize, at);
+        if (bsize == 0) {
+            *not_bgzf = true;
+            break;
+        }
+        const uint8_t *h = ing->zmap + at;
+        const uint32_t xlen = h[10] | (h[11] << 8);
+        const uint8_t *tail = h + bsize - 8;
+        const uint32_t crc = tail[0] | (tail[1] << 8) | (tail[2] << 16) | ((uint32_t)tail[3] << 24);
+        const uint32_t isize = tail[4] | (tail[5] << 8) | (tail[6] << 16) | ((uint32_t)tail[7] << 24);
+        members.push_back({at + 12 + xlen, bsize - 12 - xlen - 8, out_total, isize, crc});
+        out_total += isize;
+        at += bsize;
+    }
+    if (*not_bgzf && members.empty()) return false;
+    const uint64_t carry = ing->carry.size();
+    const uint64_t need = carry + out_total + 64;
+    if (need > s.own_text_cap) {
+        uint8_t *q = static_cast<uint8_t *>(realloc(s.own_text, need + need / 8));
+        if (!q) {
+            orph_set_error(ORPH_E_NOMEM, "out of host memory");
+            return false;
+        }
+        s.own_text = q;
+        s.own_text_cap = need + need / 8;
+    }
+    if (carry) memcpy(s.own_text, ing->carry.data(), carry);
+    ing->carry.clear();
+    std::atomic<int> bad{0};
+    uint8_t *dst = s.own_text + carry;
+    const uint8_t *zmap = ing->zmap;
+    auto inflate_some = [&](uint64_t blk) {  // 16 members per work item
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, -15) != Z_OK) {
+            bad = 1;
+            return;
+        }
+        const uint64_t m1 = std::min<uint64_t>(members.size(), (blk + 1) * 16);
+        for (uint64_t m = blk * 16; m < m1; m++) {
+            const Member &mb = members[m];
+            if (mb.out_len == 0) continue;
+            inflateReset(&zs);
+            zs.next_in = const_cast<Bytef *>(zmap + mb.in);
+            zs.avail_in = (uInt)mb.in_len;
+            zs.next_out = dst + mb.out;
+            zs.avail_out = (uInt)mb.out_len;
+            const int rc = inflate(&zs, Z_FINISH);
+            if (rc != Z_STREAM_END || zs.avail_out != 0 || (uint32_t)crc32(0L, dst + mb.out, (uInt)mb.out_len) != mb.crc) bad = 1;
+        }
+        inflateEnd(&zs);
+    };
+    const uint64_t n_items = (members.size() + 15) / 16;
+    if (ing->pool) ing->pool->run(n_items, inflate_some);
+    else
+        for (uint64_t b = 0; b < n_items; b++) inflate_some(b);
+    if (bad) {
+        orph_set_error(ORPH_E_IO, "%s: a damaged BGZF block (inflate / CRC)", ing->path.c_str());
+        return false;
+    }
+    ing->zpos = at;
+    if (at >= ing->zsize) ing->gz_eof = true;
+    s.text = s.own_text;
+    s.text_len = carry + out_total;
+    return true;
+}
+
 // gzip: the slot's text = what the previous window left over + freshly inflated bytes
 static bool fill_gz_text(orph_ingest *ing, IngestSlot &s, uint64_t want)
 {
@@ -258,6 +375,19 @@ int orph_ingest_next_slot(orph_ingest *ing, uint64_t max_reads, IngestSlot **out
                 at_eof = hi == ing->map_size;
                 text_end = ing->map_size;
                 s.text = text;
+            } else if (ing->zmap) {
+                bool not_bgzf = false;
+                if (!fill_bgzf_text(ing, s, want, &not_bgzf)) {
+                    if (!not_bgzf) return ORPH_E_IO;
+                    // blocked gzip followed by something else: only a file that is BGZF from its first to its last member is
+                    // read in parallel
+                    return orph_set_error(ORPH_E_IO, "%s: not a BGZF member at byte %llu (mixed gzip / BGZF files are not supported)", ing->path.c_str(),
+                                          (unsigned long long)ing->zpos);
+                }
+                text = s.own_text;
+                lo = 0;
+                hi = text_end = s.text_len;
+                at_eof = ing->gz_eof;
             } else {
                 if (!fill_gz_text(ing, s, want)) return orph_set_error(ORPH_E_NOMEM, "out of host memory");
                 text = s.own_text;

@@ -49,6 +49,8 @@ struct orph_ingest {
     uint64_t map_size = 0, pos = 0;
     gzFile gz = nullptr;           // compressed FASTQ: blocks inflated into the slots
     bool gz_eof = false;
+    const uint8_t *zmap = nullptr; // BGZF (blocked gzip: bgzip, samtools, many sequencing pipelines): the compressed file, mapped;
+    uint64_t zsize = 0, zpos = 0;  //   its independent <= 64 KiB members are inflated in parallel on the pool
     std::vector<uint8_t> carry;    // text of a record cut by the end of the previous block
     bool general = false;          // the general sequential parser has taken over
     orph_fastx *fx = nullptr;

@@ -211,3 +211,18 @@ def counter_reads(indices, residues, prot_offsets, seed=3003, length=150):
             rd[flip] = rd[flip][:, ::-1] ^ 2
             codes[ev] = rd
     return _BASE_OF[codes]
+
+
+def write_bgzf(path, data, block=65280, level=1, eof_marker=True):
+    """Blocked gzip (BGZF, SAM spec 4.1): independent members of at most 64 KiB with a "BC" extra field that holds the
+    member's size -- what bgzip / samtools and many sequencing pipelines write."""
+    import struct
+    import zlib
+
+    with open(path, "wb") as f:
+        chunks = [data[i:i + block] for i in range(0, len(data), block)] + ([b""] if eof_marker else [])
+        for chunk in chunks:
+            comp = zlib.compressobj(level, zlib.DEFLATED, -15)
+            body = comp.compress(chunk) + comp.flush()
+            f.write(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, len(body) + 25))
+            f.write(body + struct.pack("<II", zlib.crc32(chunk), len(chunk)))

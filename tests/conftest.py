@@ -81,3 +81,4 @@ def read_fastx(path):
         if name is not None:
             out.append((name, "".join(chunks)))
     return out
+

@@ -438,6 +438,19 @@ def test_columnar_writers_against_row_list_writers_random(tmp_path):
         a, b = pq.read_table(str(d / "c.parquet")), pq.read_table(str(d / "r.parquet"))
         assert a.schema.equals(b.schema) and a.to_pandas().equals(b.to_pandas()), case
         assert js.load(open(d / "c.json")) == js.load(open(d / "r.json")), case
+        if case % 4 == 3:
+            # the same table with the parser's name blobs (fastx.NameList): the summary is computed straight from the record
+            # arrays (ids proven distinct by their hashes) and must be the same dict, floats to the last bit
+            fast = ScoreTable(alphabet)
+            for names_, rec_, (filename_, _) in zip(table._names, table._records, table._files):
+                enc = [nm.encode(*fastx.TEXT_CODEC) for nm in names_]
+                offs = np.zeros(len(enc) + 1, dtype=np.uint64)
+                offs[1:] = np.cumsum([len(e) for e in enc])
+                fast.append(fastx.NameList(b"".join(enc), offs), rec_, filename_)
+            assert fast._ids_all_distinct()
+            fast.write_json_summary(str(d / "f.json"), files, "f.nodegraph", 7, 0.5)
+            assert js.load(open(d / "f.json")) == js.load(open(d / "r.json")), case
+            assert (d / "f.json").read_text() == (d / "c.json").read_text(), case
 
 
 def test_non_ascii_read_ids_keep_their_bytes(tmp_path):

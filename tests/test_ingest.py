@@ -91,10 +91,24 @@ def write_fastq(path, seqs, rng, eol=b"\n", final_newline=True, opener=open, plu
         f.write(blob)
 
 
-@pytest.mark.parametrize("layout", ["plain", "crlf", "no_final_newline", "gz", "plus_repeats_name", "tiny_reads", "long_reads"])
+def bgzf_opener(path, mode):
+    """file-like whose content lands in `path` as BGZF when closed"""
+    import io
+
+    from orpheum_b200.synth import write_bgzf
+
+    class _Buf(io.BytesIO):
+        def close(self):
+            write_bgzf(path, self.getvalue())
+            super().close()
+
+    return _Buf()
+
+
+@pytest.mark.parametrize("layout", ["plain", "crlf", "no_final_newline", "gz", "bgzf", "plus_repeats_name", "tiny_reads", "long_reads"])
 def test_fused_ingest_matches_reader(lib, tmp_path, layout):
     rng = np.random.default_rng(hash(layout) % 1000)
-    path = str(tmp_path / ("r.fq.gz" if layout == "gz" else "r.fq"))
+    path = str(tmp_path / ("r.fq.gz" if layout in ("gz", "bgzf") else "r.fq"))
     if layout == "tiny_reads":
         seqs = random_reads(rng, 300_000, 1, 6)  # hundreds of thousands of records per 1 MiB segment
     elif layout == "long_reads":
@@ -102,7 +116,7 @@ def test_fused_ingest_matches_reader(lib, tmp_path, layout):
     else:
         seqs = random_reads(rng, 60_000)
     write_fastq(path, seqs, rng, eol=b"\r\n" if layout == "crlf" else b"\n", final_newline=layout != "no_final_newline",
-                opener=gzip.open if layout == "gz" else open, plus_repeats_name=layout == "plus_repeats_name")
+                opener=gzip.open if layout == "gz" else bgzf_opener if layout == "bgzf" else open, plus_repeats_name=layout == "plus_repeats_name")
     want_names, want_seqs = reference_records(path)
     assert want_seqs == [s.decode() for s in seqs]
     for max_reads, threads in ((0, 4), (5000, 1), (20_000, 3)):
@@ -144,6 +158,35 @@ def test_general_layouts_and_errors(lib, tmp_path):
         f.write("@a\nACGT\n+\nIIII\n@b\nACGTACGT\n+\nIII")
     with pytest.raises(OSError):
         ingest_all(lib, truncated)
+
+
+def test_bgzf_damage_and_odd_files(lib, tmp_path):
+    """Blocked gzip is inflated member by member in parallel: a flipped byte inside a member is an I/O error (CRC), a file
+    without the empty end-of-file member and a file of one tiny member still parse, long reads span many members."""
+    from orpheum_b200.synth import write_bgzf
+
+    rng = np.random.default_rng(8)
+    seqs = random_reads(rng, 20_000, 50, 300) + random_reads(rng, 3, 150_000, 400_000, dirty=0)
+    plain = str(tmp_path / "r.fq")
+    write_fastq(plain, seqs, rng)
+    data = open(plain, "rb").read()
+    want_names, want_seqs = reference_records(plain)
+    for name, kw in (("full.fq.gz", {}), ("no_eof.fq.gz", {"eof_marker": False}), ("small_blocks.fq.gz", {"block": 997})):
+        path = str(tmp_path / name)
+        write_bgzf(path, data, **kw)
+        assert gzip.open(path, "rb").read() == data  # a valid multi-member gzip file
+        for max_reads, threads in ((0, 4), (3000, 2)):
+            names, got, _ = ingest_all(lib, path, max_reads, threads)
+            assert got == want_seqs and names == want_names, name
+    tiny = str(tmp_path / "tiny.fq.gz")
+    write_bgzf(tiny, b"@a\nACGT\n+\nIIII\n")
+    assert ingest_all(lib, tiny)[:2] == (["a"], ["ACGT"])
+    damaged = str(tmp_path / "damaged.fq.gz")
+    blob = bytearray(open(str(tmp_path / "full.fq.gz"), "rb").read())
+    blob[len(blob) // 2] ^= 0x5A
+    open(damaged, "wb").write(bytes(blob))
+    with pytest.raises(OSError):
+        ingest_all(lib, damaged)
 
 
 def test_gather_reads(lib, tmp_path):
