@@ -449,9 +449,20 @@ def format_fasta(kind, names_blob, name_offsets, results, reads, read_offsets, p
     args = [int(kind), ptr(names_blob), ptr(name_offsets), n, ptr(results), ptr(reads) if reads is not None else None,
             ptr(read_offsets) if read_offsets is not None else None, ptr(peptides) if peptides is not None else None,
             ptr(pep_offsets) if pep_offsets is not None else None, int(bool(peptides_include_low_complexity))]
-    check(lib.orph_format_fasta(*args, None, 0, ctypes.byref(need)))
-    out = np.empty(max(int(need.value), 1), dtype=np.uint8)
-    check(lib.orph_format_fasta(*args, ptr(out), int(need.value), ctypes.byref(need)))
+    # one formatting pass in the usual case: a buffer sized from the inputs (header = name + ~60 bytes of decoration per
+    # emitted frame), a second pass only if that guess was too small
+    n_items = len(pep_offsets) - 1 if pep_offsets is not None else 0
+    per_name = (len(names_blob) // max(n, 1)) + 64
+    guess = n_items * per_name + (len(peptides) if peptides is not None else 0) + 4096
+    if kind == 1:
+        guess += 2 * int(len(reads))
+    elif kind == 2:  # up to six records per read, each with the whole read (untouched pages of np.empty cost nothing)
+        guess += 6 * (int(len(reads)) + n * per_name)
+    out = np.empty(max(guess, 1), dtype=np.uint8)
+    check(lib.orph_format_fasta(*args, ptr(out), len(out), ctypes.byref(need)))
+    if int(need.value) > len(out):
+        out = np.empty(int(need.value), dtype=np.uint8)
+        check(lib.orph_format_fasta(*args, ptr(out), len(out), ctypes.byref(need)))
     return out[: int(need.value)].tobytes()
 
 

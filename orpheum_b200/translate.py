@@ -255,19 +255,29 @@ class Translate:
         keys = np.asarray(FRAMES, dtype=np.int8)[frames_idx]
         peptides, pep_offsets = translate_frames_raw(self.peptide_bloom_filter.ctx, flat, offsets, reads_idx, keys)
 
-        def render(kind):
-            return format_fasta(kind, name_blob, name_offsets, results, flat, offsets, peptides, pep_offsets, with_lcp).decode(*fastx.TEXT_CODEC)
+        def emit(kind, handle):
+            """The formatted records as BYTES into the handle's binary layer when it has one that writes UTF-8 (the text layer
+            would decode and re-encode every byte to the same effect)."""
+            blob = format_fasta(kind, name_blob, name_offsets, results, flat, offsets, peptides, pep_offsets, with_lcp)
+            if not blob:
+                return
+            raw = getattr(handle, "buffer", None)
+            if raw is not None and str(getattr(handle, "encoding", "")).lower().replace("-", "") == "utf8" \
+                    and getattr(handle, "errors", None) in ("strict", "surrogateescape", None) and getattr(handle, "newline", None) is None \
+                    and os.linesep == "\n":
+                handle.flush()
+                raw.write(blob)
+            else:
+                handle.write(blob.decode(*fastx.TEXT_CODEC))
 
         if with_lcp:
-            handles["low_complexity_peptide"].write(render(3))
+            emit(3, handles["low_complexity_peptide"])
         if handles["coding_nucleotide"] is not None:
-            handles["coding_nucleotide"].write(render(1))
+            emit(1, handles["coding_nucleotide"])
         if has_noncoding:
-            handles["noncoding_nucleotide"].write(render(2))
-        text = render(0)
-        if text:
-            sys.stdout.write(text)
-            sys.stdout.flush()
+            emit(2, handles["noncoding_nucleotide"])
+        emit(0, sys.stdout)
+        sys.stdout.flush()
 
     def score_all_files_columnar(self):
         """Score every input file and return a columnar ``ScoreTable`` (same information as ``coding_scores``,

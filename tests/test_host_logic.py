@@ -447,7 +447,8 @@ def test_columnar_writers_against_row_list_writers_random(tmp_path):
                 offs = np.zeros(len(enc) + 1, dtype=np.uint64)
                 offs[1:] = np.cumsum([len(e) for e in enc])
                 fast.append(fastx.NameList(b"".join(enc), offs), rec_, filename_)
-            assert fast._ids_all_distinct()
+            every_id = [nm for names_ in table._names for nm in names_]
+            assert fast._ids_all_distinct() == (len(set(every_id)) == len(every_id))
             fast.write_json_summary(str(d / "f.json"), files, "f.nodegraph", 7, 0.5)
             assert js.load(open(d / "f.json")) == js.load(open(d / "r.json")), case
             assert (d / "f.json").read_text() == (d / "c.json").read_text(), case
