@@ -172,7 +172,9 @@ int orph_filter_replicate(const orph_filter *src, orph_ctx *dst_ctx, orph_filter
  * the same) and orph_filter_n_unique_kmers() then over-counts k-mers that were inserted concurrently. */
 int orph_filter_add_peptides(orph_filter *f, const uint8_t *residues, const uint64_t *offsets, uint64_t n_records,
                              const uint8_t lut[256], uint64_t *n_unique_kmers_inc);
-/* Nodegraph.add(hash) for a batch of precomputed hashes (index.py:119); is_new (optional) gets 0/1. */
+/* Nodegraph.add(hash) for a batch of precomputed hashes (index.py:119); is_new (optional) gets 0/1.  The bits are exact;
+ * is_new / n_unique_kmers are what khmer reports only for batches without duplicates and without k-mers racing for the same
+ * new bit (concurrent insertion: two such hashes can both see themselves as new). */
 int orph_filter_add_hashes(orph_filter *f, const uint64_t *hashes, uint64_t n, uint8_t *is_new);
 /* Nodegraph.get(hash) for a batch of hashes (translate.py:190); out01[i] = 0/1.  Host arrays. */
 int orph_filter_query_hashes(const orph_filter *f, const uint64_t *hashes, uint64_t n, uint8_t *out01);

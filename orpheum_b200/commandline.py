@@ -1,15 +1,17 @@
 """``orpheum`` command group with the two sub-commands on the GPU path, ``translate`` and ``index``
 (same names, options and help behaviour as ``orpheum/commandline.py:21-36``; ``compare-kmers`` is a separate
 analysis tool outside the scoring path and is not provided)."""
-import functools
-
 import click
 
-# every option shows its default in --help, as in the reference's command line (commandline.py:16)
-click.option = functools.partial(click.option, show_default=True)
+from . import index as _index
+from . import translate as _translate
 
-from . import index as _index  # noqa: E402  (imported after the patch above, so their options inherit it)
-from . import translate as _translate  # noqa: E402
+# every option shows its default in --help, as in the reference's command line (commandline.py:16 patches click.option for
+# the whole process; here only the options of these two commands are touched, whatever the import order)
+for _command in (_index.cli, _translate.cli):
+    for _param in _command.params:
+        if isinstance(_param, click.Option) and _param.show_default is None:
+            _param.show_default = True
 
 cli = click.Group(
     name="orpheum",

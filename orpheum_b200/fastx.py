@@ -1,6 +1,11 @@
 """FASTA / FASTQ(.gz/.bz2) reading with screed's record semantics (the reference calls ``screed.open``
 at translate.py:370 and index.py:83): ``name`` is the full header line, ``sequence`` is returned
 untouched (no upper-casing), an empty file yields nothing, anything else raises ValueError.
+
+Deliberate choice, NOT checked against the pinned screed (it is not installable here): a blank line between FASTQ records
+is skipped and parsing continues (python reader and csrc/fastx.cpp alike).  screed 1.0.x may instead stop at the blank line
+and drop the rest of the file; sequencers do not write such files, the reference's fixtures hold none, and silently losing
+records seemed the worse of the two behaviours.
 """
 import bz2
 import gzip
@@ -238,9 +243,15 @@ def _prefetched(make_iter, depth):
                         continue
                 if stop.is_set():
                     return
-            q.put((None, StopIteration()))
+            final = (None, StopIteration())
         except BaseException as exc:  # re-raised in the consumer
-            q.put((None, exc))
+            final = (None, exc)
+        while not stop.is_set():  # the sentinel too: a consumer that left early must not leave this thread blocked on a full queue
+            try:
+                q.put(final, timeout=0.1)
+                return
+            except queue.Full:
+                continue
 
     t = threading.Thread(target=work, daemon=True)
     t.start()

@@ -417,6 +417,8 @@ def cli(peptides, reads, peptide_ksize=None, save_peptide_bloom_filter=True, pep
         if csv:
             pending.append(pool.submit(table.write_csv, csv))
         if parquet and len(table):
+            # (no read scored -- an empty input -- writes no parquet file; the reference builds a RecordBatch from six empty
+            # python lists there, whose column types pyarrow cannot infer: nothing useful to be faithful to)
             pending.append(pool.submit(table.write_parquet, parquet))
         if json_summary:
             table.write_json_summary(json_summary, reads, translate_obj.peptide_bloom_filter_filename,
