@@ -129,6 +129,14 @@ static cudaError_t wait_event_polling(cudaEvent_t e)
     }
 }
 
+static bool input_is_pinned(const void *p)
+{
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess) return attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    return false;
+}
+
 static int pipe_setup(orph_ctx *ctx)
 {
     if (ctx->pipe_ready) return ORPH_OK;
@@ -411,12 +419,7 @@ static int score_host_pipeline(orph_ctx *ctx, const orph_filter *f, const void *
         ctx->pool = new (std::nothrow) orph_host::Pool(n);
         if (!ctx->pool) return fail(ORPH_E_NOMEM, "out of host memory");
     }
-    bool input_pinned = false;
-    {
-        cudaPointerAttributes attr;
-        if (cudaPointerGetAttributes(&attr, reads) == cudaSuccess) input_pinned = attr.type == cudaMemoryTypeHost;
-        else cudaGetLastError();
-    }
+    const bool input_pinned = input_is_pinned(reads);
     if (allow_pack && !ctx->lane_ctx) {
         if ((rc = orph_ctx_create(ctx->device, nullptr, &ctx->lane_ctx)) != ORPH_OK) return rc;
     }
@@ -508,8 +511,15 @@ extern "C" int orph_score_reads(orph_ctx *ctx, const orph_filter *f, const void 
     if (n_reads == 0) return ORPH_OK;
     DeviceGuard guard(ctx->device);
     // host packing pays once a batch is large enough to keep the pool busy; small batches go out as they are
-    const bool allow_pack = reads_format == ORPH_READS_ASCII && ctx->host_threads != 0 && offsets[n_reads] >= offsets[0] &&
-                            offsets[n_reads] - offsets[0] >= (1ULL << 22);
+    bool allow_pack = reads_format == ORPH_READS_ASCII && ctx->host_threads != 0 && offsets[n_reads] >= offsets[0] &&
+                      offsets[n_reads] - offsets[0] >= (1ULL << 22);
+    // A host-packed chunk costs the host's memory 1.5 bytes per base (read, write 2 bits, DMA reads them) against 1 for a
+    // chunk the copy engine takes as it is: when the pool packs clearly slower than the wire carries -- many ranks sharing
+    // one host, measured: eight ranks with four threads each pack 12 GB/s next to 20 GB/s links and the call is 5 % faster
+    // without the packing lane -- the lane stays off, and is tried again every 16th call in case the host got quieter.
+    if (allow_pack && input_is_pinned(reads) && ctx->pack_s_per_byte > 0 && 1.0 / ctx->pack_s_per_byte < 0.75 * ctx->h2d_bytes_per_s &&
+        (++ctx->pack_lane_skips & 15) != 0)
+        allow_pack = false;
     std::vector<uint64_t> exceptions;
     rc = score_host_pipeline(ctx, f, reads, reads_format, offsets, n_reads, lut, jaccard_threshold, out, allow_pack, &exceptions);
     if (rc != ORPH_OK && rc != ORPH_E_EMPTY_READ && rc != ORPH_E_TOO_LONG) return rc;

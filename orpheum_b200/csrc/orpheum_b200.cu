@@ -262,6 +262,7 @@ struct orph_ctx {
     double pack_s_per_byte = 0;                          // measured host packing cost (running average)
     double h2d_bytes_per_s = 50e9;                       // planning estimate of the H2D rate
     uint64_t chunks_packed_on_host = 0, chunks_sent_ascii = 0;
+    uint32_t pack_lane_skips = 0;                        // calls that went without the packing lane because it was the slower route
     DevBuf misc;                 // small transfers (hash batches, ...)
     bool timing = false;
     struct Interval { cudaEvent_t a, b; int id; };

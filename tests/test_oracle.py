@@ -202,3 +202,51 @@ def test_batch_matches_single_and_threads(refdata):
     assert one.tobytes() == many.tobytes()
     for i, s in enumerate(seqs):
         assert orc.score_read(g, s, lut, 0.5).tobytes() == one[i].tobytes()
+
+
+def test_staged_reference_with_native_shims_reproduces_the_golden_cli_outputs(golden_dir, tmp_path):
+    """The thing `bench.py --impl reference` times -- the unmodified reference modules staged in oracle/_ref with khmer's
+    Nodegraph and sourmash's hash_murmur as a native extension over the oracle's C code (oracle/refnative) -- must produce
+    the committed outputs of the reference CLI (tests/golden/ref_cli, generated through the independent pure-python stand-ins
+    of oracle/shims): same CSV, same stdout, same JSON summary.  Runs in a subprocess (the staged package is called
+    `orpheum`); skipped where oracle/_ref has not been staged (no /root/reference and no prebuilt copy)."""
+    import json
+    import shutil
+    import subprocess
+    import sys
+
+    from oracle import stage_reference
+
+    if not stage_reference.staged() and not stage_reference.stage():
+        pytest.skip("oracle/_ref is not staged and /root/reference is absent")
+    root = os.path.dirname(golden_dir.rstrip("/"))  # tests/
+    work = tmp_path / "golden_copy"
+    for sub in ("reference_data", "ref_cli"):
+        shutil.copytree(os.path.join(golden_dir, sub), work / sub)
+    (work / "ours").mkdir()
+    runs = json.load(open(os.path.join(golden_dir, "ref_cli", "manifest.json")))
+    code = (
+        "import sys, json, io, contextlib\n"
+        f"sys.path.insert(0, {os.path.dirname(root)!r})\n"
+        "from oracle import stage_reference\n"
+        "stage_reference.activate()\n"
+        "import khmer, orpheum.translate as T\n"
+        "assert type(khmer.Nodegraph).__module__ == 'builtins' and khmer.Nodegraph.__module__ == '_orph_refnative'\n"
+        "argv = json.loads(sys.argv[1])\n"
+        "buf = io.StringIO()\n"
+        "with contextlib.redirect_stdout(buf):\n"
+        "    T.cli.main(argv, standalone_mode=False)\n"
+        "open(sys.argv[2], 'w').write(buf.getvalue())\n"
+    )
+    for run in runs:
+        tag = run["tag"]
+        argv = [a.replace("ref_cli/" + tag, "ours/" + tag) for a in run["argv"]]
+        proc = subprocess.run([sys.executable, "-c", code, json.dumps(argv), f"ours/{tag}.stdout.txt"], cwd=work, capture_output=True, text=True, timeout=600)
+        assert proc.returncode == 0, proc.stderr[-2000:]
+        ref = lambda ext: open(work / "ref_cli" / (tag + ext)).read()
+        ours = lambda ext: open(work / "ours" / (tag + ext)).read()
+        ref_stdout = ref(".stdout.txt")
+        ref_stdout = ref_stdout[ref_stdout.index(">"):] if ">" in ref_stdout else ""
+        assert ours(".stdout.txt") == ref_stdout, tag
+        assert ours(".csv") == ref(".csv"), tag
+        assert json.loads(ours(".json")) == json.loads(ref(".json")), tag

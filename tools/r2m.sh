@@ -2,7 +2,7 @@ python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127
 tail -c 1200 gpurun_out/r2m_bench_n$1.err
 python - <<PY
 import json
-d=json.load(open("gpurun_out/r2m_bench_n$1.json"))
+d=json.loads([l for l in open("gpurun_out/r2m_bench_n$1.json") if l.startswith("{")][-1])
 e=d["e2e"]
 print("value", d["value"], "e2e", e["value"], e["ms_per_step"], "pcie_only", e["ascii_over_pcie_only"]["value"], "packed", e["packed_input"]["value"], e["packed_input"]["ms_per_step"])
 print("from_fastq", e["from_fastq"])
