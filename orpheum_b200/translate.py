@@ -316,8 +316,9 @@ class Translate:
         """Every GPU of the box takes part in scoring (the reference walks its files and reads serially,
         translate.py:367-379): the filter is replicated once over NVLink and batches are dealt round-robin to the devices
         by one native parser (orph_stream_open_multi); the outputs do not depend on the number of lanes.
-        ORPHEUM_B200_DEVICES="0,1,..." names the lanes explicitly (repeats allowed); otherwise one lane per 512 MB of
-        input, up to the visible GPUs -- a small input is not worth a CUDA context per GPU."""
+        ORPHEUM_B200_DEVICES="0,1,..." names the lanes explicitly (repeats allowed); otherwise one lane per 2 GB of
+        input, up to the visible GPUs -- a CUDA context per extra GPU costs a few tenths of a second, and one B200 already
+        scores several times what the host's parser delivers, so small inputs stay on one GPU."""
         if getattr(self, "_lanes", None) is not None:
             return self._lanes
         from .gpu import device_count, replica_lanes
@@ -334,7 +335,7 @@ class Translate:
                 total += os.path.getsize(path)
             except OSError:
                 pass
-        n = max(1, min(device_count(), total // (512 << 20)))
+        n = max(1, min(device_count(), total // (2 << 30)))
         self._lanes = replica_lanes(graph, n) if n > 1 else []
         return self._lanes
 
