@@ -298,6 +298,13 @@ int orph_stream_open_multi(orph_ctx *const *ctxs, const orph_filter *const *filt
                            orph_stream **out);
 /* Blocks until the next batch is scored.  The pointers stay valid until the next call on the same stream. */
 int orph_stream_next(orph_stream *st, orph_stream_batch *out);
+/* The FASTA records Translate emits for the batch last returned by orph_stream_next (translate.py:244-298), formatted by
+ * the library: bit k of kinds_mask asks for kind k of orph_format_fasta (0 coding peptides = the stdout stream, 1 / 2 coding /
+ * non-coding nucleotides, 3 low-complexity peptides).  The emitting frames are found in the records, their reads gathered
+ * from the text, their peptides translated by one orph_translate_frames call on `ctx` (a context of the caller's, not the
+ * stream's), the text formatted block-parallel.  out[k] / out_len[k]: the bytes of kind k (NULL / 0 if not requested or
+ * empty), valid until the next call on the stream. */
+int orph_stream_emit(orph_stream *st, orph_ctx *ctx, uint32_t kinds_mask, const uint8_t *out[4], uint64_t out_len[4]);
 void orph_stream_close(orph_stream *st);
 
 /* ---- score CSV straight from the result records -------------------------------------------------- */

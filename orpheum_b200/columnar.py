@@ -20,9 +20,15 @@ _FRAMES = np.asarray(FRAMES, dtype=np.int64)
 class ScoreTable:
     """Accumulates (names, orph_read_result records, file name) batches in read order."""
 
-    def __init__(self, alphabet):
+    def __init__(self, alphabet, background_summary=False):
+        """background_summary: every appended batch's share of the JSON summary (read classes, coding-frame histogram,
+        jaccard column, id hashes) is computed right away on a background thread -- numpy and the native calls release the
+        GIL -- so that only the order statistics over the whole jaccard column are left when the last batch is in."""
         self.alphabet = alphabet
         self._names, self._records, self._files = [], [], []
+        self._partials = [] if background_summary else None
+        self._csv_path = self._csv_tmp = None
+        self._csv_jobs = []
 
     def append(self, names, records, filename):
         """names: a list of str or a fastx.NameList (byte blob + offsets, kept as is for the CSV writer)."""
@@ -30,6 +36,28 @@ class ScoreTable:
             self._names.append(names)
             self._records.append(records)
             self._files.append((filename, len(names)))
+            if self._partials is not None:
+                self._partials.append(_background().submit(_partial_summary, names, records))
+            if self._csv_tmp is not None:
+                self._csv_jobs.append(_background("csv").submit(self.append_csv_batch, self._csv_tmp, names, records, filename))
+
+    def stream_csv_to(self, path):
+        """From now on every appended batch's rows are formatted and appended to the CSV right away, on a background thread
+        (the native formatter releases the GIL), into ``path + ".partial"``; ``write_csv(path)`` then only waits and renames.
+        A run that fails leaves no CSV behind (``discard_csv_stream``), as with the reference, which writes it last."""
+        self._csv_path, self._csv_tmp = path, path + ".partial"
+        self.write_csv_header(self._csv_tmp)
+
+    def discard_csv_stream(self):
+        for job in self._csv_jobs:
+            try:
+                job.result()
+            except Exception:
+                pass
+        if self._csv_tmp is not None and os.path.exists(self._csv_tmp):
+            os.remove(self._csv_tmp)
+        self._csv_path = self._csv_tmp = None
+        self._csv_jobs = []
 
     def __len__(self):
         return sum(len(n) for n in self._names)
@@ -105,6 +133,13 @@ class ScoreTable:
     def write_csv(self, path):
         """Byte-identical to ``csv.writer(lineterminator="\n")`` over the reference's row lists; the rows are
         formatted by the native writer (orph_csv_write_scores) batch by batch."""
+        if self._csv_tmp is not None and path == self._csv_path:  # streamed while the batches came in
+            for job in self._csv_jobs:
+                job.result()
+            os.replace(self._csv_tmp, path)
+            self._csv_path = self._csv_tmp = None
+            self._csv_jobs = []
+            return
         self.write_csv_header(path)
         for names, records, (filename, _) in zip(self._names, self._records, self._files):
             self.append_csv_batch(path, names, records, filename)
@@ -154,14 +189,10 @@ class ScoreTable:
         lib = _lib.load()
         hashes = []
         for names in self._names:
-            blob, offsets = getattr(names, "blob", None), getattr(names, "offsets", None)
-            if blob is None or offsets is None:
+            h = _name_hashes(names)
+            if h is None:
                 return False
-            raw = np.frombuffer(blob, dtype=np.uint8) if len(blob) else np.zeros(1, dtype=np.uint8)
-            offs = np.ascontiguousarray(offsets, dtype=np.uint64)
-            out = np.empty(len(names), dtype=np.uint64)
-            _lib.check(lib.orph_hash_names(_lib.ptr(raw), _lib.ptr(offs), len(names), _lib.ptr(out), 0))
-            hashes.append(out)
+            hashes.append(h)
         allh = np.concatenate(hashes) if len(hashes) > 1 else hashes[0]
         flag = ctypes.c_int(0)
         _lib.check(lib.orph_u64_all_distinct(_lib.ptr(allh), len(allh), 0, ctypes.byref(flag)))
@@ -171,18 +202,38 @@ class ScoreTable:
         """The summary of a table whose read ids are all different (the usual case), straight from the record arrays: no
         per-row python objects, no 6-rows-per-read expansion of anything but the jaccard column."""
         rec = np.concatenate(self._records) if len(self._records) > 1 else self._records[0]
-        cat = rec["category"]                                     # [n, 6] uint8
-        bits = np.bitwise_or.reduce(np.left_shift(np.uint8(1), cat), axis=1)  # categories present per read, one bit each
-        present = (bits[:, None] >> np.arange(6, dtype=np.uint8)) & 1 != 0
-        per_read = (cat == _lib.CAT_CODING).sum(axis=1)
-        scored = ((cat == _lib.CAT_CODING) | (cat == _lib.CAT_NON_CODING)).reshape(-1)
-        jaccard = np.full(scored.shape, np.nan)
-        np.divide(rec["n_hits"].reshape(-1), rec["n_kmers"].reshape(-1), out=jaccard, where=scored)  # translate.py:204
-        return summarize(self.alphabet, (present, None, per_read[per_read > 0], (jaccard, scored)), filenames, peptide_bloom_filter_filename,
-                         peptide_ksize, jaccard_threshold)
+        present, coding_counts, jaccard, scored = _record_columns(rec)
+        return _finish_summary(self.alphabet, _class_counts(present), _coding_histogram(coding_counts), (jaccard, scored), filenames,
+                               peptide_bloom_filter_filename, peptide_ksize, jaccard_threshold)
+
+    def _summary_from_partials(self, filenames, peptide_bloom_filter_filename, peptide_ksize, jaccard_threshold):
+        """Combines the per-batch shares computed in the background; None if the read ids are not provably distinct."""
+        import ctypes
+
+        parts = [job.result() for job in self._partials]
+        if any(p["hashes"] is None for p in parts):
+            return None
+        hashes = np.concatenate([p["hashes"] for p in parts]) if len(parts) > 1 else parts[0]["hashes"]
+        flag = ctypes.c_int(0)
+        _lib.check(_lib.load().orph_u64_all_distinct(_lib.ptr(hashes), len(hashes), 0, ctypes.byref(flag)))
+        if not flag.value:
+            return None
+        classes = [sum(p["classes"][i] for p in parts) for i in range(3)] + [sum(p["classes"][3] for p in parts), sum(p["classes"][4] for p in parts)]
+        histogram = {}
+        for p in parts:  # keys in order of first appearance over the whole table
+            for value, count in p["histogram"].items():
+                histogram[value] = histogram.get(value, 0) + count
+        jaccard = np.concatenate([p["jaccard"] for p in parts]) if len(parts) > 1 else parts[0]["jaccard"]
+        scored = np.concatenate([p["scored"] for p in parts]) if len(parts) > 1 else parts[0]["scored"]
+        return _finish_summary(self.alphabet, classes, histogram, (jaccard, scored), filenames, peptide_bloom_filter_filename, peptide_ksize,
+                               jaccard_threshold)
 
     def summary(self, filenames, peptide_bloom_filter_filename, peptide_ksize, jaccard_threshold):
         """The dict ``CreateSaveSummary.maybe_write_json_summary`` dumps (create_save_summary.py:91-240)."""
+        if self._names and self._partials is not None and len(self._partials) == len(self._names):
+            done = self._summary_from_partials(filenames, peptide_bloom_filter_filename, peptide_ksize, jaccard_threshold)
+            if done is not None:
+                return done
         if self._names and self._ids_all_distinct():
             return self._summary_from_records(filenames, peptide_bloom_filter_filename, peptide_ksize, jaccard_threshold)
         c = self._columns()
@@ -206,6 +257,95 @@ class ScoreTable:
         with open(path, "w") as handle:
             json.dump(summary, fp=handle)
         return summary
+
+
+_bg_executors = {}
+
+
+def _background(which="summary"):
+    """One background thread per kind of work ("summary", "csv"), shared by every table of the process, created on first
+    use: jobs of one kind run in submission order."""
+    if which not in _bg_executors:
+        from concurrent.futures import ThreadPoolExecutor
+
+        _bg_executors[which] = ThreadPoolExecutor(1, thread_name_prefix="orph-" + which)
+    return _bg_executors[which]
+
+
+def _name_hashes(names):
+    """64-bit hashes of a batch's read ids, taken natively from the parser's name blob; None for python lists."""
+    blob, offsets = getattr(names, "blob", None), getattr(names, "offsets", None)
+    if blob is None or offsets is None:
+        return None
+    raw = np.frombuffer(blob, dtype=np.uint8) if len(blob) else np.zeros(1, dtype=np.uint8)
+    offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+    out = np.empty(len(names), dtype=np.uint64)
+    _lib.check(_lib.load().orph_hash_names(_lib.ptr(raw), _lib.ptr(offs), len(names), _lib.ptr(out), 0))
+    return out
+
+
+def _record_columns(rec):
+    """(presence matrix [n, 6], coding frames per read that has any, jaccard per row, scored mask per row) of a record array
+    whose read ids are all different."""
+    cat = rec["category"]                                     # [n, 6] uint8
+    bits = np.bitwise_or.reduce(np.left_shift(np.uint8(1), cat), axis=1)  # categories present per read, one bit each
+    present = (bits[:, None] >> np.arange(6, dtype=np.uint8)) & 1 != 0
+    per_read = (cat == _lib.CAT_CODING).sum(axis=1)
+    scored = ((cat == _lib.CAT_CODING) | (cat == _lib.CAT_NON_CODING)).reshape(-1)
+    jaccard = np.full(scored.shape, np.nan)
+    np.divide(rec["n_hits"].reshape(-1), rec["n_kmers"].reshape(-1), out=jaccard, where=scored)  # translate.py:204
+    return present, per_read[per_read > 0], jaccard, scored
+
+
+def _class_counts(present):
+    """One category per read: Coding > too-short peptide > too-short read > the only category > Non-coding.
+    -> (coding, too-short peptide, too-short read, reads whose only category is code c [6], non-coding)."""
+    coding = present[:, _lib.CAT_CODING]
+    short_pep = ~coding & present[:, _lib.CAT_TOO_SHORT_PEPTIDE]
+    short_read = ~coding & ~short_pep & present[:, _lib.CAT_LOW_COMPLEXITY_NUCLEOTIDE]
+    undecided = ~coding & ~short_pep & ~short_read
+    single = undecided & (present.sum(axis=1) == 1)
+    only = np.bincount(np.argmax(present[single], axis=1), minlength=6).astype(np.int64)
+    return [int(coding.sum()), int(short_pep.sum()), int(short_read.sum()), only, int((undecided & ~single).sum())]
+
+
+def _coding_histogram(coding_counts):
+    """{coding frames per id: number of ids}, keys in order of first appearance (as Counter / dict insertion gives them)."""
+    histogram = {}
+    values, first, n_ids = np.unique(coding_counts, return_index=True, return_counts=True)
+    for at in np.argsort(first):
+        histogram[int(values[at])] = int(n_ids[at])
+    return histogram
+
+
+def _partial_summary(names, records):
+    present, coding_counts, jaccard, scored = _record_columns(records)
+    return {"classes": _class_counts(present), "histogram": _coding_histogram(coding_counts), "jaccard": jaccard, "scored": scored,
+            "hashes": _name_hashes(names)}
+
+
+def _finish_summary(alphabet, classes, histogram, jaccard, filenames, peptide_bloom_filter_filename, peptide_ksize, jaccard_threshold):
+    input_files = [os.path.basename(f) for f in ([filenames] if isinstance(filenames, str) else filenames)]
+    counts = empty_categories(alphabet)
+    counts["Coding"] += classes[0]
+    counts[PROTEIN_CODING_CATEGORIES["too_short_peptide"]] += classes[1]
+    counts[PROTEIN_CODING_CATEGORIES["too_short_nucleotide"]] += classes[2]
+    for code in np.nonzero(classes[3])[0]:
+        counts[category_text(int(code), alphabet)] += int(classes[3][code])
+    counts["Non-coding"] += classes[4]
+    total = sum(counts.values())
+    n_coding_ids = sum(histogram.values())
+    label = "Number of reads with {} putative protein-coding translations".format
+    return {
+        "input_files": input_files,
+        "jaccard_info": jaccard_info(jaccard),
+        "categorization_counts": counts,
+        "categorization_percentages": {k: 100 * v / total for k, v in counts.items()},
+        "histogram_n_coding_frames_per_read": {label(k): v for k, v in histogram.items()},
+        "histogram_n_coding_frames_per_read_percentages": {label(k): 100 * v / n_coding_ids for k, v in histogram.items()},
+        "peptide_bloom_filter": peptide_bloom_filter_filename, "peptide_alphabet": alphabet, "peptide_ksize": peptide_ksize,
+        "jaccard_threshold": jaccard_threshold,
+    }
 
 
 def empty_categories(alphabet):
@@ -278,41 +418,14 @@ def summarize(alphabet, rows, filenames, peptide_bloom_filter_filename, peptide_
     else:
         present = np.zeros((int(group[-1]) + 1, 6), dtype=bool)
         present[group, codes] = True
-    coding = present[:, _lib.CAT_CODING]
-    short_pep = ~coding & present[:, _lib.CAT_TOO_SHORT_PEPTIDE]
-    short_read = ~coding & ~short_pep & present[:, _lib.CAT_LOW_COMPLEXITY_NUCLEOTIDE]
-    undecided = ~coding & ~short_pep & ~short_read
-    single = undecided & (present.sum(axis=1) == 1)
-    counts = empty_categories(alphabet)
-    counts["Coding"] += int(coding.sum())
-    counts[PROTEIN_CODING_CATEGORIES["too_short_peptide"]] += int(short_pep.sum())
-    counts[PROTEIN_CODING_CATEGORIES["too_short_nucleotide"]] += int(short_read.sum())
-    only = np.argmax(present[single], axis=1)
-    for code in np.unique(only):
-        counts[category_text(int(code), alphabet)] += int((only == code).sum())
-    counts["Non-coding"] += int((undecided & ~single).sum())
-    total = sum(counts.values())
+    classes = _class_counts(present)
     # coding frames per read id; ids are merged by value here, as collections.Counter does (:216-222)
-    histogram = {}
     if isinstance(coding_ids, np.ndarray):  # already the number of coding frames of each id that has any (unique ids)
-        values, first, n_ids = np.unique(coding_ids, return_index=True, return_counts=True)
-        for at in np.argsort(first):        # keys in order of first appearance, as Counter / dict insertion gives them
-            histogram[int(values[at])] = int(n_ids[at])
+        histogram = _coding_histogram(coding_ids)
     else:
-        per_id = {}
+        histogram, per_id = {}, {}
         for read_id in coding_ids:
             per_id[read_id] = per_id.get(read_id, 0) + 1
         for n in per_id.values():
             histogram[n] = histogram.get(n, 0) + 1
-    n_coding_ids = sum(histogram.values())
-    label = "Number of reads with {} putative protein-coding translations".format
-    return {
-        "input_files": input_files,
-        "jaccard_info": jaccard_info(jaccard),
-        "categorization_counts": counts,
-        "categorization_percentages": {k: 100 * v / total for k, v in counts.items()},
-        "histogram_n_coding_frames_per_read": {label(k): v for k, v in histogram.items()},
-        "histogram_n_coding_frames_per_read_percentages": {label(k): 100 * v / n_coding_ids for k, v in histogram.items()},
-        "peptide_bloom_filter": peptide_bloom_filter_filename, "peptide_alphabet": alphabet, "peptide_ksize": peptide_ksize,
-        "jaccard_threshold": jaccard_threshold,
-    }
+    return _finish_summary(alphabet, classes, histogram, jaccard, filenames, peptide_bloom_filter_filename, peptide_ksize, jaccard_threshold)

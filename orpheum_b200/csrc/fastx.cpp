@@ -23,6 +23,7 @@
 
 #include "../../include/orpheum_b200.h"
 #include "hostpack.h"
+#include "ingest_internal.h"
 
 extern int orph_set_error(int code, const char *fmt, ...);  // defined in orpheum_b200.cu
 
@@ -626,6 +627,61 @@ extern "C" int orph_csv_write_scores(const char *path, int append, const uint8_t
 // FASTA records Translate emits for one batch (translate.py:244-298), in read order then frame order, formatted
 // straight from the result records.
 // ------------------------------------------------------------------------------------------------
+// Records of reads [r0, r1) of a batch; `item0` = number of peptide-bearing frames before read r0.  Writes at most `cap`
+// bytes and returns the full length.  -1: a peptide was needed and is missing.
+int64_t orph_format_fasta_range(int kind, const OrphFastaSource &src, uint64_t r0, uint64_t r1, uint64_t item0, uint8_t *out, uint64_t out_cap)
+{
+    static const int kFrameKeys[6] = {1, 2, 3, -1, -2, -3};
+    static const char kLowSuffix[] = " translation_frame: {}.format(frame)";  // verbatim, translate.py:247
+    uint64_t at = 0, item = item0;
+    char num[48], mid[80];
+    auto put = [&](const void *p, uint64_t n) {
+        if (at + n <= out_cap && out) memcpy(out + at, p, n);
+        at += n;
+    };
+    for (uint64_t r = r0; r < r1; r++) {
+        const orph_read_result &res = src.results[r];
+        const uint8_t *name = src.names + src.name_offsets[r];
+        const uint64_t name_len = src.name_offsets[r + 1] - src.name_offsets[r];
+        for (int f = 0; f < 6; f++) {
+            const unsigned cat = res.category[f];
+            const bool has_pep = cat == ORPH_CAT_CODING || (src.peptides_include_low_complexity && cat == ORPH_CAT_LOW_COMPLEXITY_PEPTIDE);
+            const uint64_t my_item = item;
+            if (has_pep) item++;
+            const bool wanted = kind == 0 ? cat == ORPH_CAT_CODING : kind == 1 ? cat == ORPH_CAT_CODING
+                                : kind == 2 ? cat == ORPH_CAT_NON_CODING : cat == ORPH_CAT_LOW_COMPLEXITY_PEPTIDE;
+            if (!wanted) continue;
+            if ((kind == 0 || kind == 3) && (!has_pep || !src.peptides || !src.pep_offsets)) return -1;
+            put(">", 1);
+            if (kind == 3) {
+                put(name, name_len);
+                put(kLowSuffix, sizeof(kLowSuffix) - 1);
+            } else {
+                // "{name}__translation_frame:{frame}__jaccard:{jaccard}" with every space replaced by "__"
+                uint64_t run = 0;
+                for (uint64_t i = 0; i < name_len; i++) {
+                    if (name[i] == ' ') {
+                        if (i > run) put(name + run, i - run);
+                        put("__", 2);
+                        run = i + 1;
+                    }
+                }
+                if (name_len > run) put(name + run, name_len - run);
+                const size_t nj = py_repr_double((double)res.n_hits[f] / (double)res.n_kmers[f], num);
+                const int nm = snprintf(mid, sizeof(mid), "__translation_frame:%d__jaccard:", kFrameKeys[f]);
+                put(mid, (uint64_t)nm);
+                put(num, nj);
+            }
+            put("\n", 1);
+            if (kind == 0 || kind == 3) put(src.peptides + src.pep_offsets[my_item], src.pep_offsets[my_item + 1] - src.pep_offsets[my_item]);
+            else if (src.reads) put(src.reads + src.read_offsets[r], src.read_offsets[r + 1] - src.read_offsets[r]);
+            else put(src.text + src.seq_start[r], src.seq_len[r]);
+            put("\n", 1);
+        }
+    }
+    return (int64_t)at;
+}
+
 extern "C" int orph_format_fasta(int kind, const uint8_t *names, const uint64_t *name_offsets, uint64_t n_reads,
                                  const orph_read_result *results, const uint8_t *reads, const uint64_t *read_offsets,
                                  const uint8_t *peptides, const uint64_t *pep_offsets, int peptides_include_low_complexity,
@@ -634,49 +690,18 @@ extern "C" int orph_format_fasta(int kind, const uint8_t *names, const uint64_t 
     if (kind < 0 || kind > 3 || !out_len || (n_reads && (!names || !name_offsets || !results)))
         return orph_set_error(ORPH_E_INVALID, "orph_format_fasta: bad arguments");
     if ((kind == 1 || kind == 2) && n_reads && (!reads || !read_offsets)) return orph_set_error(ORPH_E_INVALID, "orph_format_fasta: reads missing");
-    static const int kFrameKeys[6] = {1, 2, 3, -1, -2, -3};
-    static const char kLowSuffix[] = " translation_frame: {}.format(frame)";  // verbatim, translate.py:247
-    uint64_t at = 0, item = 0;
-    char num[48], mid[80];
-    auto put = [&](const void *src, uint64_t n) {
-        if (at + n <= out_cap && out) memcpy(out + at, src, n);
-        at += n;
-    };
-    for (uint64_t r = 0; r < n_reads; r++) {
-        const orph_read_result &res = results[r];
-        const uint8_t *name = names + name_offsets[r];
-        const uint64_t name_len = name_offsets[r + 1] - name_offsets[r];
-        for (int f = 0; f < 6; f++) {
-            const unsigned cat = res.category[f];
-            const bool has_pep = cat == ORPH_CAT_CODING || (peptides_include_low_complexity && cat == ORPH_CAT_LOW_COMPLEXITY_PEPTIDE);
-            const uint64_t my_item = item;
-            if (has_pep) item++;
-            const bool wanted = kind == 0 ? cat == ORPH_CAT_CODING : kind == 1 ? cat == ORPH_CAT_CODING
-                                : kind == 2 ? cat == ORPH_CAT_NON_CODING : cat == ORPH_CAT_LOW_COMPLEXITY_PEPTIDE;
-            if (!wanted) continue;
-            if ((kind == 0 || kind == 3) && (!has_pep || !peptides || !pep_offsets)) return orph_set_error(ORPH_E_INVALID, "orph_format_fasta: peptides missing");
-            put(">", 1);
-            if (kind == 3) {
-                put(name, name_len);
-                put(kLowSuffix, sizeof(kLowSuffix) - 1);
-            } else {
-                // "{name}__translation_frame:{frame}__jaccard:{jaccard}" with every space replaced by "__"
-                for (uint64_t i = 0; i < name_len; i++) {
-                    if (name[i] == ' ') put("__", 2);
-                    else put(name + i, 1);
-                }
-                const size_t nj = py_repr_double((double)res.n_hits[f] / (double)res.n_kmers[f], num);
-                const int nm = snprintf(mid, sizeof(mid), "__translation_frame:%d__jaccard:", kFrameKeys[f]);
-                put(mid, (uint64_t)nm);
-                put(num, nj);
-            }
-            put("\n", 1);
-            if (kind == 0 || kind == 3) put(peptides + pep_offsets[my_item], pep_offsets[my_item + 1] - pep_offsets[my_item]);
-            else put(reads + read_offsets[r], read_offsets[r + 1] - read_offsets[r]);
-            put("\n", 1);
-        }
-    }
-    *out_len = at;
+    OrphFastaSource src{};
+    src.names = names;
+    src.name_offsets = name_offsets;
+    src.results = results;
+    src.reads = reads;
+    src.read_offsets = read_offsets;
+    src.peptides = peptides;
+    src.pep_offsets = pep_offsets;
+    src.peptides_include_low_complexity = peptides_include_low_complexity;
+    const int64_t n = orph_format_fasta_range(kind, src, 0, n_reads, 0, out, out_cap);
+    if (n < 0) return orph_set_error(ORPH_E_INVALID, "orph_format_fasta: peptides missing");
+    *out_len = (uint64_t)n;
     return ORPH_OK;
 }
 

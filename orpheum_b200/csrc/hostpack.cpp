@@ -142,7 +142,10 @@ __attribute__((target("avx2"))) static void pack_words_avx2(const uint8_t *src, 
         const __m256i expect = _mm256_shuffle_epi8(lut, code);
         const uint32_t bad = ~(uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(expect, v));
         const __m256i g = _mm256_shuffle_epi8(_mm256_madd_epi16(_mm256_maddubs_epi16(code, w1), w2), gather);
-        dst[w] = (uint64_t)(uint32_t)_mm256_extract_epi32(g, 0) | ((uint64_t)(uint32_t)_mm256_extract_epi32(g, 4) << 32);
+        // streaming store: the words go to pinned staging that only the DMA engine reads -- no read-for-ownership of the
+        // destination line, no cache pollution (the packer is bound by the host's memory system, not by its arithmetic)
+        _mm_stream_si64(reinterpret_cast<long long *>(dst + w),
+                        (long long)((uint64_t)(uint32_t)_mm256_extract_epi32(g, 0) | ((uint64_t)(uint32_t)_mm256_extract_epi32(g, 4) << 32)));
         if (bad) {
             bad_words[2 * *n_bad] = (uint32_t)w;
             bad_words[2 * *n_bad + 1] = bad;
@@ -219,10 +222,12 @@ void pack_stream(Pool *pool, const uint8_t *src, uint64_t abase0, uint64_t total
             dst[full1] = pack_word_scalar(src + 32 * full1, (uint32_t)(total - 32 * full1), &bad);
             if (bad && needs_ascii) mark(full1, bad);
         }
+        _mm_sfence();  // streaming stores are weakly ordered: visible before the item is handed back
     };
     if (pool) pool->run(n_blocks, work);
     else
         for (uint64_t b = 0; b < n_blocks; b++) work(b);
+    _mm_sfence();  // (streaming stores of the calling thread; the pool's hand-back already orders the workers')
 }
 
 }  // namespace orph_host

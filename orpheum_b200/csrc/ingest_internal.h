@@ -65,3 +65,19 @@ struct orph_ingest {
 int orph_ingest_open_with(const char *path, int n_threads, int n_slots, IngestAlloc alloc, orph_ingest **out);
 // the next batch, in the slot ring's next slot (valid until the ring wraps around)
 int orph_ingest_next_slot(orph_ingest *ing, uint64_t max_reads, IngestSlot **out);
+
+// the inputs of orph_format_fasta; the reads either contiguous (reads + read_offsets) or scattered in a text (stream batches)
+struct OrphFastaSource {
+    const uint8_t *names;
+    const uint64_t *name_offsets;
+    const orph_read_result *results;
+    const uint8_t *reads;
+    const uint64_t *read_offsets;
+    const uint8_t *text;
+    const uint64_t *seq_start;
+    const uint32_t *seq_len;
+    const uint8_t *peptides;
+    const uint64_t *pep_offsets;
+    int peptides_include_low_complexity;
+};
+int64_t orph_format_fasta_range(int kind, const OrphFastaSource &src, uint64_t r0, uint64_t r1, uint64_t item0, uint8_t *out, uint64_t out_cap);

@@ -513,12 +513,13 @@ extern "C" int orph_score_reads(orph_ctx *ctx, const orph_filter *f, const void 
     // host packing pays once a batch is large enough to keep the pool busy; small batches go out as they are
     bool allow_pack = reads_format == ORPH_READS_ASCII && ctx->host_threads != 0 && offsets[n_reads] >= offsets[0] &&
                       offsets[n_reads] - offsets[0] >= (1ULL << 22);
-    // A host-packed chunk costs the host's memory 1.5 bytes per base (read, write 2 bits, DMA reads them) against 1 for a
-    // chunk the copy engine takes as it is: when the pool packs clearly slower than the wire carries -- many ranks sharing
-    // one host, measured: eight ranks with four threads each pack 12 GB/s next to 20 GB/s links and the call is 5 % faster
-    // without the packing lane -- the lane stays off, and is tried again every 16th call in case the host got quieter.
-    if (allow_pack && input_is_pinned(reads) && ctx->pack_s_per_byte > 0 && 1.0 / ctx->pack_s_per_byte < 0.75 * ctx->h2d_bytes_per_s &&
-        (++ctx->pack_lane_skips & 15) != 0)
+    // A host-packed chunk costs the host's memory 1.25-1.5 bytes per base (read, write 2 bits, DMA reads them) against 1 for a
+    // chunk the copy engine takes as it is.  That is a loss only when the host's memory system is what everything waits for:
+    // many ranks sharing one host -- measured with eight ranks of four threads each: links at 20 GB/s instead of 50, the pool
+    // packing 12 GB/s next to them, the call 5 % faster without the packing lane.  (With the same four threads and the link at
+    // full rate the lane is worth 25 %.)  Then the lane stays off, and is tried again every 16th call.
+    if (allow_pack && input_is_pinned(reads) && ctx->pack_s_per_byte > 0 && ctx->h2d_bytes_per_s < 25e9 &&
+        1.0 / ctx->pack_s_per_byte < 0.75 * ctx->h2d_bytes_per_s && (++ctx->pack_lane_skips & 15) != 0)
         allow_pack = false;
     std::vector<uint64_t> exceptions;
     rc = score_host_pipeline(ctx, f, reads, reads_format, offsets, n_reads, lut, jaccard_threshold, out, allow_pack, &exceptions);

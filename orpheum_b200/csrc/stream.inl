@@ -126,6 +126,11 @@ struct orph_stream {
     bool eof = false, stop = false;
     int error = ORPH_OK;
     std::string error_text;
+    // orph_stream_emit: its own small pool (the parser's pool is busy with the next batch) and output buffers
+    orph_host::Pool *emit_pool = nullptr;
+    std::vector<uint8_t> emit_out[4], emit_reads, emit_peptides;
+    std::vector<uint64_t> emit_read_off, emit_item_read, emit_pep_off;
+    std::vector<int8_t> emit_item_frame;
     size_t lanes() const { return rs.size(); }
     StreamRes *res_of(uint64_t k) const { return rs[k % rs.size()]; }
     StreamRes::Job &job_of(uint64_t k) const { return rs[k % rs.size()]->jobs[(k / rs.size()) % kStreamSlots]; }
@@ -390,6 +395,156 @@ extern "C" int orph_stream_next(orph_stream *st, orph_stream_batch *out)
     return ORPH_OK;
 }
 
+// The FASTA records Translate writes for the batch the caller holds (translate.py:244-298), formatted in the library: the
+// frames that emit something are found in the records, the reads that carry them are gathered from the text, their
+// peptides come from ONE orph_translate_frames call on `ctx`, and the text of every requested kind (see
+// orph_format_fasta) is formatted block-parallel.  Nothing here runs per read in the caller's language.
+extern "C" int orph_stream_emit(orph_stream *st, orph_ctx *ctx, uint32_t kinds_mask, const uint8_t *out[4], uint64_t out_len[4])
+{
+    if (!st || !ctx || !out || !out_len) return fail(ORPH_E_INVALID, "orph_stream_emit: NULL argument");
+    for (int k = 0; k < 4; k++) {
+        out[k] = nullptr;
+        out_len[k] = 0;
+    }
+    if (!st->holding) return fail(ORPH_E_INVALID, "orph_stream_emit: no batch is held (call orph_stream_next first)");
+    const StreamRes::Job &job = st->job_of(st->held);
+    const orph_host::FusedBatch &b = job.slot->b;
+    const uint64_t n = job.n;
+    const orph_read_result *res = (const orph_read_result *)job.results.p;
+    const bool with_lcp = (kinds_mask & 8u) != 0;
+    if (n == 0 || (kinds_mask & 15u) == 0) return ORPH_OK;
+    if (!st->emit_pool) {
+        cpu_set_t set;
+        int cores = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+        const char *lws = getenv("LOCAL_WORLD_SIZE");
+        if (lws && atoi(lws) > 1) cores /= atoi(lws);
+        st->emit_pool = new (std::nothrow) orph_host::Pool(std::max(1, std::min(cores / 2, 16)));
+        if (!st->emit_pool) return fail(ORPH_E_NOMEM, "out of host memory");
+    }
+    orph_host::Pool *pool = st->emit_pool;
+    constexpr uint64_t kBlock = 4096;
+    const uint64_t n_blk = (n + kBlock - 1) / kBlock;
+    auto has_pep = [&](unsigned cat) { return cat == ORPH_CAT_CODING || (with_lcp && cat == ORPH_CAT_LOW_COMPLEXITY_PEPTIDE); };
+    // ---- pass A: per block, the peptide-bearing frames, the reads that carry one, their bases and residues
+    struct BlockCount { uint64_t items, reads, bases, residues, out_bound[4]; };
+    std::vector<BlockCount> cnt(n_blk + 1);
+    pool->run(n_blk, [&](uint64_t blk) {
+        BlockCount c{};
+        const uint64_t r1 = std::min(n, (blk + 1) * kBlock);
+        for (uint64_t r = blk * kBlock; r < r1; r++) {
+            const uint64_t name_len = b.name_off[r + 1] - b.name_off[r];
+            const uint32_t L = b.seq_len[r];
+            uint32_t here = 0;
+            for (int f = 0; f < 6; f++) {
+                const unsigned cat = res[r].category[f];
+                const uint32_t phase = f % 3;
+                const uint64_t plen = L >= phase ? (L - phase) / 3 : 0;
+                if (has_pep(cat)) {
+                    here++;
+                    c.residues += plen;
+                }
+                const uint64_t head = 2 * name_len + 96;  // '>' + name (spaces doubled) + frame / jaccard decoration + newlines
+                if (cat == ORPH_CAT_CODING) {
+                    c.out_bound[0] += head + plen;
+                    c.out_bound[1] += head + L;
+                } else if (cat == ORPH_CAT_NON_CODING) {
+                    c.out_bound[2] += head + L;
+                } else if (cat == ORPH_CAT_LOW_COMPLEXITY_PEPTIDE) {
+                    c.out_bound[3] += head + plen;
+                }
+            }
+            if (here) {
+                c.items += here;
+                c.reads++;
+                c.bases += L;
+            }
+        }
+        cnt[blk] = c;
+    });
+    std::vector<BlockCount> at(n_blk + 1);
+    BlockCount run{};
+    for (uint64_t blk = 0; blk <= n_blk; blk++) {
+        at[blk] = run;
+        if (blk == n_blk) break;
+        run.items += cnt[blk].items;
+        run.reads += cnt[blk].reads;
+        run.bases += cnt[blk].bases;
+        run.residues += cnt[blk].residues;
+        for (int k = 0; k < 4; k++) run.out_bound[k] += cnt[blk].out_bound[k];
+    }
+    const uint64_t n_items = run.items, m = run.reads;
+    // ---- pass B: gather the emitting reads, list the (read, frame) items with their peptide offsets
+    const bool need_peptides = (kinds_mask & 9u) != 0 && n_items > 0;
+    if (need_peptides) {
+        st->emit_reads.resize(run.bases + 64);
+        st->emit_read_off.resize(m + 1);
+        st->emit_item_read.resize(n_items);
+        st->emit_item_frame.resize(n_items);
+        st->emit_pep_off.resize(n_items + 1);
+        st->emit_peptides.resize(run.residues + 64);
+        const uint8_t *text = job.slot->text;
+        static const int8_t kFrameKeys[6] = {1, 2, 3, -1, -2, -3};
+        pool->run(n_blk, [&](uint64_t blk) {
+            uint64_t item = at[blk].items, rd = at[blk].reads, base = at[blk].bases, pep = at[blk].residues;
+            const uint64_t r1 = std::min(n, (blk + 1) * kBlock);
+            for (uint64_t r = blk * kBlock; r < r1; r++) {
+                const uint32_t L = b.seq_len[r];
+                bool any = false;
+                for (int f = 0; f < 6; f++) {
+                    if (!has_pep(res[r].category[f])) continue;
+                    const uint32_t phase = f % 3;
+                    st->emit_item_read[item] = rd;
+                    st->emit_item_frame[item] = kFrameKeys[f];
+                    st->emit_pep_off[item] = pep;
+                    pep += L >= phase ? (L - phase) / 3 : 0;
+                    item++;
+                    any = true;
+                }
+                if (any) {
+                    st->emit_read_off[rd++] = base;
+                    memcpy(st->emit_reads.data() + base, text + b.seq_start[r], L);
+                    base += L;
+                }
+            }
+        });
+        st->emit_read_off[m] = run.bases;
+        st->emit_pep_off[n_items] = run.residues;
+        const int rc = orph_translate_frames(ctx, st->emit_reads.data(), st->emit_read_off.data(), m, st->emit_item_read.data(), st->emit_item_frame.data(),
+                                             n_items, st->emit_pep_off.data(), st->emit_peptides.data());
+        if (rc != ORPH_OK) return rc;
+    }
+    // ---- pass C: the text of each requested kind, block-parallel into bounded segments, then closed up
+    OrphFastaSource src{};
+    src.names = b.names;
+    src.name_offsets = b.name_off;
+    src.results = res;
+    src.text = job.slot->text;
+    src.seq_start = b.seq_start;
+    src.seq_len = b.seq_len;
+    src.peptides = st->emit_peptides.data();
+    src.pep_offsets = st->emit_pep_off.data();
+    src.peptides_include_low_complexity = with_lcp ? 1 : 0;
+    for (int kind = 0; kind < 4; kind++) {
+        if (!(kinds_mask & (1u << kind)) || run.out_bound[kind] == 0) continue;
+        std::vector<uint8_t> &buf = st->emit_out[kind];
+        buf.resize(run.out_bound[kind]);
+        std::vector<int64_t> len(n_blk);
+        pool->run(n_blk, [&](uint64_t blk) {
+            len[blk] = orph_format_fasta_range(kind, src, blk * kBlock, std::min(n, (blk + 1) * kBlock), at[blk].items, buf.data() + at[blk].out_bound[kind],
+                                               cnt[blk].out_bound[kind]);
+        });
+        uint64_t total = 0;
+        for (uint64_t blk = 0; blk < n_blk; blk++) {
+            if (len[blk] < 0 || (uint64_t)len[blk] > cnt[blk].out_bound[kind]) return fail(ORPH_E_INVALID, "orph_stream_emit: internal size bound violated");
+            if (len[blk] && at[blk].out_bound[kind] != total) memmove(buf.data() + total, buf.data() + at[blk].out_bound[kind], (size_t)len[blk]);
+            total += (uint64_t)len[blk];
+        }
+        out[kind] = buf.data();
+        out_len[kind] = total;
+    }
+    return ORPH_OK;
+}
+
 extern "C" void orph_stream_close(orph_stream *st)
 {
     if (!st) return;
@@ -409,5 +564,6 @@ extern "C" void orph_stream_close(orph_stream *st)
         st->ing = nullptr;
     }
     for (StreamRes *r : st->rs) stream_res_release(r);
+    delete st->emit_pool;
     delete st;
 }

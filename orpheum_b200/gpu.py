@@ -395,6 +395,15 @@ class ScoringStream:
         except Exception:
             pass
 
+    def emit(self, ctx, kinds_mask):
+        """FASTA text of the batch the iteration currently holds, formatted by the library (orph_stream_emit): bit k of
+        ``kinds_mask`` asks for kind k of ``format_fasta``.  -> list of 4 ``bytes`` (empty where nothing was asked or emitted).
+        ``ctx`` runs the peptide translation: a context of the caller's, e.g. the filter's."""
+        ptrs = (ctypes.c_void_p * 4)()
+        lens = (ctypes.c_uint64 * 4)()
+        check(self._lib.orph_stream_emit(self._h, ctx._h, int(kinds_mask), ctypes.byref(ptrs), ctypes.byref(lens)))
+        return [ctypes.string_at(ptrs[k], int(lens[k])) if lens[k] else b"" for k in range(4)]
+
     def __iter__(self):
         raw = _lib.StreamBatch()
         while True:

@@ -256,19 +256,7 @@ class Translate:
         peptides, pep_offsets = translate_frames_raw(self.peptide_bloom_filter.ctx, flat, offsets, reads_idx, keys)
 
         def emit(kind, handle):
-            """The formatted records as BYTES into the handle's binary layer when it has one that writes UTF-8 (the text layer
-            would decode and re-encode every byte to the same effect)."""
-            blob = format_fasta(kind, name_blob, name_offsets, results, flat, offsets, peptides, pep_offsets, with_lcp)
-            if not blob:
-                return
-            raw = getattr(handle, "buffer", None)
-            if raw is not None and str(getattr(handle, "encoding", "")).lower().replace("-", "") == "utf8" \
-                    and getattr(handle, "errors", None) in ("strict", "surrogateescape", None) and getattr(handle, "newline", None) is None \
-                    and os.linesep == "\n":
-                handle.flush()
-                raw.write(blob)
-            else:
-                handle.write(blob.decode(*fastx.TEXT_CODEC))
+            self._write_bytes(handle, format_fasta(kind, name_blob, name_offsets, results, flat, offsets, peptides, pep_offsets, with_lcp))
 
         if with_lcp:
             emit(3, handles["low_complexity_peptide"])
@@ -279,12 +267,16 @@ class Translate:
         emit(0, sys.stdout)
         sys.stdout.flush()
 
-    def score_all_files_columnar(self):
+    def score_all_files_columnar(self, stream_csv=None):
         """Score every input file and return a columnar ``ScoreTable`` (same information as ``coding_scores``,
-        6 rows per read, without building python rows); stdout / FASTA outputs are written on the way."""
+        6 rows per read, without building python rows); stdout / FASTA outputs are written on the way.  ``stream_csv``: the
+        path the score CSV will be written to -- its rows are then formatted batch by batch while the next batches are
+        scored (``table.write_csv(stream_csv)`` completes it)."""
         from .columnar import ScoreTable
 
-        table = ScoreTable(self.alphabet)
+        table = ScoreTable(self.alphabet, background_summary=bool(getattr(self, "json_summary", None)))
+        if stream_csv:
+            table.stream_csv_to(stream_csv)
         self.maybe_open_fastas()
         try:
             for reads in self.reads:
@@ -306,8 +298,11 @@ class Translate:
                         _lib.check(batch.status)  # an empty read: ZeroDivisionError, as in the reference (translate.py:83)
                         results = batch.results.copy()
                         names = batch.names()
-                        self._emit_stream_batch(batch, names, results)
+                        self._emit_stream_batch_native(stream)
                         table.append(names, results, reads)
+        except BaseException:
+            table.discard_csv_stream()
+            raise
         finally:
             self.maybe_close_fastas()
         return table
@@ -339,21 +334,35 @@ class Translate:
         self._lanes = replica_lanes(graph, n) if n > 1 else []
         return self._lanes
 
-    def _emit_stream_batch(self, batch, names, results):
-        """Side effects of one stream batch: only the reads that emit something (a coding frame; a low-complexity
-        peptide or a non-coding frame when those files were asked for) are gathered from the text."""
-        cat = results["category"]
-        handles = self.file_handles
-        want = cat == _lib.CAT_CODING
-        if handles["low_complexity_peptide"] is not None:
-            want = want | (cat == _lib.CAT_LOW_COMPLEXITY_PEPTIDE)
-        if handles["noncoding_nucleotide"] is not None:
-            want = want | (cat == _lib.CAT_NON_CODING)
-        index = np.nonzero(want.any(axis=1))[0]
-        if len(index) == 0:
+    @staticmethod
+    def _write_bytes(handle, blob):
+        """FASTA bytes into a text handle: through its binary layer when that writes the same bytes (UTF-8, no newline
+        translation), else decoded."""
+        if not blob:
             return
-        flat, offsets = batch.reads(index)
-        self._emit_batch(names.take(index), flat, offsets, results[index])
+        raw = getattr(handle, "buffer", None)
+        if raw is not None and str(getattr(handle, "encoding", "")).lower().replace("-", "") == "utf8" \
+                and getattr(handle, "errors", None) in ("strict", "surrogateescape", None) and os.linesep == "\n":
+            handle.flush()
+            raw.write(blob)
+        else:
+            handle.write(blob.decode(*fastx.TEXT_CODEC))
+
+    def _emit_stream_batch_native(self, stream):
+        """Side effects of the stream batch being held (translate.py:244-298), every byte of them produced by the library
+        (orph_stream_emit): same files, same order of writes as _emit_batch."""
+        handles = self.file_handles
+        kinds = 1 | (8 if handles["low_complexity_peptide"] is not None else 0) | (2 if handles["coding_nucleotide"] is not None else 0) \
+            | (4 if handles["noncoding_nucleotide"] is not None else 0)
+        blobs = stream.emit(self.peptide_bloom_filter.ctx, kinds)
+        if handles["low_complexity_peptide"] is not None:
+            self._write_bytes(handles["low_complexity_peptide"], blobs[3])
+        if handles["coding_nucleotide"] is not None:
+            self._write_bytes(handles["coding_nucleotide"], blobs[1])
+        if handles["noncoding_nucleotide"] is not None:
+            self._write_bytes(handles["noncoding_nucleotide"], blobs[2])
+        self._write_bytes(sys.stdout, blobs[0])
+        sys.stdout.flush()
 
     def set_coding_scores_all_files(self):
         self.maybe_open_fastas()
@@ -408,7 +417,7 @@ def cli(peptides, reads, peptide_ksize=None, save_peptide_bloom_filter=True, pep
         n_tables=constants_index.DEFAULT_N_TABLES, long_reads=False, verbose=False):
     """Writes coding peptides from reads to standard output"""
     translate_obj = Translate(locals())
-    table = translate_obj.score_all_files_columnar()
+    table = translate_obj.score_all_files_columnar(stream_csv=csv)
     # the three outputs are independent: the CSV is formatted by the native writer (GIL released) while the parquet
     # table and the JSON summary are built here
     from concurrent.futures import ThreadPoolExecutor

@@ -199,3 +199,44 @@ def test_multi_lane_stream_delivers_the_same_batches_in_file_order(env, tmp_path
         for i, batch in enumerate(st):
             if i == 3:
                 break
+
+
+def test_stream_emit_matches_the_python_side_formatting(env, tmp_path):
+    """orph_stream_emit (emitting frames found in the records, reads gathered from the text, one orph_translate_frames
+    call, block-parallel formatting) against the pieces it replaces, called one by one from Python: orph_gather_reads ->
+    orph_translate_frames -> orph_format_fasta, for all four kinds, with and without low-complexity peptides among the
+    translated frames, on batches with N / lower-case reads, short reads and reads that emit nothing."""
+    gpu = env["gpu"]
+    from orpheum_b200 import _lib
+    from orpheum_b200.constants_translate import FRAMES
+
+    n = 60_000
+    flat, offsets = mixed_reads(env, n, seed=23)
+    path = str(tmp_path / "reads.fq")
+    write_fastq(path, flat, offsets)
+    ctx = env["graph"].ctx
+    for kinds in (15, 1, 9, 6):
+        with_lcp = bool(kinds & 8)
+        total = [0, 0, 0, 0]
+        with gpu.ScoringStream(env["graph"], path, env["lut"], 0.5, batch_reads=16384) as st:
+            for batch in st:
+                got = st.emit(ctx, kinds)
+                results = batch.results.copy()
+                names = batch.names()
+                rflat, roffs = batch.reads()
+                cat = results["category"]
+                want = cat == _lib.CAT_CODING
+                if with_lcp:
+                    want = want | (cat == _lib.CAT_LOW_COMPLEXITY_PEPTIDE)
+                reads_idx, frames_idx = np.nonzero(want)
+                keys = np.asarray(FRAMES, dtype=np.int8)[frames_idx]
+                peptides, pep_offsets = gpu.translate_frames_raw(ctx, rflat, roffs, reads_idx, keys)
+                blob = np.frombuffer(names.blob, dtype=np.uint8) if len(names.blob) else np.zeros(1, dtype=np.uint8)
+                for kind in range(4):
+                    if not kinds & (1 << kind):
+                        assert got[kind] == b""
+                        continue
+                    expect = gpu.format_fasta(kind, blob, names.offsets, results, rflat, roffs, peptides, pep_offsets, with_lcp)
+                    assert got[kind] == expect, (kinds, kind)
+                    total[kind] += len(expect)
+        assert (not kinds & 1 or total[0] > 100_000) and (not kinds & 4 or total[2] > 100_000) and (not kinds & 8 or total[3] > 0)

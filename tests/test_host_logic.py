@@ -441,7 +441,7 @@ def test_columnar_writers_against_row_list_writers_random(tmp_path):
         if case % 4 == 3:
             # the same table with the parser's name blobs (fastx.NameList): the summary is computed straight from the record
             # arrays (ids proven distinct by their hashes) and must be the same dict, floats to the last bit
-            fast = ScoreTable(alphabet)
+            fast = ScoreTable(alphabet, background_summary=case % 8 == 3)  # (half of them through the per-batch background shares)
             for names_, rec_, (filename_, _) in zip(table._names, table._records, table._files):
                 enc = [nm.encode(*fastx.TEXT_CODEC) for nm in names_]
                 offs = np.zeros(len(enc) + 1, dtype=np.uint64)
