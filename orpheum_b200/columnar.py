@@ -43,9 +43,9 @@ class ScoreTable:
 
     def stream_csv_to(self, path):
         """From now on every appended batch's rows are formatted and appended to the CSV right away, on a background thread
-        (the native formatter releases the GIL), into ``path + ".partial"``; ``write_csv(path)`` then only waits and renames.
-        A run that fails leaves no CSV behind (``discard_csv_stream``), as with the reference, which writes it last."""
-        self._csv_path, self._csv_tmp = path, path + ".partial"
+        (the native formatter releases the GIL); ``write_csv(path)`` then only waits for the last batch.  A run that fails
+        leaves no CSV behind (``discard_csv_stream``), as with the reference, which writes it last."""
+        self._csv_path = self._csv_tmp = path
         self.write_csv_header(self._csv_tmp)
 
     def discard_csv_stream(self):
@@ -136,7 +136,6 @@ class ScoreTable:
         if self._csv_tmp is not None and path == self._csv_path:  # streamed while the batches came in
             for job in self._csv_jobs:
                 job.result()
-            os.replace(self._csv_tmp, path)
             self._csv_path = self._csv_tmp = None
             self._csv_jobs = []
             return
@@ -311,11 +310,17 @@ def _class_counts(present):
 
 def _coding_histogram(coding_counts):
     """{coding frames per id: number of ids}, keys in order of first appearance (as Counter / dict insertion gives them)."""
-    histogram = {}
-    values, first, n_ids = np.unique(coding_counts, return_index=True, return_counts=True)
-    for at in np.argsort(first):
-        histogram[int(values[at])] = int(n_ids[at])
-    return histogram
+    coding_counts = np.asarray(coding_counts)
+    if coding_counts.size == 0:
+        return {}
+    if coding_counts.max() < 64:  # the usual case (at most six frames per read): no sort
+        n_ids = np.bincount(coding_counts)
+        values = np.nonzero(n_ids)[0]
+        first = [int(np.argmax(coding_counts == v)) for v in values]
+    else:
+        values, first, n_ids_ = np.unique(coding_counts, return_index=True, return_counts=True)
+        n_ids = dict(zip(values.tolist(), n_ids_.tolist()))
+    return {int(values[at]): int(n_ids[values[at]]) for at in np.argsort(first)}
 
 
 def _partial_summary(names, records):
