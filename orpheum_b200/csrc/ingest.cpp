@@ -269,6 +269,10 @@ static bool fill_bgzf_text(orph_ingest *ing, IngestSlot &s, uint64_t want, bool 
         const uint8_t *tail = h + bsize - 8;
         const uint32_t crc = tail[0] | (tail[1] << 8) | (tail[2] << 16) | ((uint32_t)tail[3] << 24);
         const uint32_t isize = tail[4] | (tail[5] << 8) | (tail[6] << 16) | ((uint32_t)tail[7] << 24);
+        if (isize > (1u << 16)) {  // a BGZF member holds at most 64 KiB of text
+            orph_set_error(ORPH_E_IO, "%s: a damaged BGZF block (size field)", ing->path.c_str());
+            return false;
+        }
         members.push_back({at + 12 + xlen, bsize - 12 - xlen - 8, out_total, isize, crc});
         out_total += isize;
         at += bsize;

@@ -35,7 +35,7 @@ def write_file(path, layout, names, seqs, rng):
             w = int(rng.integers(20, 200))
             parts.append(b">" + name + eol + eol.join(s[j:j + w] for j in range(0, len(s), w)) + eol)
     else:
-        wrap = int(rng.integers(30, 120)) if layout == "wrapped" else 0
+        wrap = int(rng.integers(30, 120)) if layout in ("wrapped", "bgzf_wrapped") else 0
         for name, s in zip(names, seqs):
             q = rng.integers(33, 74, len(s)).astype(np.uint8).tobytes()
             if wrap:
@@ -50,7 +50,7 @@ def write_file(path, layout, names, seqs, rng):
     if layout == "gz":
         with gzip.open(path, "wb", compresslevel=1) as f:
             f.write(blob)
-    elif layout == "bgzf":
+    elif layout in ("bgzf", "bgzf_wrapped"):
         synth.write_bgzf(path, blob, block=int(rng.choice([997, 8192, 65280])), eof_marker=bool(rng.random() < 0.7))
     else:
         with open(path, "wb") as f:
@@ -65,7 +65,7 @@ def main():
     tmp = tempfile.mkdtemp(prefix="orph_fuzz_stream_")
     t_end = time.time() + seconds
     rounds = reads_total = 0
-    layouts = ["plain", "plain", "crlf", "no_final_newline", "gz", "bgzf", "bgzf", "wrapped", "fasta"]
+    layouts = ["plain", "plain", "crlf", "no_final_newline", "gz", "bgzf", "bgzf", "wrapped", "fasta", "bgzf_wrapped"]
     while time.time() < t_end:
         alphabet = str(rng.choice(["protein", "dayhoff", "hp", "botvinnik"]))
         ksize = int(rng.choice([BEST_KSIZES[alphabet], int(rng.integers(2, 20))]))
@@ -87,7 +87,7 @@ def main():
         names = [b"r%d fuzz/%d" % (i, i % 3) for i in range(n)]
         flat, offsets = gpu.concat_reads(seqs)
         layout = str(rng.choice(layouts))
-        path = os.path.join(tmp, "reads.fq.gz" if layout in ("gz", "bgzf") else "reads.fa" if layout == "fasta" else "reads.fq")
+        path = os.path.join(tmp, "reads.fq.gz" if layout in ("gz", "bgzf", "bgzf_wrapped") else "reads.fa" if layout == "fasta" else "reads.fq")
         write_file(path, layout, names, seqs, rng)
         n_lanes = int(rng.choice([1, 1, 2, 3]))
         lanes = gpu.replica_lanes(gg, n_lanes, devices=[0] * (n_lanes - 1)) if n_lanes > 1 else None
