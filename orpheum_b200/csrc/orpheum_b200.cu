@@ -249,7 +249,9 @@ struct orph_ctx {
     DevBuf queue, bytes_queue;   // uint32 read indices
     DevBuf task_queue;           // uint32 (read << 3 | frame), up to 6 per read
     DevBuf task_queue_sorted;    // the same entries ordered by peptide length (mixed-length batches)
-    DevBuf needs_bytes;          // uint8 per read (ASCII input)
+    DevBuf needs_bytes;          // ASCII input: uint8 per read "holds a byte other than ACGTN", then uint8 per read "holds an N"
+    DevBuf nmask;                // ASCII input: the N plane of the 2-bit stream (one bit per base)
+    DevBuf task_queue_n;         // tasks of the reads that hold N
     DevBuf packed;               // 2-bit stream built from ASCII input
     DevBuf in_reads, in_offsets, out_results;  // staging for the index build
     PipeSlot lane_slots[2][kLaneSlots];                  // [0] the copy-engine lane, [1] the host-packing lane of orph_score_reads
@@ -279,6 +281,7 @@ static int verify_guards(orph_ctx *ctx)
     struct Named { const char *name; const DevBuf *b; };
     std::vector<Named> all = {{"counters", &ctx->counters}, {"queue", &ctx->queue}, {"bytes_queue", &ctx->bytes_queue}, {"task_queue", &ctx->task_queue},
                               {"task_queue_sorted", &ctx->task_queue_sorted}, {"needs_bytes", &ctx->needs_bytes}, {"packed", &ctx->packed},
+                              {"nmask", &ctx->nmask}, {"task_queue_n", &ctx->task_queue_n},
                               {"in_reads", &ctx->in_reads}, {"in_offsets", &ctx->in_offsets}, {"out_results", &ctx->out_results}, {"misc", &ctx->misc},
                               {"seen", &ctx->seen}, {"long_scratch", &ctx->long_scratch}};
     for (auto &lane : ctx->lane_slots)
@@ -408,7 +411,7 @@ extern "C" void orph_ctx_destroy(orph_ctx *ctx)
     if (!ctx) return;
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf *b : {&ctx->counters, &ctx->queue, &ctx->bytes_queue, &ctx->task_queue, &ctx->task_queue_sorted, &ctx->needs_bytes, &ctx->packed, &ctx->in_reads,
+    for (DevBuf *b : {&ctx->counters, &ctx->queue, &ctx->bytes_queue, &ctx->task_queue, &ctx->task_queue_sorted, &ctx->needs_bytes, &ctx->packed, &ctx->nmask, &ctx->task_queue_n, &ctx->in_reads,
                       &ctx->in_offsets, &ctx->out_results, &ctx->misc, &ctx->seen, &ctx->long_scratch})
         b->release();
     for (auto &lane : ctx->lane_slots)
@@ -905,7 +908,7 @@ static int launch_score_tasks(orph_ctx *ctx, const ScoreParams &P_in, uint32_t t
     P.read_words = (2 * tier_len + 34) / 32 + 2;  // aligned strand words incl. the words the look-ahead window fetch may touch
     P.seen_words = long_tier ? kSeenWordsLong : kSeenWordsShort;
     const size_t smem = (size_t)kTaskBlock * (P.seen_words * 8 + P.read_words * 4);
-    auto kern = score_tasks_kernel<K>;
+    auto kern = score_tasks_kernel<K, false>;
     // attribute + occupancy query once per (device, smem size): they cost tens of microseconds per call
     static thread_local int cached_dev = -1, cached_per_sm[2] = {0, 0};
     static thread_local size_t cached_smem[2] = {0, 0};
@@ -922,7 +925,32 @@ static int launch_score_tasks(orph_ctx *ctx, const ScoreParams &P_in, uint32_t t
     {
         Timed timed(ctx, 4);
         kern<<<ctx->sm_count * per_sm, kTaskBlock, smem, ctx->stream>>>(P, reinterpret_cast<const uint32_t *>(packed), d_offsets,
-                                                                          pbase0, tasks, tasks_sorted, long_tier, counters, d_out);
+                                                                          pbase0, tasks, tasks_sorted, long_tier, counters, d_out, nullptr);
+    }
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ORPH_OK;
+}
+
+// the instantiation with an N plane, over the queue of reads that hold N (ASCII input only; usually a few per cent of a batch)
+template <int K>
+static int launch_score_tasks_n(orph_ctx *ctx, const ScoreParams &P_in, uint32_t tier_len, const uint64_t *packed, const uint64_t *d_offsets,
+                                uint64_t pbase0, const uint32_t *tasks_n, const uint32_t *nmask, ScoreCounters *counters, orph_read_result *d_out)
+{
+    ScoreParams P = P_in;
+    P.read_words = (2 * tier_len + 34) / 32 + 2;
+    P.seen_words = tier_len > kThreadMaxLenShort ? kSeenWordsLong : kSeenWordsShort;
+    const uint32_t mask_words = (P.read_words + 1) / 2 + 1;
+    const size_t smem = (size_t)kTaskBlock * (P.seen_words * 8 + P.read_words * 4 + mask_words * 4);
+    auto kern = score_tasks_kernel<K, true>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTaskBlock, smem));
+    if (per_sm < 1) per_sm = 1;
+    {
+        Timed timed(ctx, 4);
+        kern<<<ctx->sm_count * per_sm, kTaskBlock, smem, ctx->stream>>>(P, reinterpret_cast<const uint32_t *>(packed), d_offsets, pbase0, tasks_n, nullptr, 2,
+                                                                          counters, d_out, nmask);
     }
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -991,22 +1019,30 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
 
     const uint64_t *d_packed = d_packed_in;
     uint64_t pbase0 = pbase0_in;
-    const uint8_t *d_needs = nullptr;
+    const uint8_t *d_needs = nullptr, *d_has_n = nullptr;
+    const uint32_t *d_nmask = nullptr;
+    uint32_t *d_tasks_n = nullptr;
     if (d_ascii) {
         const uint64_t n_words = (total_bases_ascii + 31) / 32;
         if ((rc = ctx->packed.ensure((n_words + 2) * 8)) != ORPH_OK) return rc;
-        if ((rc = ctx->needs_bytes.ensure(n_reads)) != ORPH_OK) return rc;
-        CUDA_TRY(cudaMemsetAsync(ctx->needs_bytes.p, 0, n_reads, s));
+        if ((rc = ctx->needs_bytes.ensure(2 * n_reads)) != ORPH_OK) return rc;
+        if ((rc = ctx->nmask.ensure((n_words + 2) * 4)) != ORPH_OK) return rc;
+        if (thread_len && (rc = ctx->task_queue_n.ensure(n_reads * 6 * 4)) != ORPH_OK) return rc;
+        CUDA_TRY(cudaMemsetAsync(ctx->needs_bytes.p, 0, 2 * n_reads, s));
         pbase0 = abase0;
         if (n_words) {
             Timed timed(ctx, 0);
             pack_ascii_kernel<<<grid_for(n_words, 256, ctx->sm_count, 16), 256, 0, s>>>(
-                d_ascii, abase0, d_offsets, n_reads, pbase0, total_bases_ascii, (uint64_t *)ctx->packed.p, (uint8_t *)ctx->needs_bytes.p);
+                d_ascii, abase0, d_offsets, n_reads, pbase0, total_bases_ascii, (uint64_t *)ctx->packed.p, (uint8_t *)ctx->needs_bytes.p,
+                (uint32_t *)ctx->nmask.p, (uint8_t *)ctx->needs_bytes.p + n_reads);
             ctx->launches++;
             CUDA_TRY(cudaGetLastError());
         }
         d_packed = (const uint64_t *)ctx->packed.p;
         d_needs = (const uint8_t *)ctx->needs_bytes.p;
+        d_has_n = d_needs + n_reads;
+        d_nmask = (const uint32_t *)ctx->nmask.p;
+        if (thread_len) d_tasks_n = (uint32_t *)ctx->task_queue_n.p;
     }
 
     {
@@ -1014,7 +1050,7 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
         prefilter_kernel<<<grid_for(n_reads, 256, ctx->sm_count, 16), 256, 0, s>>>(
             d_packed, d_offsets, pbase0, n_reads, d_needs, P.k, fast_len, thread_len, short_len, P.task_capacity, bound, bytes_max_len, d_out,
             (uint32_t *)ctx->queue.p,
-            (uint32_t *)ctx->task_queue.p, (uint32_t *)ctx->bytes_queue.p, counters);
+            (uint32_t *)ctx->task_queue.p, (uint32_t *)ctx->bytes_queue.p, counters, d_nmask, d_has_n, d_tasks_n);
     }
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -1044,6 +1080,21 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
         default: rc = fail(ORPH_E_INVALID, "internal: no task kernel for k=%u", P.k); break;
         }
         if (rc != ORPH_OK) return rc;
+        if (d_tasks_n) {  // reads that hold N: the same kernel with an N plane
+            switch (P.k) {
+            case 7: rc = launch_score_tasks_n<7>(ctx, P, thread_len, d_packed, d_offsets, pbase0, d_tasks_n, d_nmask, counters, d_out); break;
+            case 8: rc = launch_score_tasks_n<8>(ctx, P, thread_len, d_packed, d_offsets, pbase0, d_tasks_n, d_nmask, counters, d_out); break;
+            case 9: rc = launch_score_tasks_n<9>(ctx, P, thread_len, d_packed, d_offsets, pbase0, d_tasks_n, d_nmask, counters, d_out); break;
+            case 10: rc = launch_score_tasks_n<10>(ctx, P, thread_len, d_packed, d_offsets, pbase0, d_tasks_n, d_nmask, counters, d_out); break;
+            case 11: rc = launch_score_tasks_n<11>(ctx, P, thread_len, d_packed, d_offsets, pbase0, d_tasks_n, d_nmask, counters, d_out); break;
+            case 12: rc = launch_score_tasks_n<12>(ctx, P, thread_len, d_packed, d_offsets, pbase0, d_tasks_n, d_nmask, counters, d_out); break;
+            case 16: rc = launch_score_tasks_n<16>(ctx, P, thread_len, d_packed, d_offsets, pbase0, d_tasks_n, d_nmask, counters, d_out); break;
+            case 21: rc = launch_score_tasks_n<21>(ctx, P, thread_len, d_packed, d_offsets, pbase0, d_tasks_n, d_nmask, counters, d_out); break;
+            case 31: rc = launch_score_tasks_n<31>(ctx, P, thread_len, d_packed, d_offsets, pbase0, d_tasks_n, d_nmask, counters, d_out); break;
+            default: break;
+            }
+            if (rc != ORPH_OK) return rc;
+        }
         {
             Timed timed(ctx, 5);
             finalize_best_kernel<<<grid_for(n_reads, 256, ctx->sm_count, 16), 256, 0, s>>>(d_out, n_reads);

@@ -59,6 +59,8 @@ struct ScoreCounters {
     uint32_t cursor[2][kLenBuckets]; // scatter cursors of the counting sort (longest peptides first)
     uint32_t n_long;       // reads queued for score_long_kernel (block per read), from the back of the byte queue
     uint32_t next_long;
+    uint32_t n_tasks_n;    // tasks of reads that hold N (and nothing else unusual): thread per frame with an N mask
+    uint32_t next_task_n;
     uint32_t pad;
     uint32_t status;       // kStatus* bits; sticky until orph_ctx_check -- keep it last
 };
@@ -212,9 +214,13 @@ __device__ __forceinline__ uint32_t find_read(const uint64_t *offsets, uint64_t 
 }
 
 // `ascii` points at the byte of absolute base index abase0; the packed stream starts at absolute base pbase0.
+// Besides the 2-bit words it writes an N plane -- bit i of nmask[w] is set where base 32 w + i is an upper-case 'N' -- and
+// classifies the reads: needs_bytes[r] = 1 if read r holds a byte that is neither ACGT nor N (lower case, IUPAC codes, ...:
+// only the byte-exact kernels can score it), has_n[r] = 1 if it holds an N (scored on the 2-bit path with the N plane).
 __global__ void pack_ascii_kernel(const uint8_t *__restrict__ ascii, uint64_t abase0, const uint64_t *__restrict__ offsets,
                                   uint64_t n_reads, uint64_t pbase0, uint64_t total_bases,
-                                  uint64_t *__restrict__ packed, uint8_t *__restrict__ needs_bytes)
+                                  uint64_t *__restrict__ packed, uint8_t *__restrict__ needs_bytes, uint32_t *__restrict__ nmask,
+                                  uint8_t *__restrict__ has_n)
 {
     const uint8_t *reads = ascii + (pbase0 - abase0);  // byte of the first base to pack
     const uint64_t n_words = (total_bases + 31) / 32;
@@ -224,6 +230,7 @@ __global__ void pack_ascii_kernel(const uint8_t *__restrict__ ascii, uint64_t ab
         const uint32_t count = (uint32_t)((total_bases - 32 * w) < 32 ? (total_bases - 32 * w) : 32);
         uint64_t bits = 0;
         uint32_t bad = 0;  // bit i: byte i is not upper-case ACGT
+        uint32_t isn = 0;  // bit i: byte i is 'N'
         if (count == 32 && ((reinterpret_cast<uintptr_t>(reads + g0) & 15) == 0)) {
             const uint4 *p = reinterpret_cast<const uint4 *>(reads + g0);
             const uint4 v0 = __ldg(p), v1 = __ldg(p + 1);
@@ -236,6 +243,9 @@ __global__ void pack_ascii_kernel(const uint8_t *__restrict__ ascii, uint64_t ab
                 uint32_t d = e ^ x[q];
                 d |= d >> 4; d |= d >> 2; d |= d >> 1; d &= 0x01010101u;                // any bit differs, per byte
                 bad |= ((d | (d >> 7) | (d >> 14) | (d >> 21)) & 0xFu) << (4 * q);
+                uint32_t dn = x[q] ^ 0x4E4E4E4Eu;                                       // zero byte where the byte is 'N'
+                dn |= dn >> 4; dn |= dn >> 2; dn |= dn >> 1; dn = ~dn & 0x01010101u;
+                isn |= ((dn | (dn >> 7) | (dn >> 14) | (dn >> 21)) & 0xFu) << (4 * q);
                 const uint32_t c = (x[q] >> 1) & 0x03030303u;
                 const uint32_t b8 = (c | (c >> 6) | (c >> 12) | (c >> 18)) & 0xFFu;
                 bits |= (uint64_t)b8 << (8 * q);
@@ -245,14 +255,18 @@ __global__ void pack_ascii_kernel(const uint8_t *__restrict__ ascii, uint64_t ab
                 const uint8_t b = reads[g0 + i];
                 const uint32_t c = (b >> 1) & 3u;
                 if (b != (uint8_t)"ACTG"[c]) bad |= 1u << i;
+                if (b == 'N') isn |= 1u << i;
                 bits |= (uint64_t)c << (2 * i);
             }
         }
         packed[w] = bits;
+        nmask[w] = isn;
         while (bad) {
             const int i = __ffs(bad) - 1;
             bad &= bad - 1;
-            needs_bytes[find_read(offsets, n_reads, pbase0 + g0 + i)] = 1;
+            const uint32_t r = find_read(offsets, n_reads, pbase0 + g0 + i);
+            if ((isn >> i) & 1u) has_n[r] = 1;
+            else needs_bytes[r] = 1;
         }
     }
 }
@@ -293,7 +307,8 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
                  uint32_t thread_max_len, uint32_t thread_short_len, uint32_t task_capacity, uint32_t max_len,
                  uint32_t bytes_max_len, orph_read_result *__restrict__ out,
                  uint32_t *__restrict__ queue, uint32_t *__restrict__ task_queue, uint32_t *__restrict__ bytes_queue,
-                 ScoreCounters *__restrict__ counters)
+                 ScoreCounters *__restrict__ counters, const uint32_t *__restrict__ nmask, const uint8_t *__restrict__ has_n,
+                 uint32_t *__restrict__ task_queue_n)
 {
     const int lane = threadIdx.x & 31;
     __shared__ uint32_t s_hist[2][kLenBuckets];
@@ -304,7 +319,7 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
         const uint64_t r = r0 + lane;
         const bool in_range = r < n_reads;
         bool to_queue = false, to_bytes = false, to_long = false;
-        uint32_t open_bits = 0, n_my_tasks = 0, n_my_tasks_long = 0;
+        uint32_t open_bits = 0, n_my_tasks = 0, n_my_tasks_long = 0, n_my_tasks_n = 0;
         if (in_range) {
             const uint64_t o0 = offsets[r], o1 = offsets[r + 1];
             const uint64_t L = o1 - o0;
@@ -321,9 +336,53 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
                 // (beyond ORPH_MAX_READ_LEN too: score_long_kernel classifies such a read from its stop codons alone)
                 to_long = true;
                 rec.flags = ORPH_FLAG_BYTE_PATH;
-            } else if ((needs_bytes && needs_bytes[r]) || L > fast_max_len) {
+            } else if ((needs_bytes && needs_bytes[r]) || L > fast_max_len || (has_n && has_n[r] && (L > thread_max_len || !task_queue_n))) {
                 to_bytes = true;
                 rec.flags = ORPH_FLAG_BYTE_PATH;
+            } else if (has_n && has_n[r]) {
+                // A read with N (and no other unusual byte), short enough for the thread-per-frame kernel: the same tests as
+                // below, base by base, with the reference's string semantics for N -- N differs from every base and equals
+                // N in the complexity count (translate.py:79-84); a codon that holds an N is never a stop codon.  Rare reads:
+                // a plain loop instead of the bit-plane arithmetic.
+                const uint32_t *p32 = reinterpret_cast<const uint32_t *>(packed);
+                const uint64_t g0 = o0 - base0;
+                auto code = [&](uint32_t i) { const uint64_t b = 2 * (g0 + i); return (p32[b >> 5] >> (b & 31)) & 3u; };
+                auto is_n = [&](uint32_t i) { const uint64_t g = g0 + i; return (nmask[g >> 5] >> (g & 31)) & 1u; };
+                const uint32_t Ln = (uint32_t)L;
+                uint32_t ndiff = 0, stops = 0;
+                uint32_t c0 = code(0), m0 = is_n(0), c1 = Ln > 1 ? code(1) : 0u, m1 = Ln > 1 ? is_n(1) : 0u;
+                for (uint32_t p = 0; p + 1 < Ln; p++) {
+                    ndiff += (m0 != m1) || (!m0 && c0 != c1);
+                    uint32_t c2 = 0, m2 = 0;
+                    if (p + 2 < Ln) {
+                        c2 = code(p + 2);
+                        m2 = is_n(p + 2);
+                        if (!(m0 | m1 | m2)) {
+                            // codes A0 C1 T2 G3: forward stops TAA TAG TGA; triples whose reverse complement is one: TTA CTA TCA
+                            if (c0 == 2 && ((c1 == 0 && (c2 == 0 || c2 == 3)) || (c1 == 3 && c2 == 0))) stops |= 1u << (p % 3);
+                            if (c2 == 0 && ((c1 == 2 && (c0 == 2 || c0 == 1)) || (c1 == 1 && c0 == 2))) stops |= 8u << ((Ln - p) % 3);
+                        }
+                    }
+                    c0 = c1; m0 = m1; c1 = c2; m1 = m2;
+                }
+                if (10ull * ndiff < 3ull * L) {
+                    rec.flags = ORPH_FLAG_LOW_COMPLEXITY;
+#pragma unroll
+                    for (int f = 0; f < 6; f++) rec.category[f] = ORPH_CAT_LOW_COMPLEXITY_NUCLEOTIDE;
+                } else {
+                    uint32_t open = 0;
+#pragma unroll
+                    for (int f = 0; f < 6; f++) {
+                        const uint32_t phase = f % 3;
+                        const uint32_t plen = Ln >= phase ? (Ln - phase) / 3 : 0;
+                        if ((stops >> f) & 1u) rec.category[f] = ORPH_CAT_STOP_CODONS;
+                        else if (plen <= k) rec.category[f] = ORPH_CAT_TOO_SHORT_PEPTIDE;
+                        else open |= 1u << f;
+                    }
+                    rec.flags = (uint8_t)open;
+                    open_bits = open;
+                    n_my_tasks_n = __popc(open);
+                }
             } else {
                 // the read as aligned 32-bit words: A[j] = bases [16j, 16j+16), one funnel shift each
                 const uint64_t bitpos = 2 * (o0 - base0);
@@ -450,8 +509,8 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
             bytes_queue[(uint32_t)n_reads - 1 - atomicAdd(&counters->n_long, 1u)] = (uint32_t)r;
         // per-frame tasks: warp-wide scan of the per-read task counts, one atomic per warp and tier
 #pragma unroll
-        for (int tier = 0; tier < 2; tier++) {
-            const uint32_t mine = tier == 0 ? n_my_tasks : n_my_tasks_long;
+        for (int tier = 0; tier < 3; tier++) {
+            const uint32_t mine = tier == 0 ? n_my_tasks : tier == 1 ? n_my_tasks_long : n_my_tasks_n;
             uint32_t incl = mine;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -461,14 +520,15 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
             const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
             if (total) {
                 uint32_t base_t = 0;
-                if (lane == 0) base_t = atomicAdd(tier == 0 ? &counters->n_tasks : &counters->n_tasks_long, total);
+                if (lane == 0) base_t = atomicAdd(tier == 0 ? &counters->n_tasks : tier == 1 ? &counters->n_tasks_long : &counters->n_tasks_n, total);
                 base_t = __shfl_sync(0xffffffffu, base_t, 0) + incl - mine;
                 uint32_t bits = mine ? open_bits : 0u;
                 while (bits) {
                     const uint32_t f = __ffs(bits) - 1;
                     bits &= bits - 1;
-                    // the short tier grows from the front of the queue, the long tier from the back
-                    task_queue[tier == 0 ? base_t : task_capacity - 1 - base_t] = ((uint32_t)r << 3) | f;
+                    // the short tier grows from the front of the queue, the long tier from the back; N reads have their own
+                    if (tier == 2) task_queue_n[base_t] = ((uint32_t)r << 3) | f;
+                    else task_queue[tier == 0 ? base_t : task_capacity - 1 - base_t] = ((uint32_t)r << 3) | f;
                     base_t++;
                 }
             }

@@ -95,17 +95,41 @@ struct KmerWindow {
 // or its reverse complement), re-aligned so that base 0 sits at bit 0 of word 0.  Word t at col[t * kTaskBlock].
 // With the strand materialised every frame is a forward walk: residue i of frame phase ph is the codon at
 // bits [2*ph + 6*i, +6), looked up in ONE table (forward codon x alphabet).
+// NM: the strand also has an N plane (one bit per base, column `mcol`, same alignment): reads that hold N.  A codon with an N
+// is X -- encoded like every other residue, `x_res` -- unless the N is its third base and the first two are one of the seven
+// four-fold families the reference's table lists (ACN CTN CGN GTN GCN GGN TCN, constants_translate.py:59-131; CCN is not
+// in it), which translate like any member of the family.
+constexpr uint32_t kFourFoldWithN = (1u << 4) | (1u << 9) | (1u << 13) | (1u << 11) | (1u << 7) | (1u << 15) | (1u << 6);  // index b0 | b1 << 2
+
+__device__ __forceinline__ uint32_t residue_with_n(const uint8_t *lut, uint32_t codon, uint32_t n3, uint32_t x_res)
+{
+    if (n3 == 0) return lut[codon];
+    if (n3 == 4u && ((kFourFoldWithN >> (codon & 15u)) & 1u)) return lut[codon & 15u];
+    return x_res;
+}
+
+template <bool NM>
 struct StrandColumn {
     const uint32_t *col;
+    const uint32_t *mcol;
+    uint32_t x_res;
     // 32 bits of the strand starting at `bit`
     __device__ __forceinline__ uint32_t window(uint32_t bit) const
     {
         const uint32_t wi = bit >> 5;
         return __funnelshift_r(col[wi * kTaskBlock], col[(wi + 1) * kTaskBlock], bit & 31u);
     }
+    // the N bits of the three bases starting at base `b`
+    __device__ __forceinline__ uint32_t n_bits(uint32_t b) const
+    {
+        const uint32_t wi = b >> 5;
+        return __funnelshift_r(mcol[wi * kTaskBlock], mcol[(wi + 1) * kTaskBlock], b & 31u) & 7u;
+    }
     __device__ __forceinline__ uint32_t residue(const uint8_t *lut, uint32_t phase, uint32_t i) const
     {
-        return lut[window(2u * phase + 6u * i) & 63u];
+        const uint32_t codon = window(2u * phase + 6u * i) & 63u;
+        if constexpr (NM) return residue_with_n(lut, codon, n_bits(phase + 3u * i), x_res);
+        else return lut[codon];
     }
 };
 
@@ -119,8 +143,8 @@ __device__ __forceinline__ uint32_t revcomp_word(uint32_t x)
 
 // Exact answer behind a seen-filter alarm: does the k-mer ending at residue s (window `cur`) also end
 // at an earlier residue of the same frame?  Walks backwards, so a tandem repeat answers after one period.
-template <int K>
-__device__ __forceinline__ bool kmer_seen_before(const StrandColumn &sc, const uint8_t *lut, uint32_t phase, int s,
+template <int K, bool NM>
+__device__ __forceinline__ bool kmer_seen_before(const StrandColumn<NM> &sc, const uint8_t *lut, uint32_t phase, int s,
                                                  const KmerWindow<K> &cur)
 {
     KmerWindow<K> win = cur;
@@ -131,13 +155,16 @@ __device__ __forceinline__ bool kmer_seen_before(const StrandColumn &sc, const u
     return false;
 }
 
-template <int K>
+// NM = true: the instantiation for reads that hold N (tasks_unsorted = their queue, `nmask` = the N plane of the 2-bit
+// stream, long_tier = 2: the long tier's shared-memory geometry plus one N-plane column per thread).
+template <int K, bool NM>
 __global__ void __launch_bounds__(kTaskBlock)
 score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, const uint64_t *__restrict__ offsets,
                    uint64_t base0, const uint32_t *__restrict__ tasks_unsorted, const uint32_t *__restrict__ tasks_sorted,
-                   int long_tier, ScoreCounters *__restrict__ counters, orph_read_result *__restrict__ out)
+                   int long_tier, ScoreCounters *__restrict__ counters, orph_read_result *__restrict__ out,
+                   const uint32_t *__restrict__ nmask)
 {
-    extern __shared__ __align__(16) uint8_t dyn_smem[];  // [seen: P.seen_words u64 x 256][strand words: P.read_words u32 x 256]
+    extern __shared__ __align__(16) uint8_t dyn_smem[];  // [seen: P.seen_words u64 x 256][strand words: P.read_words u32 x 256][NM: N-plane words]
     __shared__ FilterDev sF;
     __shared__ uint8_t lut_fwd[64];
     __shared__ uint16_t s_min_hits[kThreadMaxLen / 3 + 2];
@@ -170,14 +197,16 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
             (out) = r__;                                                                      \
         }                                                                                     \
     }
-    const uint32_t n_tasks = long_tier ? counters->n_tasks_long : counters->n_tasks;
-    const uint32_t *tasks = counters->sort_tier[long_tier ? 1 : 0] ? tasks_sorted : tasks_unsorted;
-    uint32_t *next_task = long_tier ? &counters->next_task_long : &counters->next_task;
+    const uint32_t n_tasks = NM ? counters->n_tasks_n : long_tier ? counters->n_tasks_long : counters->n_tasks;
+    const uint32_t *tasks = NM ? tasks_unsorted : counters->sort_tier[long_tier ? 1 : 0] ? tasks_sorted : tasks_unsorted;
+    uint32_t *next_task = NM ? &counters->next_task_n : long_tier ? &counters->next_task_long : &counters->next_task;
     const uint32_t seen_words = P.seen_words;
     unsigned long long *seen = reinterpret_cast<unsigned long long *>(dyn_smem) + threadIdx.x;
     uint32_t *strand = reinterpret_cast<uint32_t *>(dyn_smem + (size_t)seen_words * 8 * kTaskBlock) + threadIdx.x;
     const uint32_t strand_words = P.read_words;
-    const StrandColumn sc{strand};
+    const uint32_t mask_words = (strand_words + 1) / 2 + 1;  // one bit per base against two (+ the word a 3-bit fetch may touch)
+    uint32_t *mstrand = strand + (size_t)strand_words * kTaskBlock;
+    const StrandColumn<NM> sc{strand, mstrand, (uint32_t)P.lut['X']};
 
     while (true) {
         uint32_t base = 0;
@@ -188,7 +217,7 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
         uint32_t r = 0, f = 0, L = 0, plen = 0;
         uint64_t o0 = 0;
         if (valid) {
-            const uint32_t entry = long_tier ? tasks[P.task_capacity - 1 - (base + lane)] : tasks[base + lane];
+            const uint32_t entry = (long_tier && !NM) ? tasks[P.task_capacity - 1 - (base + lane)] : tasks[base + lane];
             r = entry >> 3;
             f = entry & 7u;
             o0 = offsets[r];
@@ -214,6 +243,28 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
                 uint32_t w = 0;
                 if (t < n_need) w = f < 3 ? read_bits((int)(32 * t)) : revcomp_word(read_bits(2 * (int)L - 32 * (int)(t + 1)));
                 strand[t * kTaskBlock] = w;
+            }
+            if constexpr (NM) {
+                // the N plane of the strand: bit i = base i of the read, or of its reverse complement (N is its own complement)
+                const uint64_t g0 = o0 - base0;
+                const uint32_t mb0 = (uint32_t)(g0 & 31);
+                const uint32_t *msrc = nmask + (g0 >> 5);
+                const uint32_t n_msrc = valid ? (mb0 + L + 31) / 32 : 0;
+                auto msrc_word = [&](uint32_t i) { return i < n_msrc ? __ldg(msrc + i) : 0u; };
+                auto mask_bits = [&](int start) {  // 32 N bits from (possibly negative) read-relative base `start`; beyond the read: 0
+                    const uint32_t a = mb0 + (uint32_t)(start > 0 ? start : 0);
+                    uint32_t v = __funnelshift_r(msrc_word(a >> 5), msrc_word((a >> 5) + 1), a & 31u);
+                    const int first = start > 0 ? start : 0;
+                    const int left = (int)L - first;  // bases of the read from `first` on
+                    if (left < 32) v &= left > 0 ? ((1u << left) - 1u) : 0u;
+                    return start >= 0 ? v : v << (uint32_t)(-start);
+                };
+                const uint32_t n_mneed = valid ? (L + 31) / 32 : 0;
+                for (uint32_t t = 0; t < mask_words; t++) {
+                    uint32_t w = 0;
+                    if (t < n_mneed) w = f < 3 ? mask_bits((int)(32 * t)) : __brev(mask_bits((int)L - 32 * (int)(t + 1)));
+                    mstrand[t * kTaskBlock] = w;
+                }
             }
         }
         KmerWindow<K> win;
@@ -242,7 +293,7 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
         unsigned long long seen_bits = 0, seen_old = 0;
         // window state: win32 holds codons of residues [5*g, 5*g+5); raw words of the next group are fetched early
         uint32_t win32 = sc.window(2u * phase), win_next = 0, raw_a = 0, raw_b = 0, raw_sh = 0;
-        uint32_t res_cur = lut_fwd[win32 & 63u];  // residue 0
+        uint32_t res_cur = NM ? residue_with_n(lut_fwd, win32 & 63u, sc.n_bits(phase), sc.x_res) : lut_fwd[win32 & 63u];  // residue 0
         uint32_t mod5 = 0;                         // s % 5, uniform
         for (uint32_t s = 0; s < max_plen + 2; s++) {
             // (1)
@@ -251,7 +302,7 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
                 *seen_slot = seen_old | seen_bits;
                 kmer_new = true;
                 if ((seen_old & seen_bits) == seen_bits || force_exact)
-                    kmer_new = !kmer_seen_before<K>(sc, lut_fwd, phase, (int)s - 1, win);
+                    kmer_new = !kmer_seen_before<K, NM>(sc, lut_fwd, phase, (int)s - 1, win);
                 nd += kmer_new ? 1u : 0u;
                 seen_pending = false;
             }
@@ -314,7 +365,8 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
                 mod5++;
                 codon = (win32 >> (6u * mod5)) & 63u;
             }
-            res_cur = lut_fwd[codon];
+            if constexpr (NM) res_cur = residue_with_n(lut_fwd, codon, sc.n_bits(phase + 3u * (s + 1)), sc.x_res);
+            else res_cur = lut_fwd[codon];
         }
 #undef ORPH_BIN
         if (valid) {
