@@ -73,7 +73,9 @@ typedef struct orph_read_result {
 
 #define ORPH_FLAG_OPEN_MASK 0x3f      /* bit f: frame f had no stop codon and was longer than k (was scored) */
 #define ORPH_FLAG_LOW_COMPLEXITY 0x40 /* fastp nucleotide complexity < 0.3 (translate.py:56-84) */
-#define ORPH_FLAG_BYTE_PATH 0x80      /* read went through the byte-exact path (non-ACGT bytes or over-long) */
+#define ORPH_FLAG_BYTE_PATH 0x80      /* read went through a byte-exact kernel (lower case / IUPAC bytes, N in a read longer than
+                                         320 nt, reads beyond the packed kernels' length); informational: the other fields do
+                                         not depend on the route */
 
 /* Input encodings of read batches. */
 typedef enum orph_reads_format {

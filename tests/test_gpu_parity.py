@@ -315,6 +315,69 @@ def test_synthetic_mixed_vs_oracle(gpu, enc, orc, refdata, alphabet, ksize, thr)
     np.testing.assert_array_equal((res_warp["flags"] & 0x80) != 0, has_n)  # ... and are the byte path's without the thread kernel
 
 
+@pytest.mark.parametrize("alphabet,ksize", [("protein", 7), ("dayhoff", 12), ("hp", 31)])
+def test_reads_with_n_on_the_two_bit_path(gpu, enc, orc, refdata, alphabet, ksize):
+    """Reads that hold N (and no other unusual byte) are scored by the thread-per-frame kernel with an N plane: every N
+    placement that matters -- third base of each of the 16 two-base prefixes (seven of them translate, CCN and the rest are
+    X), first and second codon positions, both strands, the first and last base of the read, runs of N, all-N reads, N in
+    reads of every length up to 320 nt and just beyond (byte path) -- against the oracle."""
+    from orpheum_b200 import synth
+
+    fasta = os.path.join(refdata, "index", "Homo_sapiens.GRCh38.pep.subset.fa.gz")
+    go = oracle_filter(orc, fasta, alphabet, ksize, 1e6)
+    gg = gpu_filter(gpu, enc, fasta, alphabet, ksize, 1e6)
+    res_, offs_ = fasta_arrays(fasta)
+    standard = np.zeros(256, dtype=bool)
+    standard[np.frombuffer(synth.AMINO_ACIDS.encode(), dtype=np.uint8)] = True
+    keep = [i for i in range(len(offs_) - 1) if offs_[i + 1] - offs_[i] >= 120 and standard[res_[int(offs_[i]):int(offs_[i + 1])]].all()]
+    residues = np.concatenate([res_[int(offs_[i]):int(offs_[i + 1])] for i in keep])
+    poffs = np.zeros(len(keep) + 1, dtype=np.uint64)
+    poffs[1:] = np.cumsum([int(offs_[i + 1] - offs_[i]) for i in keep])
+    rng = np.random.default_rng(77)
+    reads = []
+    coding = synth.make_reads_fixed(6000, residues, poffs, length=330, seed=78)  # even rows are back-translated, odd rows random
+    for i in range(6000):
+        L = int(rng.choice([31, 64, 95, 96, 150, 151, 191, 192, 193, 250, 319, 320, 321, 330]))
+        s = bytearray(coding[i, :L].tobytes())
+        mode = (i // 2) % 8  # (even rows are coding reads, odd rows random: both kinds get every mode)
+        if mode == 0:
+            s[int(rng.integers(0, L))] = ord("N")
+        elif mode == 1:
+            for p in rng.integers(0, L, int(rng.integers(2, 7))):
+                s[int(p)] = ord("N")
+        elif mode == 2:
+            a = int(rng.integers(0, L))
+            b_ = min(L, a + int(rng.integers(2, 40)))
+            s[a:b_] = b"N" * (b_ - a)
+        elif mode == 3:
+            s[0] = ord("N")
+            s[L - 1] = ord("N")
+        elif mode == 4:  # every third base from a random phase: one N per codon of one frame
+            for p in range(int(rng.integers(0, 3)), L, 3):
+                if rng.random() < 0.3:
+                    s[p] = ord("N")
+        elif mode == 5:
+            s = bytearray(b"N" * L)
+        elif mode == 6:  # all 16 prefixes followed by N, back to back
+            pre = b"".join(bytes([a, b]) + b"N" for a in b"ACGT" for b in b"ACGT")
+            at = int(rng.integers(0, max(1, L - len(pre))))
+            s[at:at + len(pre)] = pre[: L - at]
+        reads.append(bytes(s))
+    flat, offsets = gpu.concat_reads(reads)
+    olut = orc.encode_lut(alphabet)
+    thr = 0.8 if alphabet == "hp" else 0.5
+    ora, n_empty = orc.score_reads(go, flat, offsets, olut, thr, n_threads=0)
+    assert n_empty == 0
+    res = gpu.score_reads(gg, flat, offsets, enc.encode_lut(alphabet), thr)
+    assert_same_as_oracle(res, ora, f"N reads {alphabet}")
+    lengths = np.diff(offsets.astype(np.int64))
+    has_n = np.array([b"N" in r for r in reads])
+    byte_path = (res["flags"] & 0x80) != 0
+    np.testing.assert_array_equal(byte_path, has_n & (lengths > 320))
+    scored_with_n = ((ora["category"] == 3) | (ora["category"] == 4)).any(axis=1) & has_n & ~byte_path
+    assert scored_with_n.sum() > 300  # frames of N reads were really scored on the new path
+
+
 def test_sub_batch_offsets_and_device_api(gpu, enc, orc, refdata):
     """offsets[0] != 0 (a view into a larger buffer) and the device-pointer entry point."""
     import torch
