@@ -362,16 +362,36 @@ def config_leg(name, ctx, stream, dev, alphabet, workload, n_reads, tablesize, n
     graph = gpu.GpuNodegraph(ksize, int(tablesize), n_tables, ctx=ctx)
     graph.add_peptides(residues, poffs, lut, count_unique=False)
     packed, needs = gpu.pack_reads(flat, offsets)
-    if needs.any():
-        d_reads, fmt = torch.from_numpy(flat).to(dev), _lib.READS_ASCII
-    else:
-        d_reads, fmt = torch.from_numpy(packed.view(np.int64)).to(dev), _lib.READS_PACKED2
     d_offsets = torch.from_numpy(offsets.view(np.int64)).to(dev)
     d_out = torch.zeros(n_reads * 32, dtype=torch.uint8, device=dev)
     max_len = int(np.diff(offsets.astype(np.int64)).max())
+    n_plane = None
+    if needs.any():
+        # reads with N: the device-resident form is the 2-bit stream + N plane, built on the device from the ASCII reads before
+        # the clock starts (what a caller with N reads keeps in HBM); bytes other than ACGTN would force the ASCII form
+        d_ascii = torch.from_numpy(flat).to(dev)
+        total = int(offsets[-1])
+        d_reads = torch.zeros((total + 31) // 32 + 2, dtype=torch.int64, device=dev)
+        n_plane = (torch.zeros((total + 31) // 32 + 2, dtype=torch.int32, device=dev), torch.zeros(n_reads, dtype=torch.uint8, device=dev))
+        d_needs = torch.zeros(n_reads, dtype=torch.uint8, device=dev)
+        with torch.cuda.stream(stream):
+            gpu.pack_reads_device(ctx, d_ascii.data_ptr(), d_offsets.data_ptr(), n_reads, total, d_reads.data_ptr(), n_plane[0].data_ptr(),
+                                  n_plane[1].data_ptr(), d_needs.data_ptr())
+        torch.cuda.synchronize()
+        fmt = "packed2 + N plane"
+        if bool(d_needs.any().item()):
+            d_reads, fmt, n_plane = d_ascii, _lib.READS_ASCII, None
+        else:
+            del d_ascii
+    else:
+        d_reads, fmt = torch.from_numpy(packed.view(np.int64)).to(dev), _lib.READS_PACKED2
 
     def step():
-        gpu.score_reads_device(graph, d_reads.data_ptr(), d_offsets.data_ptr(), n_reads, max_len, lut, thr, d_out.data_ptr(), reads_format=fmt, ctx=ctx)
+        if n_plane is not None:
+            gpu.score_reads_device_n(graph, d_reads.data_ptr(), n_plane[0].data_ptr(), n_plane[1].data_ptr(), d_offsets.data_ptr(), n_reads, max_len, lut, thr,
+                                     d_out.data_ptr(), ctx=ctx)
+        else:
+            gpu.score_reads_device(graph, d_reads.data_ptr(), d_offsets.data_ptr(), n_reads, max_len, lut, thr, d_out.data_ptr(), reads_format=fmt, ctx=ctx)
 
     with torch.cuda.stream(stream):
         for _ in range(warmup):
@@ -409,7 +429,7 @@ def config_leg(name, ctx, stream, dev, alphabet, workload, n_reads, tablesize, n
     out = {"workload": f"{n_reads} {'mixed 50-300 nt (cfg5 recipe)' if workload == 'mixed' else '150-nt'} reads vs {proteins}-protein proteome, {alphabet} k={ksize}, "
                        f"tablesize {int(tablesize):.0e} x {n_tables} ({fbytes / 1e6:.0f} MB filter)",
            "value": n_reads / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "reads": n_reads,
-           "input_format": "ascii (reads with N cannot be 2-bit packed)" if fmt == _lib.READS_ASCII else "packed2",
+           "input_format": fmt if isinstance(fmt, str) else "ascii (bytes other than ACGTN)" if fmt == _lib.READS_ASCII else "packed2",
            "dominant_kernel": dominant + "_kernel", "dominant_kernel_ms_per_step": dom_ms, "probing_kernels_ms_per_step": probing_ms,
            "kernel_ms_per_step": {k: v[0] / steps for k, v in ktimes.items() if v[0] > 0},
            "probes_min_per_read": pmin, "probe_sectors_per_s": probe_rate, "gather_peak_sectors_per_s": peak,

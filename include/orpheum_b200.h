@@ -202,6 +202,21 @@ int orph_score_reads(orph_ctx *ctx, const orph_filter *f, const void *reads, int
 int orph_score_reads_device(orph_ctx *ctx, const orph_filter *f, const void *d_reads, int reads_format,
                             const uint64_t *d_offsets, uint64_t n_reads, uint32_t max_read_len,
                             const uint8_t lut[256], double jaccard_threshold, orph_read_result *d_out);
+/* 2-bit reads WITH N: ORPH_READS_PACKED2 plus an N plane -- bit g % 32 of 32-bit word g / 32 of d_nmask is set where base g
+ * of the stream is an upper-case 'N' (its 2-bit code is then ignored) -- and d_has_n[i] = 1 for every read that holds one.
+ * Reads with N translate as in the reference (translate_single_seq.py:13-32 over constants_translate.py:59-131: a codon with
+ * an N is X unless it is one of ACN CTN CGN GTN GCN GGN TCN) on the same kernels as plain reads; only bytes other than ACGTN
+ * (lower case, IUPAC codes) still need the ASCII form.  Same contract as orph_score_reads_device otherwise. */
+int orph_score_reads_device_n(orph_ctx *ctx, const orph_filter *f, const void *d_packed, const uint32_t *d_nmask,
+                              const uint8_t *d_has_n, const uint64_t *d_offsets, uint64_t n_reads, uint32_t max_read_len,
+                              const uint8_t lut[256], double jaccard_threshold, orph_read_result *d_out);
+/* Builds that form on the device from ASCII reads (all DEVICE pointers; d_offsets[0] must be 0, total_bases =
+ * d_offsets[n_reads]): d_packed_out ((total_bases + 31) / 32 u64 words), d_nmask_out (as many u32 words), d_has_n_out and
+ * d_needs_bytes_out (n_reads bytes each; needs_bytes[i] = 1: read i holds a byte other than ACGTN and must be scored from
+ * its ASCII form).  Only enqueues on the context's stream. */
+int orph_pack_reads_device(orph_ctx *ctx, const uint8_t *d_ascii, const uint64_t *d_offsets, uint64_t n_reads,
+                           uint64_t total_bases, uint64_t *d_packed_out, uint32_t *d_nmask_out, uint8_t *d_has_n_out,
+                           uint8_t *d_needs_bytes_out);
 /* Host helper for callers that want to ship 2-bit reads over PCIe: packs the concatenated ASCII stream
  * [offsets[0], offsets[n_reads]) into out_packed (ceil(total/32) u64 words) and sets needs_ascii[i]=1
  * for every read that contains a byte other than upper-case ACGT (its packed bits are unspecified).

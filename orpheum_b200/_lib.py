@@ -95,6 +95,8 @@ PROTOTYPES = {
     "orph_ingest_close": (None, [_vp]),
     "orph_gather_reads": (ctypes.c_int, [_vp, _vp, _vp, _u64p, ctypes.c_uint64, _u8p, _u64p]),
     "orph_stream_open": (ctypes.c_int, [_vp, _vp, ctypes.c_char_p, _u8p, ctypes.c_double, ctypes.c_uint64, ctypes.c_int, _pp]),
+    "orph_score_reads_device_n": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _u64p, ctypes.c_uint64, ctypes.c_uint32, _u8p, ctypes.c_double, _vp]),
+    "orph_pack_reads_device": (ctypes.c_int, [_vp, _vp, _u64p, ctypes.c_uint64, ctypes.c_uint64, _vp, _vp, _vp, _vp]),
     "orph_stream_emit": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.POINTER(ctypes.c_void_p * 4), ctypes.POINTER(ctypes.c_uint64 * 4)]),
     "orph_stream_open_multi": (ctypes.c_int, [_pp, _pp, ctypes.c_int, ctypes.c_char_p, _u8p, ctypes.c_double, ctypes.c_uint64, ctypes.c_int, _pp]),
     "orph_stream_next": (ctypes.c_int, [_vp, ctypes.POINTER(StreamBatch)]),

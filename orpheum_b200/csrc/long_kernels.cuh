@@ -31,7 +31,7 @@ template <bool PACKED_SRC>
 __global__ void __launch_bounds__(kLongBlock)
 score_long_kernel(const ScoreParams P, const void *__restrict__ src, const uint64_t *__restrict__ offsets, uint64_t base0,
                   const uint32_t *__restrict__ list_back, uint32_t list_capacity, ScoreCounters *__restrict__ counters,
-                  orph_read_result *__restrict__ out, uint8_t *__restrict__ scratch)
+                  orph_read_result *__restrict__ out, uint8_t *__restrict__ scratch, const uint32_t *__restrict__ nmask)
 {
     __shared__ FilterDev sF;
     __shared__ uint8_t s_lut[256];
@@ -69,10 +69,10 @@ score_long_kernel(const ScoreParams P, const void *__restrict__ src, const uint6
         {
             uint32_t ndiff = 0, stops = 0;
             for (uint32_t p = threadIdx.x; p + 1 < L; p += blockDim.x) {
-                const uint8_t a = read_base<PACKED_SRC>(src, base0, o0 + p), b = read_base<PACKED_SRC>(src, base0, o0 + p + 1);
+                const uint8_t a = read_base<PACKED_SRC>(src, base0, o0 + p, nmask), b = read_base<PACKED_SRC>(src, base0, o0 + p + 1, nmask);
                 ndiff += a != b;
                 if (p + 2 < L) {
-                    const uint8_t c = read_base<PACKED_SRC>(src, base0, o0 + p + 2);
+                    const uint8_t c = read_base<PACKED_SRC>(src, base0, o0 + p + 2, nmask);
                     if (translate_bytes(a, b, c) == '*') stops |= 1u << (p % 3);
                     if (translate_bytes(complement_byte(c), complement_byte(b), complement_byte(a)) == '*')
                         stops |= 8u << ((L - p) % 3);
@@ -116,13 +116,13 @@ score_long_kernel(const ScoreParams P, const void *__restrict__ src, const uint6
                     uint8_t aa;
                     if (f < 3) {
                         const uint64_t g = o0 + phase + 3 * i;
-                        aa = translate_bytes(read_base<PACKED_SRC>(src, base0, g), read_base<PACKED_SRC>(src, base0, g + 1),
-                                             read_base<PACKED_SRC>(src, base0, g + 2));
+                        aa = translate_bytes(read_base<PACKED_SRC>(src, base0, g, nmask), read_base<PACKED_SRC>(src, base0, g + 1, nmask),
+                                             read_base<PACKED_SRC>(src, base0, g + 2, nmask));
                     } else {
                         const uint64_t g = o0 + (L - 3 - phase - 3 * i);  // forward position of the codon's last base
-                        aa = translate_bytes(complement_byte(read_base<PACKED_SRC>(src, base0, g + 2)),
-                                             complement_byte(read_base<PACKED_SRC>(src, base0, g + 1)),
-                                             complement_byte(read_base<PACKED_SRC>(src, base0, g)));
+                        aa = translate_bytes(complement_byte(read_base<PACKED_SRC>(src, base0, g + 2, nmask)),
+                                             complement_byte(read_base<PACKED_SRC>(src, base0, g + 1, nmask)),
+                                             complement_byte(read_base<PACKED_SRC>(src, base0, g, nmask)));
                     }
                     pep[i] = s_lut[aa];
                 }

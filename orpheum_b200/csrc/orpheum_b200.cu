@@ -252,6 +252,8 @@ struct orph_ctx {
     DevBuf needs_bytes;          // ASCII input: uint8 per read "holds a byte other than ACGTN", then uint8 per read "holds an N"
     DevBuf nmask;                // ASCII input: the N plane of the 2-bit stream (one bit per base)
     DevBuf task_queue_n;         // tasks of the reads that hold N
+    cudaStream_t side = nullptr; // the N reads' two kernels run here, next to the main kernels of the batch (fork / join by events)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     DevBuf packed;               // 2-bit stream built from ASCII input
     DevBuf in_reads, in_offsets, out_results;  // staging for the index build
     PipeSlot lane_slots[2][kLaneSlots];                  // [0] the copy-engine lane, [1] the host-packing lane of orph_score_reads
@@ -424,6 +426,9 @@ extern "C" void orph_ctx_destroy(orph_ctx *ctx)
                 if (e) cudaEventDestroy(e);
         }
     delete ctx->pool;
+    if (ctx->side) cudaStreamDestroy(ctx->side);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->lane_ctx) orph_ctx_destroy(ctx->lane_ctx);
     for (cudaStream_t st : {ctx->s_in[0], ctx->s_out[0], ctx->s_out[1]})  // s_in[1] is s_in[0]
         if (st) cudaStreamDestroy(st);
@@ -475,16 +480,17 @@ struct Timed {
     orph_ctx *ctx;
     cudaEvent_t a = nullptr, b = nullptr;
     int id;
-    Timed(orph_ctx *c, int kernel_id) : ctx(c), id(kernel_id)
+    cudaStream_t on;
+    Timed(orph_ctx *c, int kernel_id, cudaStream_t stream = nullptr) : ctx(c), id(kernel_id), on(stream ? stream : c->stream)
     {
         if (!ctx->timing) return;
         if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { a = b = nullptr; cudaGetLastError(); return; }
-        cudaEventRecord(a, ctx->stream);
+        cudaEventRecord(a, on);
     }
     ~Timed()
     {
         if (!a) return;
-        cudaEventRecord(b, ctx->stream);
+        cudaEventRecord(b, on);
         ctx->intervals.push_back({a, b, id});
     }
 };
@@ -948,9 +954,10 @@ static int launch_score_tasks_n(orph_ctx *ctx, const ScoreParams &P_in, uint32_t
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTaskBlock, smem));
     if (per_sm < 1) per_sm = 1;
     {
-        Timed timed(ctx, 4);
-        kern<<<ctx->sm_count * per_sm, kTaskBlock, smem, ctx->stream>>>(P, reinterpret_cast<const uint32_t *>(packed), d_offsets, pbase0, tasks_n, nullptr, 2,
-                                                                          counters, d_out, nmask);
+        // few tasks (a few per cent of the batch): one block per SM is plenty, and leaves the SMs to the main kernel
+        Timed timed(ctx, 4, ctx->side);
+        kern<<<ctx->sm_count * std::min(per_sm, 1), kTaskBlock, smem, ctx->side>>>(P, reinterpret_cast<const uint32_t *>(packed), d_offsets, pbase0, tasks_n, nullptr, 2,
+                                                                                    counters, d_out, nmask);
     }
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -980,10 +987,11 @@ static bool has_task_kernel(uint32_t k)
 // Core pipeline on device-resident inputs.  Exactly one of (d_ascii, d_packed_in) is the source:
 //   ASCII : pack_ascii -> prefilter -> score_frames -> score_bytes<ASCII> on flagged reads
 //   PACKED: prefilter -> score_frames -> score_bytes<PACKED> on over-long reads
+//   PACKED + N plane (d_nmask_in / d_has_n_in): as PACKED, reads with N on the N-aware kernels
 static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t *d_ascii, uint64_t abase0,
                              const uint64_t *d_packed_in, uint64_t pbase0_in, uint64_t total_bases_ascii,
                              const uint64_t *d_offsets, uint64_t n_reads, uint32_t max_read_len, const uint8_t lut[256],
-                             double thr, orph_read_result *d_out)
+                             double thr, orph_read_result *d_out, const uint32_t *d_nmask_in = nullptr, const uint8_t *d_has_n_in = nullptr)
 {
     if (n_reads > (1ULL << 26)) return fail(ORPH_E_INVALID, "internal: more than 2^26 reads in one launch");
     cudaStream_t s = ctx->stream;
@@ -1027,7 +1035,7 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
         if ((rc = ctx->packed.ensure((n_words + 2) * 8)) != ORPH_OK) return rc;
         if ((rc = ctx->needs_bytes.ensure(2 * n_reads)) != ORPH_OK) return rc;
         if ((rc = ctx->nmask.ensure((n_words + 2) * 4)) != ORPH_OK) return rc;
-        if (thread_len && (rc = ctx->task_queue_n.ensure(n_reads * 6 * 4)) != ORPH_OK) return rc;
+        if (thread_len && (rc = ctx->task_queue_n.ensure(n_reads * 7 * 4)) != ORPH_OK) return rc;
         CUDA_TRY(cudaMemsetAsync(ctx->needs_bytes.p, 0, 2 * n_reads, s));
         pbase0 = abase0;
         if (n_words) {
@@ -1042,6 +1050,11 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
         d_needs = (const uint8_t *)ctx->needs_bytes.p;
         d_has_n = d_needs + n_reads;
         d_nmask = (const uint32_t *)ctx->nmask.p;
+        if (thread_len) d_tasks_n = (uint32_t *)ctx->task_queue_n.p;
+    } else if (d_nmask_in && d_has_n_in) {
+        if (thread_len && (rc = ctx->task_queue_n.ensure(n_reads * 7 * 4)) != ORPH_OK) return rc;
+        d_has_n = d_has_n_in;
+        d_nmask = d_nmask_in;
         if (thread_len) d_tasks_n = (uint32_t *)ctx->task_queue_n.p;
     }
 
@@ -1059,6 +1072,38 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
     if (thread_len) {
         const uint32_t *tq = (const uint32_t *)ctx->task_queue.p;
         const uint32_t *tq_sorted = (const uint32_t *)ctx->task_queue_sorted.p;
+        if (d_tasks_n) {
+            // reads that hold N: their own prefilter (warp per read), then the same kernel with an N plane -- on the side
+            // stream, so that this small, latency-bound launch runs next to the main kernel instead of after it
+            if (!ctx->side) {
+                CUDA_TRY(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+                CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+                CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+            }
+            CUDA_TRY(cudaEventRecord(ctx->ev_fork, s));
+            CUDA_TRY(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+            {
+                Timed timed(ctx, 1, ctx->side);
+                prefilter_n_kernel<<<grid_for(n_reads, 256, ctx->sm_count, 4), 256, 0, ctx->side>>>(d_packed, d_nmask, d_offsets, pbase0, P.k, P.task_capacity, d_tasks_n,
+                                                                                                 counters, d_out);
+            }
+            ctx->launches++;
+            CUDA_TRY(cudaGetLastError());
+            switch (P.k) {
+            case 7: rc = launch_score_tasks_n<7>(ctx, P, thread_len, d_packed, d_offsets, pbase0, d_tasks_n, d_nmask, counters, d_out); break;
+            case 8: rc = launch_score_tasks_n<8>(ctx, P, thread_len, d_packed, d_offsets, pbase0, d_tasks_n, d_nmask, counters, d_out); break;
+            case 9: rc = launch_score_tasks_n<9>(ctx, P, thread_len, d_packed, d_offsets, pbase0, d_tasks_n, d_nmask, counters, d_out); break;
+            case 10: rc = launch_score_tasks_n<10>(ctx, P, thread_len, d_packed, d_offsets, pbase0, d_tasks_n, d_nmask, counters, d_out); break;
+            case 11: rc = launch_score_tasks_n<11>(ctx, P, thread_len, d_packed, d_offsets, pbase0, d_tasks_n, d_nmask, counters, d_out); break;
+            case 12: rc = launch_score_tasks_n<12>(ctx, P, thread_len, d_packed, d_offsets, pbase0, d_tasks_n, d_nmask, counters, d_out); break;
+            case 16: rc = launch_score_tasks_n<16>(ctx, P, thread_len, d_packed, d_offsets, pbase0, d_tasks_n, d_nmask, counters, d_out); break;
+            case 21: rc = launch_score_tasks_n<21>(ctx, P, thread_len, d_packed, d_offsets, pbase0, d_tasks_n, d_nmask, counters, d_out); break;
+            case 31: rc = launch_score_tasks_n<31>(ctx, P, thread_len, d_packed, d_offsets, pbase0, d_tasks_n, d_nmask, counters, d_out); break;
+            default: break;
+            }
+            if (rc != ORPH_OK) return rc;
+            CUDA_TRY(cudaEventRecord(ctx->ev_join, ctx->side));
+        }
         {
             Timed timed(ctx, 6);
             task_scan_kernel<<<1, 64, 0, s>>>(counters);
@@ -1080,21 +1125,7 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
         default: rc = fail(ORPH_E_INVALID, "internal: no task kernel for k=%u", P.k); break;
         }
         if (rc != ORPH_OK) return rc;
-        if (d_tasks_n) {  // reads that hold N: the same kernel with an N plane
-            switch (P.k) {
-            case 7: rc = launch_score_tasks_n<7>(ctx, P, thread_len, d_packed, d_offsets, pbase0, d_tasks_n, d_nmask, counters, d_out); break;
-            case 8: rc = launch_score_tasks_n<8>(ctx, P, thread_len, d_packed, d_offsets, pbase0, d_tasks_n, d_nmask, counters, d_out); break;
-            case 9: rc = launch_score_tasks_n<9>(ctx, P, thread_len, d_packed, d_offsets, pbase0, d_tasks_n, d_nmask, counters, d_out); break;
-            case 10: rc = launch_score_tasks_n<10>(ctx, P, thread_len, d_packed, d_offsets, pbase0, d_tasks_n, d_nmask, counters, d_out); break;
-            case 11: rc = launch_score_tasks_n<11>(ctx, P, thread_len, d_packed, d_offsets, pbase0, d_tasks_n, d_nmask, counters, d_out); break;
-            case 12: rc = launch_score_tasks_n<12>(ctx, P, thread_len, d_packed, d_offsets, pbase0, d_tasks_n, d_nmask, counters, d_out); break;
-            case 16: rc = launch_score_tasks_n<16>(ctx, P, thread_len, d_packed, d_offsets, pbase0, d_tasks_n, d_nmask, counters, d_out); break;
-            case 21: rc = launch_score_tasks_n<21>(ctx, P, thread_len, d_packed, d_offsets, pbase0, d_tasks_n, d_nmask, counters, d_out); break;
-            case 31: rc = launch_score_tasks_n<31>(ctx, P, thread_len, d_packed, d_offsets, pbase0, d_tasks_n, d_nmask, counters, d_out); break;
-            default: break;
-            }
-            if (rc != ORPH_OK) return rc;
-        }
+        if (d_tasks_n) CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_join, 0));  // the N reads' kernels have written their records
         {
             Timed timed(ctx, 5);
             finalize_best_kernel<<<grid_for(n_reads, 256, ctx->sm_count, 16), 256, 0, s>>>(d_out, n_reads);
@@ -1119,7 +1150,7 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
     }
 
     // byte-exact path for whatever prefilter routed away (non-ACGT bytes, reads longer than the fast path)
-    if (d_ascii || bound > fast_len) {
+    if (d_ascii || d_nmask || bound > fast_len) {
         ScoreParams B = P;
         const uint32_t bbound = std::min(bound, bytes_max_len);
         B.max_len = bbound;
@@ -1135,13 +1166,15 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
             CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int per_sm = 0;
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
-            kern<<<ctx->sm_count * std::max(1, per_sm), warps * 32, smem, s>>>(B, d_ascii, d_offsets, abase0, n_reads, (const uint32_t *)ctx->bytes_queue.p, counters, d_out);
+            kern<<<ctx->sm_count * std::max(1, per_sm), warps * 32, smem, s>>>(B, d_ascii, d_offsets, abase0, n_reads, (const uint32_t *)ctx->bytes_queue.p, counters, d_out,
+                                                                               nullptr);
         } else {
             auto kern = score_bytes_kernel<true>;
             CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int per_sm = 0;
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
-            kern<<<ctx->sm_count * std::max(1, per_sm), warps * 32, smem, s>>>(B, d_packed, d_offsets, pbase0, n_reads, (const uint32_t *)ctx->bytes_queue.p, counters, d_out);
+            kern<<<ctx->sm_count * std::max(1, per_sm), warps * 32, smem, s>>>(B, d_packed, d_offsets, pbase0, n_reads, (const uint32_t *)ctx->bytes_queue.p, counters, d_out,
+                                                                               d_nmask);
         }
         ctx->launches++;
         CUDA_TRY(cudaGetLastError());
@@ -1154,10 +1187,10 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
         Timed timed(ctx, 7);
         if (d_ascii)
             score_long_kernel<false><<<grid, kLongBlock, 0, s>>>(P, d_ascii, d_offsets, abase0, (const uint32_t *)ctx->bytes_queue.p, (uint32_t)n_reads,
-                                                              counters, d_out, (uint8_t *)ctx->long_scratch.p);
+                                                              counters, d_out, (uint8_t *)ctx->long_scratch.p, nullptr);
         else
             score_long_kernel<true><<<grid, kLongBlock, 0, s>>>(P, d_packed, d_offsets, pbase0, (const uint32_t *)ctx->bytes_queue.p, (uint32_t)n_reads,
-                                                             counters, d_out, (uint8_t *)ctx->long_scratch.p);
+                                                             counters, d_out, (uint8_t *)ctx->long_scratch.p, d_nmask);
         ctx->launches++;
         CUDA_TRY(cudaGetLastError());
     }
@@ -1203,6 +1236,47 @@ extern "C" int orph_score_reads_device(orph_ctx *ctx, const orph_filter *f, cons
             rc = score_device_impl(ctx, f, (const uint8_t *)d_reads + ends[0], ends[0], nullptr, 0, ends[1] - ends[0], d_offsets + lo, m,
                                    max_read_len, lut, jaccard_threshold, d_out + lo);
         }
+        if (rc != ORPH_OK) return rc;
+    }
+    return ORPH_OK;
+}
+
+extern "C" int orph_pack_reads_device(orph_ctx *ctx, const uint8_t *d_ascii, const uint64_t *d_offsets, uint64_t n_reads, uint64_t total_bases,
+                                      uint64_t *d_packed_out, uint32_t *d_nmask_out, uint8_t *d_has_n_out, uint8_t *d_needs_bytes_out)
+{
+    if (!ctx || (n_reads && (!d_ascii || !d_offsets || !d_packed_out || !d_nmask_out || !d_has_n_out || !d_needs_bytes_out)))
+        return fail(ORPH_E_INVALID, "orph_pack_reads_device: NULL argument");
+    if (n_reads == 0) return ORPH_OK;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = ctx->stream;
+    const uint64_t n_words = (total_bases + 31) / 32;
+    CUDA_TRY(cudaMemsetAsync(d_has_n_out, 0, n_reads, s));
+    CUDA_TRY(cudaMemsetAsync(d_needs_bytes_out, 0, n_reads, s));
+    if (n_words) {
+        pack_ascii_kernel<<<grid_for(n_words, 256, ctx->sm_count, 16), 256, 0, s>>>(d_ascii, 0, d_offsets, n_reads, 0, total_bases, d_packed_out, d_needs_bytes_out,
+                                                                                     d_nmask_out, d_has_n_out);
+        ctx->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    return ORPH_OK;
+}
+
+extern "C" int orph_score_reads_device_n(orph_ctx *ctx, const orph_filter *f, const void *d_packed, const uint32_t *d_nmask, const uint8_t *d_has_n,
+                                         const uint64_t *d_offsets, uint64_t n_reads, uint32_t max_read_len, const uint8_t lut[256],
+                                         double jaccard_threshold, orph_read_result *d_out)
+{
+    int rc = check_score_args(ctx, f, d_packed, ORPH_READS_PACKED2, d_offsets, n_reads, lut, jaccard_threshold, d_out);
+    if (rc != ORPH_OK) return rc;
+    if (n_reads == 0) return ORPH_OK;
+    if (!d_nmask || !d_has_n) return fail(ORPH_E_INVALID, "orph_score_reads_device_n: NULL N plane");
+    if ((reinterpret_cast<uintptr_t>(d_packed) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15))
+        return fail(ORPH_E_INVALID, "orph_score_reads_device_n: reads and out must be 16-byte aligned");
+    DeviceGuard guard(ctx->device);
+    const uint64_t kMaxLaunchReads = 1ULL << 26;
+    for (uint64_t lo = 0; lo < n_reads; lo += kMaxLaunchReads) {
+        const uint64_t m = std::min(kMaxLaunchReads, n_reads - lo);
+        rc = score_device_impl(ctx, f, nullptr, 0, (const uint64_t *)d_packed, 0, 0, d_offsets + lo, m, max_read_len, lut, jaccard_threshold, d_out + lo, d_nmask,
+                               d_has_n + lo);
         if (rc != ORPH_OK) return rc;
     }
     return ORPH_OK;

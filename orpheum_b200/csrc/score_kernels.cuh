@@ -61,7 +61,8 @@ struct ScoreCounters {
     uint32_t next_long;
     uint32_t n_tasks_n;    // tasks of reads that hold N (and nothing else unusual): thread per frame with an N mask
     uint32_t next_task_n;
-    uint32_t pad;
+    uint32_t n_reads_n;    // such reads, queued by prefilter_kernel for prefilter_n_kernel
+    uint32_t pad[2];
     uint32_t status;       // kStatus* bits; sticky until orph_ctx_check -- keep it last
 };
 
@@ -318,8 +319,8 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
     for (uint64_t r0 = first; r0 < n_reads; r0 += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t r = r0 + lane;
         const bool in_range = r < n_reads;
-        bool to_queue = false, to_bytes = false, to_long = false;
-        uint32_t open_bits = 0, n_my_tasks = 0, n_my_tasks_long = 0, n_my_tasks_n = 0;
+        bool to_queue = false, to_bytes = false, to_long = false, to_n = false;
+        uint32_t open_bits = 0, n_my_tasks = 0, n_my_tasks_long = 0;
         if (in_range) {
             const uint64_t o0 = offsets[r], o1 = offsets[r + 1];
             const uint64_t L = o1 - o0;
@@ -340,49 +341,7 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
                 to_bytes = true;
                 rec.flags = ORPH_FLAG_BYTE_PATH;
             } else if (has_n && has_n[r]) {
-                // A read with N (and no other unusual byte), short enough for the thread-per-frame kernel: the same tests as
-                // below, base by base, with the reference's string semantics for N -- N differs from every base and equals
-                // N in the complexity count (translate.py:79-84); a codon that holds an N is never a stop codon.  Rare reads:
-                // a plain loop instead of the bit-plane arithmetic.
-                const uint32_t *p32 = reinterpret_cast<const uint32_t *>(packed);
-                const uint64_t g0 = o0 - base0;
-                auto code = [&](uint32_t i) { const uint64_t b = 2 * (g0 + i); return (p32[b >> 5] >> (b & 31)) & 3u; };
-                auto is_n = [&](uint32_t i) { const uint64_t g = g0 + i; return (nmask[g >> 5] >> (g & 31)) & 1u; };
-                const uint32_t Ln = (uint32_t)L;
-                uint32_t ndiff = 0, stops = 0;
-                uint32_t c0 = code(0), m0 = is_n(0), c1 = Ln > 1 ? code(1) : 0u, m1 = Ln > 1 ? is_n(1) : 0u;
-                for (uint32_t p = 0; p + 1 < Ln; p++) {
-                    ndiff += (m0 != m1) || (!m0 && c0 != c1);
-                    uint32_t c2 = 0, m2 = 0;
-                    if (p + 2 < Ln) {
-                        c2 = code(p + 2);
-                        m2 = is_n(p + 2);
-                        if (!(m0 | m1 | m2)) {
-                            // codes A0 C1 T2 G3: forward stops TAA TAG TGA; triples whose reverse complement is one: TTA CTA TCA
-                            if (c0 == 2 && ((c1 == 0 && (c2 == 0 || c2 == 3)) || (c1 == 3 && c2 == 0))) stops |= 1u << (p % 3);
-                            if (c2 == 0 && ((c1 == 2 && (c0 == 2 || c0 == 1)) || (c1 == 1 && c0 == 2))) stops |= 8u << ((Ln - p) % 3);
-                        }
-                    }
-                    c0 = c1; m0 = m1; c1 = c2; m1 = m2;
-                }
-                if (10ull * ndiff < 3ull * L) {
-                    rec.flags = ORPH_FLAG_LOW_COMPLEXITY;
-#pragma unroll
-                    for (int f = 0; f < 6; f++) rec.category[f] = ORPH_CAT_LOW_COMPLEXITY_NUCLEOTIDE;
-                } else {
-                    uint32_t open = 0;
-#pragma unroll
-                    for (int f = 0; f < 6; f++) {
-                        const uint32_t phase = f % 3;
-                        const uint32_t plen = Ln >= phase ? (Ln - phase) / 3 : 0;
-                        if ((stops >> f) & 1u) rec.category[f] = ORPH_CAT_STOP_CODONS;
-                        else if (plen <= k) rec.category[f] = ORPH_CAT_TOO_SHORT_PEPTIDE;
-                        else open |= 1u << f;
-                    }
-                    rec.flags = (uint8_t)open;
-                    open_bits = open;
-                    n_my_tasks_n = __popc(open);
-                }
+                to_n = true;  // prefilter_n_kernel classifies it (and writes its record)
             } else {
                 // the read as aligned 32-bit words: A[j] = bases [16j, 16j+16), one funnel shift each
                 const uint64_t bitpos = 2 * (o0 - base0);
@@ -487,10 +446,12 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
                 }
             }
             // one 32-byte record per read
-            uint4 *dst = reinterpret_cast<uint4 *>(out + r);
-            const uint4 *src = reinterpret_cast<const uint4 *>(&rec);
-            dst[0] = src[0];
-            dst[1] = src[1];
+            if (!to_n) {
+                uint4 *dst = reinterpret_cast<uint4 *>(out + r);
+                const uint4 *src = reinterpret_cast<const uint4 *>(&rec);
+                dst[0] = src[0];
+                dst[1] = src[1];
+            }
         }
         // warp-aggregated queue pushes
         const uint32_t mq = __ballot_sync(0xffffffffu, to_queue);
@@ -507,10 +468,12 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
         if (to_bytes) bytes_queue[base_b + __popc(mb & below)] = (uint32_t)r;
         if (to_long)  // rare: the byte queue is filled from the back, one atomic per read
             bytes_queue[(uint32_t)n_reads - 1 - atomicAdd(&counters->n_long, 1u)] = (uint32_t)r;
+        if (to_n)     // reads with N: listed behind the 6 n task slots of their queue
+            task_queue_n[task_capacity + atomicAdd(&counters->n_reads_n, 1u)] = (uint32_t)r;
         // per-frame tasks: warp-wide scan of the per-read task counts, one atomic per warp and tier
 #pragma unroll
-        for (int tier = 0; tier < 3; tier++) {
-            const uint32_t mine = tier == 0 ? n_my_tasks : tier == 1 ? n_my_tasks_long : n_my_tasks_n;
+        for (int tier = 0; tier < 2; tier++) {
+            const uint32_t mine = tier == 0 ? n_my_tasks : n_my_tasks_long;
             uint32_t incl = mine;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -520,15 +483,14 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
             const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
             if (total) {
                 uint32_t base_t = 0;
-                if (lane == 0) base_t = atomicAdd(tier == 0 ? &counters->n_tasks : tier == 1 ? &counters->n_tasks_long : &counters->n_tasks_n, total);
+                if (lane == 0) base_t = atomicAdd(tier == 0 ? &counters->n_tasks : &counters->n_tasks_long, total);
                 base_t = __shfl_sync(0xffffffffu, base_t, 0) + incl - mine;
                 uint32_t bits = mine ? open_bits : 0u;
                 while (bits) {
                     const uint32_t f = __ffs(bits) - 1;
                     bits &= bits - 1;
-                    // the short tier grows from the front of the queue, the long tier from the back; N reads have their own
-                    if (tier == 2) task_queue_n[base_t] = ((uint32_t)r << 3) | f;
-                    else task_queue[tier == 0 ? base_t : task_capacity - 1 - base_t] = ((uint32_t)r << 3) | f;
+                    // the short tier grows from the front of the queue, the long tier from the back
+                    task_queue[tier == 0 ? base_t : task_capacity - 1 - base_t] = ((uint32_t)r << 3) | f;
                     base_t++;
                 }
             }
@@ -538,6 +500,76 @@ prefilter_kernel(const uint64_t *__restrict__ packed, const uint64_t *__restrict
     for (uint32_t i = threadIdx.x; i < 2 * kLenBuckets; i += blockDim.x) {
         const uint32_t v = (&s_hist[0][0])[i];
         if (v) atomicAdd(&counters->hist[0][0] + i, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// prefilter_n_kernel: one WARP per read that holds N (and no other unusual byte, <= thread_max_len bases): the tests of
+// prefilter_kernel with the reference's string semantics for N -- N differs from every base and equals N in the complexity
+// count (translate.py:79-84); a codon that holds an N is never a stop codon -- on the 2-bit words and the N plane.  Writes
+// the read's record and queues its open frames for score_tasks_kernel<K, true>.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+prefilter_n_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ nmask, const uint64_t *__restrict__ offsets, uint64_t base0,
+                   uint32_t k, uint32_t task_capacity, uint32_t *__restrict__ task_queue_n, ScoreCounters *__restrict__ counters,
+                   orph_read_result *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t n = counters->n_reads_n;
+    const uint32_t *p32 = reinterpret_cast<const uint32_t *>(packed);
+    for (uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < n; item += (gridDim.x * blockDim.x) >> 5) {
+        const uint64_t r = task_queue_n[task_capacity + item];
+        const uint64_t o0 = offsets[r];
+        const uint32_t L = (uint32_t)(offsets[r + 1] - o0);
+        const uint64_t g0 = o0 - base0;
+        auto code = [&](uint32_t i) { const uint64_t b = 2 * (g0 + i); return (p32[b >> 5] >> (b & 31)) & 3u; };
+        auto is_n = [&](uint32_t i) { const uint64_t g = g0 + i; return (nmask[g >> 5] >> (g & 31)) & 1u; };
+        uint32_t ndiff = 0, stops = 0;
+        for (uint32_t p = lane; p + 1 < L; p += 32) {
+            const uint32_t c0 = code(p), m0 = is_n(p), c1 = code(p + 1), m1 = is_n(p + 1);
+            ndiff += (m0 != m1) || (!m0 && c0 != c1);
+            if (p + 2 < L) {
+                const uint32_t c2 = code(p + 2), m2 = is_n(p + 2);
+                if (!(m0 | m1 | m2)) {
+                    // codes A0 C1 T2 G3: forward stops TAA TAG TGA; triples whose reverse complement is one: TTA CTA TCA
+                    if (c0 == 2 && ((c1 == 0 && (c2 == 0 || c2 == 3)) || (c1 == 3 && c2 == 0))) stops |= 1u << (p % 3);
+                    if (c2 == 0 && ((c1 == 2 && (c0 == 2 || c0 == 1)) || (c1 == 1 && c0 == 2))) stops |= 8u << ((L - p) % 3);
+                }
+            }
+        }
+        ndiff = __reduce_add_sync(0xffffffffu, ndiff);
+        stops = __reduce_or_sync(0xffffffffu, stops);
+        if (lane == 0) {
+            __align__(16) orph_read_result rec;
+#pragma unroll
+            for (int f = 0; f < 6; f++) { rec.n_kmers[f] = 0; rec.n_hits[f] = 0; rec.category[f] = ORPH_CAT_INVALID; }
+            rec.best_frame = 0;
+            rec.flags = 0;
+            if (10ull * ndiff < 3ull * L) {  // (see prefilter_kernel for the integer form of ndiff / L < 0.3)
+                rec.flags = ORPH_FLAG_LOW_COMPLEXITY;
+#pragma unroll
+                for (int f = 0; f < 6; f++) rec.category[f] = ORPH_CAT_LOW_COMPLEXITY_NUCLEOTIDE;
+            } else {
+                uint32_t open = 0;
+#pragma unroll
+                for (int f = 0; f < 6; f++) {
+                    const uint32_t phase = f % 3;
+                    const uint32_t plen = L >= phase ? (L - phase) / 3 : 0;
+                    if ((stops >> f) & 1u) rec.category[f] = ORPH_CAT_STOP_CODONS;
+                    else if (plen <= k) rec.category[f] = ORPH_CAT_TOO_SHORT_PEPTIDE;
+                    else open |= 1u << f;
+                }
+                rec.flags = (uint8_t)open;
+                if (open) {
+                    uint32_t at = atomicAdd(&counters->n_tasks_n, __popc(open));
+                    for (uint32_t bits = open; bits; bits &= bits - 1) task_queue_n[at++] = ((uint32_t)r << 3) | (__ffs(bits) - 1);
+                }
+            }
+            uint4 *dst = reinterpret_cast<uint4 *>(out + r);
+            const uint4 *src = reinterpret_cast<const uint4 *>(&rec);
+            dst[0] = src[0];
+            dst[1] = src[1];
+        }
     }
 }
 
@@ -707,12 +739,14 @@ score_frames_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, 
 // ------------------------------------------------------------------------------------------------
 // score_bytes_kernel: byte-exact path, one warp per read taken from `list` (or all reads if list is null)
 // ------------------------------------------------------------------------------------------------
+// nmask (2-bit source only, may be NULL): the N plane of the stream -- a set bit reads back as 'N'
 template <bool PACKED_SRC>
-__device__ __forceinline__ uint8_t read_base(const void *src, uint64_t base0, uint64_t g)
+__device__ __forceinline__ uint8_t read_base(const void *src, uint64_t base0, uint64_t g, const uint32_t *nmask = nullptr)
 {
     if (PACKED_SRC) {
         const uint64_t *w = static_cast<const uint64_t *>(src);
         const uint64_t rel = g - base0;
+        if (nmask && ((nmask[rel >> 5] >> (rel & 31)) & 1u)) return (uint8_t)'N';
         return (uint8_t)"ACTG"[(w[rel >> 5] >> (2 * (rel & 31))) & 3];
     }
     return static_cast<const uint8_t *>(src)[g - base0];
@@ -722,7 +756,7 @@ template <bool PACKED_SRC>
 __global__ void __launch_bounds__(256)
 score_bytes_kernel(const ScoreParams P, const void *__restrict__ src, const uint64_t *__restrict__ offsets,
                    uint64_t base0, uint64_t n_reads, const uint32_t *__restrict__ list,
-                   ScoreCounters *__restrict__ counters, orph_read_result *__restrict__ out)
+                   ScoreCounters *__restrict__ counters, orph_read_result *__restrict__ out, const uint32_t *__restrict__ nmask)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ FilterDev sF;
@@ -760,7 +794,7 @@ score_bytes_kernel(const ScoreParams P, const void *__restrict__ src, const uint
         } else {
             const uint32_t L = (uint32_t)L64;
             __syncwarp();
-            for (uint32_t i = lane; i < L; i += kWarp) rb[i] = read_base<PACKED_SRC>(src, base0, o0 + i);
+            for (uint32_t i = lane; i < L; i += kWarp) rb[i] = read_base<PACKED_SRC>(src, base0, o0 + i, nmask);
             __syncwarp();
             // compute_fastp_complexity (translate.py:79-84): case-sensitive byte compare
             uint32_t ndiff = 0;

@@ -312,6 +312,23 @@ def score_reads_device(graph, d_reads_ptr, d_offsets_ptr, n_reads, max_read_len,
                                               float(jaccard_threshold), ctypes.c_void_p(d_out_ptr)))
 
 
+def pack_reads_device(ctx, d_ascii_ptr, d_offsets_ptr, n_reads, total_bases, d_packed_ptr, d_nmask_ptr, d_has_n_ptr, d_needs_bytes_ptr):
+    """ASCII reads resident in HBM -> 2-bit words + N plane + per-read "holds N" / "needs its bytes" flags (raw device
+    pointers; orph_pack_reads_device).  Only enqueues."""
+    check(_lib.load().orph_pack_reads_device(ctx._h, ctypes.c_void_p(d_ascii_ptr), ctypes.c_void_p(d_offsets_ptr), int(n_reads), int(total_bases),
+                                             ctypes.c_void_p(d_packed_ptr), ctypes.c_void_p(d_nmask_ptr), ctypes.c_void_p(d_has_n_ptr),
+                                             ctypes.c_void_p(d_needs_bytes_ptr)))
+
+
+def score_reads_device_n(graph, d_packed_ptr, d_nmask_ptr, d_has_n_ptr, d_offsets_ptr, n_reads, max_read_len, lut, jaccard_threshold, d_out_ptr, ctx=None):
+    """score_reads_device for 2-bit reads with an N plane (orph_score_reads_device_n)."""
+    ctx = ctx or graph.ctx
+    lut = np.ascontiguousarray(lut, dtype=np.uint8)
+    check(_lib.load().orph_score_reads_device_n(ctx._h, graph._h, ctypes.c_void_p(d_packed_ptr), ctypes.c_void_p(d_nmask_ptr), ctypes.c_void_p(d_has_n_ptr),
+                                                ctypes.c_void_p(d_offsets_ptr), int(n_reads), int(max_read_len), ptr(lut), float(jaccard_threshold),
+                                                ctypes.c_void_p(d_out_ptr)))
+
+
 class StreamBatch:
     """One scored batch of a ScoringStream.  ``results`` is a view into the library's pinned memory and, like every other
     pointer here, only valid until the stream moves on: copy what must outlive the iteration."""

@@ -376,6 +376,28 @@ def test_reads_with_n_on_the_two_bit_path(gpu, enc, orc, refdata, alphabet, ksiz
     np.testing.assert_array_equal(byte_path, has_n & (lengths > 320))
     scored_with_n = ((ora["category"] == 3) | (ora["category"] == 4)).any(axis=1) & has_n & ~byte_path
     assert scored_with_n.sum() > 300  # frames of N reads were really scored on the new path
+    # the same batch as 2-bit words + N plane resident in HBM (orph_pack_reads_device -> orph_score_reads_device_n)
+    import torch
+
+    from orpheum_b200._lib import READ_RESULT_DTYPE
+
+    n = len(reads)
+    dev = torch.device("cuda", gg.ctx.device)
+    d_ascii = torch.from_numpy(flat).to(dev)
+    d_off = torch.from_numpy(offsets.view(np.int64)).to(dev)
+    total = int(offsets[-1])
+    d_packed = torch.zeros((total + 31) // 32 + 2, dtype=torch.int64, device=dev)
+    d_nmask = torch.zeros((total + 31) // 32 + 2, dtype=torch.int32, device=dev)
+    d_has_n = torch.zeros(n, dtype=torch.uint8, device=dev)
+    d_needs = torch.zeros(n, dtype=torch.uint8, device=dev)
+    d_out = torch.zeros(n * 32, dtype=torch.uint8, device=dev)
+    gpu.pack_reads_device(gg.ctx, d_ascii.data_ptr(), d_off.data_ptr(), n, total, d_packed.data_ptr(), d_nmask.data_ptr(), d_has_n.data_ptr(), d_needs.data_ptr())
+    gpu.score_reads_device_n(gg, d_packed.data_ptr(), d_nmask.data_ptr(), d_has_n.data_ptr(), d_off.data_ptr(), n, int(lengths.max()),
+                             enc.encode_lut(alphabet), thr, d_out.data_ptr())
+    gg.ctx.check()
+    assert not d_needs.cpu().numpy().any()
+    np.testing.assert_array_equal(d_has_n.cpu().numpy().astype(bool), has_n)
+    assert d_out.cpu().numpy().view(READ_RESULT_DTYPE).tobytes() == res.tobytes()
 
 
 def test_sub_batch_offsets_and_device_api(gpu, enc, orc, refdata):
