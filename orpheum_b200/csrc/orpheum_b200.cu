@@ -883,6 +883,21 @@ static void apply_l2_window(orph_ctx *ctx, const orph_filter *f)
     if (cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
 }
 
+// Raises a kernel's dynamic shared-memory allowance to the device's opt-in maximum (never to the size of the launch at hand):
+// the attribute belongs to the kernel, not to the launch, and contexts on several host threads launch the same kernels with
+// different sizes -- a thread that set it to ITS size between another thread's set and launch made that launch fail.
+template <class Kernel>
+static cudaError_t allow_max_dynamic_smem(const orph_ctx *ctx, Kernel kern, size_t needed)
+{
+    cudaFuncAttributes attr;
+    const cudaError_t e = cudaFuncGetAttributes(&attr, kern);
+    if (e != cudaSuccess) return e;
+    const size_t room = (size_t)ctx->max_smem_optin - std::min<size_t>((size_t)ctx->max_smem_optin, attr.sharedSizeBytes);  // static + dynamic share the limit
+    if (needed > room) return cudaErrorInvalidValue;
+    if ((size_t)attr.maxDynamicSharedSizeBytes >= room) return cudaSuccess;  // already raised
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)room);
+}
+
 template <int K>
 static int launch_score_frames(orph_ctx *ctx, const ScoreParams &P, const uint32_t *packed32, const uint64_t *d_offsets,
                                uint64_t pbase0, const uint32_t *queue, ScoreCounters *counters, orph_read_result *d_out)
@@ -892,7 +907,7 @@ static int launch_score_frames(orph_ctx *ctx, const ScoreParams &P, const uint32
     const size_t smem = (size_t)per_warp * warps;
     if (smem > (size_t)ctx->max_smem_optin) return fail(ORPH_E_INVALID, "score_frames: %zu bytes of shared memory needed", smem);
     auto kern = score_frames_kernel<K>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(allow_max_dynamic_smem(ctx, kern, smem));
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
     if (per_sm < 1) per_sm = 1;
@@ -949,7 +964,7 @@ static int launch_score_tasks_n(orph_ctx *ctx, const ScoreParams &P_in, uint32_t
     const uint32_t mask_words = (P.read_words + 1) / 2 + 1;
     const size_t smem = (size_t)kTaskBlock * (P.seen_words * 8 + P.read_words * 4 + mask_words * 4);
     auto kern = score_tasks_kernel<K, true>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(allow_max_dynamic_smem(ctx, kern, smem));
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTaskBlock, smem));
     if (per_sm < 1) per_sm = 1;
@@ -1163,14 +1178,14 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
         Timed timed(ctx, 3);
         if (d_ascii) {
             auto kern = score_bytes_kernel<false>;
-            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_TRY(allow_max_dynamic_smem(ctx, kern, smem));
             int per_sm = 0;
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
             kern<<<ctx->sm_count * std::max(1, per_sm), warps * 32, smem, s>>>(B, d_ascii, d_offsets, abase0, n_reads, (const uint32_t *)ctx->bytes_queue.p, counters, d_out,
                                                                                nullptr);
         } else {
             auto kern = score_bytes_kernel<true>;
-            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_TRY(allow_max_dynamic_smem(ctx, kern, smem));
             int per_sm = 0;
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
             kern<<<ctx->sm_count * std::max(1, per_sm), warps * 32, smem, s>>>(B, d_packed, d_offsets, pbase0, n_reads, (const uint32_t *)ctx->bytes_queue.p, counters, d_out,

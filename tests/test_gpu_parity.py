@@ -383,7 +383,7 @@ def test_reads_with_n_on_the_two_bit_path(gpu, enc, orc, refdata, alphabet, ksiz
 
     n = len(reads)
     dev = torch.device("cuda", gg.ctx.device)
-    d_ascii = torch.from_numpy(flat).to(dev)
+    d_ascii = torch.from_numpy(flat.copy()).to(dev)
     d_off = torch.from_numpy(offsets.view(np.int64)).to(dev)
     total = int(offsets[-1])
     d_packed = torch.zeros((total + 31) // 32 + 2, dtype=torch.int64, device=dev)
@@ -988,6 +988,56 @@ def test_two_host_threads_two_contexts(gpu, enc, orc):
         t.join()
     assert not errors, errors
     assert got == [True, True]
+    del graphs
+    for c in ctxs:
+        c.close()
+
+
+def test_threads_with_different_batch_geometries(gpu, enc, orc):
+    """Two host threads whose batches need DIFFERENT amounts of dynamic shared memory from the same kernels (reads of up to
+    120 nt with N in one thread, of up to 320 and 1500 nt with N in the other), many small calls each: a kernel's
+    shared-memory allowance is a property of the kernel, not of the launch, so a thread that lowers it to its own size
+    between another thread's set and launch makes that launch fail (found as a 1-in-25 flake of the two-streams test)."""
+    import threading
+
+    from orpheum_b200 import synth
+
+    residues, poffs = synth.make_proteome(n_proteins=300, seed=81)
+    lut, olut = enc.encode_lut("protein"), orc.encode_lut("protein")
+    base = gpu.GpuNodegraph(7, 1e6, 4)
+    base.add_peptides(residues, poffs, lut)
+    go = orc.Nodegraph(7, int(1e6), 4)
+    go.add_peptides(residues, poffs, olut)
+    rng = np.random.default_rng(82)
+
+    def batch(max_len, seed):
+        flat, offsets = synth.make_reads_mixed(400, residues, poffs, ksize=7, seed=seed, min_len=40, max_len=max_len)
+        flat = flat.copy()
+        for r in range(0, 400, 3):  # every third read holds an N
+            flat[int(offsets[r]) + int(rng.integers(0, int(offsets[r + 1] - offsets[r])))] = ord("N")
+        return flat, offsets
+
+    batches = [[batch(120, 100 + j) for j in range(4)], [batch(320 if j % 2 else 1500, 200 + j) for j in range(4)]]
+    want = [[orc.score_reads(go, f, o, olut, 0.5, n_threads=0)[0] for f, o in bs] for bs in batches]
+    ctxs = [gpu.Context(0), gpu.Context(0)]
+    graphs = [base.replicate(c) for c in ctxs]
+    errors = []
+
+    def work(i):
+        try:
+            for it in range(150):
+                f, o = batches[i][it % 4]
+                res = gpu.score_reads(graphs[i], f, o, lut, 0.5, ctx=ctxs[i])
+                assert_same_as_oracle(res, want[i][it % 4], f"thread {i} call {it}")
+        except BaseException as exc:  # noqa: BLE001 - reported in the main thread
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
     del graphs
     for c in ctxs:
         c.close()
