@@ -9,7 +9,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <tuple>
 #include <sched.h>
 #include <thread>
 #include <vector>
@@ -898,6 +900,38 @@ static cudaError_t allow_max_dynamic_smem(const orph_ctx *ctx, Kernel kern, size
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)room);
 }
 
+// Resident blocks per SM of a kernel at a block size and dynamic shared-memory size: asked of the runtime once per
+// (device, kernel, geometry) of the process, not on every chunk.
+template <class Kernel>
+static int resident_blocks(const orph_ctx *ctx, Kernel kern, int block, size_t smem, int *out)
+{
+    struct Key {
+        int device;
+        const void *kern;
+        int block;
+        size_t smem;
+        bool operator<(const Key &o) const { return std::tie(device, kern, block, smem) < std::tie(o.device, o.kern, o.block, o.smem); }
+    };
+    static std::mutex mu;
+    static std::map<Key, int> cache;
+    const Key key{ctx->device, reinterpret_cast<const void *>(kern), block, smem};
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) {
+            *out = it->second;
+            return ORPH_OK;
+        }
+    }
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem));
+    if (per_sm < 1) per_sm = 1;
+    std::lock_guard<std::mutex> lk(mu);
+    cache[key] = per_sm;
+    *out = per_sm;
+    return ORPH_OK;
+}
+
 template <int K>
 static int launch_score_frames(orph_ctx *ctx, const ScoreParams &P, const uint32_t *packed32, const uint64_t *d_offsets,
                                uint64_t pbase0, const uint32_t *queue, ScoreCounters *counters, orph_read_result *d_out)
@@ -908,9 +942,8 @@ static int launch_score_frames(orph_ctx *ctx, const ScoreParams &P, const uint32
     if (smem > (size_t)ctx->max_smem_optin) return fail(ORPH_E_INVALID, "score_frames: %zu bytes of shared memory needed", smem);
     auto kern = score_frames_kernel<K>;
     CUDA_TRY(allow_max_dynamic_smem(ctx, kern, smem));
-    int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
-    if (per_sm < 1) per_sm = 1;
+    int per_sm = 0, rc_occ;
+    if ((rc_occ = resident_blocks(ctx, kern, warps * 32, smem, &per_sm)) != ORPH_OK) return rc_occ;
     {
         Timed timed(ctx, 2);
         kern<<<ctx->sm_count * per_sm, warps * 32, smem, ctx->stream>>>(P, packed32, d_offsets, pbase0, queue, counters, d_out);
@@ -965,9 +998,8 @@ static int launch_score_tasks_n(orph_ctx *ctx, const ScoreParams &P_in, uint32_t
     const size_t smem = (size_t)kTaskBlock * (P.seen_words * 8 + P.read_words * 4 + mask_words * 4);
     auto kern = score_tasks_kernel<K, true>;
     CUDA_TRY(allow_max_dynamic_smem(ctx, kern, smem));
-    int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTaskBlock, smem));
-    if (per_sm < 1) per_sm = 1;
+    int per_sm = 0, rc_occ;
+    if ((rc_occ = resident_blocks(ctx, kern, kTaskBlock, smem, &per_sm)) != ORPH_OK) return rc_occ;
     {
         // few tasks (a few per cent of the batch): one block per SM is plenty, and leaves the SMs to the main kernel
         Timed timed(ctx, 4, ctx->side);
@@ -1180,14 +1212,14 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
             auto kern = score_bytes_kernel<false>;
             CUDA_TRY(allow_max_dynamic_smem(ctx, kern, smem));
             int per_sm = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+            if ((rc = resident_blocks(ctx, kern, warps * 32, smem, &per_sm)) != ORPH_OK) return rc;
             kern<<<ctx->sm_count * std::max(1, per_sm), warps * 32, smem, s>>>(B, d_ascii, d_offsets, abase0, n_reads, (const uint32_t *)ctx->bytes_queue.p, counters, d_out,
                                                                                nullptr);
         } else {
             auto kern = score_bytes_kernel<true>;
             CUDA_TRY(allow_max_dynamic_smem(ctx, kern, smem));
             int per_sm = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+            if ((rc = resident_blocks(ctx, kern, warps * 32, smem, &per_sm)) != ORPH_OK) return rc;
             kern<<<ctx->sm_count * std::max(1, per_sm), warps * 32, smem, s>>>(B, d_packed, d_offsets, pbase0, n_reads, (const uint32_t *)ctx->bytes_queue.p, counters, d_out,
                                                                                d_nmask);
         }

@@ -1,5 +1,6 @@
-"""Host-side six-frame translation, used only to *emit* peptides of frames the GPU classified
-(stdout / FASTA output); mirror of ``orpheum/translate_single_seq.py:7-78``.
+"""Host mirror of ``orpheum/translate_single_seq.py:7-78`` (``TranslateSingleSeq``), kept because it is part of the
+reference's importable surface and pinned by the CPU tests.  It is NOT on the product path: frames are translated on the
+GPU, both for scoring (the kernels) and for the peptides the CLI emits (``orph_translate_frames`` / ``orph_stream_emit``).
 
 Codon semantics (constants_translate.py:59-141): the 64 upper-case ACGT codons, the seven ``xxN``
 codons ACN CTN CGN GTN GCN GGN TCN, everything else -> ``X``; reverse complement maps only ACGT.

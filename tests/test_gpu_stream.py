@@ -71,13 +71,13 @@ def stream_all(env, path, **kw):
     return names, res, byte_path
 
 
-@pytest.mark.parametrize("layout", ["plain", "crlf", "no_final_newline", "gz", "wrapped", "blank_lines_tail"])
+@pytest.mark.parametrize("layout", ["plain", "crlf", "no_final_newline", "gz", "bgzf", "wrapped", "blank_lines_tail"])
 def test_stream_matches_batch_call(env, tmp_path, layout):
     gpu = env["gpu"]
     n = 120_000
     flat, offsets = mixed_reads(env, n, seed=3)
     want = gpu.score_reads(env["graph"], flat, offsets, env["lut"], 0.5)
-    path = str(tmp_path / ("reads.fq.gz" if layout == "gz" else "reads.fq"))
+    path = str(tmp_path / ("reads.fq.gz" if layout in ("gz", "bgzf") else "reads.fq"))
     expect_n = n
     if layout == "plain":
         write_fastq(path, flat, offsets)
@@ -87,6 +87,10 @@ def test_stream_matches_batch_call(env, tmp_path, layout):
         write_fastq(path, flat, offsets, final_newline=False)
     elif layout == "gz":
         write_fastq(path, flat, offsets, opener=gzip.open)
+    elif layout == "bgzf":  # blocked gzip: members inflated in parallel
+        plain = str(tmp_path / "plain.fq")
+        write_fastq(plain, flat, offsets)
+        env["synth"].write_bgzf(path, open(plain, "rb").read())
     elif layout == "wrapped":
         write_fastq(path, flat, offsets, wrap=60)
     else:  # strict records, then a blank line in the middle of the file: the general parser takes over there
