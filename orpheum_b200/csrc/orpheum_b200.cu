@@ -953,16 +953,34 @@ static int launch_score_frames(orph_ctx *ctx, const ScoreParams &P, const uint32
     return ORPH_OK;
 }
 
-template <int K>
-static int launch_score_tasks(orph_ctx *ctx, const ScoreParams &P_in, uint32_t tier_len, int long_tier, const uint64_t *packed,
-                              const uint64_t *d_offsets, uint64_t pbase0, const uint32_t *tasks, const uint32_t *tasks_sorted,
-                              ScoreCounters *counters, orph_read_result *d_out)
+#ifndef ORPH_TINY4
+#define ORPH_TINY4 1  // 0: the generic table geometry code for every filter (A/B switch)
+#endif
+
+// four tables of at most kTinyPrimeMax bits: the geometry score_tasks_kernel<K, NM, true> is compiled for
+static bool filter_is_tiny4(const FilterDev &F)
+{
+#if ORPH_TINY4
+    if (F.n_tables != 4) return false;
+    for (int t = 0; t < 4; t++)
+        if (F.size[t] < 2 || F.size[t] > kTinyPrimeMax) return false;
+    return true;
+#else
+    (void)F;
+    return false;
+#endif
+}
+
+template <int K, bool T4>
+static int launch_score_tasks_geom(orph_ctx *ctx, const ScoreParams &P_in, uint32_t tier_len, int long_tier, const uint64_t *packed,
+                                   const uint64_t *d_offsets, uint64_t pbase0, const uint32_t *tasks, const uint32_t *tasks_sorted,
+                                   ScoreCounters *counters, orph_read_result *d_out)
 {
     ScoreParams P = P_in;
     P.read_words = (2 * tier_len + 34) / 32 + 2;  // aligned strand words incl. the words the look-ahead window fetch may touch
     P.seen_words = long_tier ? kSeenWordsLong : kSeenWordsShort;
     const size_t smem = (size_t)kTaskBlock * (P.seen_words * 8 + P.read_words * 4);
-    auto kern = score_tasks_kernel<K, false>;
+    auto kern = score_tasks_kernel<K, false, T4>;
     // attribute + occupancy query once per (device, smem size): they cost tens of microseconds per call
     static thread_local int cached_dev = -1, cached_per_sm[2] = {0, 0};
     static thread_local size_t cached_smem[2] = {0, 0};
@@ -986,6 +1004,16 @@ static int launch_score_tasks(orph_ctx *ctx, const ScoreParams &P_in, uint32_t t
     return ORPH_OK;
 }
 
+template <int K>
+static int launch_score_tasks(orph_ctx *ctx, const ScoreParams &P, uint32_t tier_len, int long_tier, const uint64_t *packed,
+                              const uint64_t *d_offsets, uint64_t pbase0, const uint32_t *tasks, const uint32_t *tasks_sorted,
+                              ScoreCounters *counters, orph_read_result *d_out)
+{
+    if (filter_is_tiny4(P.F))
+        return launch_score_tasks_geom<K, true>(ctx, P, tier_len, long_tier, packed, d_offsets, pbase0, tasks, tasks_sorted, counters, d_out);
+    return launch_score_tasks_geom<K, false>(ctx, P, tier_len, long_tier, packed, d_offsets, pbase0, tasks, tasks_sorted, counters, d_out);
+}
+
 // the instantiation with an N plane, over the queue of reads that hold N (ASCII input only; usually a few per cent of a batch)
 template <int K>
 static int launch_score_tasks_n(orph_ctx *ctx, const ScoreParams &P_in, uint32_t tier_len, const uint64_t *packed, const uint64_t *d_offsets,
@@ -996,7 +1024,7 @@ static int launch_score_tasks_n(orph_ctx *ctx, const ScoreParams &P_in, uint32_t
     P.seen_words = tier_len > kThreadMaxLenShort ? kSeenWordsLong : kSeenWordsShort;
     const uint32_t mask_words = (P.read_words + 1) / 2 + 1;
     const size_t smem = (size_t)kTaskBlock * (P.seen_words * 8 + P.read_words * 4 + mask_words * 4);
-    auto kern = score_tasks_kernel<K, true>;
+    auto kern = score_tasks_kernel<K, true, false>;
     CUDA_TRY(allow_max_dynamic_smem(ctx, kern, smem));
     int per_sm = 0, rc_occ;
     if ((rc_occ = resident_blocks(ctx, kern, kTaskBlock, smem, &per_sm)) != ORPH_OK) return rc_occ;

@@ -18,6 +18,10 @@
 #include "device_common.cuh"
 #include "score_kernels.cuh"
 
+#ifndef ORPH_S2_MASK
+#define ORPH_S2_MASK 1  // tables 1..3: the wanted bits as one mask over the three bytes (0: three shifts; A/B switch)
+#endif
+
 namespace orph {
 
 constexpr uint32_t kThreadMaxLenShort = 192;  // short tier: 1024-bit seen filter per thread
@@ -157,7 +161,9 @@ __device__ __forceinline__ bool kmer_seen_before(const StrandColumn<NM> &sc, con
 
 // NM = true: the instantiation for reads that hold N (tasks_unsorted = their queue, `nmask` = the N plane of the 2-bit
 // stream, long_tier = 2: the long tier's shared-memory geometry plus one N-plane column per thread).
-template <int K, bool NM>
+// T4 = true: the filter has four tables of at most kTinyPrimeMax bits each (khmer's default geometry up to --tablesize 1.4e9):
+// the table count is a compile-time fact and the bins come from mod_prime_tiny.
+template <int K, bool NM, bool T4>
 __global__ void __launch_bounds__(kTaskBlock)
 score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, const uint64_t *__restrict__ offsets,
                    uint64_t base0, const uint32_t *__restrict__ tasks_unsorted, const uint32_t *__restrict__ tasks_sorted,
@@ -180,11 +186,13 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
     __syncthreads();
     const bool force_exact = P.force_exact != 0;
     const uint32_t n_tables = P.F.n_tables;
-    const bool four_tables = n_tables == 4;
+    const bool four_tables = T4 || n_tables == 4;
     const bool small = P.F.small != 0;
     // bin of hash h in table T (static index: the geometry comes straight from the constant bank)
 #define ORPH_BIN(T, h, out)                                                                   \
-    {                                                                                         \
+    if constexpr (T4) {                                                                       \
+        (out) = mod_prime_tiny((h), (uint32_t)P.F.size[T], P.F.magic[T]);                     \
+    } else {                                                                                  \
         const uint64_t q__ = __umul64hi((h), P.F.magic[T]);                                   \
         if (small) {                                                                          \
             const uint32_t p__ = (uint32_t)P.F.size[T];                                       \
@@ -307,11 +315,15 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
                 seen_pending = false;
             }
             // (2)
+#if ORPH_S2_MASK
+            if (s2_pending) nh += ((s2_v1 | (s2_v2 << 8) | (s2_v3 << 16)) & s2_sh) == s2_sh ? 1u : 0u;
+#else
             if (s2_pending) nh += (s2_v1 >> (s2_sh & 7u)) & (s2_v2 >> ((s2_sh >> 3) & 7u)) & (s2_v3 >> (s2_sh >> 6)) & 1u;
+#endif
             s2_pending = false;
             // (3)
             if (t0_pending && kmer_new && ((t0_v >> t0_sh) & 1u)) {
-                if (n_tables == 1) {
+                if (!T4 && n_tables == 1) {
                     nh += 1;
                 } else if (four_tables) {
                     uint64_t b1, b2, b3;
@@ -321,7 +333,12 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
                     s2_v1 = ld_table_byte(P.F.table[1] + (b1 >> 3));
                     s2_v2 = ld_table_byte(P.F.table[2] + (b2 >> 3));
                     s2_v3 = ld_table_byte(P.F.table[3] + (b3 >> 3));
+#if ORPH_S2_MASK
+                    // the three wanted bits as one mask over the bytes side by side: one compare when they arrive
+                    s2_sh = (1u << ((uint32_t)b1 & 7u)) | (0x100u << ((uint32_t)b2 & 7u)) | (0x10000u << ((uint32_t)b3 & 7u));
+#else
                     s2_sh = ((uint32_t)b1 & 7u) | (((uint32_t)b2 & 7u) << 3) | (((uint32_t)b3 & 7u) << 6);
+#endif
                     s2_pending = true;
                 } else {
                     nh += filter_contains_rest(sF, t0_h) ? 1u : 0u;
