@@ -953,6 +953,14 @@ static int launch_score_frames(orph_ctx *ctx, const ScoreParams &P, const uint32
     return ORPH_OK;
 }
 
+// score_tasks_kernel's per-thread column: the 2-bit strand of a read of up to tier_len bases (incl. the words a look-ahead
+// window fetch may touch), later the frame's residues, four to a word, plus the two words the k-mer loop fetches ahead
+static uint32_t task_stage_words(uint32_t tier_len) { return (2 * tier_len + 34) / 32 + 2; }
+static uint32_t task_column_words(uint32_t tier_len)
+{
+    return std::max(task_stage_words(tier_len), (tier_len / 3 + 3) / 4 + 2);
+}
+
 #ifndef ORPH_TINY4
 #define ORPH_TINY4 1  // 0: the generic table geometry code for every filter (A/B switch)
 #endif
@@ -977,7 +985,8 @@ static int launch_score_tasks_geom(orph_ctx *ctx, const ScoreParams &P_in, uint3
                                    ScoreCounters *counters, orph_read_result *d_out)
 {
     ScoreParams P = P_in;
-    P.read_words = (2 * tier_len + 34) / 32 + 2;  // aligned strand words incl. the words the look-ahead window fetch may touch
+    P.read_words = task_column_words(tier_len);
+    P.stage_words = task_stage_words(tier_len);
     P.seen_words = long_tier ? kSeenWordsLong : kSeenWordsShort;
     const size_t smem = (size_t)kTaskBlock * (P.seen_words * 8 + P.read_words * 4);
     auto kern = score_tasks_kernel<K, false, T4>;
@@ -985,7 +994,7 @@ static int launch_score_tasks_geom(orph_ctx *ctx, const ScoreParams &P_in, uint3
     static thread_local int cached_dev = -1, cached_per_sm[2] = {0, 0};
     static thread_local size_t cached_smem[2] = {0, 0};
     if (cached_dev != ctx->device || cached_smem[long_tier] != smem) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kTaskBlock * (kSeenWordsLong * 8 + ((2 * kThreadMaxLenLong + 34) / 32 + 2) * 4))));
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kTaskBlock * (kSeenWordsLong * 8 + task_column_words(kThreadMaxLenLong) * 4))));
         int q = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, kTaskBlock, smem));
         if (cached_dev != ctx->device) cached_smem[0] = cached_smem[1] = 0;
@@ -1020,9 +1029,10 @@ static int launch_score_tasks_n(orph_ctx *ctx, const ScoreParams &P_in, uint32_t
                                 uint64_t pbase0, const uint32_t *tasks_n, const uint32_t *nmask, ScoreCounters *counters, orph_read_result *d_out)
 {
     ScoreParams P = P_in;
-    P.read_words = (2 * tier_len + 34) / 32 + 2;
+    P.read_words = task_column_words(tier_len);
+    P.stage_words = task_stage_words(tier_len);
     P.seen_words = tier_len > kThreadMaxLenShort ? kSeenWordsLong : kSeenWordsShort;
-    const uint32_t mask_words = (P.read_words + 1) / 2 + 1;
+    const uint32_t mask_words = (P.stage_words + 1) / 2 + 1;
     const size_t smem = (size_t)kTaskBlock * (P.seen_words * 8 + P.read_words * 4 + mask_words * 4);
     auto kern = score_tasks_kernel<K, true, false>;
     CUDA_TRY(allow_max_dynamic_smem(ctx, kern, smem));

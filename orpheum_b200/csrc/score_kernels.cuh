@@ -40,7 +40,8 @@ struct ScoreParams {
     uint32_t task_capacity;    // entries in the task queue: the short tier fills it from the front, the long tier from the back
     uint32_t slots;            // dedup table slots per warp (power of two >= 128, >= 2 * max k-mers per frame)
     uint32_t pep_bytes;        // peptide buffer bytes per warp (multiple of 4, incl. kPepPad)
-    uint32_t read_words;       // staged read words per warp (fast path)
+    uint32_t read_words;       // staged read words per warp (fast path); per thread: height of a task's strand / residue column
+    uint32_t stage_words;      // score_tasks_kernel: words of that column the 2-bit strand takes
     uint32_t force_exact;      // test hook: always take the exact all-pairs dedup path
 };
 

@@ -1,26 +1,25 @@
 // score_tasks_kernel: one THREAD per open frame ("task"), for reads up to kThreadMaxLen bases.
 //
-// This is the hot kernel for short reads.  A thread walks its frame codon by codon over the read's
-// 2-bit words (staged once into shared memory), keeps the current peptide k-mer as a rolling byte window
-// in registers (exactly the bytes sourmash's hash_murmur sees after encode_peptide,
-// sequence_encodings.py:457-468), hashes it (translate.py:187) and issues the table-0 Bloom probe
-// (translate.py:190).  Every lane of a warp is a different frame, so the k-mer loop runs at full lane
-// occupancy; the probe of k-mer s is consumed one iteration later so its L2 latency overlaps the next
-// hash.  K-mers that survive table 0 are compacted into a per-warp shared-memory queue and finished 32
-// at a time (tables 1..n-1), again at full occupancy.
+// This is the hot kernel for short reads.  A thread stages its strand (the read or its reverse complement, 2-bit words)
+// in its own shared-memory column, turns it in place into the frame's encoded residues (exactly the bytes sourmash's
+// hash_murmur sees after encode_peptide, sequence_encodings.py:457-468), then walks them: the current peptide k-mer is a
+// rolling byte window in registers, hashed (translate.py:187) and probed in table 0 (translate.py:190).  Every lane of a
+// warp is a different frame, so the k-mer loop runs at full lane occupancy; the probe of k-mer s is consumed one
+// iteration later so its L2 latency overlaps the next hash, and a k-mer that passes table 0 has its table 1..3 probes
+// issued together and consumed one iteration after that.
 //
-// Distinct k-mers (kmerize returns a set, compare_kmer_content.py:116-118): each thread keeps a private
-// 1024-bit (reads <= 192 nt) or 2048-bit (<= 320 nt) blocked three-hash "seen" filter in shared memory.  A k-mer whose three bits are not all set
-// is certainly new; otherwise the frame is walked backwards from the current k-mer and compared
-// byte-exactly (a tandem repeat answers after one period, a false alarm walks the whole prefix, rarely),
-// so the de-duplication is exact.
+// Distinct k-mers (kmerize returns a set, compare_kmer_content.py:116-118): each thread keeps a private 1024-bit (reads
+// <= 192 nt) or 2048-bit (<= 320 nt) blocked three-hash "seen" filter in shared memory.  A k-mer whose three bits are not
+// all set is certainly new; otherwise the frame is walked backwards from the current k-mer and compared byte-exactly (a
+// tandem repeat answers after one period, a false alarm walks the whole prefix, rarely), so the de-duplication is exact.
+//
+// What bounds it (round 2, profiles/README.md): with the table bins from mod_prime_tiny the kernel moves as many 32-byte
+// sectors through L2 per second as the random-gather micro-benchmark does (114 per read, 100.5 of them required probes);
+// fewer instructions (residue pre-pass, split seen bits) or fewer L1 look-ups (coalesced staging, table 1 first) no longer
+// change its time (profiles/r02_kernel_ab_*.log).
 #pragma once
 #include "device_common.cuh"
 #include "score_kernels.cuh"
-
-#ifndef ORPH_S2_MASK
-#define ORPH_S2_MASK 1  // tables 1..3: the wanted bits as one mask over the three bytes (0: three shifts; A/B switch)
-#endif
 
 namespace orph {
 
@@ -129,11 +128,42 @@ struct StrandColumn {
         const uint32_t wi = b >> 5;
         return __funnelshift_r(mcol[wi * kTaskBlock], mcol[(wi + 1) * kTaskBlock], b & 31u) & 7u;
     }
+    // the N bits of the twelve bases (four codons) starting at base `b`
+    __device__ __forceinline__ uint32_t n_bits12(uint32_t b) const
+    {
+        const uint32_t wi = b >> 5;
+        return __funnelshift_r(mcol[wi * kTaskBlock], mcol[(wi + 1) * kTaskBlock], b & 31u) & 0xFFFu;
+    }
     __device__ __forceinline__ uint32_t residue(const uint8_t *lut, uint32_t phase, uint32_t i) const
     {
-        const uint32_t codon = window(2u * phase + 6u * i) & 63u;
-        if constexpr (NM) return residue_with_n(lut, codon, n_bits(phase + 3u * i), x_res);
-        else return lut[codon];
+        return (col[(i >> 2) * kTaskBlock] >> (8u * (i & 3u))) & 0xFFu;  // the column holds residues by now
+    }
+    // Turns the staged strand into the frame's encoded residues, in place: word j of the column = residues 4j .. 4j+3
+    // (what encode_peptide makes of the translated frame, sequence_encodings.py:457-468).  Residues need 8 bits where
+    // their codons need 6, so the walk goes from the last word down: word j is cut from strand words
+    // floor((2 phase + 24 j) / 32) and the next one, both <= j for j >= 1 and word 0 alone for j = 0.
+    __device__ __forceinline__ void to_residues(uint32_t *column, const uint8_t *lut, uint32_t phase, uint32_t plen, uint32_t max_plen) const
+    {
+        const uint32_t nw = (plen + 3u) >> 2;
+        for (int j = (int)((max_plen + 3u) >> 2) - 1; j >= 0; j--) {
+            if ((uint32_t)j < nw) {
+                const uint32_t w = window(2u * phase + 24u * (uint32_t)j);
+                uint32_t r0, r1, r2, r3;
+                if constexpr (NM) {
+                    const uint32_t nb = n_bits12(phase + 12u * (uint32_t)j);
+                    r0 = residue_with_n(lut, w & 63u, nb & 7u, x_res);
+                    r1 = residue_with_n(lut, (w >> 6) & 63u, (nb >> 3) & 7u, x_res);
+                    r2 = residue_with_n(lut, (w >> 12) & 63u, (nb >> 6) & 7u, x_res);
+                    r3 = residue_with_n(lut, (w >> 18) & 63u, nb >> 9, x_res);
+                } else {
+                    r0 = lut[w & 63u];
+                    r1 = lut[(w >> 6) & 63u];
+                    r2 = lut[(w >> 12) & 63u];
+                    r3 = lut[(w >> 18) & 63u];
+                }
+                column[j * kTaskBlock] = r0 | (r1 << 8) | (r2 << 16) | (r3 << 24);
+            }
+        }
     }
 };
 
@@ -211,8 +241,9 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
     const uint32_t seen_words = P.seen_words;
     unsigned long long *seen = reinterpret_cast<unsigned long long *>(dyn_smem) + threadIdx.x;
     uint32_t *strand = reinterpret_cast<uint32_t *>(dyn_smem + (size_t)seen_words * 8 * kTaskBlock) + threadIdx.x;
-    const uint32_t strand_words = P.read_words;
-    const uint32_t mask_words = (strand_words + 1) / 2 + 1;  // one bit per base against two (+ the word a 3-bit fetch may touch)
+    const uint32_t strand_words = P.read_words;  // height of a thread's column
+    const uint32_t stage_words = P.stage_words;  // of those, the words the 2-bit strand takes
+    const uint32_t mask_words = (stage_words + 1) / 2 + 1;  // one bit per base against two (+ the word a 3-bit fetch may touch)
     uint32_t *mstrand = strand + (size_t)strand_words * kTaskBlock;
     const StrandColumn<NM> sc{strand, mstrand, (uint32_t)P.lut['X']};
 
@@ -247,7 +278,7 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
                 return start >= 0 ? v : v << (uint32_t)(-start);
             };
             const uint32_t n_need = valid ? (2 * L + 31) / 32 : 0;
-            for (uint32_t t = 0; t < strand_words; t++) {
+            for (uint32_t t = 0; t < stage_words; t++) {
                 uint32_t w = 0;
                 if (t < n_need) w = f < 3 ? read_bits((int)(32 * t)) : revcomp_word(read_bits(2 * (int)L - 32 * (int)(t + 1)));
                 strand[t * kTaskBlock] = w;
@@ -280,6 +311,7 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
         for (uint32_t w = 0; w < seen_words; w++) seen[w * kTaskBlock] = 0ull;
         uint32_t nd = 0, nh = 0;
         const uint32_t max_plen = __reduce_max_sync(0xffffffffu, plen);
+        sc.to_residues(strand, lut_fwd, phase, plen, max_plen);
         __syncwarp();
 
         // Software pipeline over residues: no result of a shared- or global-memory load is consumed in the
@@ -291,18 +323,18 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
         //   (3) table-0 probe of k-mer s-1 has arrived: if it is new and hit, issue its table 1..3 probes;
         //   (4) push residue s (looked up during iteration s-1), hash k-mer s, issue its table-0 probe and the
         //       load of its seen-filter word;
-        //   (5) look up residue s+1; codons come 5 at a time from a 30-bit window that is itself loaded two
-        //       iterations before it is needed.
+        //   (5) residue s+1: residues come four to a word from the column, the next word is fetched four iterations
+        //       before it is needed.
         bool t0_pending = false, s2_pending = false, seen_pending = false;
         uint64_t t0_h = 0;
         uint32_t t0_v = 0, t0_sh = 0;
-        uint32_t s2_v1 = 0, s2_v2 = 0, s2_v3 = 0, s2_sh = 0;
+        uint32_t s2_v1 = 0, s2_v2 = 0, s2_v3 = 0, s2_sh = 0;  // s2_sh: the wanted bits as a mask over v1 | v2 << 8 | v3 << 16
         unsigned long long *seen_slot = seen;
         unsigned long long seen_bits = 0, seen_old = 0;
-        // window state: win32 holds codons of residues [5*g, 5*g+5); raw words of the next group are fetched early
-        uint32_t win32 = sc.window(2u * phase), win_next = 0, raw_a = 0, raw_b = 0, raw_sh = 0;
-        uint32_t res_cur = NM ? residue_with_n(lut_fwd, win32 & 63u, sc.n_bits(phase), sc.x_res) : lut_fwd[win32 & 63u];  // residue 0
-        uint32_t mod5 = 0;                         // s % 5, uniform
+        // residues come four to a word from the column; the next word is fetched four iterations before it is needed
+        uint32_t res_word = strand[0], res_next = strand[kTaskBlock];
+        uint32_t res_cur = res_word & 0xFFu;  // residue 0
+        res_word >>= 8;
         for (uint32_t s = 0; s < max_plen + 2; s++) {
             // (1)
             bool kmer_new = false;
@@ -315,11 +347,7 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
                 seen_pending = false;
             }
             // (2)
-#if ORPH_S2_MASK
             if (s2_pending) nh += ((s2_v1 | (s2_v2 << 8) | (s2_v3 << 16)) & s2_sh) == s2_sh ? 1u : 0u;
-#else
-            if (s2_pending) nh += (s2_v1 >> (s2_sh & 7u)) & (s2_v2 >> ((s2_sh >> 3) & 7u)) & (s2_v3 >> (s2_sh >> 6)) & 1u;
-#endif
             s2_pending = false;
             // (3)
             if (t0_pending && kmer_new && ((t0_v >> t0_sh) & 1u)) {
@@ -333,12 +361,8 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
                     s2_v1 = ld_table_byte(P.F.table[1] + (b1 >> 3));
                     s2_v2 = ld_table_byte(P.F.table[2] + (b2 >> 3));
                     s2_v3 = ld_table_byte(P.F.table[3] + (b3 >> 3));
-#if ORPH_S2_MASK
                     // the three wanted bits as one mask over the bytes side by side: one compare when they arrive
                     s2_sh = (1u << ((uint32_t)b1 & 7u)) | (0x100u << ((uint32_t)b2 & 7u)) | (0x10000u << ((uint32_t)b3 & 7u));
-#else
-                    s2_sh = ((uint32_t)b1 & 7u) | (((uint32_t)b2 & 7u) << 3) | (((uint32_t)b3 & 7u) << 6);
-#endif
                     s2_pending = true;
                 } else {
                     nh += filter_contains_rest(sF, t0_h) ? 1u : 0u;
@@ -356,34 +380,22 @@ score_tasks_kernel(const ScoreParams P, const uint32_t *__restrict__ packed32, c
                     t0_sh = (uint32_t)bin0 & 7u;
                     t0_h = h;
                     t0_pending = true;
-                    // seen filter: word chosen by 4 hash bits, three bit positions inside it by 18 more
                     const uint32_t hw = (uint32_t)(h >> 32);
-                    seen_bits = (1ull << (hw & 63u)) | (1ull << ((hw >> 6) & 63u)) | (1ull << ((hw >> 12) & 63u));
-                    seen_slot = seen + ((hw >> 18) & (seen_words - 1)) * kTaskBlock;
+                    // seen filter: word chosen by 4 hash bits; two bits in its low half, one in its high half (15 more hash
+                    // bits, 32-bit shifts only; the false-alarm rate is that of three bits anywhere in the word to within 20 %)
+                    seen_bits = (unsigned long long)((1u << (hw & 31u)) | (1u << ((hw >> 5) & 31u))) | ((unsigned long long)(1u << ((hw >> 10) & 31u)) << 32);
+                    seen_slot = seen + ((hw >> 15) & (seen_words - 1)) * kTaskBlock;
                     seen_old = *seen_slot;
                     seen_pending = true;
                 }
             }
             // (5) residue s+1
-            if (mod5 == 1) {  // fetch the raw words of the next group of five codons
-                const uint32_t bit = 2u * phase + 6u * (s + 4);
-                raw_a = strand[(bit >> 5) * kTaskBlock];
-                raw_b = strand[((bit >> 5) + 1) * kTaskBlock];
-                raw_sh = bit & 31u;
-            } else if (mod5 == 3) {
-                win_next = __funnelshift_r(raw_a, raw_b, raw_sh);
+            if (((s + 1u) & 3u) == 0) {
+                res_word = res_next;
+                res_next = strand[(((s + 1u) >> 2) + 1u) * kTaskBlock];
             }
-            uint32_t codon;
-            if (mod5 == 4) {
-                win32 = win_next;
-                mod5 = 0;
-                codon = win32 & 63u;
-            } else {
-                mod5++;
-                codon = (win32 >> (6u * mod5)) & 63u;
-            }
-            if constexpr (NM) res_cur = residue_with_n(lut_fwd, codon, sc.n_bits(phase + 3u * (s + 1)), sc.x_res);
-            else res_cur = lut_fwd[codon];
+            res_cur = res_word & 0xFFu;
+            res_word >>= 8;
         }
 #undef ORPH_BIN
         if (valid) {
