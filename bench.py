@@ -816,9 +816,12 @@ def run_ours(args):
     # DRAM bytes of the dominant kernel per launch are NOT measured by this run (that needs ncu): the figure below is the
     # committed `ncu --set full` capture of the same kernel and workload on 2 M reads, scaled to this launch's reads
     if args.workload == "r150" and dominant == "score_tasks" and args.alphabet == "protein":
-        roofline["traffic"] = 115.8 * args.reads
-        roofline["traffic_source"] = ("ncu --set full, profiles/r01_ncu_full_final_score_tasks.csv: dram__bytes_read.sum 187.4 MB + "
-                                      "dram__bytes_write.sum 44.2 MB per 2 M-read launch = 115.8 B/read (kernel unchanged since), scaled by reads")
+        roofline["traffic"] = 115.4 * args.reads
+        roofline["traffic_source"] = ("ncu --set full, profiles/r02b_ncu_full_tasks.csv: dram__bytes_read.sum 187.3 MB + "
+                                      "dram__bytes_write.sum 43.5 MB per 2 M-read launch = 115.4 B/read, scaled by reads")
+        roofline["l2_sectors_per_read_ncu"] = 115.1
+        roofline["l2_sectors_source"] = ("same capture: lts__t_sectors 2.302e8 per 2 M reads; l1tex__m_l1tex2xbar_req_cycles_active 90.2 % "
+                                         "(the binding unit); all sectors / gather peak = 0.94")
     else:
         roofline["traffic"] = None
     configs = None

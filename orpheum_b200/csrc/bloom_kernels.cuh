@@ -15,7 +15,7 @@ __device__ __forceinline__ bool filter_add(const FilterDev &F, uint64_t h)
 {
     bool is_new = false;
     for (uint32_t t = 0; t < F.n_tables; t++) {
-        const uint64_t bin = mod_prime(h, F.size[t], F.magic[t]);
+        const uint64_t bin = filter_bin(F, t, h);
         // byte bin>>3, bit bin&7 of a little-endian table == bit (bin & 31) of u32 word bin>>5
         uint32_t *word = reinterpret_cast<uint32_t *>(const_cast<uint8_t *>(F.table[t])) + (bin >> 5);
         const uint32_t bit = 1u << (bin & 31);

@@ -30,7 +30,7 @@ struct FilterDev {
     uint64_t magic[ORPH_MAX_TABLES];  // floor((2^64-1) / size)
     const uint8_t *table[ORPH_MAX_TABLES];
     uint32_t small;                   // every size < 2^31: remainders fit 32-bit arithmetic
-    uint32_t pad;
+    uint32_t tiny;                    // every size <= kTinyPrimeMax: mod_prime_tiny applies
 };
 
 __device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
@@ -131,6 +131,7 @@ __device__ __forceinline__ uint32_t mod_prime_tiny(uint64_t h, uint32_t p, uint6
 // bin of hash h in table t.  F lives in shared memory (uniform, conflict-free broadcast reads).
 __device__ __forceinline__ uint64_t filter_bin(const FilterDev &F, uint32_t t, uint64_t h)
 {
+    if (F.tiny) return mod_prime_tiny(h, (uint32_t)F.size[t], F.magic[t]);
     const uint64_t q = __umul64hi(h, F.magic[t]);
     if (F.small) {  // the remainder before correction is < 2p < 2^32: low words suffice
         const uint32_t p = (uint32_t)F.size[t];

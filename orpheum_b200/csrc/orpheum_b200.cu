@@ -333,14 +333,16 @@ static FilterDev filter_dev(const orph_filter *f)
     memset(&F, 0, sizeof(F));
     F.ksize = f->ksize;
     F.n_tables = f->n_tables;
-    bool small = true;
+    bool small = true, tiny = true;
     for (uint32_t i = 0; i < f->n_tables; i++) {
         F.size[i] = f->sizes[i];
         F.magic[i] = ~0ULL / f->sizes[i];
         F.table[i] = f->buf + f->offsets[i];
         if (f->sizes[i] >= (1ULL << 31)) small = false;
+        if (f->sizes[i] < 2 || f->sizes[i] > kTinyPrimeMax) tiny = false;
     }
     F.small = small ? 1u : 0u;
+    F.tiny = tiny ? 1u : 0u;
     return F;
 }
 
@@ -969,10 +971,7 @@ static uint32_t task_column_words(uint32_t tier_len)
 static bool filter_is_tiny4(const FilterDev &F)
 {
 #if ORPH_TINY4
-    if (F.n_tables != 4) return false;
-    for (int t = 0; t < 4; t++)
-        if (F.size[t] < 2 || F.size[t] > kTinyPrimeMax) return false;
-    return true;
+    return F.n_tables == 4 && F.tiny;
 #else
     (void)F;
     return false;

@@ -618,6 +618,35 @@ def test_reads_beyond_the_scoring_limit_are_classified_from_their_stop_codons(gp
     assert_same_as_oracle(out[[0, 2]], ora2[[0, 2]], "records next to a refused read")
 
 
+@pytest.mark.parametrize("tablesize,tiny", [(1_431_655_766, True), (1_431_656_200, False)])
+def test_tables_at_the_32_bit_reduction_limit(gpu, enc, orc, tablesize, tiny):
+    """Four tables just below / across (2^32 - 1) / 3 bits: the largest geometry whose bins come from mod_prime_tiny
+    (device_common.cuh: the un-corrected remainder must stay below 3p < 2^32) and the smallest that must not."""
+    from orpheum_b200 import synth
+
+    limit = 0xFFFFFFFF // 3
+    residues, poffs = synth.make_proteome(n_proteins=300, seed=27)
+    lut, olut = enc.encode_lut("protein"), orc.encode_lut("protein")
+    gg = gpu.GpuNodegraph(7, tablesize, 4)
+    sizes = gg.hashsizes()
+    assert all(s <= limit for s in sizes) == tiny and max(sizes) > limit - 400
+    gg.add_peptides(residues, poffs, lut)
+    go = orc.Nodegraph(7, tablesize, 4)
+    assert list(go.hashsizes()) == list(sizes)
+    go.add_peptides(residues, poffs, olut)
+    assert [gg.n_occupied(i) for i in range(4)] == [go.n_occupied(i) for i in range(4)]
+    flat, offsets = synth.make_reads_mixed(5000, residues, poffs, ksize=7, seed=28, min_len=30, max_len=900)
+    ora, _ = orc.score_reads(go, flat, offsets, olut, 0.5, n_threads=0)
+    res = gpu.score_reads(gg, flat, offsets, lut, 0.5)
+    assert_same_as_oracle(res, ora, f"tablesize {tablesize}")
+    assert int((res["category"] == 3).sum()) > 300
+    rng = np.random.default_rng(7)
+    hashes = np.concatenate([rng.integers(0, 2**64, 5000, dtype=np.uint64),
+                             np.array([0, 1, 2**32 - 1, 2**32, 2**64 - 1, 2**64 - 2] + [s * q + d for s in sizes for q in (1, 2**32 // s, 2**64 // s - 1)
+                                                                                 for d in (0, s - 1)], dtype=np.uint64)])
+    np.testing.assert_array_equal(gg.get_many(hashes), np.array([go.get(int(h)) for h in hashes], dtype=np.uint8))
+
+
 def test_scoring_against_hbm_resident_filter(gpu, enc, orc):
     """BASELINE cfg4's filter geometry (tablesize 1e9 x 4 = 500 MB, four times the L2): 1e5 reads scored on the GPU against
     the oracle -- the probes of every table go to HBM, the persisting-L2 window covers only part of the buffer."""

@@ -567,3 +567,29 @@ def test_native_csv_writer_many_blocks_and_threads(tmp_path):
                 w.writerow([names[i], jac, int(rec["n_kmers"][i, fr]) if c in (2, 3, 4) else np.nan, category_text(c, "protein"), FRAMES[fr],
                             "a.fq" if i < half else "b,with comma.fq"])
     assert (tmp_path / "native.csv").read_bytes() == (tmp_path / "python.csv").read_bytes()
+
+
+def test_mod_prime_tiny_arithmetic():
+    """The 32-bit Barrett pieces of device_common.cuh's mod_prime_tiny, restated on Python integers: exact for every prime the
+    kernels may hand it (p <= (2^32 - 1) / 3), at the limit and at values chosen against each dropped term."""
+    import random
+
+    M32, M64 = 0xFFFFFFFF, 0xFFFFFFFFFFFFFFFF
+
+    def tiny(h, p):
+        magic = M64 // p
+        hi, lo, mhi, mlo = h >> 32, h & M32, magic >> 32, magic & M32
+        mid = (hi * mlo + lo * mhi) & M64
+        q = (hi * mhi + (mid >> 32)) & M32
+        r = (lo - q * p) & M32
+        for _ in range(2):
+            r = min(r, (r - p) & M32)
+        return r
+
+    rng = random.Random(4)
+    primes = [2, 3, 251, 65521, 99999989, 99999971, 999999937, 999999883, 1073741789, 1431655751, M32 // 3]
+    for p in primes:
+        edge = [0, 1, p - 1, p, p + 1, M32, M32 + 1, M64, M64 - 1, (M64 // p) * p, (M64 // p) * p - 1, M64 - p, M32 << 32]
+        for h in edge + [rng.getrandbits(64) for _ in range(20000)] + [rng.getrandbits(64) | (M32 << 32) for _ in range(2000)] \
+                + [rng.randrange(M64 // p) * p + d for _ in range(2000) for d in (0, p - 1)]:
+            assert tiny(h, p) == h % p, (h, p)
