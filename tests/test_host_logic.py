@@ -531,9 +531,10 @@ def test_native_fasta_formatter_against_python(tmp_path):
             assert got.decode("utf-8") == "".join(want[kind]), (kind, with_lcp)
 
 
-def test_native_csv_writer_many_blocks_and_threads(tmp_path):
+def test_native_csv_writer_many_blocks_and_threads(tmp_path, monkeypatch):
     """orph_csv_write_scores formats blocks of reads on several threads and writes them at their places in the file: a
-    table of many blocks, appended in two calls, against csv.writer over the reference's rows."""
+    table of many blocks, appended in two calls (copied into a shared mapping of the file's tail, or pwritten), against
+    csv.writer over the reference's rows."""
     import csv as pycsv
 
     from orpheum_b200 import _lib, build
@@ -567,6 +568,10 @@ def test_native_csv_writer_many_blocks_and_threads(tmp_path):
                 w.writerow([names[i], jac, int(rec["n_kmers"][i, fr]) if c in (2, 3, 4) else np.nan, category_text(c, "protein"), FRAMES[fr],
                             "a.fq" if i < half else "b,with comma.fq"])
     assert (tmp_path / "native.csv").read_bytes() == (tmp_path / "python.csv").read_bytes()
+    # the same table through the pwrite() route (taken where the file cannot be mapped)
+    monkeypatch.setenv("ORPHEUM_B200_CSV_PWRITE", "1")
+    table.write_csv(str(tmp_path / "native_pwrite.csv"))
+    assert (tmp_path / "native_pwrite.csv").read_bytes() == (tmp_path / "python.csv").read_bytes()
 
 
 def test_mod_prime_tiny_arithmetic():
