@@ -163,6 +163,37 @@ class ClockSampler:
         }
 
 
+def n_host_threads():
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    return max(1, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
+
+
+def host_memory_read_rate(threads, mb=128, reps=3):
+    """GB/s at which `threads` threads of this process sum private arrays (numpy releases the GIL): the host-memory read rate
+    the packing lane and the DMA engines share."""
+    import threading
+
+    arrays = [np.ones(mb << 20, dtype=np.uint8).view(np.uint64) for _ in range(threads)]
+    gate = threading.Barrier(threads + 1)
+
+    def work(a):
+        gate.wait()
+        for _ in range(reps):
+            a.sum()
+        gate.wait()
+
+    pool = [threading.Thread(target=work, args=(a,)) for a in arrays]
+    for t in pool:
+        t.start()
+    gate.wait()
+    t0 = time.perf_counter()
+    gate.wait()
+    dt = time.perf_counter() - t0
+    for t in pool:
+        t.join()
+    return {"threads": threads, "read_GBps": threads * reps * (mb << 20) / dt / 1e9}
+
+
 def make_inputs(args, rank):
     from orpheum_b200 import synth
 
@@ -577,7 +608,15 @@ def run_ours(args):
 
     # ---- end to end through the host-buffer C ABI (pinned host ASCII in, records out) ----
     e2e = None
+    host_info = None
     if not args.no_e2e:
+        # what the host can do, for reading the e2e figures: cores of this process and the rate at which they read memory
+        # (every rank's threads run at once, as they do in the legs below)
+        host_info = host_memory_read_rate(n_host_threads())
+        if world > 1:
+            t = torch.tensor([host_info["read_GBps"]], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            host_info["read_GBps_all_ranks"] = float(t.item())
         h_reads = torch.empty(flat.size, dtype=torch.uint8).pin_memory()
         h_reads.numpy()[:] = flat
         h_offsets = torch.empty(offsets.size, dtype=torch.int64).pin_memory()
@@ -614,6 +653,7 @@ def run_ours(args):
                "input": "pinned host ASCII reads + u64 offsets via orph_score_reads(); the library 2-bit packs part of the "
                         "chunks on the host threads while the copy engine ships the others as ASCII",
                "ms_per_step": 1e3 * dt / args.steps, "identical_to_device_path": bool(same),
+               "host": host_info,
                "ingest": {"host_threads": stats1["host_threads"], "fraction_of_chunks_packed_on_host": frac_packed,
                           "host_pack_GBps": stats1["pack_bytes_per_s"] / 1e9, "h2d_GBps_measured": stats1["h2d_bytes_per_s"] / 1e9}}
         # the same call with host packing disabled: every byte of ASCII crosses PCIe

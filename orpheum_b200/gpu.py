@@ -412,14 +412,18 @@ class ScoringStream:
         except Exception:
             pass
 
-    def emit(self, ctx, kinds_mask):
+    def emit(self, ctx, kinds_mask, copy=True):
         """FASTA text of the batch the iteration currently holds, formatted by the library (orph_stream_emit): bit k of
         ``kinds_mask`` asks for kind k of ``format_fasta``.  -> list of 4 ``bytes`` (empty where nothing was asked or emitted).
-        ``ctx`` runs the peptide translation: a context of the caller's, e.g. the filter's."""
+        ``ctx`` runs the peptide translation: a context of the caller's, e.g. the filter's.  ``copy=False``: memoryviews of the
+        library's own buffers instead (valid until the next call on this stream) -- what a caller that only writes them out
+        wants; the coding peptides of a batch are a hundred megabytes."""
         ptrs = (ctypes.c_void_p * 4)()
         lens = (ctypes.c_uint64 * 4)()
         check(self._lib.orph_stream_emit(self._h, ctx._h, int(kinds_mask), ctypes.byref(ptrs), ctypes.byref(lens)))
-        return [ctypes.string_at(ptrs[k], int(lens[k])) if lens[k] else b"" for k in range(4)]
+        if copy:
+            return [ctypes.string_at(ptrs[k], int(lens[k])) if lens[k] else b"" for k in range(4)]
+        return [memoryview((ctypes.c_char * int(lens[k])).from_address(ptrs[k])).cast("B") if lens[k] else b"" for k in range(4)]
 
     def __iter__(self):
         raw = _lib.StreamBatch()

@@ -22,6 +22,19 @@ from .sequence_encodings import encode_lut, encode_peptide
 from .translate_single_seq import TranslateSingleSeq  # noqa: F401  (re-exported: part of the reference's surface)
 
 NAN = np.nan
+_TRACE = bool(os.environ.get("ORPHEUM_B200_CLI_TRACE"))
+_T0 = [0.0]
+
+
+def _trace(what):
+    """ORPHEUM_B200_CLI_TRACE=1: phase timestamps of the CLI on stderr (seconds since the command started)."""
+    if _TRACE:
+        import time
+
+        now = time.perf_counter()
+        if not _T0[0]:
+            _T0[0] = now
+        print("[orpheum_b200] %8.3f s  %s" % (now - _T0[0], what), file=sys.stderr)
 
 
 def get_jaccard_threshold(jaccard_threshold, alphabet):
@@ -290,6 +303,7 @@ class Translate:
                 # batch on its way while this one is expanded into the outputs
                 with ScoringStream(self.peptide_bloom_filter, reads, self._lut, self.jaccard_threshold, replicas=self._replica_lanes()) as stream:
                     for batch in stream:
+                        _trace("batch of %d reads scored" % len(batch.results))
                         if batch.status == _lib.ORPH_E_TOO_LONG:
                             bad = np.nonzero((batch.results["category"] == _lib.CAT_INVALID).all(axis=1))[0]
                             name = batch.names().tolist()[int(bad[0])] if len(bad) else "?"
@@ -298,8 +312,11 @@ class Translate:
                         _lib.check(batch.status)  # an empty read: ZeroDivisionError, as in the reference (translate.py:83)
                         results = batch.results.copy()
                         names = batch.names()
+                        _trace("records and names copied")
                         self._emit_stream_batch_native(stream)
+                        _trace("FASTA outputs written")
                         table.append(names, results, reads)
+                        _trace("batch handed to the CSV / summary workers")
         except BaseException:
             table.discard_csv_stream()
             raise
@@ -338,7 +355,7 @@ class Translate:
     def _write_bytes(handle, blob):
         """FASTA bytes into a text handle: through its binary layer when that writes the same bytes (UTF-8, no newline
         translation), else decoded."""
-        if not blob:
+        if not len(blob):
             return
         raw = getattr(handle, "buffer", None)
         if raw is not None and str(getattr(handle, "encoding", "")).lower().replace("-", "") == "utf8" \
@@ -346,7 +363,7 @@ class Translate:
             handle.flush()
             raw.write(blob)
         else:
-            handle.write(blob.decode(*fastx.TEXT_CODEC))
+            handle.write(bytes(blob).decode(*fastx.TEXT_CODEC))
 
     def _emit_stream_batch_native(self, stream):
         """Side effects of the stream batch being held (translate.py:244-298), every byte of them produced by the library
@@ -354,7 +371,7 @@ class Translate:
         handles = self.file_handles
         kinds = 1 | (8 if handles["low_complexity_peptide"] is not None else 0) | (2 if handles["coding_nucleotide"] is not None else 0) \
             | (4 if handles["noncoding_nucleotide"] is not None else 0)
-        blobs = stream.emit(self.peptide_bloom_filter.ctx, kinds)
+        blobs = stream.emit(self.peptide_bloom_filter.ctx, kinds, copy=False)  # written out before the stream moves on
         if handles["low_complexity_peptide"] is not None:
             self._write_bytes(handles["low_complexity_peptide"], blobs[3])
         if handles["coding_nucleotide"] is not None:
@@ -416,8 +433,12 @@ def cli(peptides, reads, peptide_ksize=None, save_peptide_bloom_filter=True, pep
         low_complexity_peptide_fasta=None, tablesize=constants_index.DEFAULT_MAX_TABLESIZE,
         n_tables=constants_index.DEFAULT_N_TABLES, long_reads=False, verbose=False):
     """Writes coding peptides from reads to standard output"""
+    _T0[0] = 0.0
+    _trace("start")
     translate_obj = Translate(locals())
+    _trace("filter loaded")
     table = translate_obj.score_all_files_columnar(stream_csv=csv)
+    _trace("all batches scored")
     # the three outputs are independent: the CSV is formatted by the native writer (GIL released) while the parquet
     # table and the JSON summary are built here
     from concurrent.futures import ThreadPoolExecutor
@@ -433,8 +454,10 @@ def cli(peptides, reads, peptide_ksize=None, save_peptide_bloom_filter=True, pep
         if json_summary:
             table.write_json_summary(json_summary, reads, translate_obj.peptide_bloom_filter_filename,
                                      translate_obj.peptide_ksize, translate_obj.jaccard_threshold)
+            _trace("JSON summary written")
         for job in pending:
             job.result()
+        _trace("CSV / parquet complete")
 
 
 if __name__ == "__main__":

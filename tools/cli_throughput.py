@@ -58,6 +58,11 @@ def main():
         result = CliRunner().invoke(translate.cli, argv)
         prof.disable()
         pstats.Stats(prof, stream=sys.stderr).sort_stats("cumulative").print_stats(45)
+    if os.environ.get("ORPHEUM_B200_CLI_TRACE"):
+        try:
+            sys.stderr.write(result.stderr)
+        except Exception:  # stderr not captured separately by this click version
+            sys.stderr.write("\n".join(ln for ln in result.output.splitlines() if ln.startswith("[orpheum_b200]")) + "\n")
     summary = json.load(open(js))
     print(json.dumps({"n_reads": n_reads, "input": os.path.basename(fq), "input_bytes": size, "seconds": dt,
                       "reads_per_s": n_reads / dt, "csv_bytes": os.path.getsize(csv),
