@@ -60,38 +60,104 @@ inline uint64_t line_end(const uint8_t *t, uint64_t p, uint64_t hi, bool &found)
 
 enum class RecStatus { ok, incomplete, bad };
 
+// line_end with the newline search inlined (32 bytes per compare): the lines of a short-read record are 2 .. 300 bytes, a
+// memchr() call per line costs more than the search itself
+__attribute__((target("avx2"))) inline uint64_t line_end_avx2(const uint8_t *t, uint64_t p, uint64_t hi, bool &found)
+{
+    const __m256i nl = _mm256_set1_epi8('\n');
+    uint64_t q = p;
+    for (; q + 32 <= hi; q += 32) {
+        const uint32_t m = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_loadu_si256(reinterpret_cast<const __m256i *>(t + q)), nl));
+        if (m) {
+            found = true;
+            return q + (uint64_t)__builtin_ctz(m);
+        }
+    }
+    for (; q < hi; q++)
+        if (t[q] == '\n') {
+            found = true;
+            return q;
+        }
+    found = false;
+    return hi;
+}
+
 // One strict four-line record starting at p < hi.  On ok, `next` is the start of the following record.
+#define ORPH_PARSE_RECORD_BODY(LINE_END)                                                                                       \
+    const RecStatus cut = at_eof ? RecStatus::bad : RecStatus::incomplete; /* the text ends inside the record */               \
+    bool found;                                                                                                                \
+    if (t[p] != '@') return RecStatus::bad;                                                                                    \
+    uint64_t h0 = p + 1, h1 = LINE_END(t, p, hi, found);                                                                       \
+    if (!found) return cut;                                                                                                    \
+    uint64_t s0 = h1 + 1, s1 = LINE_END(t, s0, hi, found);                                                                     \
+    if (!found) return cut;                                                                                                    \
+    const uint64_t p0 = s1 + 1;                                                                                                \
+    if (p0 >= hi) return cut;                                                                                                  \
+    if (t[p0] != '+') return RecStatus::bad;                                                                                   \
+    uint64_t p1;                                                                                                               \
+    if (p0 + 1 < hi && t[p0 + 1] == '\n') p1 = p0 + 1; /* the usual bare "+" */                                                \
+    else {                                                                                                                     \
+        p1 = LINE_END(t, p0, hi, found);                                                                                       \
+        if (!found) return cut;                                                                                                \
+    }                                                                                                                          \
+    uint64_t q0 = p1 + 1;                                                                                                      \
+    const uint64_t q_nl = LINE_END(t, q0, hi, found);                                                                          \
+    if (!found && (!at_eof || q0 >= hi)) return cut; /* only the very last line of the file may lack its terminator */         \
+    uint64_t q1 = q_nl;                                                                                                        \
+    if (s1 == s0 || t[s0] == '+' || t[s0] == '#') return RecStatus::bad;                                                       \
+    /* the usual record needs no stripping: test the end bytes before entering the loops */                                    \
+    if (h1 > h0 && (is_strip_end(t[h1 - 1]) || is_strip_begin(t[h0]))) strip_range(t, h0, h1);                                 \
+    if (is_strip_end(t[s1 - 1]) || is_strip_begin(t[s0])) strip_range(t, s0, s1);                                              \
+    if (q1 > q0 && (is_strip_end(t[q1 - 1]) || is_strip_begin(t[q0]))) strip_range(t, q0, q1);                                 \
+    if (s1 == s0 || q1 - q0 != s1 - s0 || s1 - s0 > 0xFFFFFFFFull || h1 - h0 > 0xFFFFFFFFull) return RecStatus::bad;           \
+    rec.seq_start = s0;                                                                                                        \
+    rec.seq_len = (uint32_t)(s1 - s0);                                                                                         \
+    rec.name_start = h0;                                                                                                       \
+    rec.name_len = (uint32_t)(h1 - h0);                                                                                        \
+    next = found ? q_nl + 1 : hi;                                                                                              \
+    return RecStatus::ok;
+
 inline RecStatus parse_record(const uint8_t *t, uint64_t p, uint64_t hi, bool at_eof, Rec &rec, uint64_t &next)
 {
-    const RecStatus cut = at_eof ? RecStatus::bad : RecStatus::incomplete;  // the text ends inside the record
-    bool found;
-    if (t[p] != '@') return RecStatus::bad;
-    uint64_t h0 = p + 1, h1 = line_end(t, p, hi, found);
-    if (!found) return cut;
-    uint64_t s0 = h1 + 1, s1 = line_end(t, s0, hi, found);
-    if (!found) return cut;
-    const uint64_t p0 = s1 + 1;
-    if (p0 >= hi) return cut;
-    if (t[p0] != '+') return RecStatus::bad;
-    const uint64_t p1 = line_end(t, p0, hi, found);
-    if (!found) return cut;
-    uint64_t q0 = p1 + 1;
-    const uint64_t q_nl = line_end(t, q0, hi, found);
-    if (!found && (!at_eof || q0 >= hi)) return cut;  // only the very last line of the file may lack its terminator
-    uint64_t q1 = q_nl;
-    if (s1 == s0 || t[s0] == '+' || t[s0] == '#') return RecStatus::bad;
-    // the usual record needs no stripping: test the end bytes before entering the loops
-    if (h1 > h0 && (is_strip_end(t[h1 - 1]) || is_strip_begin(t[h0]))) strip_range(t, h0, h1);
-    if (is_strip_end(t[s1 - 1]) || is_strip_begin(t[s0])) strip_range(t, s0, s1);
-    if (q1 > q0 && (is_strip_end(t[q1 - 1]) || is_strip_begin(t[q0]))) strip_range(t, q0, q1);
-    if (s1 == s0 || q1 - q0 != s1 - s0 || s1 - s0 > 0xFFFFFFFFull || h1 - h0 > 0xFFFFFFFFull) return RecStatus::bad;
-    rec.seq_start = s0;
-    rec.seq_len = (uint32_t)(s1 - s0);
-    rec.name_start = h0;
-    rec.name_len = (uint32_t)(h1 - h0);
-    next = found ? q_nl + 1 : hi;
-    return RecStatus::ok;
+    ORPH_PARSE_RECORD_BODY(line_end)
 }
+
+__attribute__((target("avx2"))) inline RecStatus parse_record_avx2(const uint8_t *t, uint64_t p, uint64_t hi, bool at_eof, Rec &rec, uint64_t &next)
+{
+    ORPH_PARSE_RECORD_BODY(line_end_avx2)
+}
+#undef ORPH_PARSE_RECORD_BODY
+
+// The records that start in [p, seg_hi), appended to `recs`; p ends behind the last complete one.
+#define ORPH_SCAN_RECORDS_BODY(PARSE)                                  \
+    while (p < seg_hi) {                                               \
+        Rec rec;                                                       \
+        uint64_t next;                                                 \
+        const RecStatus st = PARSE(t, p, hi, at_eof, rec, next);       \
+        if (st == RecStatus::incomplete) break;                        \
+        if (st == RecStatus::bad) {                                    \
+            bad = true;                                                \
+            break;                                                     \
+        }                                                              \
+        recs.push_back(rec);                                           \
+        n_bases += rec.seq_len;                                        \
+        n_name += rec.name_len;                                        \
+        max_len = std::max(max_len, rec.seq_len);                      \
+        p = next;                                                      \
+    }
+
+void scan_records(const uint8_t *t, uint64_t &p, uint64_t seg_hi, uint64_t hi, bool at_eof, std::vector<Rec> &recs, uint64_t &n_bases,
+                  uint64_t &n_name, uint32_t &max_len, bool &bad)
+{
+    ORPH_SCAN_RECORDS_BODY(parse_record)
+}
+
+__attribute__((target("avx2"))) void scan_records_avx2(const uint8_t *t, uint64_t &p, uint64_t seg_hi, uint64_t hi, bool at_eof, std::vector<Rec> &recs,
+                                                        uint64_t &n_bases, uint64_t &n_name, uint32_t &max_len, bool &bad)
+{
+    ORPH_SCAN_RECORDS_BODY(parse_record_avx2)
+}
+#undef ORPH_SCAN_RECORDS_BODY
 
 // First position >= from that looks like the start of a record: a line start holding '@' whose next-but-one line
 // starts with '+'.  (A quality line may start with '@', but the line two below it is a sequence line, which strict
@@ -267,18 +333,8 @@ FusedResult parse_fastq_window(Pool *pool, const uint8_t *text, uint64_t lo, uin
         uint64_t p = first, n_bases = 0, n_name = 0;
         uint32_t max_len = 0;
         bool bad = false;
-        while (p < seg_hi) {
-            Rec rec;
-            uint64_t next;
-            const RecStatus st = parse_record(text, p, hi, at_eof, rec, next);
-            if (st == RecStatus::incomplete) break;
-            if (st == RecStatus::bad) { bad = true; break; }
-            recs.push_back(rec);
-            n_bases += rec.seq_len;
-            n_name += rec.name_len;
-            max_len = std::max(max_len, rec.seq_len);
-            p = next;
-        }
+        if (avx2) scan_records_avx2(text, p, seg_hi, hi, at_eof, recs, n_bases, n_name, max_len, bad);
+        else scan_records(text, p, seg_hi, hi, at_eof, recs, n_bases, n_name, max_len, bad);
         // ---- running totals, in segment order (the segments before this one were handed out earlier)
         Cum prev;
         prev.end = lo;
