@@ -96,6 +96,12 @@ typedef enum orph_reads_format {
 typedef struct orph_ctx orph_ctx;
 typedef struct orph_filter orph_filter;
 
+/* ---- devices -------------------------------------------------------------------------------- */
+/* Number of CUDA devices this process can use (0 when there is none or the driver cannot be reached; never an error):
+ * what Translate asks before it spreads the lanes of a scoring stream over the GPUs of the box (the reference walks its
+ * files and reads serially, orpheum/translate.py:367-379). */
+int orph_device_count(void);
+
 /* ---- context ------------------------------------------------------------------------------- */
 /* `stream`: a cudaStream_t to enqueue on (e.g. torch.cuda.current_stream().cuda_stream), or NULL to
  * let the context create its own non-blocking stream. */
@@ -340,6 +346,19 @@ int orph_csv_write_scores(const char *path, int append, const uint8_t *name_fiel
  * 0 means two ids are equal or, very rarely, collide: the caller then compares the ids themselves. */
 int orph_hash_names(const uint8_t *names, const uint64_t *name_offsets, uint64_t n, uint64_t *out_hashes, int n_threads);
 int orph_u64_all_distinct(const uint64_t *values, uint64_t n, int n_threads, int *all_distinct);
+/* One batch's share of the JSON summary (create_save_summary.py:136-240), straight from its records (read ids proven
+ * distinct by the two calls above): per row (6 per read, frame order) jaccard[6r+f] = n_hits / n_kmers for Coding and
+ * Non-coding frames, NaN otherwise, and scored[6r+f] = 1 / 0; classes = reads by their one category {Coding, too-short
+ * peptide, too-short read, reads whose only category is code c (6 entries), Non-coding}; coding_hist[c] = reads with c
+ * coding frames (c = 1..6), first_with[c] = index of the first such read (~0 if none: the reference's histogram keeps
+ * first-appearance order). */
+int orph_summary_partial(const orph_read_result *records, uint64_t n_reads, double *jaccard, uint8_t *scored, uint64_t classes[10],
+                         uint64_t coding_hist[7], uint64_t first_with[7], int n_threads);
+/* numpy's float64 sum of a contiguous column, to the last bit (pairwise summation with numpy's tree shape: the mean and
+ * std of the jaccard column in the reference's summary are such sums, create_save_summary.py:143-151), subtrees summed on
+ * n_threads threads.  Element i is x[i] (square == 0) or (x[i] - shift)^2 (square != 0), and 0 where ok[i] == 0 (ok may be
+ * NULL: every element counts) -- np.nanmean / np.nanstd's arithmetic without their temporaries. */
+int orph_f64_pairwise_sum(const double *x, const uint8_t *ok, uint64_t n, double shift, int square, int n_threads, double *out);
 /* The FASTA records Translate emits for one batch (translate.py:244-298), in read order then frame order:
  *   kind 0  coding peptides (the stdout stream): ">{name}__translation_frame:{f}__jaccard:{j}" with every space
  *           replaced by "__", then the peptide;

@@ -53,6 +53,7 @@ class StreamBatch(ctypes.Structure):
 _vp, _u8p, _u64p = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p
 _pp = ctypes.POINTER(ctypes.c_void_p)
 PROTOTYPES = {
+    "orph_device_count": (ctypes.c_int, []),
     "orph_ctx_create": (ctypes.c_int, [ctypes.c_int, _vp, _pp]),
     "orph_ctx_destroy": (None, [_vp]),
     "orph_ctx_synchronize": (ctypes.c_int, [_vp]),
@@ -104,6 +105,8 @@ PROTOTYPES = {
     "orph_csv_write_scores": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, _u8p, _u64p, ctypes.c_uint64, _vp, _vp, ctypes.c_char_p, ctypes.c_int]),
     "orph_hash_names": (ctypes.c_int, [_u8p, _u64p, ctypes.c_uint64, _u64p, ctypes.c_int]),
     "orph_u64_all_distinct": (ctypes.c_int, [_u64p, ctypes.c_uint64, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
+    "orph_summary_partial": (ctypes.c_int, [_vp, ctypes.c_uint64, _vp, _u8p, _u64p, _u64p, _u64p, ctypes.c_int]),
+    "orph_f64_pairwise_sum": (ctypes.c_int, [_vp, _u8p, ctypes.c_uint64, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
     "orph_format_fasta": (ctypes.c_int, [ctypes.c_int, _u8p, _u64p, ctypes.c_uint64, _vp, _u8p, _u64p, _u8p, _u64p, ctypes.c_int, _u8p,
                                          ctypes.c_uint64, _u64p]),
     "orph_format_float_repr": (ctypes.c_int, [ctypes.c_double, ctypes.c_char_p]),

@@ -6,7 +6,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "liborpheum_b200.so")
-SOURCES = ["orpheum_b200.cu", "fastx.cpp", "hostpack.cpp", "fused_ingest.cpp", "ingest.cpp"]
+SOURCES = ["orpheum_b200.cu", "fastx.cpp", "hostpack.cpp", "fused_ingest.cpp", "ingest.cpp", "summary.cpp"]
 HEADERS = ["device_common.cuh", "score_kernels.cuh", "task_kernels.cuh", "bloom_kernels.cuh", "long_kernels.cuh", "ingest_pipeline.inl", "synth_kernels.cuh", "hostpack.h", "fused_ingest.h", "ingest_internal.h", "stream.inl", "../../include/orpheum_b200.h"]
 
 NVCC_FLAGS = [

@@ -210,6 +210,7 @@ class ScoreTable:
         import ctypes
 
         parts = [job.result() for job in self._partials]
+        _trace("summary: per-batch shares ready")
         if any(p["hashes"] is None for p in parts):
             return None
         hashes = np.concatenate([p["hashes"] for p in parts]) if len(parts) > 1 else parts[0]["hashes"]
@@ -222,8 +223,10 @@ class ScoreTable:
         for p in parts:  # keys in order of first appearance over the whole table
             for value, count in p["histogram"].items():
                 histogram[value] = histogram.get(value, 0) + count
+        _trace("summary: ids distinct, classes and histogram merged")
         jaccard = np.concatenate([p["jaccard"] for p in parts]) if len(parts) > 1 else parts[0]["jaccard"]
         scored = np.concatenate([p["scored"] for p in parts]) if len(parts) > 1 else parts[0]["scored"]
+        _trace("summary: jaccard column concatenated")
         return _finish_summary(self.alphabet, classes, histogram, (jaccard, scored), filenames, peptide_bloom_filter_filename, peptide_ksize,
                                jaccard_threshold)
 
@@ -253,12 +256,19 @@ class ScoreTable:
 
     def write_json_summary(self, path, filenames, peptide_bloom_filter_filename, peptide_ksize, jaccard_threshold):
         summary = self.summary(filenames, peptide_bloom_filter_filename, peptide_ksize, jaccard_threshold)
+        _trace("summary: statistics done")
         with open(path, "w") as handle:
             json.dump(summary, fp=handle)
         return summary
 
 
 _bg_executors = {}
+
+
+def _trace(what):
+    from .translate import _trace as t  # (translate imports this module lazily)
+
+    t(what)
 
 
 def _background(which="summary"):
@@ -324,9 +334,59 @@ def _coding_histogram(coding_counts):
 
 
 def _partial_summary(names, records):
-    present, coding_counts, jaccard, scored = _record_columns(records)
-    return {"classes": _class_counts(present), "histogram": _coding_histogram(coding_counts), "jaccard": jaccard, "scored": scored,
+    """One batch's share of the summary, from ONE native call over its records (orph_summary_partial: no interpreter
+    time while the main thread expands the next batch); same values as _record_columns / _class_counts / _coding_histogram."""
+    import ctypes
+
+    records = np.ascontiguousarray(records)
+    n = len(records)
+    jaccard = np.empty(6 * n, dtype=np.float64)
+    scored = np.empty(6 * n, dtype=np.uint8)
+    classes = (ctypes.c_uint64 * 10)()
+    hist = (ctypes.c_uint64 * 7)()
+    first = (ctypes.c_uint64 * 7)()
+    _lib.check(_lib.load().orph_summary_partial(_lib.ptr(records), n, _lib.ptr(jaccard), _lib.ptr(scored), classes, hist, first, 0))
+    order = sorted((first[c], c) for c in range(1, 7) if hist[c])
+    return {"classes": [int(classes[0]), int(classes[1]), int(classes[2]), np.array(classes[3:9], dtype=np.int64), int(classes[9])],
+            "histogram": {c: int(hist[c]) for _, c in order}, "jaccard": jaccard, "scored": scored.view(np.bool_),
             "hashes": _name_hashes(names)}
+
+
+_native_sums_ok = None
+
+
+def _native_sums_match_numpy():
+    """orph_f64_pairwise_sum restates numpy's float64 summation order; should a numpy build ever sum differently, this
+    one-time comparison on a column shaped like the real one notices and the statistics stay with numpy."""
+    global _native_sums_ok
+    if _native_sums_ok is None:
+        rng = np.random.default_rng(12345)
+        n = 300_007
+        x = rng.integers(0, 60, n) / rng.integers(1, 60, n)
+        ok = rng.random(n) < 0.4
+        try:
+            arr = np.where(ok, x, 0.0)
+            cnt = int(ok.sum())
+            mean = np.sum(arr) / cnt
+            dev = arr - mean
+            dev[~ok] = 0.0
+            dev *= dev
+            _native_sums_ok = (_pairwise_sum(x, ok) == float(np.sum(arr)) and _pairwise_sum(x, ok, float(mean), True) == float(np.sum(dev))
+                               and _pairwise_sum(x[:1000], None) == float(np.sum(x[:1000])))
+        except Exception:
+            _native_sums_ok = False
+    return _native_sums_ok
+
+
+def _pairwise_sum(x, ok, shift=0.0, square=False):
+    import ctypes
+
+    out = ctypes.c_double()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    mask = None if ok is None else np.ascontiguousarray(ok).view(np.uint8)
+    _lib.check(_lib.load().orph_f64_pairwise_sum(_lib.ptr(x), _lib.ptr(mask) if mask is not None else None, len(x), float(shift), int(bool(square)), 0,
+                                                 ctypes.byref(out)))
+    return out.value
 
 
 def _finish_summary(alphabet, classes, histogram, jaccard, filenames, peptide_bloom_filter_filename, peptide_ksize, jaccard_threshold):
@@ -380,13 +440,22 @@ def jaccard_info(jaccard):
         if valid.size:
             # np.nanmean / np.nanstd, step by step (numpy/lib/_nanfunctions_impl.py): NaN -> 0, pairwise sum over the FULL
             # column, divide by the count; deviations with the NaN positions reset to 0, squared, summed, divided
-            arr = np.where(ok, jaccard, 0.0)
-            cnt = int(ok.sum())
-            mean = np.sum(arr) / cnt
-            np.subtract(arr, mean, out=arr)
-            arr[~ok] = 0.0
-            np.multiply(arr, arr, out=arr)
-            std = np.sqrt(np.sum(arr) / cnt)
+            cnt = int(valid.size)
+            if jaccard.size > 1_000_000 and _native_sums_match_numpy():
+                # the same two sums in numpy's summation order, natively and on every core (orph_f64_pairwise_sum), while
+                # another thread takes the order statistics (numpy's partition drops the GIL)
+                order_stats = _background("quantiles").submit(lambda: (np.percentile(valid, [25, 50, 75]), valid.min(), valid.max()))
+                mean = np.float64(_pairwise_sum(jaccard, ok)) / cnt
+                std = np.sqrt(np.float64(_pairwise_sum(jaccard, ok, float(mean), True)) / cnt)
+                (q25, q50, q75), lowest, highest = order_stats.result()
+                return {"count": cnt, "mean": mean, "std": std, "min": lowest, "25%": q25, "50%": q50, "75%": q75, "max": highest}
+            else:
+                arr = np.where(ok, jaccard, 0.0)
+                mean = np.sum(arr) / cnt
+                np.subtract(arr, mean, out=arr)
+                arr[~ok] = 0.0
+                np.multiply(arr, arr, out=arr)
+                std = np.sqrt(np.sum(arr) / cnt)
             q25, q50, q75 = np.percentile(valid, [25, 50, 75])
             return {"count": int(valid.size), "mean": mean, "std": std, "min": valid.min(), "25%": q25, "50%": q50, "75%": q75,
                     "max": valid.max()}

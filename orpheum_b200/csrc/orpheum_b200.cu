@@ -358,6 +358,16 @@ static int grid_for(uint64_t n_items, int block, int sm_count, int waves = 8)
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
+extern "C" int orph_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();  // not sticky: a machine without a GPU is an answer, not a failure
+        return 0;
+    }
+    return n;
+}
+
 extern "C" int orph_ctx_create(int device, void *stream, orph_ctx **out)
 {
     if (!out) return fail(ORPH_E_INVALID, "orph_ctx_create: out is NULL");

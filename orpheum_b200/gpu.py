@@ -438,13 +438,8 @@ class ScoringStream:
 
 
 def device_count():
-    """GPUs visible to this process (no CUDA context is created)."""
-    try:
-        import torch
-
-        return int(torch.cuda.device_count())
-    except Exception:
-        return 1
+    """GPUs visible to this process (cudaGetDeviceCount through the library: no torch import, no context created)."""
+    return int(_lib.load().orph_device_count())
 
 
 def replica_lanes(graph, n_lanes, devices=None):

@@ -301,7 +301,10 @@ class Translate:
                     continue
                 # file in, records out: parsed, packed, copied and scored by the native stream (orph_stream_*), the next
                 # batch on its way while this one is expanded into the outputs
-                with ScoringStream(self.peptide_bloom_filter, reads, self._lut, self.jaccard_threshold, replicas=self._replica_lanes()) as stream:
+                lanes = self._replica_lanes()
+                _trace("lanes decided")
+                with ScoringStream(self.peptide_bloom_filter, reads, self._lut, self.jaccard_threshold, replicas=lanes) as stream:
+                    _trace("stream open")
                     for batch in stream:
                         _trace("batch of %d reads scored" % len(batch.results))
                         if batch.status == _lib.ORPH_E_TOO_LONG:

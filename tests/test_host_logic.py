@@ -598,3 +598,49 @@ def test_mod_prime_tiny_arithmetic():
         for h in edge + [rng.getrandbits(64) for _ in range(20000)] + [rng.getrandbits(64) | (M32 << 32) for _ in range(2000)] \
                 + [rng.randrange(M64 // p) * p + d for _ in range(2000) for d in (0, p - 1)]:
             assert tiny(h, p) == h % p, (h, p)
+
+
+def test_native_summary_shares_match_the_numpy_formulation():
+    """orph_summary_partial (classes, coding-frame histogram in first-appearance order, jaccard column) against the numpy
+    functions it replaces on the CLI's background thread, and orph_f64_pairwise_sum against np.sum / np.nanmean / np.nanstd to
+    the last bit, over sizes around every split of numpy's pairwise tree."""
+    from orpheum_b200 import _lib, build, columnar
+
+    build.build()
+    rng = np.random.default_rng(2024)
+    for n in (1, 7, 1000, 70_001):
+        rec = np.zeros(n, dtype=_lib.READ_RESULT_DTYPE)
+        cat = rng.choice(6, size=(n, 6), p=[.45, .1, .05, .15, .2, .05])
+        cat[rng.random(n) < 0.1] = 5
+        cat[rng.random(n) < 0.1] = 0
+        cat[rng.random(n) < 0.05] = 4
+        nk = rng.integers(1, 300, size=(n, 6))
+        rec["category"] = cat
+        rec["n_kmers"] = nk
+        rec["n_hits"] = np.minimum((rng.random((n, 6)) * (nk + 1)).astype(np.int64), nk)
+        got = columnar._partial_summary([f"r{i}" for i in range(n)], rec)
+        present, coding_counts, jaccard, scored = columnar._record_columns(rec)
+        want_classes = columnar._class_counts(present)
+        assert got["classes"][:3] == want_classes[:3] and got["classes"][4] == want_classes[4]
+        np.testing.assert_array_equal(got["classes"][3], want_classes[3])
+        want_hist = columnar._coding_histogram(coding_counts)
+        assert list(got["histogram"].items()) == list(want_hist.items())
+        np.testing.assert_array_equal(got["scored"], scored)
+        np.testing.assert_array_equal(got["jaccard"], jaccard)  # NaN == NaN here
+    assert columnar._native_sums_match_numpy()
+    for n in [1, 7, 8, 9, 127, 128, 129, 255, 256, 257, 1023, 4097, 131072, 131073, 262145, 1_500_003]:
+        x = rng.integers(0, 50, n) / rng.integers(1, 50, n)
+        ok = rng.random(n) < 0.5
+        assert columnar._pairwise_sum(x, None) == float(np.sum(x))
+        assert columnar._pairwise_sum(x, ok) == float(np.sum(np.where(ok, x, 0.0)))
+        if ok.any():
+            with_nan = np.where(ok, x, np.nan)
+            mean = columnar._pairwise_sum(x, ok) / int(ok.sum())
+            assert mean == float(np.nanmean(with_nan))
+            assert float(np.sqrt(np.float64(columnar._pairwise_sum(x, ok, mean, True)) / int(ok.sum()))) == float(np.nanstd(with_nan))
+    # the statistics of a large column: native sums and numpy's give the same dict
+    x = rng.integers(0, 50, 1_200_000) / rng.integers(1, 50, 1_200_000)
+    ok = rng.random(x.size) < 0.4
+    fast = columnar.jaccard_info((x, ok))
+    slow = columnar.jaccard_info(np.where(ok, x, np.nan))
+    assert fast == slow
