@@ -870,7 +870,7 @@ def run_ours(args):
         configs = {}
         for name, kw in (("cfg3_dayhoff", dict(alphabet="dayhoff", workload="r150", n_reads=2_000_000, tablesize=1e8)),
                          ("cfg3_hp", dict(alphabet="hp", workload="r150", n_reads=2_000_000, tablesize=1e8)),
-                         ("cfg5_mixed", dict(alphabet="protein", workload="mixed", n_reads=1_000_000, tablesize=1e8)),
+                         ("cfg5_mixed", dict(alphabet="protein", workload="mixed", n_reads=2_000_000, tablesize=1e8)),
                          ("cfg4_hbm_filter", dict(alphabet="protein", workload="r150", n_reads=2_000_000, tablesize=1e9))):
             try:
                 configs[name] = config_leg(name, ctx, stream, dev, n_tables=args.n_tables, proteins=args.proteins, steps=5, warmup=2, **kw)
