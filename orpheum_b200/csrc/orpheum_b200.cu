@@ -1201,8 +1201,8 @@ static int score_device_impl(orph_ctx *ctx, const orph_filter *f, const uint8_t 
         {
             Timed timed(ctx, 6);
             task_scan_kernel<<<1, 64, 0, s>>>(counters);
-            task_scatter_kernel<<<grid_for(n_reads / 8 + 1, 256, ctx->sm_count, 4), 256, 0, s>>>(d_offsets, tq, (uint32_t *)ctx->task_queue_sorted.p,
-                                                                                             P.task_capacity, counters);
+            task_scatter_kernel<<<grid_for(n_reads / 8 + 1, 256, ctx->sm_count, ORPH_SORT_LOCAL ? 2 : 4), kScatterBlock, 0, s>>>(
+                d_offsets, tq, (uint32_t *)ctx->task_queue_sorted.p, P.task_capacity, counters);
         }
         ctx->launches += 2;
         CUDA_TRY(cudaGetLastError());

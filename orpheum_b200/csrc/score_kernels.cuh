@@ -579,6 +579,14 @@ prefilter_n_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restri
 // warp walks in lock step have (nearly) the same number of residues.  Skipped when a tier's lengths span
 // at most three adjacent values (fixed-length reads), where the prefilter's read order is kept.
 // ------------------------------------------------------------------------------------------------
+#ifndef ORPH_SORT_LOCAL
+#define ORPH_SORT_LOCAL 1   // 1: tasks are ordered by frame length inside chunks of ORPH_SORT_CHUNK instead of globally (A/B switch)
+#endif
+#ifndef ORPH_SORT_CHUNK
+#define ORPH_SORT_CHUNK (ORPH_SORT_LOCAL ? 16384 : 2048)
+#endif
+constexpr int kScatterBlock = ORPH_SORT_LOCAL ? 1024 : 256;  // threads per block of task_scatter_kernel
+
 __global__ void task_scan_kernel(ScoreCounters *__restrict__ counters)
 {
     const int tier = threadIdx.x >> 5, lane = threadIdx.x & 31;  // 64 threads: one warp per tier
@@ -598,13 +606,13 @@ __global__ void task_scan_kernel(ScoreCounters *__restrict__ counters)
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kScatterBlock)
 task_scatter_kernel(const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ tasks, uint32_t *__restrict__ sorted,
                     uint32_t task_capacity, ScoreCounters *__restrict__ counters)
 {
     // Each block sorts chunks of kChunk tasks: shared-memory histogram, ONE global atomic per (chunk, length) to
     // reserve the output ranges, shared-memory cursors inside them.
-    constexpr uint32_t kChunk = 2048;
+    constexpr uint32_t kChunk = ORPH_SORT_CHUNK;
     __shared__ uint32_t s_count[kLenBuckets], s_base[kLenBuckets];
 #pragma unroll
     for (int tier = 0; tier < 2; tier++) {
@@ -622,11 +630,39 @@ task_scatter_kernel(const uint64_t *__restrict__ offsets, const uint32_t *__rest
             for (uint32_t i = c0 + threadIdx.x; i < c1; i += blockDim.x)
                 atomicAdd(&s_count[plen_of(tasks[tier == 0 ? i : task_capacity - 1 - i])], 1u);
             __syncthreads();
+#if ORPH_SORT_LOCAL
+            // the chunk keeps its place in the queue and is ordered inside it (longest frames first): the 32 tasks of a warp
+            // are still frames of similar length, and they are reads from one neighbourhood of the packed stream
+            if (threadIdx.x < 32) {  // exclusive scan over the buckets, longest first: four buckets per lane of one warp
+                static_assert(kLenBuckets == 128, "four buckets per lane");
+                const uint32_t lane = threadIdx.x;
+                uint32_t cnt[4], mine = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    cnt[j] = s_count[4 * lane + j];
+                    mine += cnt[j];
+                }
+                uint32_t from_here = mine;  // tasks in the buckets of this lane and of the lanes above it
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t up = __shfl_down_sync(0xffffffffu, from_here, o);
+                    if (lane + o < 32) from_here += up;
+                }
+                uint32_t run = c0 + from_here - mine;
+#pragma unroll
+                for (int j = 3; j >= 0; j--) {
+                    s_base[4 * lane + j] = run;
+                    run += cnt[j];
+                    s_count[4 * lane + j] = 0;
+                }
+            }
+#else
             for (uint32_t b = threadIdx.x; b < kLenBuckets; b += blockDim.x) {
                 const uint32_t cnt = s_count[b];
                 s_base[b] = cnt ? atomicAdd(&counters->cursor[tier][b], cnt) : 0u;
                 s_count[b] = 0;
             }
+#endif
             __syncthreads();
             for (uint32_t i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
                 const uint32_t entry = tasks[tier == 0 ? i : task_capacity - 1 - i];
