@@ -578,6 +578,10 @@ prefilter_n_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restri
 // Counting sort of the thread-per-frame tasks by peptide length (longest first), so that the 32 frames a
 // warp walks in lock step have (nearly) the same number of residues.  Skipped when a tier's lengths span
 // at most three adjacent values (fixed-length reads), where the prefilter's read order is kept.
+// The sort is LOCAL: every chunk of ORPH_SORT_CHUNK tasks keeps its place in the queue and is ordered inside
+// it.  A global sort makes the warps just as uniform but hands each of them 32 reads from all over the
+// packed stream -- offsets, strand words and result records of neighbouring lanes then share nothing, and
+// the task kernel ran mixed-length batches 7 % slower (profiles/r02b_kernel_ab_task_sort_locality.log).
 // ------------------------------------------------------------------------------------------------
 #ifndef ORPH_SORT_LOCAL
 #define ORPH_SORT_LOCAL 1   // 1: tasks are ordered by frame length inside chunks of ORPH_SORT_CHUNK instead of globally (A/B switch)
@@ -610,8 +614,8 @@ __global__ void __launch_bounds__(kScatterBlock)
 task_scatter_kernel(const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ tasks, uint32_t *__restrict__ sorted,
                     uint32_t task_capacity, ScoreCounters *__restrict__ counters)
 {
-    // Each block sorts chunks of kChunk tasks: shared-memory histogram, ONE global atomic per (chunk, length) to
-    // reserve the output ranges, shared-memory cursors inside them.
+    // Each block sorts chunks of kChunk tasks: shared-memory histogram, output ranges by length from a scan of it (local
+    // order) or from ONE global atomic per (chunk, length) (global order), shared-memory cursors inside them.
     constexpr uint32_t kChunk = ORPH_SORT_CHUNK;
     __shared__ uint32_t s_count[kLenBuckets], s_base[kLenBuckets];
 #pragma unroll
