@@ -337,8 +337,8 @@ void orph_stream_close(orph_stream *st);
  * the read ids ALREADY rendered as CSV fields (the caller quotes the rare ids that need it), category_text[c]
  * the CSV field of category code c (NULL where the alphabet has none), filename_field likewise.
  * Does not write the header line.  Blocks of reads are formatted on n_threads host threads (<= 0: every core) and copied to
- * their places in a shared mapping of the file's new tail by all threads (pwrite() where the file cannot be mapped, or with
- * ORPHEUM_B200_CSV_PWRITE set).  The block buffers are kept between calls (one caller at a time reuses them; a concurrent
+ * their places in a shared mapping of the file's new tail by all threads (pwrite() where the file cannot be mapped, where the
+ * file system is short of space -- a full disk must be an error code, not a SIGBUS -- or with ORPHEUM_B200_CSV_PWRITE set).  The block buffers are kept between calls (one caller at a time reuses them; a concurrent
  * call allocates its own). */
 int orph_csv_write_scores(const char *path, int append, const uint8_t *name_fields, const uint64_t *name_offsets,
                           uint64_t n_reads, const orph_read_result *results, const char *const *category_text,

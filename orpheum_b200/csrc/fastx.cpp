@@ -8,6 +8,7 @@
 #include <mutex>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/statvfs.h>
 #include <unistd.h>
 #include <zlib.h>
 
@@ -616,6 +617,12 @@ extern "C" int orph_csv_write_scores(const char *path, int append, const uint8_t
         for (uint64_t k = 0; k < g1 - g0; k++) {
             at[k] = file_at;
             file_at += used[k];
+        }
+        if (can_map && file_at > at[0]) {
+            // a store into a mapping of a file system that has run out of space is a SIGBUS, a pwrite() an error code: the
+            // mapping is used only while the file system has room to spare
+            struct statvfs vfs;
+            if (fstatvfs(fd, &vfs) != 0 || (uint64_t)vfs.f_bavail * (uint64_t)vfs.f_frsize < 2 * (file_at - at[0]) + (64u << 20)) can_map = false;
         }
         if (can_map && file_at > at[0]) {
             const uint64_t map_from = at[0] / page * page;
